@@ -1,0 +1,168 @@
+"""The CPU oracle restatement must reproduce the golden vectors that oracle/gen_golden.py made by
+running the reference's own code (criteria.py, metrics.py, network/Dorn.py). This is what PINS
+the oracle; the GPU parity tests then compare the CUDA path with the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dorn as odorn
+from oracle import losses as olosses
+from oracle import metrics as ometrics
+from oracle import vnl as ovnl
+
+T = torch.from_numpy
+
+
+def close(a, b, rtol, atol=0.0):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("name", ["l1", "mse", "berhu", "laina_berhu", "silog", "eigen"])
+def test_losses_fp64_and_fp32(golden, name):
+    g = golden("losses_small.npz")
+    pred, gt = T(g["pred"]), T(g["gt"])
+    fn = olosses.LOSSES[name]
+    l64, g64 = olosses.loss_and_grad(fn, pred.double(), gt.double())
+    close(l64, g[f"{name}_loss64"], 1e-12)
+    close(g64, g[f"{name}_grad64"], 1e-10, 1e-15)
+    l32, g32 = olosses.loss_and_grad(fn, pred, gt)
+    # same op order as the reference -> fp32 results agree to a few ulp
+    close(l32, g[f"{name}_loss32"], 2e-6)
+    close(g32, g[f"{name}_grad32"], 1e-5, 1e-9)
+    # and the fp32 reference itself is within 1e-5 of its fp64 evaluation (the tolerance budget)
+    close(g[f"{name}_loss32"], g[f"{name}_loss64"], 1e-5)
+
+
+def test_laina_variants(golden):
+    g = golden("losses_small.npz")
+    pred, gt = T(g["pred"]).double(), T(g["gt"]).double()
+    l, gr = olosses.loss_and_grad(olosses.laina_berhu, pred, gt, use_logs=False)
+    close(l, g["laina_nolog_loss64"], 1e-12); close(gr, g["laina_nolog_grad64"], 1e-10, 1e-15)
+    l, gr = olosses.loss_and_grad(olosses.laina_berhu, pred, gt, size_average=False)
+    close(l, g["laina_sum_loss64"], 1e-12); close(gr, g["laina_sum_grad64"], 1e-10, 1e-15)
+    l, gr = olosses.loss_and_grad(olosses.laina_berhu, pred, gt, T(g["laina_mask_mask"]))
+    close(l, g["laina_mask_loss64"], 1e-12); close(gr, g["laina_mask_grad64"], 1e-10, 1e-15)
+    l, gr = olosses.loss_and_grad(olosses.silog, pred, gt, 0.5)
+    close(l, g["silog_vf05_loss64"], 1e-12); close(gr, g["silog_vf05_grad64"], 1e-10, 1e-15)
+
+
+def test_berhu_worked_example(golden):
+    g = golden("losses_small.npz")
+    l, gr = olosses.loss_and_grad(olosses.berhu, T(g["berhu_ex_pred"]), T(g["berhu_ex_gt"]))
+    close(l, g["berhu_ex_loss"], 1e-6)
+    close(gr, g["berhu_ex_grad"], 1e-6)
+    close(l, 3.15, 1e-6)
+    close(gr.flatten(), [0.25, 0.25, 0.0, -1.75], 1e-6)
+
+
+def test_laina_ties(golden):
+    g = golden("losses_small.npz")
+    l, gr = olosses.loss_and_grad(olosses.laina_berhu, T(g["laina_tie_pred"]).double(), T(g["laina_tie_gt"]).double())
+    close(l, g["laina_tie_loss64"], 1e-12)
+    close(gr, g["laina_tie_grad64"], 1e-10)
+
+
+def test_all_invalid_is_nan(golden):
+    g = golden("losses_small.npz")
+    t = torch.zeros(1, 1, 4, 4); p = torch.ones(1, 1, 4, 4)
+    for name in ("l1", "mse", "silog"):
+        assert np.isnan(g[f"{name}_allinvalid"])
+        assert torch.isnan(olosses.LOSSES[name](p, t))
+
+
+def test_dim_mismatch_raises():
+    with pytest.raises(AssertionError, match="inconsistent dimensions"):
+        olosses.masked_l1(torch.ones(2, 3, 4), torch.ones(2, 1, 3, 4))
+
+
+def test_metrics(golden):
+    g = golden("metrics_small.npz")
+    names = [str(n) for n in g["names"]]
+    pred, gt = T(g["pred"]), T(g["gt"])
+    v64 = [float(v) for v in ometrics.compute(pred.double(), gt.double(), names)]
+    close(v64, g["values64"], 1e-12)
+    v32 = [float(v) for v in ometrics.compute(pred, gt, names)]
+    close(v32, g["values32"], 2e-6)
+    n, c1, c2, c3 = ometrics.delta_counts(pred, gt)
+    assert n == int(g["n_valid"])
+    assert [c1, c2, c3] == [int(c) for c in g["delta_counts"]]
+    per = [[float(v) for v in ometrics.compute(pred[b:b + 1].double(), gt[b:b + 1].double(), names)]
+           for b in range(pred.shape[0])]
+    close(per, g["per_image64"], 1e-12)
+    close(ometrics.compute_per_image_mean(pred.double(), gt.double(), names), g["per_image64"].mean(0), 1e-12)
+
+
+def test_metric_thresholds_strict(golden):
+    g = golden("metrics_small.npz")
+    v = ometrics.compute(T(g["thr_pred"]), T(g["thr_gt"]), ["delta1", "delta2", "delta3"])
+    close([float(x) for x in v], g["thr_values"], 0, 0)
+    n, c1, c2, c3 = ometrics.delta_counts(T(g["thr_pred"]), T(g["thr_gt"]))
+    assert (n, c1, c2, c3) == (7, 1, 5, 6)   # only 1.2499999 is < 1.25; exact 1.25^k ratios are NOT counted
+
+
+def test_metric_running_avg_and_errors(golden):
+    g = golden("metrics_small.npz")
+    pred, gt = T(g["pred"]), T(g["gt"])
+    rm = ometrics.RunningMetrics(["absrel", "mae"])
+    rm.compute(pred[:2], gt[:2]); rm.compute(pred[2:], gt[2:])
+    close([float(rm.avg("absrel")), float(rm.avg(1))], g["running_avg"], 1e-6)
+    with pytest.raises(AssertionError, match="invalid target!"):
+        ometrics.compute(pred, torch.zeros_like(gt), ["mae"])
+    with pytest.raises(KeyError):
+        ometrics.compute(pred, gt, ["rmsle"])     # reference test.py:71 names a key that does not exist
+
+
+def test_dorn_layer_and_losses(golden):
+    g = golden("dorn_small.npz")
+    x, gt = T(g["logits"]), T(g["gt"])
+    K = x.shape[1] // 2
+    xr = x.clone().requires_grad_(True)
+    decode, P = odorn.ordinal_layer(xr)
+    assert decode.dtype == torch.int64 and tuple(decode.shape) == (x.shape[0], 1) + tuple(x.shape[2:])
+    assert np.array_equal(decode.numpy(), g["decode"])             # bit-exact
+    assert np.array_equal(P.detach().numpy(), g["P"])              # same ops -> same bits on CPU
+    depth = odorn.label_to_depth(decode, 0.001, 1.0, K)
+    y = odorn.depth_to_label(gt, 0.001, 1.0, K)
+    assert np.array_equal(depth.numpy(), g["depth"])
+    assert np.array_equal(y.numpy(), g["y_sid"])
+    loss = odorn.ord_loss(P, y)
+    (gx,) = torch.autograd.grad(loss, xr)
+    close(loss.detach(), g["ordloss32"], 2e-6)
+    close(gx, g["ordloss_gradx32"], 1e-5, 1e-10)
+    xd = x.double().clone().requires_grad_(True)
+    _, P64 = odorn.ordinal_layer(xd)
+    y64 = K * torch.log(gt.double() / 0.001) / np.log(1.0 / 0.001)
+    l64 = odorn.ord_loss(P64, y64)
+    (g64,) = torch.autograd.grad(l64, xd)
+    close(l64.detach(), g["ordloss64"], 1e-12)
+    close(g64, g["ordloss_gradx64"], 1e-10, 1e-16)
+    Pl = T(g["P"]).clone().requires_grad_(True)
+    (gP,) = torch.autograd.grad(odorn.ord_loss(Pl, y), Pl)
+    close(gP, g["ordloss_gradP32"], 1e-6, 0)
+
+
+@pytest.mark.parametrize("disc", ["SID", "UD"])
+def test_ordinal_regression_loss(golden, disc):
+    g = golden("dorn_small.npz")
+    prob, gt = T(g["orl_prob"]), T(g["orl_gt"])
+    K = prob.shape[1] // 2
+    pr = prob.clone().requires_grad_(True)
+    l = odorn.ordinal_regression_loss(pr, gt, K, torch.tensor(0.001), torch.tensor(1.0), disc)
+    (gr,) = torch.autograd.grad(l, pr)
+    close(l.detach(), g[f"orl_{disc}_loss"], 2e-6)
+    close(gr, g[f"orl_{disc}_grad"], 1e-6, 0)
+
+
+@pytest.mark.parametrize("sel", [True, False])
+def test_vnl(golden, sel):
+    g = golden("vnl_small.npz")
+    gt, pred, trip = T(g["gt"]), T(g["pred"]), T(g["trip"])
+    for tag, dt, rt in (("64", torch.float64, 1e-11), ("32", torch.float32, 1e-5)):
+        p = pred.to(dt).clone().requires_grad_(True)
+        l = ovnl.vnl_loss(gt.to(dt), p, trip, 519.0, 519.0, select=sel)
+        (gr,) = torch.autograd.grad(l, p)
+        close(l.detach(), g[f"loss{tag}_sel{int(sel)}"], rt)
+        scale = np.abs(g[f"grad{tag}_sel{int(sel)}"]).max()
+        close(gr, g[f"grad{tag}_sel{int(sel)}"], rt * 10, rt * scale)
