@@ -1,0 +1,240 @@
+/*
+ * mde_b200.h - C ABI of libmde_b200.so: the B200 (sm_100a) kernels behind the per-pixel depth
+ * supervision / evaluation hot path of xeTaiz/mono-depth-estimation.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every buffer is CALLER-OWNED DEVICE memory unless the name says host; the library never
+ *     allocates, never synchronises the stream and never throws;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns;
+ *   - return value: MDE_OK (0) or a negative MDE_E* code; mde_last_error() gives the text
+ *     (thread-local);
+ *   - `ws` is a device workspace of mde_workspace_bytes(max_images) bytes, 16-byte aligned, that
+ *     the caller initialises ONCE with mde_workspace_init(). Kernels leave it ready for the next
+ *     call (self-cleaning accumulators), so no memset is needed between calls. One workspace
+ *     must not be used by two streams at the same time, and n_img of any call must not exceed
+ *     the max_images it was initialised with;
+ *   - `pred_dtype` is MDE_F32 / MDE_F16 / MDE_BF16 (AMP: reference train.py:60,139 runs
+ *     precision=16); arithmetic is always fp32 with fp64 cross-thread accumulation; gradients
+ *     are written in the dtype of the tensor they belong to; targets are fp32;
+ *   - tensors are contiguous NCHW; "n_img" = product of all leading dims of a depth map,
+ *     "hw" = H*W pixels per image.
+ *
+ * Each entry point cites the reference interface it replaces (file:line in
+ * /root/reference = xeTaiz/mono-depth-estimation).
+ */
+#ifndef MDE_B200_H
+#define MDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDE_OK 0
+#define MDE_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown enum) */
+#define MDE_ECUDA (-2)    /* a CUDA runtime call failed; see mde_last_error() */
+#define MDE_EALIGN (-3)   /* pointer not aligned to its element size */
+#define MDE_ETOOBIG (-4)  /* size exceeds what the workspace / index type supports */
+
+#define MDE_F32 0
+#define MDE_F16 1
+#define MDE_BF16 2
+
+/* ---- metric suite ------------------------------------------------------------------------ */
+/* raw per-image sums, one row of MDE_METRIC_NQ doubles per image */
+enum {
+  MDE_Q_NVALID = 0, /* #{t > 0} */
+  MDE_Q_D1 = 1,     /* #{valid, max(p/t,t/p) < 1.25}      (IEEE fp32 divides, bit-exact) */
+  MDE_Q_D2 = 2,     /* ... < 1.5625 */
+  MDE_Q_D3 = 3,     /* ... < 1.953125 */
+  MDE_Q_ABS = 4,    /* sum |p-t| */
+  MDE_Q_SQ = 5,     /* sum (p-t)^2 */
+  MDE_Q_LOG10 = 6,  /* sum |log10 p - log10 t| */
+  MDE_Q_SLE = 7,    /* sum (log1p p - log1p t)^2 */
+  MDE_Q_ABSREL = 8, /* sum |p-t|/t */
+  MDE_Q_SQREL = 9,  /* sum (p-t)^2/t */
+  MDE_Q_RSQ = 10,   /* sum sqrt((p-t)^2/t)      (reference's 'rmse' quirk, metrics.py:106-109) */
+  MDE_Q_LNSQ = 11,  /* sum (ln p - ln t)^2 */
+  MDE_METRIC_NQ = 12
+};
+/* finished metric values, fixed order */
+enum {
+  MDE_M_DELTA1 = 0, MDE_M_DELTA2 = 1, MDE_M_DELTA3 = 2, MDE_M_MAE = 3, MDE_M_MSE = 4,
+  MDE_M_LOG10 = 5, MDE_M_MSLE = 6, MDE_M_ABSREL = 7, MDE_M_SQREL = 8, MDE_M_RMSE = 9,
+  MDE_M_RMSE_TRUE = 10, /* sqrt(mse): not in the reference */
+  MDE_M_RMSE_LOG = 11,  /* sqrt(sum (ln p-ln t)^2 / n): not in the reference */
+  MDE_METRIC_NM = 12
+};
+
+/* flags for mde_metrics */
+#define MDE_METRICS_REFERENCE_MATH 1u /* evaluate every metric with the reference's own op sequence
+                                          (log10f/log1pf/IEEE divides everywhere); default uses the
+                                          cheaper algebraically equal forms documented in DESIGN.md.
+                                          The delta counts are bit-exact in both modes. */
+/* which float-sum groups the caller needs (0 = all); sums of groups not requested come back 0 */
+#define MDE_METRICS_NEED_LOG (1u << 8)   /* MDE_Q_LOG10, MDE_Q_LNSQ  -> log10, rmse_log */
+#define MDE_METRICS_NEED_LOG1P (1u << 9) /* MDE_Q_SLE               -> msle */
+#define MDE_METRICS_NEED_REL (1u << 10)  /* MDE_Q_ABSREL/SQREL/RSQ  -> absrel, sqrel, rmse */
+
+/*
+ * Masked error metrics over a batch of depth maps in ONE pass (8 B/px).
+ * Replaces MetricComputation.compute (reference metrics.py:58-67) and the metric functions
+ * metrics.py:75-109,116-122: pred <- max(pred, 1e-7); valid = target > 0.
+ *
+ *   out_f64 layout (doubles):
+ *     [0, NM)                 pooled values: one mean over ALL valid pixels of the call
+ *                             (= what compute() returns for the call tensor)
+ *     [NM, 2NM)               image-mean values: unweighted mean over images of per-image means
+ *                             (= the reference's eval-loop semantics with batch size 1,
+ *                             SURVEY 3.2); images without a valid pixel are skipped and counted
+ *     [2NM, 2NM+NQ)           pooled raw sums
+ *     [2NM+NQ]                number of images that had >= 1 valid pixel
+ *   out_f32 (nullable): first 2NM entries of out_f64 rounded to fp32 (what callers log)
+ *   per_image_values (nullable): [n_img][NM] doubles;  per_image_raw (nullable): [n_img][NQ]
+ */
+#define MDE_METRICS_OUT_F64 (2 * MDE_METRIC_NM + MDE_METRIC_NQ + 1)
+int mde_metrics(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t hw,
+                unsigned flags, void* ws, double* out_f64, float* out_f32,
+                double* per_image_values, double* per_image_raw, void* stream);
+
+/* Finish metric values from raw sums on the HOST (used after an all-reduce of raw sums across
+ * ranks): values[NM] from raw[NQ]. Pure arithmetic, no CUDA. */
+void mde_metrics_finalize_host(const double* raw, double* values);
+
+/* ---- masked scalar losses, forward and backward fused -------------------------------------
+ * Each call computes the loss (fp32, device scalar `loss_out`) and, if `grad` is non-null,
+ * dloss/dpred * grad_scale in pred's dtype, in ONE cooperative launch: phase A reduces, a
+ * grid-wide barrier publishes the totals, phase B writes the gradient (pred/target re-read
+ * through L2). `totals_out` (nullable, doubles) receives the phase-A totals listed per loss.
+ */
+enum {
+  MDE_LOSS_L1 = 0,          /* MaskedL1Loss      criteria.py:80-90   totals {n, sum|t-p|} */
+  MDE_LOSS_MSE = 1,         /* MaskedMSELoss     criteria.py:67-77   totals {n, sum(t-p)^2} */
+  MDE_LOSS_BERHU = 2,       /* berHuLoss         criteria.py:111-133 totals {n, sum a, n_hub, sum_hub a^2, c} */
+  MDE_LOSS_LAINA_BERHU = 3, /* LainaBerHuLoss    criteria.py:476-506 totals {M, sum, dL/dc*M, n_argmax, c} */
+  MDE_LOSS_SILOG = 4,       /* silog_loss        criteria.py:724-732 totals {n, sum d, sum d^2} */
+  MDE_LOSS_EIGEN = 5,       /* MaskedDepthLoss   criteria.py:17-64   totals {D, A, my, ey, mx, ex} */
+  MDE_LOSS_COUNT = 6
+};
+#define MDE_LOSS_NTOTALS 8
+
+typedef struct {
+  float variance_focus; /* silog: lambda (modules/bts.py:233 default 0.85) */
+  float clamp_val;      /* laina: clamp_val (criteria.py:479, 1e-9) */
+  int use_logs;         /* laina: use_logs (criteria.py:479) */
+  int size_average;     /* laina: size_average (criteria.py:479) */
+} mde_loss_params;
+
+/*
+ * kind      one of MDE_LOSS_*
+ * pred      [n_img, h, w] in pred_dtype; target fp32 same shape
+ * mask_u8   nullable; LainaBerHuLoss's optional third argument (criteria.py:485) as bytes
+ * grad      nullable -> forward only
+ * grad_scale  multiplies the gradient (autograd's grad_output when it is known up front; 1.0f otherwise)
+ */
+int mde_masked_loss(int kind, const void* pred, int pred_dtype, const float* target,
+                    const uint8_t* mask_u8, int64_t n_img, int64_t h, int64_t w,
+                    const mde_loss_params* params, float grad_scale, void* ws, float* loss_out,
+                    double* totals_out, void* grad, void* stream);
+
+/* x[i] *= *scale_dev (device scalar) - applies a late-arriving grad_output to a stashed gradient */
+int mde_scale_inplace(void* x, int dtype, int64_t n, const float* scale_dev, void* stream);
+
+/* ---- DORN ordinal head -------------------------------------------------------------------- */
+#define MDE_DISC_SID 0
+#define MDE_DISC_UD 1
+
+/*
+ * OrdinalRegressionLayer.forward (reference network/Dorn.py:292-321).
+ * x [n, 2K, hw] logits (pair k = channels 2k, 2k+1), clamp to [1e-8,1e4], P_k = softmax(a,b)[1];
+ * decode[n,hw] int64 = #{k: P_k > 0.5} (bit-exact incl. clamp ties and 1-ulp near ties).
+ * prob [n,K,hw] fp32 (nullable), decode (nullable).
+ */
+int mde_ordinal_layer_fwd(const void* x, int x_dtype, int64_t n, int64_t K, int64_t hw,
+                          float* prob, int64_t* decode, void* stream);
+/* backward of the layer: grad_x [n,2K,hw] (x's dtype) from grad_prob [n,K,hw] fp32 */
+int mde_ordinal_layer_bwd(const void* x, int x_dtype, const float* grad_prob, int64_t n, int64_t K,
+                          int64_t hw, void* grad_x, void* stream);
+
+/* DORNModule.label_to_depth / depth_to_label (reference modules/dorn.py:95-107); label is
+ * int64 (decode) for _i64 and fp32 otherwise. */
+int mde_label_to_depth_i64(const int64_t* label, int64_t n, float alpha, float beta, int ord_num,
+                           int discretization, float* depth, void* stream);
+int mde_label_to_depth_f32(const float* label, int64_t n, float alpha, float beta, int ord_num,
+                           int discretization, float* depth, void* stream);
+int mde_depth_to_label(const float* depth, int64_t n, float alpha, float beta, int ord_num,
+                       int discretization, float* label, void* stream);
+
+/* ordLoss.forward (reference criteria.py:744-787): prob [n,K,hw] fp32, target [n,hw] fp32 SID
+ * label; loss = -(sum_{k<=y} ln clamp(P) + sum_{k>y} ln clamp(1-P)) / (n*hw); grad_prob nullable. */
+int mde_ord_loss(const float* prob, const float* target_label, int64_t n, int64_t K, int64_t hw,
+                 float grad_scale, void* ws, float* loss_out, float* grad_prob, void* stream);
+
+/*
+ * Fused DORN supervision step: logits + metric gt depth -> decode, depth, loss and grad_logits
+ * in one pass over the logits (1104 B/px at K=68). Equals, in the reference,
+ *   decode, P = OrdinalRegressionLayer()(x)                 network/Dorn.py:292-321
+ *   depth     = label_to_depth(decode)                      modules/dorn.py:95-100
+ *   y_sid     = depth_to_label(gt)                          modules/dorn.py:102-107
+ *   loss      = ordLoss()(P, y_sid); loss.backward()        criteria.py:744-787
+ * Any of prob / decode / depth / grad_x may be null.
+ */
+int mde_dorn_fused(const void* x, int x_dtype, const float* gt_depth, int64_t n, int64_t K,
+                   int64_t hw, float alpha, float beta, int discretization, float grad_scale,
+                   void* ws, float* loss_out, float* prob, int64_t* decode, float* depth,
+                   void* grad_x, void* stream);
+
+/* OrdinalRegressionLoss.__call__ (reference criteria.py:789-836): prob [n,2K,hw] log-probabilities
+ * laid out [K '<=' planes | K '>' planes]; label = trunc(K ln(gt/alpha)/ln(beta/alpha)); mean over
+ * gt > 0 pixels. grad_prob nullable (same layout/dtype fp32). */
+int mde_ordinal_regression_loss(const float* prob, const float* gt_depth, int64_t n, int64_t K,
+                                int64_t hw, float alpha, float beta, int discretization,
+                                float grad_scale, void* ws, float* loss_out, float* grad_prob,
+                                void* stream);
+
+/* ---- virtual-normal loss ------------------------------------------------------------------ */
+/*
+ * VNL_Loss.forward(gt_depth, pred_depth, select) (reference criteria.py:866-1045) with a
+ * SUPPLIED triplet tensor (the select_index hook, criteria.py:912-932): trip [3, n_trip] int64
+ * flat pixel indices (y*w + x), the same triplets for every image (criteria.py:948-950).
+ * Back-projection, mask logic, the z==0 fix-up quirk (criteria.py:1004), per-triplet loss, the
+ * exact 25 % trim (radix select on the fp32 bit pattern) and the scatter-add backward are fused
+ * in one cooperative launch.
+ *   scratch  device, mde_vnl_scratch_bytes(n_img, n_trip) bytes (per-triplet losses; need not be zeroed)
+ *   stats_out (nullable) doubles {M valid, q dropped, threshold, n_below, n_tie, kept_sum}
+ */
+size_t mde_vnl_scratch_bytes(int64_t n_img, int64_t n_trip);
+int mde_vnl_loss(const float* gt_depth, const void* pred, int pred_dtype, const int64_t* trip,
+                 int64_t n_img, int64_t h, int64_t w, int64_t n_trip, float fx, float fy, int select,
+                 float grad_scale, void* ws, void* scratch, float* loss_out, double* stats_out,
+                 void* grad, void* stream);
+
+/* ---- depth -> point cloud ----------------------------------------------------------------- */
+/*
+ * point_cloud(depth, cam) (reference depth2pointcloud.py:12-31) for a batch of depth maps, with the
+ * camera->world transform of :103-108 fused when matrix_world (16 host floats, row-major 4x4) is
+ * non-null. out [n_img,h,w,3] in out_dtype64 ? fp64 (the reference's numpy promotion) : fp32.
+ * Invalid pixels (depth outside (clip_start, clip_end)) give (0,0,NaN) before the transform.
+ */
+int mde_point_cloud(const float* depth, int64_t n_img, int64_t h, int64_t w, float angle_x,
+                    float clip_start, float clip_end, const float* matrix_world_host, int out_f64,
+                    void* out, void* stream);
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+size_t mde_workspace_bytes(int64_t max_images);
+/* zero-fills the workspace and records its capacity (max_images); call once after allocating */
+int mde_workspace_init(void* ws, int64_t max_images, void* stream);
+const char* mde_last_error(void);
+const char* mde_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t mde_launch_count(void);
+/* SM count / max co-resident CTAs the cooperative kernels use on the current device */
+int mde_device_info(int* sm_count, int* coop_ctas);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDE_B200_H */

@@ -1,0 +1,356 @@
+"""Drop-in for the hot subset of the reference's criteria.py on B200.
+
+Every class keeps the reference's name, constructor arguments, forward signature, `self.loss`
+side effect, error behaviour and "no tensors in state_dict" property; the forward and
+the backward of each loss run fused in ONE cooperative CUDA launch (csrc/losses.cu, eigen.cu,
+dorn.cu, vnl.cu through the C ABI of include/mde_b200.h).
+
+  MaskedDepthLoss        reference criteria.py:17-64
+  MaskedMSELoss          reference criteria.py:67-77
+  MaskedL1Loss           reference criteria.py:80-90
+  berHuLoss              reference criteria.py:111-133
+  LainaBerHuLoss         reference criteria.py:476-506
+  silog_loss             reference criteria.py:724-732
+  ordLoss                reference criteria.py:734-787
+  OrdinalRegressionLoss  reference criteria.py:789-836
+  VNL_Loss               reference criteria.py:866-1045
+  ModelLoss              reference criteria.py:1047-1062 (VNL part on the kernels; WCEL_Loss: wcel.py)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["MaskedDepthLoss", "MaskedMSELoss", "MaskedL1Loss", "berHuLoss", "LainaBerHuLoss", "silog_loss",
+           "ordLoss", "OrdinalRegressionLoss", "VNL_Loss", "ModelLoss", "masked_loss"]
+
+
+def _scale_grad(grad, grad_output):
+    """grad *= grad_output on the device (skipped inside the kernel when grad_output == 1)."""
+    lib = _lib.load()
+    go = grad_output.detach().to(torch.float32).reshape(1).contiguous()
+    _lib.check(lib.mde_scale_inplace(_lib.ptr(grad), _lib.dtype_code(grad), grad.numel(), _lib.ptr(go),
+                                     _lib.stream_ptr(grad.device)))
+    return grad
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """Generic wrapper: `launch(pred, need_grad)` returns (loss 0-dim fp32, grad or None)."""
+
+    @staticmethod
+    def forward(ctx, pred, launch):
+        need_grad = ctx.needs_input_grad[0]
+        loss, grad = launch(pred, need_grad)
+        ctx.grad = grad
+        ctx.used = False
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if ctx.grad is None:
+            return None, None
+        if ctx.used:
+            raise RuntimeError("the fused loss gradient was already consumed; run the forward again "
+                               "(retain_graph is not supported by the fused forward+backward kernel)")
+        ctx.used = True
+        g = _scale_grad(ctx.grad, grad_output)
+        ctx.grad = None
+        return g, None
+
+
+def _as_images(pred):
+    """(n_img, h, w) of a depth tensor: trailing two dims are the image, the rest are images."""
+    if pred.dim() >= 2:
+        h, w = int(pred.shape[-2]), int(pred.shape[-1])
+    else:
+        h, w = 1, int(pred.numel())
+    n_img = pred.numel() // max(h * w, 1)
+    return n_img, h, w
+
+
+def masked_loss(kind, pred, target, mask=None, params=None, totals=False):
+    """Functional entry: fused forward(+backward when pred.requires_grad) of one masked loss."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(pred, target, mask)
+    if pred.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise TypeError("pred must be fp32/fp16/bf16")
+    tgt = target.detach()
+    if tgt.shape != pred.shape:
+        tgt = tgt.expand_as(pred)
+    tgt = tgt.to(torch.float32).contiguous()
+    mk = None
+    if mask is not None:
+        mk = mask.detach()
+        if mk.shape != pred.shape:
+            mk = mk.expand_as(pred)
+        mk = (mk != 0).to(torch.uint8).contiguous()
+    lp = _lib.LossParams(0.85, 1e-9, 1, 1)
+    if params:
+        for k, v in params.items():
+            setattr(lp, k, v)
+    tot = torch.zeros(_lib.LOSS_NTOTALS, dtype=torch.float64, device=dev) if totals else None
+
+    def launch(p, need_grad):
+        pc = p.detach().contiguous()
+        n_img, h, w = _as_images(pc)
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, n_img)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            grad = torch.empty_like(pc) if need_grad else None
+            _lib.check(lib.mde_masked_loss(kind, _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(tgt), _lib.ptr(mk),
+                                           n_img, h, w, C.byref(lp), 1.0, _lib.ptr(ws), _lib.ptr(loss),
+                                           _lib.ptr(tot), _lib.ptr(grad), _lib.stream_ptr(dev)))
+        if grad is not None and grad.shape != p.shape:
+            grad = grad.view(p.shape)
+        return loss, grad
+
+    if pred.numel() == 0:
+        return torch.full((), float("nan"), device=dev) + 0 * pred.sum()
+    loss = _FusedLossFn.apply(pred, launch)
+    return (loss, tot) if totals else loss
+
+
+class MaskedDepthLoss(nn.Module):
+    """reference criteria.py:17-64 (Eigen scale-invariant + gradient term)."""
+
+    def __init__(self):
+        super(MaskedDepthLoss, self).__init__()
+
+    def forward(self, pred, target):
+        assert pred.dim() == target.dim(), "inconsistent dimensions"
+        if pred.dim() == 4 and pred.shape[1] != 1:
+            raise ValueError("MaskedDepthLoss expects single-channel depth maps [B,1,H,W] or [B,H,W]")
+        self.loss = masked_loss(_lib.LOSS_EIGEN, pred, target)
+        return self.loss
+
+
+class MaskedMSELoss(nn.Module):
+    """reference criteria.py:67-77."""
+
+    def __init__(self):
+        super(MaskedMSELoss, self).__init__()
+
+    def forward(self, pred, target):
+        assert pred.dim() == target.dim(), "inconsistent dimensions"
+        self.loss = masked_loss(_lib.LOSS_MSE, pred, target)
+        return self.loss
+
+
+class MaskedL1Loss(nn.Module):
+    """reference criteria.py:80-90."""
+
+    def __init__(self):
+        super(MaskedL1Loss, self).__init__()
+
+    def forward(self, pred, target):
+        assert pred.dim() == target.dim(), "inconsistent dimensions"
+        self.loss = masked_loss(_lib.LOSS_L1, pred, target)
+        return self.loss
+
+
+class berHuLoss(nn.Module):
+    """reference criteria.py:111-133 (threshold = 0.2*max(pred-target) over ALL pixels, signed)."""
+
+    def __init__(self):
+        super(berHuLoss, self).__init__()
+
+    def forward(self, pred, target):
+        assert pred.dim() == target.dim(), "inconsistent dimensions"
+        self.loss = masked_loss(_lib.LOSS_BERHU, pred, target)
+        return self.loss
+
+
+class LainaBerHuLoss(nn.Module):
+    """reference criteria.py:476-506 (log-space berHu, differentiable threshold)."""
+
+    def __init__(self, size_average=True, use_logs=True, clamp_val=1e-9):
+        super(LainaBerHuLoss, self).__init__()
+        self.size_average = size_average
+        self.use_log = use_logs
+        self.clamp_val = clamp_val
+
+    def forward(self, input, target, mask=None):
+        return masked_loss(_lib.LOSS_LAINA_BERHU, input, target, mask=mask,
+                           params={"size_average": int(bool(self.size_average)), "use_logs": int(bool(self.use_log)),
+                                   "clamp_val": float(self.clamp_val)})
+
+
+class silog_loss(nn.Module):
+    """reference criteria.py:724-732 (mask is depth_gt > 1e-2)."""
+
+    def __init__(self, variance_focus):
+        super(silog_loss, self).__init__()
+        self.variance_focus = variance_focus
+
+    def forward(self, depth_est, depth_gt):
+        return masked_loss(_lib.LOSS_SILOG, depth_est, depth_gt, params={"variance_focus": float(self.variance_focus)})
+
+
+# ---- DORN ------------------------------------------------------------------------------------------------
+class ordLoss(nn.Module):
+    """reference criteria.py:734-787: ord_labels = P [N,K,H,W], target = SID label [N,1,H,W] (float)."""
+
+    def __init__(self):
+        super(ordLoss, self).__init__()
+        self.loss = 0.0
+
+    def forward(self, ord_labels, target):
+        lib = _lib.load()
+        dev = _lib.require_cuda(ord_labels, target)
+        N, K, H, W = ord_labels.size()
+        tgt = target.detach().to(torch.float32).expand(N, 1, H, W).contiguous()
+
+        def launch(p, need_grad):
+            pc = p.detach().to(torch.float32).contiguous()
+            with torch.cuda.device(dev):
+                ws = _lib.workspace(dev, 1)
+                loss = torch.empty((), dtype=torch.float32, device=dev)
+                grad = torch.empty_like(pc) if need_grad else None
+                _lib.check(lib.mde_ord_loss(_lib.ptr(pc), _lib.ptr(tgt), N, K, H * W, 1.0, _lib.ptr(ws),
+                                            _lib.ptr(loss), _lib.ptr(grad), _lib.stream_ptr(dev)))
+            if grad is not None and grad.dtype != p.dtype:
+                grad = grad.to(p.dtype)
+            return loss, grad
+
+        self.loss = _FusedLossFn.apply(ord_labels, launch)
+        return self.loss
+
+
+class OrdinalRegressionLoss(object):
+    """reference criteria.py:789-836: prob = log-probabilities [N,2K,H,W] laid out [K '<=' | K '>']."""
+
+    def __init__(self, ord_num, alpha, beta, discretization="SID"):
+        self.ord_num = ord_num
+        self.alpha = alpha
+        self.beta = beta
+        self.discretization = discretization
+
+    def __call__(self, prob, gt):
+        lib = _lib.load()
+        dev = _lib.require_cuda(prob, gt)
+        if prob.shape != gt.shape:
+            # criteria.py:826-827 (exact identity when the spatial sizes already agree)
+            prob = torch.nn.functional.interpolate(prob, size=gt.shape[-2:], mode="bilinear", align_corners=True)
+        N, C2, H, W = prob.shape
+        K = int(self.ord_num)
+        assert C2 == 2 * K, "prob must have 2*ord_num channels"
+        gtc = gt.detach().to(torch.float32).reshape(N, H * W).contiguous()
+        alpha, beta = float(self.alpha), float(self.beta)
+        disc = _lib.DISC_SID if self.discretization == "SID" else _lib.DISC_UD
+
+        def launch(p, need_grad):
+            pc = p.detach().to(torch.float32).contiguous()
+            with torch.cuda.device(dev):
+                ws = _lib.workspace(dev, 1)
+                loss = torch.empty((), dtype=torch.float32, device=dev)
+                grad = torch.empty_like(pc) if need_grad else None
+                _lib.check(lib.mde_ordinal_regression_loss(_lib.ptr(pc), _lib.ptr(gtc), N, K, H * W, alpha, beta,
+                                                           disc, 1.0, _lib.ptr(ws), _lib.ptr(loss), _lib.ptr(grad),
+                                                           _lib.stream_ptr(dev)))
+            if grad is not None and grad.dtype != p.dtype:
+                grad = grad.to(p.dtype)
+            return loss, grad
+
+        return _FusedLossFn.apply(prob, launch)
+
+
+# ---- VNL ---------------------------------------------------------------------------------------------------
+class VNL_Loss(nn.Module):
+    """reference criteria.py:866-1045 (virtual-normal loss).
+
+    `select_index()` keeps the reference's contract (criteria.py:912-932: a dict p1_x..p3_y of int
+    arrays, redrawn on every call) and is the hook for supplying fixed triplets: override it, or
+    call `set_triplets(flat_index_tensor[3, n])`.
+    """
+
+    def __init__(self, focal_x, focal_y, input_size,
+                 delta_cos=0.867, delta_diff_x=0.01,
+                 delta_diff_y=0.01, delta_diff_z=0.01,
+                 delta_z=0.0001, sample_ratio=0.15):
+        super(VNL_Loss, self).__init__()
+        self.fx = float(focal_x)
+        self.fy = float(focal_y)
+        self.input_size = input_size
+        self.u0 = float(input_size[1] // 2)
+        self.v0 = float(input_size[0] // 2)
+        self.delta_cos = delta_cos
+        self.delta_diff_x = delta_diff_x
+        self.delta_diff_y = delta_diff_y
+        self.delta_diff_z = delta_diff_z
+        self.delta_z = delta_z
+        self.sample_ratio = sample_ratio
+        self._fixed = None
+        self.last_stats = None
+
+    def set_triplets(self, trip):
+        """Fix the triplets: int64 [3, n] flat pixel indices (y*W + x); None restores random sampling."""
+        self._fixed = None if trip is None else trip.detach().to(torch.int64).contiguous()
+
+    def select_index(self):
+        H, W = int(self.input_size[0]), int(self.input_size[1])
+        num = W * H
+        n = int(num * self.sample_ratio)
+        out = {}
+        for k in (1, 2, 3):
+            p = np.random.choice(num, n, replace=True)
+            np.random.shuffle(p)
+            out["p%d_x" % k] = p % W
+            out["p%d_y" % k] = (p // W).astype(np.int64)
+        return out
+
+    def _triplets(self, device):
+        if self._fixed is not None:
+            return self._fixed.to(device)
+        W = int(self.input_size[1])
+        d = self.select_index()
+        flat = np.stack([np.asarray(d["p%d_y" % k]).astype(np.int64) * W + np.asarray(d["p%d_x" % k]).astype(np.int64)
+                         for k in (1, 2, 3)])
+        return torch.from_numpy(flat).to(device)
+
+    def forward(self, gt_depth, pred_depth, select=True):
+        lib = _lib.load()
+        dev = _lib.require_cuda(gt_depth, pred_depth)
+        B, _, H, W = gt_depth.shape
+        assert (H, W) == (int(self.input_size[0]), int(self.input_size[1])), "input_size mismatch"
+        gt = gt_depth.detach().to(torch.float32).contiguous()
+        trip = self._triplets(dev)
+        n_trip = int(trip.shape[1])
+        fx, fy = self.fx, self.fy
+        stats = torch.zeros(8, dtype=torch.float64, device=dev)
+
+        def launch(p, need_grad):
+            pc = p.detach().contiguous()
+            with torch.cuda.device(dev):
+                ws = _lib.workspace(dev, B)
+                scratch = torch.empty(int(lib.mde_vnl_scratch_bytes(B, n_trip)), dtype=torch.uint8, device=dev)
+                loss = torch.empty((), dtype=torch.float32, device=dev)
+                grad = torch.empty_like(pc) if need_grad else None
+                _lib.check(lib.mde_vnl_loss(_lib.ptr(gt), _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(trip), B, H, W,
+                                            n_trip, fx, fy, int(bool(select)), 1.0, _lib.ptr(ws), _lib.ptr(scratch),
+                                            _lib.ptr(loss), _lib.ptr(stats), _lib.ptr(grad), _lib.stream_ptr(dev)))
+            return loss, grad
+
+        loss = _FusedLossFn.apply(pred_depth, launch)
+        self.last_stats = stats
+        return loss
+
+
+class ModelLoss(nn.Module):
+    """reference criteria.py:1047-1062: WCEL(pred_logit, bins, gt) + diff_loss_weight * VNL(gt, pred_depth)."""
+
+    def __init__(self, args):
+        super(ModelLoss, self).__init__()
+        from .wcel import WCEL_Loss
+        self.args = args
+        self.weight_cross_entropy_loss = WCEL_Loss(args)
+        self.virtual_normal_loss = VNL_Loss(focal_x=args.focal_x, focal_y=args.focal_y, input_size=args.crop_size)
+
+    def forward(self, pred_depth, pred_logit, depth_bins, depth_gt):
+        loss_metric = self.weight_cross_entropy_loss(pred_logit, depth_bins, depth_gt)
+        loss_normal = self.virtual_normal_loss(depth_gt, pred_depth)
+        return loss_metric + self.args.diff_loss_weight * loss_normal

@@ -1,0 +1,248 @@
+// common.cuh - shared device/host helpers of libmde_b200 (sm_100a only).
+//
+// Design notes:
+//  * every kernel here is HBM/L2-streaming fp32 work: 128-bit coalesced loads, per-thread fp32
+//    accumulation over one tile, fp64 accumulation across tiles / warps / CTAs, warp-shuffle +
+//    shared-memory block reduction, one fp64 atomic per CTA per quantity;
+//  * grids are sized from the SM count (148 on B200) times the resident CTAs per SM, each CTA
+//    owning one CONTIGUOUS chunk of the tensor (128-byte aligned) - persistent style, no tail wave;
+//  * losses that need totals before the gradient run as ONE cooperative launch with a grid-wide
+//    barrier between the reduce and gradient phases; the gradient phase walks the chunk backwards
+//    so the most recently read lines are re-read first (L2 LRU friendly).
+#pragma once
+
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mde_b200.h"
+
+namespace cg = cooperative_groups;
+
+namespace mde {
+
+constexpr int kBlock = 512;      // threads per CTA of the streaming kernels
+constexpr int kWarps = kBlock / 32;
+constexpr int kCtasPerSm = 2;    // 1024 threads/SM -> 64 registers/thread budget
+
+// ---- host side: errors, launch accounting, device info -------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int sm_count();
+// max co-resident CTAs for a cooperative launch of `func` (cached per function)
+int coop_grid(const void* func, int block, size_t smem);
+
+#define MDE_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::mde::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                       \
+      return MDE_ECUDA;                                                                 \
+    }                                                                                   \
+  } while (0)
+
+#define MDE_REQUIRE(cond, code, msg)                        \
+  do {                                                      \
+    if (!(cond)) {                                          \
+      ::mde::set_error("%s: %s", __func__, msg);            \
+      return code;                                          \
+    }                                                       \
+  } while (0)
+
+inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---- workspace layout -----------------------------------------------------------------------
+// [0,256)      header: epoch (parity of cooperative launches), ticket (last-CTA detection),
+//              dirty[2] (# per-image rows used in each cooperative parity set), capacity, error
+//              flag, tacc[16] (accumulators of the single-pass ticket kernels, self-cleaned)
+// [256, +1024) gacc[2][64] doubles : global accumulators of cooperative kernels, two parity sets
+// [1280,+128)  ukey[2][16] unsigned: order-preserving float max keys / flags, two parity sets
+// [1536, ...)  iacc[3][max_images][16] doubles : per-image accumulators; region 0 belongs to the
+//              metrics kernel (self-cleaned), regions 1,2 are the cooperative parity sets
+struct WsHeader {
+  unsigned epoch;
+  unsigned ticket;
+  unsigned dirty[2];
+  unsigned max_images;
+  unsigned error;
+  unsigned pad0[2];
+  double tacc[16];
+  unsigned pad1[24];
+};
+static_assert(sizeof(WsHeader) == 256, "workspace header must be 256 bytes");
+constexpr int kGacc = 64;
+constexpr int kUkey = 16;
+constexpr int kIacc = 16;
+constexpr size_t kWsFixedBytes = 256 + 2 * kGacc * 8 + 2 * kUkey * 4 + 128;  // 1536
+
+struct Ws {
+  WsHeader* hdr;
+  double* gacc;     // [2][kGacc]
+  unsigned* ukey;   // [2][kUkey]
+  double* iacc;     // [3][max_images][kIacc]
+};
+
+__host__ __device__ inline Ws ws_view(void* base) {
+  Ws w;
+  char* b = static_cast<char*>(base);
+  w.hdr = reinterpret_cast<WsHeader*>(b);
+  w.gacc = reinterpret_cast<double*>(b + 256);
+  w.ukey = reinterpret_cast<unsigned*>(b + 256 + 2 * kGacc * 8);
+  w.iacc = reinterpret_cast<double*>(b + kWsFixedBytes);
+  return w;
+}
+
+#ifdef __CUDACC__
+// Prologue of every cooperative kernel: read the launch parity and let CTA 0 clean the OTHER
+// parity set (used by the previous cooperative launch, which has completed) for the next one.
+// Must run before the first grid barrier; the matching epilogue (epoch + 1) after the last one.
+__device__ __forceinline__ int coop_prologue(const Ws& ws, unsigned& epoch_out) {
+  const unsigned epoch = __ldcg(&ws.hdr->epoch);
+  const int par = static_cast<int>(epoch & 1u);
+  epoch_out = epoch;
+  if (blockIdx.x == 0) {
+    const int o = par ^ 1;
+    for (int i = threadIdx.x; i < kGacc; i += blockDim.x) ws.gacc[o * kGacc + i] = 0.0;
+    for (int i = threadIdx.x; i < kUkey; i += blockDim.x) ws.ukey[o * kUkey + i] = 0u;
+    const unsigned dirty = __ldcg(&ws.hdr->dirty[o]);
+    if (dirty) {
+      const unsigned cap = __ldcg(&ws.hdr->max_images);
+      double* rows = ws.iacc + static_cast<size_t>(1 + o) * cap * kIacc;
+      for (size_t i = threadIdx.x; i < static_cast<size_t>(dirty) * kIacc; i += blockDim.x) rows[i] = 0.0;
+      __syncthreads();
+      if (threadIdx.x == 0) ws.hdr->dirty[o] = 0u;
+    }
+  }
+  return par;
+}
+#endif
+
+// ---- typed 4-element loads / stores ----------------------------------------------------------
+// LDG.E.128 for fp32, LDG.E.64 for half/bf16 (4 elements either way). `Keep` = true leaves the
+// line in L2 for the gradient phase; false streams it (evict-first).
+template <typename T>
+struct Elem;
+
+template <>
+struct Elem<float> {
+  template <bool Keep>
+  static __device__ __forceinline__ float4 ld4(const float* p) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    return Keep ? __ldg(q) : __ldcs(q);
+  }
+  static __device__ __forceinline__ float ld1(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void st4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+  static __device__ __forceinline__ void st1(float* p, float v) { __stcs(p, v); }
+};
+
+template <>
+struct Elem<__half> {
+  template <bool Keep>
+  static __device__ __forceinline__ float4 ld4(const __half* p) {
+    const uint2* q = reinterpret_cast<const uint2*>(p);
+    uint2 r = Keep ? __ldg(q) : __ldcs(q);
+    __half2 a = *reinterpret_cast<__half2*>(&r.x), b = *reinterpret_cast<__half2*>(&r.y);
+    float2 fa = __half22float2(a), fb = __half22float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ float ld1(const __half* p) {
+    return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(p))));
+  }
+  static __device__ __forceinline__ void st4(__half* p, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<unsigned*>(&a);
+    r.y = *reinterpret_cast<unsigned*>(&b);
+    __stcs(reinterpret_cast<uint2*>(p), r);
+  }
+  static __device__ __forceinline__ void st1(__half* p, float v) { *p = __float2half_rn(v); }
+};
+
+template <>
+struct Elem<__nv_bfloat16> {
+  template <bool Keep>
+  static __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    const uint2* q = reinterpret_cast<const uint2*>(p);
+    uint2 r = Keep ? __ldg(q) : __ldcs(q);
+    // bf16 -> fp32 is a 16-bit shift
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u),
+                       __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+  }
+  static __device__ __forceinline__ float ld1(const __nv_bfloat16* p) {
+    unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(p));
+    return __uint_as_float(static_cast<unsigned>(u) << 16);
+  }
+  static __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<unsigned*>(&a);
+    r.y = *reinterpret_cast<unsigned*>(&b);
+    __stcs(reinterpret_cast<uint2*>(p), r);
+  }
+  static __device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// ---- reductions --------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum N per-thread doubles over the CTA; the totals are returned to threads 0..N-1 (thread q
+// holds total q). `sm` is N*kWarps doubles of shared memory. Ends with the data consumed, so
+// the buffer can be reused after the next __syncthreads().
+template <int N>
+__device__ __forceinline__ double block_sum(const double (&v)[N], double* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    double s = warp_sum(v[q]);
+    if (lane == 0) sm[q * kWarps + warp] = s;
+  }
+  __syncthreads();
+  double tot = 0.0;
+  if (threadIdx.x < N) {
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) tot += sm[threadIdx.x * kWarps + w];
+  }
+  __syncthreads();
+  return tot;
+}
+
+// order-preserving map float -> unsigned (for atomicMax on floats of either sign); 0 is below
+// every real float, so a zero-filled workspace is the identity.
+__device__ __forceinline__ unsigned float_key(float f) {
+  unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned k) {
+  unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(b);
+}
+
+// [begin,end) of CTA `cta` when `total` units are split over `n_cta` CTAs in chunks whose
+// boundaries are multiples of `gran` units (128-byte alignment of every chunk start).
+__device__ __forceinline__ void cta_chunk(int64_t total, int gran, int cta, int n_cta, int64_t& begin,
+                                          int64_t& end) {
+  const int64_t groups = (total + gran - 1) / gran;
+  begin = (groups * cta / n_cta) * gran;
+  end = (groups * (cta + 1) / n_cta) * gran;
+  if (end > total) end = total;
+  if (begin > total) begin = total;
+}
+
+}  // namespace mde

@@ -1,0 +1,464 @@
+// dorn.cu - DORN ordinal head: pairwise softmax + decode, SID <-> depth, ordinal losses.
+//
+//   OrdinalRegressionLayer.forward   reference network/Dorn.py:292-321
+//   label_to_depth / depth_to_label  reference modules/dorn.py:95-107
+//   ordLoss.forward                  reference criteria.py:744-787
+//   OrdinalRegressionLoss.__call__   reference criteria.py:789-836
+//
+// Layout: logits x [n, 2K, hw] with pair k = channels (2k, 2k+1) (Dorn.py:305-306). One thread
+// owns one pixel and walks the K pairs; a warp therefore reads 32 consecutive pixels of one channel
+// plane per load (fully coalesced, also when hw is odd and the planes are only 4-byte aligned),
+// with 4 pairs (8 loads) in flight per thread. Everything the step needs - P, decode, depth, the
+// loss term and both logit gradients - is produced from that single read of the logits:
+// 8K (logits) + 4 (gt) + 8K (grad) + 8 (decode) + 4 (depth) = 1104 B/px at K = 68.
+//
+// Bit-exact decode. The reference decides on softmax(clamp(a), clamp(b))[1] > 0.5 evaluated in
+// fp32: with d = fl(b' - a') > 0, P = 1/fl(1 + e), e = fl(exp(-d)). P > 0.5 <=> fl(1+e) < 2 <=>
+// e <= 1 - 2^-23 <=> exp(-d) <= 1 - 1.5*2^-24 (ties-to-even at the midpoint) <=> d > 1.5*2^-24
+// (d = 1.5*2^-24 itself gives exp(-d) just above the midpoint). So decode counts pairs with
+// fl(b' - a') > 0x1.8p-24f; equal or non-positive logit pairs (clamped to 1e-8) tie and do not count.
+#include "common.cuh"
+#include "metric_math.cuh"
+
+namespace mde {
+namespace {
+
+constexpr int kDBlock = 256;
+constexpr int kDWarps = kDBlock / 32;
+constexpr float kTieMargin = 8.940696716308594e-08f;  // 1.5 * 2^-24, exactly representable
+
+__device__ __forceinline__ float clamp_logit(float v) {
+  // torch.clamp(v, 1e-8, 1e4): NaN propagates
+  v = (v < 1e-8f) ? 1e-8f : v;
+  return (v > 1e4f) ? 1e4f : v;
+}
+__device__ __forceinline__ bool logit_passes(float v) { return v >= 1e-8f && v <= 1e4f; }
+
+// P = softmax(a', b')[1] exactly as softmax evaluates it: exp(x - max) / sum
+__device__ __forceinline__ float pair_prob(float ac, float bc) {
+  const float d = bc - ac;
+  const float e = expf(-fabsf(d));
+  const float s = 1.0f + e;
+  return (d >= 0.f) ? __fdiv_rn(1.0f, s) : __fdiv_rn(e, s);
+}
+
+__device__ __forceinline__ float ln_any(float x) {
+  if (x >= 1.17549435e-38f && x < __int_as_float(0x7f800000)) return ln_pos(x);
+  return logf(x);
+}
+
+// SID / UD label of a metric depth, op for op as modules/dorn.py:102-107 evaluates it in fp32
+__device__ __forceinline__ float depth_label(float t, float alpha, float beta, int K, int disc) {
+  if (disc == MDE_DISC_SID) {
+    const float num = static_cast<float>(K) * logf(__fdiv_rn(t, alpha));
+    return __fdiv_rn(num, logf(__fdiv_rn(beta, alpha)));
+  }
+  return __fdiv_rn(static_cast<float>(K) * (t - alpha), beta - alpha);
+}
+// modules/dorn.py:95-100
+__device__ __forceinline__ float label_depth(float label, float alpha, float beta, int K, int disc) {
+  if (disc == MDE_DISC_SID) {
+    const float e = logf(alpha) + __fdiv_rn(logf(__fdiv_rn(beta, alpha)) * label, static_cast<float>(K));
+    return expf(e);
+  }
+  return alpha + __fdiv_rn((beta - alpha) * label, static_cast<float>(K));
+}
+
+// block sum of one double -> atomicAdd to *dst (thread 0)
+__device__ __forceinline__ void publish_one(double v, double* dst, double* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kDWarps; ++w) t += sm[w];
+    if (t != 0.0) atomicAdd(dst, t);
+  }
+}
+
+// true (block-uniform) in the last CTA of the grid to get here; all earlier CTAs' atomics are visible
+__device__ __forceinline__ bool last_cta(unsigned* ticket) {
+  __shared__ bool sm_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) sm_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (sm_last) __threadfence();
+  return sm_last;
+}
+
+struct DornArgs {
+  const void* x;
+  const float* gt;     // metric depth [n,hw] (fused) or SID label [n,hw] (label_mode) or null
+  int label_mode;      // gt already holds the float label (ordLoss entry point)
+  int64_t n, hw;
+  int K;
+  float alpha, beta;
+  int disc;
+  float grad_scale;
+  void* ws;
+  float* loss_out;
+  float* prob;
+  int64_t* decode;
+  float* depth;
+  void* grad_x;
+};
+
+// One kernel for: layer forward only (gt == null), fused supervision step (gt != null).
+template <typename XT>
+__global__ void __launch_bounds__(kDBlock, 4) dorn_kernel(DornArgs a) {
+  __shared__ double sm[kDWarps];
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  XT* __restrict__ gx = static_cast<XT*>(a.grad_x);
+  const int K = a.K;
+  const int64_t hw = a.hw;
+  const int64_t npx = a.n * hw;
+  const bool want_loss = (a.gt != nullptr);
+  const float inv_nhw = a.grad_scale / static_cast<float>(npx);
+
+  double loss_acc = 0.0;
+  for (int64_t px = static_cast<int64_t>(blockIdx.x) * kDBlock + threadIdx.x; px < npx;
+       px += static_cast<int64_t>(gridDim.x) * kDBlock) {
+    const int64_t img = px / hw;
+    const int64_t off = px - img * hw;
+    const int64_t base = img * (2 * static_cast<int64_t>(K)) * hw + off;  // channel 0 of this pixel
+    const int64_t pbase = img * static_cast<int64_t>(K) * hw + off;
+
+    float y = 0.f;
+    if (want_loss) {
+      const float t = __ldg(a.gt + px);
+      y = a.label_mode ? t : depth_label(t, a.alpha, a.beta, K, a.disc);
+    }
+    int cnt = 0;
+    float lsum = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u;
+        if (k < K) {
+          av[u] = Elem<XT>::ld1(x + base + static_cast<int64_t>(2 * k) * hw);
+          bv[u] = Elem<XT>::ld1(x + base + static_cast<int64_t>(2 * k + 1) * hw);
+        } else {
+          av[u] = 0.f;
+          bv[u] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u;
+        if (k >= K) break;
+        const float ac = clamp_logit(av[u]), bc = clamp_logit(bv[u]);
+        const float P = pair_prob(ac, bc);
+        cnt += ((bc - ac) > kTieMargin) ? 1 : 0;  // == (P > 0.5) of the reference, see header
+        if (a.prob) __stcs(a.prob + pbase + static_cast<int64_t>(k) * hw, P);
+        if (want_loss) {
+          const float kf = static_cast<float>(k);
+          float gz = 0.f;  // dloss/d(b' - a')
+          if (kf <= y) {   // criteria.py:769,777: ln clamp(P, 1e-8, 1e8)
+            const bool pass = P >= 1e-8f;  // P <= 1 < 1e8 always
+            lsum += ln_any(pass ? P : 1e-8f);
+            gz = pass ? -(1.0f - P) * inv_nhw : 0.f;
+          } else if (kf > y) {  // criteria.py:770,778: ln clamp(1 - P, 1e-8, 1e8)
+            const float q = 1.0f - P;
+            const bool pass = q >= 1e-8f;
+            lsum += ln_any(pass ? q : 1e-8f);
+            gz = pass ? P * inv_nhw : 0.f;
+          }
+          if (gx) {
+            Elem<XT>::st1(gx + base + static_cast<int64_t>(2 * k) * hw, logit_passes(av[u]) ? -gz : 0.f);
+            Elem<XT>::st1(gx + base + static_cast<int64_t>(2 * k + 1) * hw, logit_passes(bv[u]) ? gz : 0.f);
+          }
+        }
+      }
+    }
+    if (a.decode) a.decode[px] = static_cast<int64_t>(cnt);
+    if (a.depth) a.depth[px] = label_depth(static_cast<float>(cnt), a.alpha, a.beta, K, a.disc);
+    loss_acc += static_cast<double>(lsum);
+  }
+
+  if (!want_loss) return;
+  Ws ws = ws_view(a.ws);
+  publish_one(loss_acc, &ws.hdr->tacc[0], sm);
+  if (last_cta(&ws.hdr->ticket)) {
+    if (threadIdx.x == 0) {
+      const double s = __ldcg(&ws.hdr->tacc[0]);
+      *a.loss_out = static_cast<float>(-s / static_cast<double>(npx));  // criteria.py:784-785
+      ws.hdr->tacc[0] = 0.0;
+      ws.hdr->ticket = 0u;
+    }
+  }
+}
+
+// ordLoss(P, y): elementwise over [n,K,hw] with the label broadcast over K
+__global__ void __launch_bounds__(kDBlock, 4)
+ord_loss_kernel(const float* __restrict__ prob, const float* __restrict__ label, int64_t n, int K, int64_t hw,
+                float grad_scale, void* ws_raw, float* loss_out, float* __restrict__ grad) {
+  __shared__ double sm[kDWarps];
+  const int64_t npx = n * hw;
+  const float inv_nhw = grad_scale / static_cast<float>(npx);
+  double loss_acc = 0.0;
+  for (int64_t px = static_cast<int64_t>(blockIdx.x) * kDBlock + threadIdx.x; px < npx;
+       px += static_cast<int64_t>(gridDim.x) * kDBlock) {
+    const int64_t img = px / hw;
+    const int64_t pbase = img * static_cast<int64_t>(K) * hw + (px - img * hw);
+    const float y = __ldg(label + px);
+    float lsum = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float pv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pv[u] = (k0 + u < K) ? __ldcs(prob + pbase + static_cast<int64_t>(k0 + u) * hw) : 0.5f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u;
+        if (k >= K) break;
+        const float P = pv[u];
+        const float kf = static_cast<float>(k);
+        float g = 0.f;
+        if (kf <= y) {
+          const float c = fminf(fmaxf(P, 1e-8f), 1e8f);
+          lsum += ln_any(P != P ? P : c);
+          g = (P >= 1e-8f && P <= 1e8f) ? -inv_nhw / P : 0.f;
+        } else if (kf > y) {
+          const float q = 1.0f - P;
+          const float c = fminf(fmaxf(q, 1e-8f), 1e8f);
+          lsum += ln_any(q != q ? q : c);
+          g = (q >= 1e-8f && q <= 1e8f) ? inv_nhw / q : 0.f;
+        }
+        if (grad) __stcs(grad + pbase + static_cast<int64_t>(k) * hw, g);
+      }
+    }
+    loss_acc += static_cast<double>(lsum);
+  }
+  Ws ws = ws_view(ws_raw);
+  publish_one(loss_acc, &ws.hdr->tacc[0], sm);
+  if (last_cta(&ws.hdr->ticket)) {
+    if (threadIdx.x == 0) {
+      const double s = __ldcg(&ws.hdr->tacc[0]);
+      *loss_out = static_cast<float>(-s / static_cast<double>(npx));
+      ws.hdr->tacc[0] = 0.0;
+      ws.hdr->ticket = 0u;
+    }
+  }
+}
+
+// backward of OrdinalRegressionLayer: grad_x from grad_P
+template <typename XT>
+__global__ void __launch_bounds__(kDBlock, 4)
+ordinal_layer_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ gp, int64_t n, int K, int64_t hw,
+                         XT* __restrict__ gx) {
+  const int64_t npx = n * hw;
+  for (int64_t px = static_cast<int64_t>(blockIdx.x) * kDBlock + threadIdx.x; px < npx;
+       px += static_cast<int64_t>(gridDim.x) * kDBlock) {
+    const int64_t img = px / hw;
+    const int64_t off = px - img * hw;
+    const int64_t base = img * (2 * static_cast<int64_t>(K)) * hw + off;
+    const int64_t pbase = img * static_cast<int64_t>(K) * hw + off;
+    for (int k = 0; k < K; ++k) {
+      const float av = Elem<XT>::ld1(x + base + static_cast<int64_t>(2 * k) * hw);
+      const float bv = Elem<XT>::ld1(x + base + static_cast<int64_t>(2 * k + 1) * hw);
+      const float g = __ldcs(gp + pbase + static_cast<int64_t>(k) * hw);
+      const float P = pair_prob(clamp_logit(av), clamp_logit(bv));
+      const float gz = g * P * (1.0f - P);  // softmax backward for the 2-way case
+      Elem<XT>::st1(gx + base + static_cast<int64_t>(2 * k) * hw, logit_passes(av) ? -gz : 0.f);
+      Elem<XT>::st1(gx + base + static_cast<int64_t>(2 * k + 1) * hw, logit_passes(bv) ? gz : 0.f);
+    }
+  }
+}
+
+// OrdinalRegressionLoss: pass 1 counts valid pixels into tacc[8]
+__global__ void __launch_bounds__(kDBlock, 4) orl_count_kernel(const float* __restrict__ gt, int64_t npx, void* ws_raw) {
+  __shared__ double sm[kDWarps];
+  double c = 0.0;
+  for (int64_t px = static_cast<int64_t>(blockIdx.x) * kDBlock + threadIdx.x; px < npx;
+       px += static_cast<int64_t>(gridDim.x) * kDBlock)
+    c += (__ldg(gt + px) > 0.f) ? 1.0 : 0.0;
+  Ws ws = ws_view(ws_raw);
+  publish_one(c, &ws.hdr->tacc[8], sm);
+}
+
+__global__ void __launch_bounds__(kDBlock, 4)
+orl_kernel(const float* __restrict__ prob, const float* __restrict__ gt, int64_t n, int K, int64_t hw, float alpha,
+           float beta, int disc, float grad_scale, void* ws_raw, float* loss_out, float* __restrict__ grad) {
+  __shared__ double sm[kDWarps];
+  Ws ws = ws_view(ws_raw);
+  const double n_valid = __ldcg(&ws.hdr->tacc[8]);
+  const float gcoef = -grad_scale / static_cast<float>(n_valid);
+  const int64_t npx = n * hw;
+  double loss_acc = 0.0;
+  for (int64_t px = static_cast<int64_t>(blockIdx.x) * kDBlock + threadIdx.x; px < npx;
+       px += static_cast<int64_t>(gridDim.x) * kDBlock) {
+    const int64_t img = px / hw;
+    const int64_t base = img * (2 * static_cast<int64_t>(K)) * hw + (px - img * hw);
+    const float t = __ldg(gt + px);
+    const bool valid = t > 0.f;  // criteria.py:829
+    long long label = 0;
+    if (valid) label = __float2ll_rz(depth_label(t, alpha, beta, K, disc));  // .long(): toward zero (:805)
+    float lsum = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const bool le = !(static_cast<long long>(k) > label);  // ord_c0 = 1 where not (k > label)  (:809-810)
+      const int64_t i0 = base + static_cast<int64_t>(k) * hw;        // '<=' plane k
+      const int64_t i1 = base + static_cast<int64_t>(K + k) * hw;    // '>'  plane k
+      if (valid) lsum += le ? __ldcs(prob + i0) : __ldcs(prob + i1);
+      if (grad) {
+        __stcs(grad + i0, (valid && le) ? gcoef : 0.f);
+        __stcs(grad + i1, (valid && !le) ? gcoef : 0.f);
+      }
+    }
+    loss_acc -= static_cast<double>(lsum);
+  }
+  publish_one(loss_acc, &ws.hdr->tacc[0], sm);
+  if (last_cta(&ws.hdr->ticket)) {
+    if (threadIdx.x == 0) {
+      const double s = __ldcg(&ws.hdr->tacc[0]);
+      *loss_out = static_cast<float>(s / n_valid);
+      ws.hdr->tacc[0] = 0.0;
+      ws.hdr->tacc[8] = 0.0;
+      ws.hdr->ticket = 0u;
+    }
+  }
+}
+
+template <typename LT>
+__global__ void __launch_bounds__(kDBlock) label_to_depth_kernel(const LT* __restrict__ label, int64_t n, float alpha,
+                                                                 float beta, int K, int disc, float* __restrict__ depth) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kDBlock + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * kDBlock)
+    depth[i] = label_depth(static_cast<float>(label[i]), alpha, beta, K, disc);
+}
+
+__global__ void __launch_bounds__(kDBlock) depth_to_label_kernel(const float* __restrict__ depth, int64_t n, float alpha,
+                                                                 float beta, int K, int disc, float* __restrict__ label) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kDBlock + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * kDBlock)
+    label[i] = depth_label(__ldg(depth + i), alpha, beta, K, disc);
+}
+
+inline unsigned px_grid(int64_t npx, int ctas_per_sm) {
+  int64_t g = (npx + kDBlock - 1) / kDBlock;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * ctas_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+int launch_dorn(DornArgs& a, int x_dtype, cudaStream_t st) {
+  const unsigned grid = px_grid(a.n * a.hw, 4);
+  switch (x_dtype) {
+    case MDE_F32: dorn_kernel<float><<<grid, kDBlock, 0, st>>>(a); break;
+    case MDE_F16: dorn_kernel<__half><<<grid, kDBlock, 0, st>>>(a); break;
+    case MDE_BF16: dorn_kernel<__nv_bfloat16><<<grid, kDBlock, 0, st>>>(a); break;
+    default: set_error("dorn: unknown x_dtype %d", x_dtype); return MDE_EINVAL;
+  }
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+}  // namespace
+}  // namespace mde
+
+using namespace mde;
+
+extern "C" int mde_ordinal_layer_fwd(const void* x, int x_dtype, int64_t n, int64_t K, int64_t hw, float* prob,
+                                     int64_t* decode, void* stream) {
+  MDE_REQUIRE(x != nullptr, MDE_EINVAL, "null logits");
+  MDE_REQUIRE(n > 0 && K > 0 && hw > 0 && K < 32768, MDE_EINVAL, "bad shape");
+  DornArgs a{};
+  a.x = x; a.gt = nullptr; a.label_mode = 0; a.n = n; a.hw = hw; a.K = static_cast<int>(K);
+  a.alpha = 1.f; a.beta = 2.f; a.disc = MDE_DISC_UD; a.grad_scale = 1.f;
+  a.ws = nullptr; a.loss_out = nullptr; a.prob = prob; a.decode = decode; a.depth = nullptr; a.grad_x = nullptr;
+  return launch_dorn(a, x_dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mde_ordinal_layer_bwd(const void* x, int x_dtype, const float* grad_prob, int64_t n, int64_t K,
+                                     int64_t hw, void* grad_x, void* stream) {
+  MDE_REQUIRE(x && grad_prob && grad_x, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(n > 0 && K > 0 && hw > 0 && K < 32768, MDE_EINVAL, "bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = px_grid(n * hw, 4);
+  const int k = static_cast<int>(K);
+  switch (x_dtype) {
+    case MDE_F32: ordinal_layer_bwd_kernel<float><<<grid, kDBlock, 0, st>>>(static_cast<const float*>(x), grad_prob, n, k, hw, static_cast<float*>(grad_x)); break;
+    case MDE_F16: ordinal_layer_bwd_kernel<__half><<<grid, kDBlock, 0, st>>>(static_cast<const __half*>(x), grad_prob, n, k, hw, static_cast<__half*>(grad_x)); break;
+    case MDE_BF16: ordinal_layer_bwd_kernel<__nv_bfloat16><<<grid, kDBlock, 0, st>>>(static_cast<const __nv_bfloat16*>(x), grad_prob, n, k, hw, static_cast<__nv_bfloat16*>(grad_x)); break;
+    default: set_error("mde_ordinal_layer_bwd: unknown x_dtype %d", x_dtype); return MDE_EINVAL;
+  }
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+extern "C" int mde_label_to_depth_i64(const int64_t* label, int64_t n, float alpha, float beta, int ord_num,
+                                      int discretization, float* depth, void* stream) {
+  MDE_REQUIRE(label && depth, MDE_EINVAL, "null pointer");
+  if (n <= 0) return MDE_OK;
+  label_to_depth_kernel<int64_t><<<px_grid(n, 8), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      label, n, alpha, beta, ord_num, discretization, depth);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+extern "C" int mde_label_to_depth_f32(const float* label, int64_t n, float alpha, float beta, int ord_num,
+                                      int discretization, float* depth, void* stream) {
+  MDE_REQUIRE(label && depth, MDE_EINVAL, "null pointer");
+  if (n <= 0) return MDE_OK;
+  label_to_depth_kernel<float><<<px_grid(n, 8), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      label, n, alpha, beta, ord_num, discretization, depth);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+extern "C" int mde_depth_to_label(const float* depth, int64_t n, float alpha, float beta, int ord_num,
+                                  int discretization, float* label, void* stream) {
+  MDE_REQUIRE(depth && label, MDE_EINVAL, "null pointer");
+  if (n <= 0) return MDE_OK;
+  depth_to_label_kernel<<<px_grid(n, 8), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(depth, n, alpha, beta, ord_num,
+                                                                                          discretization, label);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+extern "C" int mde_ord_loss(const float* prob, const float* target_label, int64_t n, int64_t K, int64_t hw,
+                            float grad_scale, void* ws, float* loss_out, float* grad_prob, void* stream) {
+  MDE_REQUIRE(prob && target_label && ws && loss_out, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(n > 0 && K > 0 && hw > 0 && K < 32768, MDE_EINVAL, "bad shape");
+  ord_loss_kernel<<<px_grid(n * hw, 4), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      prob, target_label, n, static_cast<int>(K), hw, grad_scale, ws, loss_out, grad_prob);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+extern "C" int mde_dorn_fused(const void* x, int x_dtype, const float* gt_depth, int64_t n, int64_t K, int64_t hw,
+                              float alpha, float beta, int discretization, float grad_scale, void* ws,
+                              float* loss_out, float* prob, int64_t* decode, float* depth, void* grad_x,
+                              void* stream) {
+  MDE_REQUIRE(x && gt_depth && ws && loss_out, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(n > 0 && K > 0 && hw > 0 && K < 32768, MDE_EINVAL, "bad shape");
+  DornArgs a{};
+  a.x = x; a.gt = gt_depth; a.label_mode = 0; a.n = n; a.hw = hw; a.K = static_cast<int>(K);
+  a.alpha = alpha; a.beta = beta; a.disc = discretization; a.grad_scale = grad_scale;
+  a.ws = ws; a.loss_out = loss_out; a.prob = prob; a.decode = decode; a.depth = depth; a.grad_x = grad_x;
+  return launch_dorn(a, x_dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mde_ordinal_regression_loss(const float* prob, const float* gt_depth, int64_t n, int64_t K, int64_t hw,
+                                           float alpha, float beta, int discretization, float grad_scale, void* ws,
+                                           float* loss_out, float* grad_prob, void* stream) {
+  MDE_REQUIRE(prob && gt_depth && ws && loss_out, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(n > 0 && K > 0 && hw > 0 && K < 32768, MDE_EINVAL, "bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  orl_count_kernel<<<px_grid(n * hw, 4), kDBlock, 0, st>>>(gt_depth, n * hw, ws);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  orl_kernel<<<px_grid(n * hw, 4), kDBlock, 0, st>>>(prob, gt_depth, n, static_cast<int>(K), hw, alpha, beta,
+                                                     discretization, grad_scale, ws, loss_out, grad_prob);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}

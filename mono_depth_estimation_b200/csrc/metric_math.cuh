@@ -1,0 +1,139 @@
+// metric_math.cuh - per-pixel arithmetic of the masked error metrics.
+//
+// Two evaluation modes of the SAME quantities (include/mde_b200.h, MDE_Q_*):
+//   Ref  : the reference's own op sequence (metrics.py:75-109 + torchmetrics closed forms):
+//          log10f(p)-log10f(t), log1pf(p)-log1pf(t), IEEE divides everywhere.
+//   Fast : algebraically equal forms that need ONE IEEE divide and at most two logarithms per
+//          pixel; used by default because the full suite in Ref form is issue-bound, not
+//          HBM-bound, on B200 ("metrics kernel").
+// In BOTH modes the delta counts come from r = fl(max(p,t)/min(p,t)) with an IEEE divide, which
+// equals max(fl(p/t), fl(t/p)) bit for bit (round-to-nearest is monotone), so the integer counts
+// are bit-exact against the reference.
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace mde {
+
+// metric groups a launch needs (template mask: only the requested work is compiled in)
+constexpr unsigned kGrpLog = 1u;    // MDE_Q_LOG10, MDE_Q_LNSQ
+constexpr unsigned kGrpLog1p = 2u;  // MDE_Q_SLE
+constexpr unsigned kGrpRel = 4u;    // MDE_Q_ABSREL, MDE_Q_SQREL, MDE_Q_RSQ
+constexpr unsigned kGrpAll = 7u;
+
+// ln(x) for finite x >= 2^-126 (used with x >= 1): exponent/mantissa split with the mantissa in
+// [2/3, 4/3) and ln(1+f) = f - f^2/2 + f^3 g(f), g = own degree-7 near-minimax fit on [-1/3,1/3]
+// (max abs error 6.1e-9, max rel error 1.6e-8 before fp32 rounding). NaN and +inf pass through.
+__device__ __forceinline__ float ln_pos(float x) {
+  const int ix = __float_as_int(x);
+  const int e = (ix - 0x3f2aaaab) & 0xff800000;
+  const float f = __int_as_float(ix - e) - 1.0f;
+  const float fe = static_cast<float>(e) * 1.1920928955078125e-07f;  // exponent as float
+  float g = -0.1242986634938813f;
+  g = fmaf(g, f, 0.13433774844250851f);
+  g = fmaf(g, f, -0.12287236520750586f);
+  g = fmaf(g, f, 0.14116977926319346f);
+  g = fmaf(g, f, -0.16673398305540069f);
+  g = fmaf(g, f, 0.20003835432812128f);
+  g = fmaf(g, f, -0.24999943056923857f);
+  g = fmaf(g, f, 0.33333319832784086f);
+  const float f2 = f * f;
+  float r = fmaf(f2, fmaf(g, f, -0.5f), f);  // f - f^2/2 + f^3 g
+  r = fmaf(fe, 0.69314718055994531f, r);
+  return (x < __int_as_float(0x7f800000)) ? r : x;  // +inf, NaN unchanged
+}
+
+// 1/x with one Newton step on MUFU.RCP: relative error ~1e-7, unbiased enough for sums
+__device__ __forceinline__ float rcp_nr(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return fmaf(y, fmaf(-x, y, 1.0f), y);
+}
+
+// fp32 tile accumulators of one thread: 8 float sums + 4 integer counts
+struct MetricTile {
+  float s_abs, s_sq, s_log10, s_sle, s_absrel, s_sqrel, s_rsq, s_lnsq;
+  __device__ __forceinline__ void zero() {
+    s_abs = s_sq = s_log10 = s_sle = s_absrel = s_sqrel = s_rsq = s_lnsq = 0.f;
+  }
+};
+struct MetricCounts {
+  int n, c1, c2, c3;
+  __device__ __forceinline__ void zero() { n = c1 = c2 = c3 = 0; }
+};
+
+template <unsigned G, bool Ref>
+__device__ __forceinline__ void metric_px(float p, float t, MetricTile& a, MetricCounts& c) {
+  const bool v = t > 0.f;                         // metrics.py:60
+  p = (p < 1e-7f) ? 1e-7f : p;                    // clamp_min(pred, 1e-7), NaN preserved (metrics.py:59)
+  // invalid pixels are replaced by p = t = 1: every float contribution below is then exactly 0
+  const float pp = v ? p : 1.0f;
+  const float tt = v ? t : 1.0f;
+  float hi = fmaxf(pp, tt), lo = fminf(pp, tt);
+  if (pp != pp) hi = lo = pp;                     // torch.max propagates NaN; fmaxf/fminf drop it
+  const float r = __fdiv_rn(hi, lo);              // == max(fl(p/t), fl(t/p))   (metrics.py:76)
+  c.n += v ? 1 : 0;
+  c.c1 += (v && r < 1.25f) ? 1 : 0;               // strict '<' (metrics.py:77,82,87)
+  c.c2 += (v && r < 1.5625f) ? 1 : 0;
+  c.c3 += (v && r < 1.953125f) ? 1 : 0;
+  const float d = pp - tt;
+  const float ad = fabsf(d);
+  const float sq = d * d;
+  a.s_abs += ad;
+  a.s_sq += sq;
+  if (Ref) {
+    if (G & kGrpLog) {
+      a.s_log10 += fabsf(log10f(pp) - log10f(tt));            // metrics.py:90-91
+      const float dl = logf(pp) - logf(tt);
+      a.s_lnsq = fmaf(dl, dl, a.s_lnsq);
+    }
+    if (G & kGrpLog1p) {
+      const float dl = log1pf(pp) - log1pf(tt);               // torchmetrics msle
+      a.s_sle = fmaf(dl, dl, a.s_sle);
+    }
+    if (G & kGrpRel) {
+      a.s_absrel += __fdiv_rn(ad, tt);                        // metrics.py:97
+      const float sr = __fdiv_rn(sq, tt);                     // metrics.py:103
+      a.s_sqrel += sr;
+      a.s_rsq += __fsqrt_rn(sr);                              // metrics.py:109
+    }
+  } else {
+    if (G & kGrpLog) {
+      const float L = ln_pos(r);                              // |ln p - ln t| = ln(hi/lo)
+      a.s_log10 = fmaf(L, 0.43429448190325182f, a.s_log10);
+      a.s_lnsq = fmaf(L, L, a.s_lnsq);
+    }
+    if (G & kGrpLog1p) {
+      // |log1p p - log1p t| = ln((1+hi)/(1+lo))
+      const float s = (1.0f + hi) * rcp_nr(1.0f + lo);
+      const float L = ln_pos(s < 1.0f ? 1.0f : s);        // NaN stays NaN
+      a.s_sle = fmaf(L, L, a.s_sle);
+    }
+    if (G & kGrpRel) {
+      const float it = rcp_nr(tt);
+      const float ar = ad * it;
+      a.s_absrel += ar;
+      a.s_sqrel = fmaf(ar, ad, a.s_sqrel);
+      a.s_rsq = fmaf(ad, rsqrtf(tt), a.s_rsq);                // sqrt((p-t)^2/t) = |p-t| / sqrt(t)
+    }
+  }
+}
+
+// finished values from raw sums (shared by the device finaliser and mde_metrics_finalize_host)
+__host__ __device__ inline void metric_values(const double* raw, double* val) {
+  const double n = raw[MDE_Q_NVALID];
+  val[MDE_M_DELTA1] = raw[MDE_Q_D1] / n;
+  val[MDE_M_DELTA2] = raw[MDE_Q_D2] / n;
+  val[MDE_M_DELTA3] = raw[MDE_Q_D3] / n;
+  val[MDE_M_MAE] = raw[MDE_Q_ABS] / n;
+  val[MDE_M_MSE] = raw[MDE_Q_SQ] / n;
+  val[MDE_M_LOG10] = raw[MDE_Q_LOG10] / n;
+  val[MDE_M_MSLE] = raw[MDE_Q_SLE] / n;
+  val[MDE_M_ABSREL] = raw[MDE_Q_ABSREL] / n;
+  val[MDE_M_SQREL] = raw[MDE_Q_SQREL] / n;
+  val[MDE_M_RMSE] = raw[MDE_Q_RSQ] / n;
+  val[MDE_M_RMSE_TRUE] = sqrt(raw[MDE_Q_SQ] / n);
+  val[MDE_M_RMSE_LOG] = sqrt(raw[MDE_Q_LNSQ] / n);
+}
+
+}  // namespace mde

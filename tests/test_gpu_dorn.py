@@ -1,0 +1,156 @@
+"""GPU parity of the DORN ordinal head kernels against the pinned CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from mono_depth_estimation_b200 import synth
+from oracle import dorn as odorn
+from tests.gpu_util import LOSS_RTOL, T, close, grad_close, run_loss
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def D():
+    from mono_depth_estimation_b200 import dorn
+    return dorn
+
+
+@pytest.fixture(scope="module")
+def Cr():
+    from mono_depth_estimation_b200 import criteria
+    return criteria
+
+
+def test_small_golden_layer_and_ordloss(D, Cr, golden):
+    g = golden("dorn_small.npz")
+    x, gt = T(g["logits"]).cuda(), T(g["gt"]).cuda()
+    K = x.shape[1] // 2
+    xr = x.clone().requires_grad_(True)
+    decode, P = D.OrdinalRegressionLayer()(xr)
+    assert decode.dtype == torch.int64 and tuple(decode.shape) == (x.shape[0], 1) + tuple(x.shape[2:])
+    assert tuple(P.shape) == (x.shape[0], K) + tuple(x.shape[2:])
+    assert np.array_equal(decode.cpu().numpy(), g["decode"])                  # bit-exact incl. ties / near ties
+    close(P, g["P64"], 1e-5, 1e-7)
+    alpha, beta = torch.tensor(0.001), torch.tensor(1.0)
+    depth = D.label_to_depth(decode, alpha, beta, torch.tensor(K).int())
+    y = D.depth_to_label(gt, alpha, beta, torch.tensor(K).int())
+    close(depth, g["depth"], 1e-5)
+    yref = torch.from_numpy(g["y_sid"])
+    fin = torch.isfinite(yref)
+    close(y.cpu()[fin], yref[fin], 1e-5, 1e-5)
+    assert torch.equal(torch.isinf(y.cpu()), torch.isinf(yref))                # gt = 0 -> -inf label
+    loss = Cr.ordLoss()(P, y)                                                   # the reference's two-module path
+    loss.backward()
+    close(loss, g["ordloss64"], LOSS_RTOL)
+    grad_close(xr.grad, g["ordloss_gradx64"])
+    Pl = T(g["P"]).cuda().requires_grad_(True)
+    lp = Cr.ordLoss()(Pl, T(g["y_sid"]).cuda())
+    lp.backward()
+    close(lp, g["ordloss32"], LOSS_RTOL)
+    grad_close(Pl.grad, g["ordloss_gradP32"])
+
+
+def test_small_golden_fused(D, golden):
+    g = golden("dorn_small.npz")
+    x, gt = T(g["logits"]).cuda(), T(g["gt"]).cuda()
+    K = x.shape[1] // 2
+    xr = x.clone().requires_grad_(True)
+    loss, decode, depth, P = D.dorn_fused(xr, gt, K, 0.001, 1.0, "SID", want_prob=True)
+    loss.backward()
+    assert np.array_equal(decode.cpu().numpy(), g["decode"])
+    close(depth, g["depth"], 1e-5)
+    close(P, g["P64"], 1e-5, 1e-7)
+    close(loss, g["ordloss64"], LOSS_RTOL)
+    grad_close(xr.grad, g["ordloss_gradx64"])
+    head = D.DornOrdinalHead(K, 0.001, 1.0)
+    l2, d2, dec2 = head(x, gt)                                                   # no grad requested
+    close(l2, g["ordloss64"], LOSS_RTOL)
+    assert torch.equal(dec2, decode)
+
+
+@pytest.mark.parametrize("disc", ["SID", "UD"])
+def test_ordinal_regression_loss(Cr, golden, disc):
+    g = golden("dorn_small.npz")
+    prob, gt = T(g["orl_prob"]).cuda(), T(g["orl_gt"]).cuda()
+    K = prob.shape[1] // 2
+    orl = Cr.OrdinalRegressionLoss(K, torch.tensor(0.001), torch.tensor(1.0), disc)
+    loss, grad = run_loss(orl, prob, gt)
+    close(loss, g[f"orl_{disc}_loss"], LOSS_RTOL)
+    grad_close(grad, g[f"orl_{disc}_grad"])
+
+
+@pytest.mark.parametrize("shape,K", [((2, 136, 64, 80), 68), ((3, 20, 33, 41), 10), ((1, 142, 17, 19), 71)])
+def test_random_vs_oracle(D, shape, K):
+    x, gt = synth.dorn_inputs(shape, 41)
+    x[0, :, 0, 0] = 0.0                      # all-tie pixel
+    x[0, 0::2, 0, 1] = 5.0; x[0, 1::2, 0, 1] = -5.0
+    x[0, 0::2, 0, 2] = -5.0; x[0, 1::2, 0, 2] = 5.0      # all pairs counted -> decode == K
+    dec_ref, P_ref = odorn.ordinal_layer(x)
+    xd = x.double().clone().requires_grad_(True)
+    _, P64 = odorn.ordinal_layer(xd)
+    y64 = odorn.depth_to_label(gt.double(), 0.001, 1.0, K)
+    l64 = odorn.ord_loss(P64, y64)
+    (g64,) = torch.autograd.grad(l64, xd)
+    xr = x.cuda().requires_grad_(True)
+    loss, decode, depth, _ = D.dorn_fused(xr, gt.cuda(), K, 0.001, 1.0)
+    loss.backward()
+    assert torch.equal(decode.cpu(), dec_ref)                                    # bit-exact
+    assert int(decode[0, 0, 0, 0]) == 0 and int(decode[0, 0, 0, 2]) == K
+    close(depth, odorn.label_to_depth(dec_ref, 0.001, 1.0, K), 1e-5)
+    close(loss, l64.detach(), LOSS_RTOL)
+    grad_close(xr.grad, g64)
+    dec2, P = D.OrdinalRegressionLayer()(x.cuda())
+    assert torch.equal(dec2.cpu(), dec_ref)
+    close(P, P64.detach(), 1e-5, 1e-7)
+
+
+def test_decode_near_ties_bit_exact(D):
+    """Adversarial: 1..5-ulp near ties at many magnitudes, clamp ties, clamp saturation."""
+    g = torch.Generator().manual_seed(9)
+    M = 300_000
+    base = torch.rand(M, generator=g) * 8 + 1e-3
+    base[: M // 4] = torch.rand(M // 4, generator=g) * 0.5
+    ulps = torch.randint(0, 6, (M,), generator=g)
+    b = base.clone()
+    for k in range(1, 6):
+        b = torch.where(ulps >= k, torch.nextafter(b, torch.tensor(float("inf"))), b)
+    swap = torch.rand(M, generator=g) < 0.5
+    A, B = torch.where(swap, b, base), torch.where(swap, base, b)
+    extra = torch.tensor([[0.0, 0.0], [-1.0, -2.0], [1e-8, 2e-8], [2e4, 3e4], [9999.0, 2e4], [-5.0, 1e-8], [1e-9, 1.1e-8]])
+    A, B = torch.cat([A, extra[:, 0]]), torch.cat([B, extra[:, 1]])
+    x = torch.stack([A, B], 0).view(1, 2, 1, -1).contiguous()
+    dec_ref, P_ref = odorn.ordinal_layer(x)
+    dec, P = D.OrdinalRegressionLayer()(x.cuda())
+    assert torch.equal(dec.cpu(), dec_ref)
+    close(P, P_ref, 1e-6, 1e-7)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_logits(D, dtype):
+    x, gt = synth.dorn_inputs((2, 24, 9, 16), 42)
+    xh = x.to(dtype)
+    dec_ref, _ = odorn.ordinal_layer(xh.float())
+    xd = xh.double().clone().requires_grad_(True)
+    _, P64 = odorn.ordinal_layer(xd)
+    l64 = odorn.ord_loss(P64, odorn.depth_to_label(gt.double(), 0.001, 1.0, 12))
+    (g64,) = torch.autograd.grad(l64, xd)
+    xr = xh.cuda().requires_grad_(True)
+    loss, decode, depth, _ = D.dorn_fused(xr, gt.cuda(), 12, 0.001, 1.0)
+    loss.backward()
+    assert torch.equal(decode.cpu(), dec_ref) and xr.grad.dtype == dtype
+    close(loss, l64.detach(), LOSS_RTOL)
+    eps = 1e-3 if dtype == torch.float16 else 8e-3
+    close(xr.grad, g64, eps, eps * float(g64.abs().max()))
+
+
+def test_sid_tables(D):
+    lab = torch.arange(0, 69).view(1, 1, 3, 23)
+    for ds in ("kitti", "nyu", "floorplan3d"):
+        close(D.get_depth_sid(ds, lab.cuda()), odorn.sid_table_depth(ds, lab), 1e-5)
+    d = torch.rand(1, 1, 8, 8) * 9 + 0.5
+    # truncation toward zero of a float label computed with CUDA logf: allow the rare off-by-one at integers
+    a, b = D.get_labels_sid("nyu", d.cuda()).cpu(), odorn.sid_table_labels("nyu", d)
+    assert a.dtype == torch.int32 and int((a - b).abs().max()) <= 1 and float((a != b).float().mean()) < 0.02
+    close(D.label_to_depth(lab.cuda().float(), 0.5, 10.0, 68, "UD"), odorn.label_to_depth(lab.float(), 0.5, 10.0, 68, "UD"), 1e-6)
+    close(D.depth_to_label(d.cuda(), 0.5, 10.0, 68, "UD"), odorn.depth_to_label(d, 0.5, 10.0, 68, "UD"), 1e-5, 1e-5)

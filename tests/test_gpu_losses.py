@@ -1,0 +1,173 @@
+"""GPU parity of the fused masked losses (C ABI mde_masked_loss) against the pinned CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from mono_depth_estimation_b200 import synth
+from oracle import losses as olosses
+from tests.gpu_util import LOSS_RTOL, T, close, grad_close, run_loss
+
+pytestmark = pytest.mark.gpu
+NAMES = ["l1", "mse", "berhu", "laina_berhu", "silog", "eigen"]
+
+
+@pytest.fixture(scope="module")
+def Cr():
+    from mono_depth_estimation_b200 import criteria
+    return criteria
+
+
+def make(Cr, name):
+    return {"l1": Cr.MaskedL1Loss, "mse": Cr.MaskedMSELoss, "berhu": Cr.berHuLoss, "laina_berhu": Cr.LainaBerHuLoss,
+            "silog": lambda: Cr.silog_loss(0.85), "eigen": Cr.MaskedDepthLoss}[name]()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_small_golden(Cr, golden, name):
+    g = golden("losses_small.npz")
+    pred, gt = T(g["pred"]).cuda(), T(g["gt"]).cuda()
+    m = make(Cr, name)
+    loss, grad = run_loss(m, pred, gt)
+    assert loss.dim() == 0 and loss.is_cuda and grad.shape == pred.shape and grad.dtype == pred.dtype
+    close(loss, g[f"{name}_loss64"], LOSS_RTOL)
+    grad_close(grad, g[f"{name}_grad64"])
+    if name not in ("laina_berhu", "silog"):
+        assert m.loss is not None                     # side effect callers may read (criteria.py:63,76,89,131)
+    # forward only (no autograd) gives the same value and no gradient work
+    with torch.no_grad():
+        close(make(Cr, name)(pred, gt), g[f"{name}_loss64"], LOSS_RTOL)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_config_c1_golden(Cr, golden, name):
+    g = golden("config_c1.npz")
+    pred, gt = synth.config_inputs("C1")
+    loss, grad = run_loss(make(Cr, name), pred.cuda(), gt.cuda())
+    close(loss, g[f"{name}_loss64"], LOSS_RTOL)
+    gd = grad.double().cpu()
+    probe = torch.from_numpy(g["probe_idx"])
+    scale = float(g[f"{name}_gradabssum64"]) / pred.numel()
+    close(gd.flatten()[probe], g[f"{name}_gradprobe64"], 1e-5, 2e-5 * scale)
+    close(gd.abs().sum(), g[f"{name}_gradabssum64"], 1e-5)
+    close(gd.sum(), g[f"{name}_gradsum64"], 1e-5, 1e-5 * float(g[f"{name}_gradabssum64"]))
+
+
+@pytest.mark.parametrize("name", ["silog", "berhu", "l1"])
+def test_config_c2_vs_oracle(Cr, name):
+    pred, gt = synth.config_inputs("C2")
+    l64, g64 = olosses.loss_and_grad(olosses.LOSSES[name], pred.double(), gt.double())
+    loss, grad = run_loss(make(Cr, name), pred.cuda(), gt.cuda())
+    close(loss, l64, LOSS_RTOL)
+    grad_close(grad, g64)
+
+
+def test_laina_variants_and_silog_focus(Cr, golden):
+    g = golden("losses_small.npz")
+    pred, gt = T(g["pred"]).cuda(), T(g["gt"]).cuda()
+    for tag, mod, extra in (("laina_nolog", Cr.LainaBerHuLoss(use_logs=False), ()),
+                            ("laina_sum", Cr.LainaBerHuLoss(size_average=False), ()),
+                            ("laina_mask", Cr.LainaBerHuLoss(), (T(g["laina_mask_mask"]).cuda(),))):
+        loss, grad = run_loss(mod, pred, gt, *extra)
+        close(loss, g[f"{tag}_loss64"], LOSS_RTOL, msg=tag)
+        grad_close(grad, g[f"{tag}_grad64"], msg=tag)
+    loss, grad = run_loss(Cr.silog_loss(0.5), pred, gt)
+    close(loss, g["silog_vf05_loss64"], LOSS_RTOL)
+    grad_close(grad, g["silog_vf05_grad64"])
+
+
+def test_worked_examples(Cr, golden):
+    g = golden("losses_small.npz")
+    loss, grad = run_loss(Cr.berHuLoss(), T(g["berhu_ex_pred"]).cuda(), T(g["berhu_ex_gt"]).cuda())
+    close(loss, 3.15, 1e-6)
+    close(grad.flatten(), [0.25, 0.25, 0.0, -1.75], 1e-6)
+    loss, grad = run_loss(Cr.LainaBerHuLoss(), T(g["laina_tie_pred"]).cuda(), T(g["laina_tie_gt"]).cuda())
+    close(loss, g["laina_tie_loss64"], LOSS_RTOL)
+    grad_close(grad, g["laina_tie_grad64"])          # gradient through c is split evenly over tied maxima
+
+
+def test_empty_mask_and_errors(Cr):
+    t = torch.zeros(1, 1, 4, 4).cuda(); p = torch.ones(1, 1, 4, 4).cuda()
+    for m in (Cr.MaskedL1Loss(), Cr.MaskedMSELoss(), Cr.silog_loss(0.85)):
+        assert torch.isnan(m(p, t))                   # reference: empty mask -> NaN, no exception
+    with pytest.raises(AssertionError, match="inconsistent dimensions"):
+        Cr.MaskedMSELoss()(torch.ones(2, 3, 4).cuda(), torch.ones(2, 1, 3, 4).cuda())
+
+
+@pytest.mark.parametrize("name", ["l1", "silog", "berhu", "eigen"])
+def test_layouts_tails_and_alignment(Cr, name):
+    fn = olosses.LOSSES[name]
+    # odd sizes (n % 4 != 0), 3-D input, non-contiguous view, 4-byte-offset storage (scalar path)
+    for shape in ((3, 1, 33, 41), (2, 1, 7, 5), (4, 1, 16, 24)):
+        pred, gt = synth.depth_pair(shape, 31, border=1)
+        l64, g64 = olosses.loss_and_grad(fn, pred.double(), gt.double())
+        loss, grad = run_loss(make(Cr, name), pred.cuda(), gt.cuda())
+        close(loss, l64, LOSS_RTOL, msg=str(shape)); grad_close(grad, g64, msg=str(shape))
+    pred, gt = synth.depth_pair((4, 1, 16, 24), 32, border=1)
+    l64, g64 = olosses.loss_and_grad(fn, pred.double(), gt.double())
+    buf = torch.zeros(pred.numel() + 1).cuda()
+    buf[1:] = pred.flatten().cuda()
+    shifted = buf[1:].view(pred.shape)                # data_ptr is 4 bytes off a 16-byte boundary
+    loss, grad = run_loss(make(Cr, name), shifted, gt.cuda())
+    close(loss, l64, LOSS_RTOL); grad_close(grad, g64)
+    wide = torch.zeros(4, 1, 16, 48).cuda()
+    wide[..., ::2] = pred.cuda()
+    loss, grad = run_loss(make(Cr, name), wide[..., ::2], gt.cuda())   # non-contiguous
+    close(loss, l64, LOSS_RTOL); grad_close(grad, g64)
+    if name != "eigen":
+        p3, t3 = pred[:, 0], gt[:, 0]
+        loss, grad = run_loss(make(Cr, name), p3.cuda(), t3.cuda())
+        close(loss, l64, LOSS_RTOL); grad_close(grad, g64[:, 0])
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_amp_pred_dtypes(Cr, dtype):
+    pred, gt = synth.depth_pair((2, 1, 24, 32), 33, border=1)
+    ph = pred.to(dtype)
+    for name in ("silog", "berhu", "eigen"):
+        l64, g64 = olosses.loss_and_grad(olosses.LOSSES[name], ph.double(), gt.double())
+        loss, grad = run_loss(make(Cr, name), ph.cuda(), gt.cuda())
+        assert grad.dtype == dtype
+        close(loss, l64, LOSS_RTOL, msg=name)
+        eps = 1e-3 if dtype == torch.float16 else 8e-3   # the gradient is ROUNDED to pred's dtype
+        close(grad, g64, eps, eps * float(g64.abs().max()), msg=name)
+
+
+def test_grad_output_scaling_and_reuse(Cr):
+    pred, gt = synth.depth_pair((2, 1, 24, 32), 34, border=1)
+    l64, g64 = olosses.loss_and_grad(olosses.silog, pred.double(), gt.double())
+    p = pred.cuda().requires_grad_(True)
+    loss = Cr.silog_loss(0.85)(p, gt.cuda())
+    (loss * 65536.0).backward()                        # GradScaler-style grad_output
+    grad_close(p.grad / 65536.0, g64)
+    # the loss composes with other autograd ops
+    p2 = pred.cuda().requires_grad_(True)
+    total = Cr.MaskedL1Loss()(p2 * 1.0, gt.cuda()) + 0.5 * Cr.MaskedMSELoss()(p2, gt.cuda())
+    total.backward()
+    _, ga = olosses.loss_and_grad(olosses.masked_l1, pred.double(), gt.double())
+    _, gb = olosses.loss_and_grad(olosses.masked_mse, pred.double(), gt.double())
+    grad_close(p2.grad, ga + 0.5 * gb)
+    # many calls in a row on one workspace (parity sets alternate)
+    m = Cr.berHuLoss()
+    ref, _ = olosses.loss_and_grad(olosses.berhu, pred.double(), gt.double())
+    for _ in range(5):
+        close(run_loss(m, pred.cuda(), gt.cuda())[0], ref, LOSS_RTOL)
+
+
+def test_shift_property_at_scale(Cr):
+    """Size-independent checks at a size the CPU oracle is not run on: MaskedL1 and SILog are invariant
+    under the transforms the math says they are, and the gradient integrates the loss."""
+    pred, gt = synth.depth_pair((64, 1, 480, 640), 35, device="cuda")
+    l1 = Cr.MaskedL1Loss()
+    a = l1(pred, gt)
+    b = l1(pred * 2, gt * 2)
+    close(b, 2 * a, 1e-6)
+    si = Cr.silog_loss(1.0)                            # lambda = 1: invariant to a global scale of pred
+    close(si(pred * 1.7, gt), si(pred, gt), 1e-5)
+    # MSE is quadratic in pred: L(p + h g) = L(p) + h |g|^2 + h^2 |g|^2 / n_valid  (g = dL/dp, zero off-mask)
+    loss, grad = run_loss(Cr.MaskedMSELoss(), pred, gt)
+    g2 = float((grad.double() ** 2).sum())
+    n_valid = float((gt > 0).sum())
+    h = 0.05 * float(loss) / g2
+    with torch.no_grad():
+        l2 = Cr.MaskedMSELoss()(pred + h * grad, gt)
+    close(float(l2) - float(loss), h * g2 + h * h * g2 / n_valid, 1e-3)

@@ -1,0 +1,142 @@
+"""GPU parity of the fused metrics kernel (C ABI mde_metrics) against the pinned CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from mono_depth_estimation_b200 import synth
+from oracle import metrics as ometrics
+from tests.gpu_util import T, close
+
+pytestmark = pytest.mark.gpu
+ALL = ["delta1", "delta2", "delta3", "mae", "mse", "log10", "msle", "absrel", "sqrel", "rmse", "rmse_true", "rmse_log"]
+METRIC_RTOL = 1e-5   # BASELINE.json: float metrics within 1e-5 relative
+
+
+@pytest.fixture(scope="module")
+def M():
+    from mono_depth_estimation_b200 import metrics
+    return metrics
+
+
+def _counts(res):
+    raw = res["f64"][24:36].cpu().numpy()
+    return [int(round(v)) for v in raw[:4]]
+
+
+@pytest.mark.parametrize("ref_math", [False, True])
+def test_small_golden(M, golden, ref_math):
+    g = golden("metrics_small.npz")
+    names = [str(n) for n in g["names"]]
+    pred, gt = T(g["pred"]).cuda(), T(g["gt"]).cuda()
+    mc = M.MetricComputation(names, reference_math=ref_math)
+    vals = mc.compute(pred, gt)
+    assert all(v.dim() == 0 and v.is_cuda and v.dtype == torch.float32 for v in vals)
+    close(torch.stack(vals), g["values64"], METRIC_RTOL)
+    res = M.fused_metrics(pred, gt, per_image=True, reference_math=ref_math)
+    assert _counts(res) == [int(g["n_valid"])] + [int(c) for c in g["delta_counts"]]      # bit-exact
+    idx = [ALL.index(n) for n in names]
+    close(res["per_image"][:, idx], g["per_image64"], METRIC_RTOL)
+    close(res["image_mean"][idx], g["per_image64"].mean(0), METRIC_RTOL)
+    vb = M.MetricComputation(names, reference_math=ref_math).compute_batch(pred, gt)
+    close(torch.stack(vb), g["per_image64"].mean(0), METRIC_RTOL)
+
+
+def test_thresholds_are_strict(M, golden):
+    g = golden("metrics_small.npz")
+    p, t = T(g["thr_pred"]).cuda(), T(g["thr_gt"]).cuda()
+    vals = M.MetricComputation(["delta1", "delta2", "delta3"]).compute(p, t)
+    close(torch.stack(vals), g["thr_values"], 1e-7)
+    assert _counts(M.fused_metrics(p, t)) == [7, 1, 5, 6]
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_config_vs_oracle(M, golden, name):
+    pred, gt = synth.config_inputs(name)
+    res = M.fused_metrics(pred.cuda(), gt.cuda())
+    v64 = [float(v) for v in ometrics.compute(pred.double(), gt.double(), ALL)]
+    close(res["f64"][:12], v64, METRIC_RTOL)
+    assert _counts(res) == list(ometrics.delta_counts(pred, gt))                            # bit-exact
+    res_ref = M.fused_metrics(pred.cuda(), gt.cuda(), reference_math=True)
+    close(res_ref["f64"][:12], v64, METRIC_RTOL)
+    assert _counts(res_ref) == _counts(res)
+    if name == "C1":
+        g = golden("config_c1.npz")
+        names = [str(n) for n in g["metric_names"]]
+        close(res["f64"][[ALL.index(n) for n in names]], g["metrics64"], METRIC_RTOL)
+        assert _counts(res) == [int(g["n_valid"])] + [int(c) for c in g["delta_counts"]]
+
+
+def test_default_metric_groups_and_running_avg(M, golden):
+    g = golden("metrics_small.npz")
+    pred, gt = T(g["pred"]).cuda(), T(g["gt"]).cuda()
+    names = ["delta1", "delta2", "delta3", "mse", "mae", "log10", "rmse"]           # reference evaluate.py:11
+    mc = M.MetricComputation(names)
+    vals = mc.compute(pred, gt)
+    ref = [float(v) for v in ometrics.compute(pred.cpu().double(), gt.cpu().double(), names)]
+    close(torch.stack(vals), ref, METRIC_RTOL)
+    mc2 = M.MetricComputation(["absrel", "mae"])
+    mc2.compute(pred[:2], gt[:2]); mc2.compute(pred[2:], gt[2:])
+    close(torch.stack([mc2.avg("absrel"), mc2.avg(1)]), g["running_avg"], METRIC_RTOL)
+    assert mc2.count == 2
+    mc2.reset()
+    assert mc2.count == 0 and mc2.sum == [0.0, 0.0]
+    for n in ("absrel", "msle", "delta2"):                                             # METRICS[name](p_1d, t_1d)
+        p1, t1 = ometrics.gather_valid(pred.cpu(), gt.cpu())
+        close(M.METRICS[n](p1.cuda(), t1.cuda()), float(ometrics.METRIC_FNS[n](p1.double(), t1.double())), METRIC_RTOL)
+
+
+@pytest.mark.parametrize("shape", [(3, 1, 33, 41), (2, 1, 7, 5), (1, 1, 1, 3), (5, 2, 12, 20)])
+def test_odd_shapes_and_repeat_calls(M, shape):
+    pred, gt = synth.depth_pair(shape, 21, border=1)
+    for _ in range(2):   # second call checks the self-cleaning workspace
+        res = M.fused_metrics(pred.cuda(), gt.cuda(), per_image=True)
+        v64 = [float(v) for v in ometrics.compute(pred.double(), gt.double(), ALL)]
+        close(res["f64"][:12], v64, METRIC_RTOL)
+        assert _counts(res) == list(ometrics.delta_counts(pred, gt))
+        n_img = pred.numel() // (shape[-1] * shape[-2])
+        assert res["per_image"].shape == (n_img, 12)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_precision_pred(M, dtype):
+    pred, gt = synth.depth_pair((2, 1, 24, 32), 22, border=1)
+    ph = pred.to(dtype)
+    res = M.fused_metrics(ph.cuda(), gt.cuda())
+    v64 = [float(v) for v in ometrics.compute(ph.double(), gt.double(), ALL)]
+    close(res["f64"][:12], v64, METRIC_RTOL)
+    assert _counts(res) == list(ometrics.delta_counts(ph.float(), gt))
+
+
+def test_invalid_target_and_clamp(M):
+    pred = torch.ones(1, 1, 8, 8).cuda()
+    with pytest.raises(AssertionError, match="invalid target!"):
+        M.MetricComputation(["mae"]).compute(pred, torch.zeros(1, 1, 8, 8).cuda())
+    vals = M.MetricComputation(["mae"], strict=False).compute(pred, torch.zeros(1, 1, 8, 8).cuda())
+    assert torch.isnan(vals[0])
+    # negative / zero predictions are clamped to 1e-7 (metrics.py:59)
+    p = torch.tensor([[[[-1.0, 0.0, 2.0, 3.0]]]]); t = torch.tensor([[[[1.0, 2.0, 2.0, 0.0]]]])
+    res = M.fused_metrics(p.cuda(), t.cuda())
+    close(res["f64"][:12], [float(v) for v in ometrics.compute(p.double(), t.double(), ALL)], METRIC_RTOL)
+    # NaN prediction on a valid pixel poisons the float metrics but not the counts' validity
+    p = torch.tensor([[[[float("nan"), 1.0, 2.0, 3.0]]]]); t = torch.tensor([[[[1.0, 1.0, 2.0, 3.0]]]])
+    res = M.fused_metrics(p.cuda(), t.cuda())
+    assert torch.isnan(res["values"][3]) and _counts(res) == [4, 3, 3, 3]
+
+
+def test_batch_linearity_at_scale(M):
+    """Size-independent property at a large size: raw sums over a batch = sum over its halves, counts
+    exactly, and per-image rows do not depend on which other images share the launch."""
+    pred, gt = synth.depth_pair((48, 1, 480, 640), 23, device="cuda")
+    full = M.fused_metrics(pred, gt, per_image=True)
+    a = M.fused_metrics(pred[:17], gt[:17], per_image=True)
+    b = M.fused_metrics(pred[17:], gt[17:], per_image=True)
+    raw_f, raw_a, raw_b = full["f64"][24:36], a["f64"][24:36], b["f64"][24:36]
+    assert torch.equal(raw_f[:4], raw_a[:4] + raw_b[:4])
+    close(raw_f[4:], raw_a[4:] + raw_b[4:], 2e-6)   # different CTA partitions -> different fp32 tile groupings
+    pir = torch.cat([a["per_image_raw"], b["per_image_raw"]])
+    assert torch.equal(full["per_image_raw"][:, :4], pir[:, :4])
+    close(full["per_image_raw"], pir, 2e-6)
+    # and against the oracle on a 3-image slice
+    sl = slice(5, 8)
+    v64 = ometrics.compute_per_image_mean(pred[sl].cpu().double(), gt[sl].cpu().double(), ALL)
+    close(full["per_image"][sl].mean(0), v64, METRIC_RTOL)

@@ -1,0 +1,86 @@
+"""GPU parity of the virtual-normal loss and the point-cloud back-projection."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from mono_depth_estimation_b200 import synth
+from oracle import pointcloud as opc
+from oracle import vnl as ovnl
+from tests.gpu_util import LOSS_RTOL, T, close, grad_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Cr():
+    from mono_depth_estimation_b200 import criteria
+    return criteria
+
+
+def _vnl(Cr, gt, pred, trip, select=True):
+    H, W = gt.shape[-2:]
+    v = Cr.VNL_Loss(519.0, 519.0, (H, W))
+    v.set_triplets(trip.cuda())
+    p = pred.cuda().clone().requires_grad_(True)
+    loss = v(gt.cuda(), p, select=select)
+    loss.backward()
+    return loss.detach(), p.grad.detach(), v.last_stats.cpu()
+
+
+@pytest.mark.parametrize("sel", [True, False])
+def test_vnl_small_golden(Cr, golden, sel):
+    g = golden("vnl_small.npz")
+    gt, pred, trip = T(g["gt"]), T(g["pred"]), T(g["trip"])
+    loss, grad, stats = _vnl(Cr, gt, pred, trip, sel)
+    close(loss, g[f"loss64_sel{int(sel)}"], LOSS_RTOL)
+    grad_close(grad, g[f"grad64_sel{int(sel)}"])
+    _, per, mask = ovnl.vnl_loss(gt.double(), pred.double(), trip, 519.0, 519.0, select=sel, return_parts=True)
+    assert int(stats[0]) == int(mask.sum())                                    # same valid-triplet set
+    if sel:
+        assert int(stats[1]) == int(int(mask.sum()) * 0.25)
+
+
+def test_vnl_vs_oracle_medium(Cr):
+    gt, pred, trip = synth.vnl_inputs((4, 1, 97, 129), 51, n_triplets=6000, pad_rows=10, zero_frac=5e-3)
+    p64 = pred.double().clone().requires_grad_(True)
+    l64 = ovnl.vnl_loss(gt.double(), p64, trip, 519.0, 519.0)
+    (g64,) = torch.autograd.grad(l64, p64)
+    loss, grad, stats = _vnl(Cr, gt, pred, trip)
+    close(loss, l64.detach(), LOSS_RTOL)
+    grad_close(grad, g64)
+    assert float(stats[4]) == 1.0                                               # no tie at the threshold
+
+
+def test_vnl_random_sampling_runs(Cr):
+    """select_index() default path (random triplets, reference criteria.py:912-932): finite, repeatable shape."""
+    gt, pred, _ = synth.vnl_inputs((2, 1, 64, 80), 52, n_triplets=10)
+    v = Cr.VNL_Loss(519.0, 519.0, (64, 80))
+    p = pred.cuda().requires_grad_(True)
+    loss = v(gt.cuda(), p)
+    loss.backward()
+    assert torch.isfinite(loss) and p.grad.shape == pred.shape and float(p.grad.abs().sum()) > 0
+
+
+def test_point_cloud(Cr):
+    from mono_depth_estimation_b200 import pointcloud as PC
+    rs = np.random.RandomState(3)
+    depth = (rs.rand(37, 53) * 12).astype(np.float32)
+    depth[0, :5] = 0.05; depth[3, 3] = 200.0                                    # outside the clip planes
+    cam = PC.Camera(angle_x=0.8575560450553894, clip_start=0.1, clip_end=100.0,
+                    matrix_world=[[0.68, -0.32, 0.65, 7.35], [0.73, 0.31, -0.61, -6.92], [-0.01, 0.89, 0.45, 4.95], [0, 0, 0, 1]])
+    ref = opc.point_cloud(depth, cam.angle_x, cam.clip_start, cam.clip_end)
+    out = PC.point_cloud(depth, cam)
+    assert out.dtype == np.float64 and out.shape == (37, 53, 3)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    np.testing.assert_allclose(np.nan_to_num(out), np.nan_to_num(ref), rtol=1e-7, atol=1e-9)
+    out32 = PC.point_cloud(torch.from_numpy(depth).cuda(), cam, dtype=torch.float32)
+    np.testing.assert_allclose(np.nan_to_num(out32.cpu().numpy()), np.nan_to_num(ref), rtol=1e-6, atol=1e-6)
+    refw = opc.to_world(ref, cam.matrix_world)
+    outw = PC.point_cloud_world(depth, cam)
+    assert np.array_equal(np.isnan(outw), np.isnan(refw))
+    np.testing.assert_allclose(np.nan_to_num(outw), np.nan_to_num(refw), rtol=1e-6, atol=1e-6)
+    batch = torch.from_numpy(np.stack([depth, depth * 0.5])).cuda()
+    ob = PC.point_cloud(batch, cam)
+    np.testing.assert_allclose(np.nan_to_num(ob[0].cpu().numpy()), np.nan_to_num(ref), rtol=1e-7, atol=1e-9)
