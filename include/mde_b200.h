@@ -140,6 +140,21 @@ int mde_masked_loss(int kind, const void* pred, int pred_dtype, const float* tar
                     const mde_loss_params* params, float grad_scale, void* ws, float* loss_out,
                     double* totals_out, void* grad, void* stream);
 
+/*
+ * Same as mde_masked_loss (L1, MSE, BERHU, LAINA_BERHU, SILOG) with the POOLED metric suite of
+ * mde_metrics fused into the reduce phase of the same launch: the training-step tail
+ * `loss = criterion(pred, gt); loss.backward(); metric_logger.log_train(pred, gt, loss)`
+ * (reference modules/eigen.py:31-33, modules/bts.py:106-108) costs 12 B/px instead of 12 + 8.
+ * metric_flags: MDE_METRICS_NEED_* (fast metric forms only). metrics_f64 / metrics_f32 use the
+ * layout of mde_metrics; only the pooled values [0,NM) and pooled raw sums [2NM, 2NM+NQ) are
+ * formed (image-mean entries equal the pooled ones when n_img == 1 and are NaN otherwise).
+ */
+int mde_masked_loss_metrics(int kind, const void* pred, int pred_dtype, const float* target,
+                            const uint8_t* mask_u8, int64_t n_img, int64_t h, int64_t w,
+                            const mde_loss_params* params, float grad_scale, unsigned metric_flags,
+                            void* ws, float* loss_out, double* totals_out, void* grad,
+                            double* metrics_f64, float* metrics_f32, void* stream);
+
 /* x[i] *= *scale_dev (device scalar) - applies a late-arriving grad_output to a stashed gradient */
 int mde_scale_inplace(void* x, int dtype, int64_t n, const float* scale_dev, void* stream);
 

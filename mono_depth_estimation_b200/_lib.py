@@ -45,6 +45,8 @@ SIGNATURES = {
     "mde_metrics_finalize_host": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mde_masked_loss": (_i32, [_i32, _vp, _i32, _vp, _vp, _i64, _i64, _i64, C.POINTER(LossParams), _f32,
                                _vp, _vp, _vp, _vp, _vp]),
+    "mde_masked_loss_metrics": (_i32, [_i32, _vp, _i32, _vp, _vp, _i64, _i64, _i64, C.POINTER(LossParams), _f32,
+                                       _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mde_scale_inplace": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "mde_ordinal_layer_fwd": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
     "mde_ordinal_layer_bwd": (_i32, [_vp, _i32, _vp, _i64, _i64, _i64, _vp, _vp]),

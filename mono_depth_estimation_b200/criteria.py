@@ -73,8 +73,27 @@ def _as_images(pred):
     return n_img, h, w
 
 
-def masked_loss(kind, pred, target, mask=None, params=None, totals=False):
-    """Functional entry: fused forward(+backward when pred.requires_grad) of one masked loss."""
+def _tensor_key(pred, target):
+    return (pred.data_ptr(), pred._version, tuple(pred.shape), pred.dtype, target.data_ptr(), target._version)
+
+
+class _FusesMetrics:
+    """Mixin: `criterion.fuse_metrics(metric_computation)` makes the loss launch ALSO produce the pooled
+    metric suite of `metric_computation` from the same read of pred/target (C ABI
+    mde_masked_loss_metrics). The next `metric_computation.compute(pred, target)` on the same tensors -
+    what MetricLogger.log_train does right after the criterion call (reference modules/bts.py:106-108) -
+    is then served from that launch instead of reading the tensors again. Pass None to undo."""
+
+    _fused_metrics = None
+
+    def fuse_metrics(self, metric_computation):
+        self._fused_metrics = metric_computation
+        return self
+
+
+def masked_loss(kind, pred, target, mask=None, params=None, totals=False, metrics=None):
+    """Functional entry: fused forward(+backward when pred.requires_grad) of one masked loss.
+    `metrics`: an optional metrics.MetricComputation to feed from the same launch."""
     lib = _lib.load()
     dev = _lib.require_cuda(pred, target, mask)
     if pred.dtype not in (torch.float32, torch.float16, torch.bfloat16):
@@ -94,6 +113,8 @@ def masked_loss(kind, pred, target, mask=None, params=None, totals=False):
         for k, v in params.items():
             setattr(lp, k, v)
     tot = torch.zeros(_lib.LOSS_NTOTALS, dtype=torch.float64, device=dev) if totals else None
+    fuse = metrics is not None and kind != _lib.LOSS_EIGEN and not getattr(metrics, "reference_math", False)
+    key = _tensor_key(pred, target) if fuse else None
 
     def launch(p, need_grad):
         pc = p.detach().contiguous()
@@ -102,9 +123,19 @@ def masked_loss(kind, pred, target, mask=None, params=None, totals=False):
             ws = _lib.workspace(dev, n_img)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             grad = torch.empty_like(pc) if need_grad else None
-            _lib.check(lib.mde_masked_loss(kind, _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(tgt), _lib.ptr(mk),
-                                           n_img, h, w, C.byref(lp), 1.0, _lib.ptr(ws), _lib.ptr(loss),
-                                           _lib.ptr(tot), _lib.ptr(grad), _lib.stream_ptr(dev)))
+            if fuse:
+                m64 = torch.empty(_lib.METRICS_OUT_F64, dtype=torch.float64, device=dev)
+                m32 = torch.empty(2 * _lib.METRIC_NM, dtype=torch.float32, device=dev)
+                _lib.check(lib.mde_masked_loss_metrics(kind, _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(tgt),
+                                                       _lib.ptr(mk), n_img, h, w, C.byref(lp), 1.0,
+                                                       metrics.group_flags(), _lib.ptr(ws), _lib.ptr(loss),
+                                                       _lib.ptr(tot), _lib.ptr(grad), _lib.ptr(m64), _lib.ptr(m32),
+                                                       _lib.stream_ptr(dev)))
+                metrics.offer(key, m32, m64)
+            else:
+                _lib.check(lib.mde_masked_loss(kind, _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(tgt), _lib.ptr(mk),
+                                               n_img, h, w, C.byref(lp), 1.0, _lib.ptr(ws), _lib.ptr(loss),
+                                               _lib.ptr(tot), _lib.ptr(grad), _lib.stream_ptr(dev)))
         if grad is not None and grad.shape != p.shape:
             grad = grad.view(p.shape)
         return loss, grad
@@ -129,7 +160,7 @@ class MaskedDepthLoss(nn.Module):
         return self.loss
 
 
-class MaskedMSELoss(nn.Module):
+class MaskedMSELoss(nn.Module, _FusesMetrics):
     """reference criteria.py:67-77."""
 
     def __init__(self):
@@ -137,11 +168,11 @@ class MaskedMSELoss(nn.Module):
 
     def forward(self, pred, target):
         assert pred.dim() == target.dim(), "inconsistent dimensions"
-        self.loss = masked_loss(_lib.LOSS_MSE, pred, target)
+        self.loss = masked_loss(_lib.LOSS_MSE, pred, target, metrics=self._fused_metrics)
         return self.loss
 
 
-class MaskedL1Loss(nn.Module):
+class MaskedL1Loss(nn.Module, _FusesMetrics):
     """reference criteria.py:80-90."""
 
     def __init__(self):
@@ -149,11 +180,11 @@ class MaskedL1Loss(nn.Module):
 
     def forward(self, pred, target):
         assert pred.dim() == target.dim(), "inconsistent dimensions"
-        self.loss = masked_loss(_lib.LOSS_L1, pred, target)
+        self.loss = masked_loss(_lib.LOSS_L1, pred, target, metrics=self._fused_metrics)
         return self.loss
 
 
-class berHuLoss(nn.Module):
+class berHuLoss(nn.Module, _FusesMetrics):
     """reference criteria.py:111-133 (threshold = 0.2*max(pred-target) over ALL pixels, signed)."""
 
     def __init__(self):
@@ -161,11 +192,11 @@ class berHuLoss(nn.Module):
 
     def forward(self, pred, target):
         assert pred.dim() == target.dim(), "inconsistent dimensions"
-        self.loss = masked_loss(_lib.LOSS_BERHU, pred, target)
+        self.loss = masked_loss(_lib.LOSS_BERHU, pred, target, metrics=self._fused_metrics)
         return self.loss
 
 
-class LainaBerHuLoss(nn.Module):
+class LainaBerHuLoss(nn.Module, _FusesMetrics):
     """reference criteria.py:476-506 (log-space berHu, differentiable threshold)."""
 
     def __init__(self, size_average=True, use_logs=True, clamp_val=1e-9):
@@ -175,12 +206,12 @@ class LainaBerHuLoss(nn.Module):
         self.clamp_val = clamp_val
 
     def forward(self, input, target, mask=None):
-        return masked_loss(_lib.LOSS_LAINA_BERHU, input, target, mask=mask,
+        return masked_loss(_lib.LOSS_LAINA_BERHU, input, target, mask=mask, metrics=self._fused_metrics,
                            params={"size_average": int(bool(self.size_average)), "use_logs": int(bool(self.use_log)),
                                    "clamp_val": float(self.clamp_val)})
 
 
-class silog_loss(nn.Module):
+class silog_loss(nn.Module, _FusesMetrics):
     """reference criteria.py:724-732 (mask is depth_gt > 1e-2)."""
 
     def __init__(self, variance_focus):
@@ -188,7 +219,8 @@ class silog_loss(nn.Module):
         self.variance_focus = variance_focus
 
     def forward(self, depth_est, depth_gt):
-        return masked_loss(_lib.LOSS_SILOG, depth_est, depth_gt, params={"variance_focus": float(self.variance_focus)})
+        return masked_loss(_lib.LOSS_SILOG, depth_est, depth_gt, metrics=self._fused_metrics,
+                           params={"variance_focus": float(self.variance_focus)})
 
 
 # ---- DORN ------------------------------------------------------------------------------------------------

@@ -234,15 +234,32 @@ __device__ __forceinline__ float key_float(unsigned k) {
   return __uint_as_float(b);
 }
 
-// [begin,end) of CTA `cta` when `total` units are split over `n_cta` CTAs in chunks whose
-// boundaries are multiples of `gran` units (128-byte alignment of every chunk start).
-__device__ __forceinline__ void cta_chunk(int64_t total, int gran, int cta, int n_cta, int64_t& begin,
-                                          int64_t& end) {
-  const int64_t groups = (total + gran - 1) / gran;
-  begin = (groups * cta / n_cta) * gran;
-  end = (groups * (cta + 1) / n_cta) * gran;
-  if (end > total) end = total;
-  if (begin > total) begin = total;
+// Balanced contiguous partition of `total` units over the CTAs of a grid, every chunk boundary a
+// multiple of `gran` units (128-byte alignment of every chunk start). The quotient / remainder are
+// computed once on the host so that the kernels do no 64-bit division.
+struct Chunking {
+  int64_t total;     // units
+  int64_t groups;    // ceil(total / gran)
+  int64_t base;      // groups / n_cta
+  int rem;           // groups % n_cta
+  int gran;
+};
+inline Chunking make_chunking(int64_t total, int gran, int n_cta) {
+  Chunking c;
+  c.total = total;
+  c.gran = gran;
+  c.groups = (total + gran - 1) / gran;
+  c.base = c.groups / n_cta;
+  c.rem = static_cast<int>(c.groups % n_cta);
+  return c;
+}
+__device__ __forceinline__ void cta_chunk(const Chunking& c, int cta, int64_t& begin, int64_t& end) {
+  const int64_t g0 = c.base * cta + (cta < c.rem ? cta : c.rem);
+  const int64_t g1 = g0 + c.base + (cta < c.rem ? 1 : 0);
+  begin = g0 * c.gran;
+  end = g1 * c.gran;
+  if (end > c.total) end = c.total;
+  if (begin > c.total) begin = c.total;
 }
 
 }  // namespace mde

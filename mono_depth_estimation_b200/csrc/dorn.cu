@@ -42,11 +42,6 @@ __device__ __forceinline__ float pair_prob(float ac, float bc) {
   return (d >= 0.f) ? __fdiv_rn(1.0f, s) : __fdiv_rn(e, s);
 }
 
-__device__ __forceinline__ float ln_any(float x) {
-  if (x >= 1.17549435e-38f && x < __int_as_float(0x7f800000)) return ln_pos(x);
-  return logf(x);
-}
-
 // SID / UD label of a metric depth, op for op as modules/dorn.py:102-107 evaluates it in fp32
 __device__ __forceinline__ float depth_label(float t, float alpha, float beta, int K, int disc) {
   if (disc == MDE_DISC_SID) {

@@ -19,6 +19,7 @@ struct EigenArgs {
   const void* pred;
   const float* gt;
   int n_img, h, w;
+  Chunking chunk;  // elements
   float grad_scale;
   void* ws;
   float* loss_out;
@@ -37,7 +38,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) eigen_loss_kernel(EigenArg
   PT* __restrict__ grad = static_cast<PT*>(a.grad);
   const int H = a.h, W = a.w;
   const unsigned HW = static_cast<unsigned>(H) * static_cast<unsigned>(W);
-  const unsigned n = HW * static_cast<unsigned>(a.n_img);  // host guarantees < 2^31
 
   Ws ws = ws_view(a.ws);
   const unsigned cap = __ldcg(&ws.hdr->max_images);
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) eigen_loss_kernel(EigenArg
   double* irow = ws.iacc + static_cast<size_t>(1 + par) * cap * kIacc;
 
   int64_t cb64, ce64;
-  cta_chunk(n, 32, blockIdx.x, gridDim.x, cb64, ce64);
+  cta_chunk(a.chunk, blockIdx.x, cb64, ce64);
   const unsigned cb = static_cast<unsigned>(cb64), ce = static_cast<unsigned>(ce64);
 
   // ---------------- phase A ---------------------------------------------------------------------------
@@ -198,6 +198,7 @@ int launch_eigen(EigenArgs& a, cudaStream_t st) {
   if (cap <= 0) return MDE_ECUDA;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
+  a.chunk = make_chunking(n, 32, static_cast<int>(grid));
   void* args[] = {&a};
   MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, 0, st));
   count_launch();

@@ -1,0 +1,568 @@
+// losses_kernel.cuh - the cooperative masked-loss kernel template (see losses.cu for the overview).
+// Included by losses.cu (plain losses) and losses_fused.cu (losses with the pooled metric suite
+// fused into the reduce phase), which instantiate it for different metric-group masks MG.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+#include "metric_math.cuh"
+
+namespace mde {
+namespace {
+
+struct LossArgs {
+  const void* pred;
+  const float* gt;
+  const uint8_t* mask;
+  int64_t n;
+  Chunking chunk;  // quads (VEC) or elements
+  float vf, clamp_val;
+  int use_logs, size_average;
+  float grad_scale;
+  void* ws;
+  float* loss_out;
+  double* totals_out;
+  void* grad;
+  double* met_f64;  // fused metrics (MG != 0): same layout as mde_metrics' out_f64
+  float* met_f32;
+  int64_t n_img;
+};
+
+constexpr unsigned kStashInvalid = 0xffc0dead;  // quiet-NaN payload marking "pixel outside the mask"
+
+// ---- chunk iteration ----------------------------------------------------------------------------
+// forward: body(idx, p, t) for every element of this CTA's chunk; fold() after every batch of <= 8
+// (VEC) / 4 (scalar) elements per thread. If STASH, body returns a float that is written to `stash`
+// (same layout as pred) with 128-bit stores.
+template <typename PT, bool VEC, bool STASH, typename Body, typename Fold>
+__device__ __forceinline__ void chunk_forward(const PT* __restrict__ pred, const float* __restrict__ gt,
+                                              float* stash, const LossArgs& a, Body&& body, Fold&& fold) {
+  const int64_t n = a.n;
+  int64_t cb, ce;
+  cta_chunk(a.chunk, blockIdx.x, cb, ce);
+  if constexpr (VEC) {
+    const int64_t nq = n >> 2;
+    int64_t q = cb + threadIdx.x;
+    for (; q + kBlock < ce; q += 2 * kBlock) {
+      const int64_t q1 = q + kBlock;
+      const float4 p0 = Elem<PT>::template ld4<true>(pred + 4 * q);
+      const float4 t0 = Elem<float>::template ld4<true>(gt + 4 * q);
+      const float4 p1 = Elem<PT>::template ld4<true>(pred + 4 * q1);
+      const float4 t1 = Elem<float>::template ld4<true>(gt + 4 * q1);
+      float4 s0, s1;
+      s0.x = body(4 * q + 0, p0.x, t0.x); s0.y = body(4 * q + 1, p0.y, t0.y);
+      s0.z = body(4 * q + 2, p0.z, t0.z); s0.w = body(4 * q + 3, p0.w, t0.w);
+      s1.x = body(4 * q1 + 0, p1.x, t1.x); s1.y = body(4 * q1 + 1, p1.y, t1.y);
+      s1.z = body(4 * q1 + 2, p1.z, t1.z); s1.w = body(4 * q1 + 3, p1.w, t1.w);
+      if constexpr (STASH) {
+        if (stash) {
+          *reinterpret_cast<float4*>(stash + 4 * q) = s0;
+          *reinterpret_cast<float4*>(stash + 4 * q1) = s1;
+        }
+      }
+      fold();
+    }
+    if (q < ce) {
+      const float4 p0 = Elem<PT>::template ld4<true>(pred + 4 * q);
+      const float4 t0 = Elem<float>::template ld4<true>(gt + 4 * q);
+      float4 s0;
+      s0.x = body(4 * q + 0, p0.x, t0.x); s0.y = body(4 * q + 1, p0.y, t0.y);
+      s0.z = body(4 * q + 2, p0.z, t0.z); s0.w = body(4 * q + 3, p0.w, t0.w);
+      if constexpr (STASH) {
+        if (stash) *reinterpret_cast<float4*>(stash + 4 * q) = s0;
+      }
+      fold();
+    }
+    if (blockIdx.x == gridDim.x - 1) {  // n % 4 tail
+      const int64_t i = (nq << 2) + threadIdx.x;
+      if (i < n) {
+        const float s = body(i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
+        if constexpr (STASH) {
+          if (stash) stash[i] = s;
+        }
+        fold();
+      }
+    }
+  } else {
+    int64_t i = cb + threadIdx.x;
+    for (; i + 3 * kBlock < ce; i += 4 * kBlock) {
+      float p[4], t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        p[k] = Elem<PT>::ld1(pred + i + k * kBlock);
+        t[k] = __ldg(gt + i + k * kBlock);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float s = body(i + k * kBlock, p[k], t[k]);
+        if constexpr (STASH) {
+          if (stash) stash[i + k * kBlock] = s;
+        }
+      }
+      fold();
+    }
+    for (; i < ce; i += kBlock) {
+      const float s = body(i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
+      if constexpr (STASH) {
+        if (stash) stash[i] = s;
+      }
+      fold();
+    }
+  }
+}
+
+// backward walk: out[idx] = body(idx, p, x) where x is the target, or (INPLACE) the value stashed in
+// out[idx] itself. Last-touched lines first.
+template <typename PT, bool VEC, bool INPLACE, typename Body>
+__device__ __forceinline__ void chunk_map_reverse(const PT* __restrict__ pred, const float* second, PT* out,
+                                                  const LossArgs& a, Body&& body) {
+  const int64_t n = a.n;
+  int64_t cb, ce;
+  cta_chunk(a.chunk, blockIdx.x, cb, ce);
+  if constexpr (VEC) {
+    const int64_t nq = n >> 2;
+    if (blockIdx.x == gridDim.x - 1) {
+      const int64_t i = (nq << 2) + threadIdx.x;
+      if (i < n) Elem<PT>::st1(out + i, body(i, Elem<PT>::ld1(pred + i), INPLACE ? second[i] : __ldg(second + i)));
+    }
+    int64_t q = ce - 1 - threadIdx.x;
+    for (; q - kBlock >= cb; q -= 2 * kBlock) {
+      const int64_t q1 = q - kBlock;
+      const float4 p0 = Elem<PT>::template ld4<false>(pred + 4 * q);
+      const float4 p1 = Elem<PT>::template ld4<false>(pred + 4 * q1);
+      float4 t0, t1;
+      if constexpr (INPLACE) {
+        t0 = *reinterpret_cast<const float4*>(second + 4 * q);
+        t1 = *reinterpret_cast<const float4*>(second + 4 * q1);
+      } else {
+        t0 = Elem<float>::template ld4<false>(second + 4 * q);
+        t1 = Elem<float>::template ld4<false>(second + 4 * q1);
+      }
+      float4 g0, g1;
+      g0.x = body(4 * q + 0, p0.x, t0.x); g0.y = body(4 * q + 1, p0.y, t0.y);
+      g0.z = body(4 * q + 2, p0.z, t0.z); g0.w = body(4 * q + 3, p0.w, t0.w);
+      g1.x = body(4 * q1 + 0, p1.x, t1.x); g1.y = body(4 * q1 + 1, p1.y, t1.y);
+      g1.z = body(4 * q1 + 2, p1.z, t1.z); g1.w = body(4 * q1 + 3, p1.w, t1.w);
+      Elem<PT>::st4(out + 4 * q, g0);
+      Elem<PT>::st4(out + 4 * q1, g1);
+    }
+    if (q >= cb) {
+      const float4 p0 = Elem<PT>::template ld4<false>(pred + 4 * q);
+      float4 t0;
+      if constexpr (INPLACE) t0 = *reinterpret_cast<const float4*>(second + 4 * q);
+      else t0 = Elem<float>::template ld4<false>(second + 4 * q);
+      float4 g0;
+      g0.x = body(4 * q + 0, p0.x, t0.x); g0.y = body(4 * q + 1, p0.y, t0.y);
+      g0.z = body(4 * q + 2, p0.z, t0.z); g0.w = body(4 * q + 3, p0.w, t0.w);
+      Elem<PT>::st4(out + 4 * q, g0);
+    }
+  } else {
+    for (int64_t i = ce - 1 - threadIdx.x; i >= cb; i -= kBlock)
+      Elem<PT>::st1(out + i, body(i, Elem<PT>::ld1(pred + i), INPLACE ? second[i] : __ldg(second + i)));
+  }
+}
+
+// block-reduce N doubles and add them to gacc[0..N)
+template <int N>
+__device__ __forceinline__ void publish_sums(const double (&v)[N], double* gacc, double* sm) {
+  const double tot = block_sum<N>(v, sm);
+  if (threadIdx.x < N && tot != 0.0) atomicAdd(&gacc[threadIdx.x], tot);
+}
+
+// block max -> order-preserving atomicMax; NaN anywhere sets the flag word
+__device__ __forceinline__ void publish_max(float m, bool saw_nan, unsigned* ukey, float* sm_f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  m = warp_max(m);
+  const bool any_nan = __any_sync(0xffffffffu, saw_nan);
+  if (lane == 0) {
+    sm_f[warp] = m;
+    if (any_nan) atomicOr(&ukey[1], 1u);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float x = (lane < kWarps) ? sm_f[lane] : -INFINITY;
+    x = warp_max(x);
+    if (lane == 0) atomicMax(&ukey[0], float_key(x));
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float read_max(const unsigned* ukey) {
+  const unsigned k = __ldcg(&ukey[0]);
+  const unsigned f = __ldcg(&ukey[1]);
+  if (f) return __int_as_float(0x7fc00000);
+  return k == 0u ? -INFINITY : key_float(k);
+}
+
+__device__ __forceinline__ float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// SILog residual d = ln p - ln t on the mask t > 1e-2 (criteria.py:730-731), 0 off the mask
+__device__ __forceinline__ float silog_resid(float p, float t, bool& v) {
+  v = t > 0.01f;
+  return log_ratio(v ? p : 1.0f, v ? t : 1.0f);
+}
+
+// Laina residual (criteria.py:488-494): r = ln max(p,cv) - ln max(t,cv) (or p - t); n_i = |r| * m
+__device__ __forceinline__ float laina_resid(float p, float t, bool m, bool use_logs, float cv, float& r_out) {
+  float r;
+  if (use_logs) {
+    const float pc = (p < cv) ? cv : p;  // clamp(min=cv), NaN preserved
+    const float tc = (t < cv) ? cv : t;
+    r = log_ratio(pc, tc);
+  } else {
+    r = p - t;
+  }
+  r_out = r;
+  return fabsf(r) * (m ? 1.f : 0.f);
+}
+
+// raw-quantity index of the 8 float metric sums, in MetricTile order
+__constant__ int kTileToQ[8] = {MDE_Q_ABS, MDE_Q_SQ, MDE_Q_LOG10, MDE_Q_SLE, MDE_Q_ABSREL, MDE_Q_SQREL, MDE_Q_RSQ, MDE_Q_LNSQ};
+__constant__ int kValNumL[MDE_METRIC_NM] = {MDE_Q_D1, MDE_Q_D2, MDE_Q_D3, MDE_Q_ABS, MDE_Q_SQ, MDE_Q_LOG10, MDE_Q_SLE,
+                                            MDE_Q_ABSREL, MDE_Q_SQREL, MDE_Q_RSQ, MDE_Q_SQ, MDE_Q_LNSQ};
+constexpr int kMetBase = 16;  // gacc[kMetBase + q] = pooled raw metric sum q
+
+template <int KIND, typename PT, bool VEC, unsigned MG>
+__global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sm_d[(MG ? 12 : 4) * kWarps];
+  __shared__ float sm_f[kWarps];
+  constexpr bool kCanStash = (KIND == MDE_LOSS_SILOG) && std::is_same<PT, float>::value;
+
+  const PT* __restrict__ pred = static_cast<const PT*>(a.pred);
+  const float* __restrict__ gt = a.gt;
+  const uint8_t* __restrict__ mask = a.mask;
+  PT* grad = static_cast<PT*>(a.grad);
+
+  Ws ws = ws_view(a.ws);
+  unsigned epoch;
+  const int par = coop_prologue(ws, epoch);
+  double* gacc = ws.gacc + par * kGacc;
+  unsigned* ukey = ws.ukey + par * kUkey;
+
+  // ---------------- phase A0: global max (berHu: max(p - t) over ALL pixels; Laina: max n_i) ----
+  float cthr = 0.f, gmax = 0.f;
+  if constexpr (KIND == MDE_LOSS_BERHU || KIND == MDE_LOSS_LAINA_BERHU) {
+    float mx = -INFINITY;
+    bool saw_nan = false;
+    chunk_forward<PT, VEC, false>(
+        pred, gt, nullptr, a,
+        [&](int64_t i, float p, float t) -> float {
+          float x;
+          if constexpr (KIND == MDE_LOSS_BERHU) {
+            x = p - t;  // criteria.py:118 - signed, unmasked
+          } else {
+            const bool m = mask ? (mask[i] != 0) : (t > 0.f);
+            float r;
+            x = laina_resid(p, t, m, a.use_logs != 0, a.clamp_val, r);
+          }
+          saw_nan |= (x != x);
+          mx = fmaxf(mx, x);
+          return 0.f;
+        },
+        [] {});
+    publish_max(mx, saw_nan, ukey, sm_f);
+    grid.sync();
+    gmax = read_max(ukey);
+    cthr = 0.2f * gmax;  // criteria.py:119 / :496 (fp32 product)
+  }
+
+  // ---------------- phase A1: masked sums and counts ------------------------------------------------
+  {
+    float s0 = 0.f, s1 = 0.f;
+    int c0 = 0, c1 = 0;
+    double run[4] = {0.0, 0.0, 0.0, 0.0};
+    MetricTile mt;
+    MetricCounts mc;
+    double mrun[8];
+    if constexpr (MG != 0) {
+      mt.zero();
+      mc.zero();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mrun[q] = 0.0;
+    }
+    auto fold = [&] {
+      run[0] += s0;
+      run[1] += s1;
+      s0 = 0.f;
+      s1 = 0.f;
+      if constexpr (MG != 0) {
+        mrun[0] += mt.s_abs; mrun[1] += mt.s_sq;
+        if (MG & kGrpLog) { mrun[2] += mt.s_log10; mrun[7] += mt.s_lnsq; }
+        if (MG & kGrpLog1p) mrun[3] += mt.s_sle;
+        if (MG & kGrpRel) { mrun[4] += mt.s_absrel; mrun[5] += mt.s_sqrel; mrun[6] += mt.s_rsq; }
+        mt.zero();
+      }
+    };
+    float* stash = kCanStash ? reinterpret_cast<float*>(grad) : nullptr;
+    chunk_forward<PT, VEC, kCanStash>(
+        pred, gt, stash, a,
+        [&](int64_t i, float p, float t) -> float {
+          float mL = 0.f, md = 0.f;
+          if constexpr (MG != 0) metric_px_ex<MG, false>(p, t, mt, mc, mL, md);
+          if constexpr (KIND == MDE_LOSS_L1) {
+            const bool v = t > 0.f;
+            s0 += v ? fabsf(t - p) : 0.f;
+            c0 += v ? 1 : 0;
+            return 0.f;
+          } else if constexpr (KIND == MDE_LOSS_MSE) {
+            const bool v = t > 0.f;
+            const float d = t - p;
+            s0 += v ? d * d : 0.f;
+            c0 += v ? 1 : 0;
+            return 0.f;
+          } else if constexpr (KIND == MDE_LOSS_SILOG) {
+            bool v;
+            float d;
+            if constexpr ((MG & kGrpLog) != 0) {
+              // the metric suite already has |ln p - ln t| = ln(max/min): reuse it, signed by p - t.
+              // Only predictions below the metrics' clamp (1e-7) need their own logarithm.
+              v = t > 0.01f;
+              d = (md >= 0.f) ? mL : -mL;
+              if (v && !(p >= 1e-7f)) d = log_ratio_slow(p, t);
+              d = v ? d : 0.f;
+            } else {
+              d = silog_resid(p, t, v);
+            }
+            s0 += d;
+            s1 = fmaf(d, d, s1);
+            c0 += v ? 1 : 0;
+            return v ? d : __uint_as_float(kStashInvalid);
+          } else if constexpr (KIND == MDE_LOSS_BERHU) {
+            const bool v = t > 0.f;
+            const float ad = fabsf(t - p);
+            const bool hub = v && (ad > cthr);  // criteria.py:126
+            s0 += v ? ad : 0.f;
+            s1 += hub ? ad * ad : 0.f;
+            c0 += v ? 1 : 0;
+            c1 += hub ? 1 : 0;
+            return 0.f;
+          } else {  // LAINA
+            const bool m = mask ? (mask[i] != 0) : (t > 0.f);
+            float r;
+            const float ni = laina_resid(p, t, m, a.use_logs != 0, a.clamp_val, r);
+            const bool big = !(ni < cthr);  // criteria.py:497-498
+            const float D = 2.f * cthr + 1e-9f;
+            const float num = fmaf(ni, ni, cthr * cthr);
+            s0 += big ? num / D : ni;
+            s1 += big ? (2.f * cthr * D - 2.f * num) / (D * D) : 0.f;  // d/dc of the quadratic branch
+            c0 += m ? 1 : 0;
+            c1 += (ni == gmax) ? 1 : 0;
+            return 0.f;
+          }
+        },
+        fold);
+    run[2] = static_cast<double>(c0);
+    run[3] = static_cast<double>(c1);
+    publish_sums<4>(run, gacc, sm_d);
+    if constexpr (MG != 0) {
+      // 4 counts + 8 float sums: 32-lane tree in fp32 / REDUX, widened before crossing warps and CTAs
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int r0 = __reduce_add_sync(0xffffffffu, mc.n), r1 = __reduce_add_sync(0xffffffffu, mc.c1);
+      const int r2 = __reduce_add_sync(0xffffffffu, mc.c2), r3 = __reduce_add_sync(0xffffffffu, mc.c3);
+      if (lane == 0) {
+        sm_d[0 * kWarps + warp] = r0; sm_d[1 * kWarps + warp] = r1;
+        sm_d[2 * kWarps + warp] = r2; sm_d[3 * kWarps + warp] = r3;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float sq = warp_sum(static_cast<float>(mrun[q]));
+        if (lane == 0) sm_d[(4 + q) * kWarps + warp] = static_cast<double>(sq);
+      }
+      __syncthreads();
+      if (threadIdx.x < 12) {
+        double tot = 0.0;
+        for (int w = 0; w < kWarps; ++w) tot += sm_d[threadIdx.x * kWarps + w];
+        const int qi = (threadIdx.x < 4) ? threadIdx.x : kTileToQ[threadIdx.x - 4];
+        if (tot != 0.0) atomicAdd(&gacc[kMetBase + qi], tot);
+      }
+      __syncthreads();
+    }
+  }
+  grid.sync();
+
+  if constexpr (MG != 0) {
+    // CTA 0, warp 0: pooled metric values (one mean over all valid pixels of the call, metrics.py:58-67)
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      const bool own = lane < MDE_METRIC_NM;
+      const double P = own ? __ldcg(&gacc[kMetBase + lane]) : 0.0;
+      const double nn = __shfl_sync(0xffffffffu, P, MDE_Q_NVALID);
+      const double num = __shfl_sync(0xffffffffu, P, own ? kValNumL[lane] : 0);
+      double val = num / nn;
+      if (lane >= MDE_M_RMSE_TRUE) val = sqrt(val);
+      if (own) {
+        const double im = (a.n_img == 1) ? val : __longlong_as_double(0x7ff8000000000000LL);
+        a.met_f64[lane] = val;
+        a.met_f64[MDE_METRIC_NM + lane] = im;   // per-image means are not formed by the fused path
+        a.met_f64[2 * MDE_METRIC_NM + lane] = P;
+        if (a.met_f32) {
+          a.met_f32[lane] = static_cast<float>(val);
+          a.met_f32[MDE_METRIC_NM + lane] = static_cast<float>(im);
+        }
+      }
+      if (lane == 0) a.met_f64[2 * MDE_METRIC_NM + MDE_METRIC_NQ] = (a.n_img == 1 && nn > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
+    }
+  }
+
+  const double S0 = __ldcg(&gacc[0]), S1 = __ldcg(&gacc[1]);
+  const double N0 = __ldcg(&gacc[2]), N1 = __ldcg(&gacc[3]);
+
+  // ---------------- loss value and gradient coefficients (every thread, fp64) --------------------
+  double loss;
+  float k1 = 0.f, k2 = 0.f, k3 = 0.f;
+  const double gs = static_cast<double>(a.grad_scale);
+  if constexpr (KIND == MDE_LOSS_L1) {
+    loss = S0 / N0;
+    k1 = static_cast<float>(gs / N0);
+  } else if constexpr (KIND == MDE_LOSS_MSE) {
+    loss = S0 / N0;
+    k1 = static_cast<float>(2.0 * gs / N0);
+  } else if constexpr (KIND == MDE_LOSS_SILOG) {
+    const double dm = S0 / N0, q = S1 / N0;
+    const double s = sqrt(q - static_cast<double>(a.vf) * dm * dm);
+    loss = 10.0 * s;
+    k1 = static_cast<float>(10.0 * gs / (s * N0));     // dL/dd_i = k1 * (d_i - k2)
+    k2 = static_cast<float>(static_cast<double>(a.vf) * dm);
+  } else if constexpr (KIND == MDE_LOSS_BERHU) {
+    loss = (S0 + S1) / (N0 + N1);                        // mean of the concatenation (criteria.py:131)
+    k1 = static_cast<float>(gs / (N0 + N1));
+  } else {
+    const double Mdiv = a.size_average ? N0 : 1.0;
+    loss = S0 / Mdiv;
+    k1 = static_cast<float>(gs / Mdiv);
+    k2 = static_cast<float>(gs * 0.2 * S1 / (N1 * Mdiv));  // share of dL/dc per tied maximum
+    k3 = 2.f * cthr + 1e-9f;
+  }
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *a.loss_out = static_cast<float>(loss);
+    if (a.totals_out) {
+      a.totals_out[0] = S0;
+      a.totals_out[1] = S1;
+      a.totals_out[2] = N0;
+      a.totals_out[3] = N1;
+      a.totals_out[4] = static_cast<double>(gmax);
+      a.totals_out[5] = loss;
+    }
+    ws.hdr->epoch = epoch + 1u;
+  }
+  if (grad == nullptr) return;
+
+  // ---------------- phase B: gradient, chunk walked backwards ----------------------------------------
+  if constexpr (kCanStash) {
+    // grad[i] holds d_i (or the off-mask marker): g = k1 (d - k2) / p
+    chunk_map_reverse<PT, VEC, true>(pred, reinterpret_cast<const float*>(grad), grad, a,
+                                     [&](int64_t, float p, float d) -> float {
+                                       const bool v = __float_as_uint(d) != kStashInvalid;
+                                       return v ? k1 * (d - k2) * rcp_nr(p) : 0.f;
+                                     });
+  } else {
+    chunk_map_reverse<PT, VEC, false>(pred, gt, grad, a, [&](int64_t i, float p, float t) -> float {
+      if constexpr (KIND == MDE_LOSS_L1) {
+        const bool v = t > 0.f;
+        return v ? -sgn(t - p) * k1 : 0.f;
+      } else if constexpr (KIND == MDE_LOSS_MSE) {
+        const bool v = t > 0.f;
+        return v ? -(t - p) * k1 : 0.f;
+      } else if constexpr (KIND == MDE_LOSS_SILOG) {
+        bool v;
+        const float d = silog_resid(p, t, v);
+        return v ? k1 * (d - k2) * rcp_nr(p) : 0.f;
+      } else if constexpr (KIND == MDE_LOSS_BERHU) {
+        const bool v = t > 0.f;
+        const float d = t - p;
+        const float ad = fabsf(d);
+        const bool hub = v && (ad > cthr);
+        return v ? -sgn(d) * (hub ? fmaf(2.f, ad, 1.f) : 1.f) * k1 : 0.f;
+      } else {
+        const bool m = mask ? (mask[i] != 0) : (t > 0.f);
+        float r;
+        const float ni = laina_resid(p, t, m, a.use_logs != 0, a.clamp_val, r);
+        const bool big = !(ni < cthr);
+        float dn = (big ? 2.f * ni / k3 : 1.f) * k1;
+        if (ni == gmax) dn += k2;
+        // dn_i/dp = sign(r) * m * [p >= cv] / p   (clamp passes the gradient where p >= cv)
+        float dp = m ? sgn(r) : 0.f;
+        if (a.use_logs) dp = (p >= a.clamp_val) ? dp / p : 0.f;
+        return dn * dp;
+      }
+    });
+  }
+}
+
+template <int KIND, typename PT, bool VEC, unsigned MG>
+int launch_loss(LossArgs& a, cudaStream_t st) {
+  const void* fn = reinterpret_cast<const void*>(&masked_loss_kernel<KIND, PT, VEC, MG>);
+  const int64_t units = VEC ? (a.n >> 2) : a.n;
+  int64_t grid = (units + kBlock - 1) / kBlock;
+  const int cap = coop_grid(fn, kBlock, 0);
+  if (cap <= 0) return MDE_ECUDA;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  a.chunk = make_chunking(units, VEC ? 8 : 32, static_cast<int>(grid));
+  void* args[] = {&a};
+  MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, 0, st));
+  count_launch();
+  return MDE_OK;
+}
+
+template <int KIND, typename PT, unsigned MG>
+int launch_loss_vec(LossArgs& a, cudaStream_t st) {
+  const bool vec = aligned_to(a.pred, 4 * sizeof(PT)) && aligned_to(a.gt, 16) &&
+                   (a.grad == nullptr || aligned_to(a.grad, 16));
+  return vec ? launch_loss<KIND, PT, true, MG>(a, st) : launch_loss<KIND, PT, false, MG>(a, st);
+}
+
+template <int KIND, unsigned MG>
+int launch_loss_dtype(LossArgs& a, int dtype, cudaStream_t st) {
+  switch (dtype) {
+    case MDE_F32: return launch_loss_vec<KIND, float, MG>(a, st);
+    case MDE_F16: return launch_loss_vec<KIND, __half, MG>(a, st);
+    case MDE_BF16: return launch_loss_vec<KIND, __nv_bfloat16, MG>(a, st);
+    default: set_error("mde_masked_loss: unknown pred_dtype %d", dtype); return MDE_EINVAL;
+  }
+}
+
+}  // namespace
+}  // namespace mde
+
+namespace mde {
+namespace {
+inline LossArgs make_loss_args(const void* pred, const float* target, const uint8_t* mask_u8, int64_t n_img, int64_t h,
+                               int64_t w, const mde_loss_params* params, float grad_scale, void* ws, float* loss_out,
+                               double* totals_out, void* grad) {
+  LossArgs a;
+  a.pred = pred;
+  a.gt = target;
+  a.mask = mask_u8;
+  a.n = n_img * h * w;
+  a.vf = params ? params->variance_focus : 0.85f;
+  a.clamp_val = params ? params->clamp_val : 1e-9f;
+  a.use_logs = params ? params->use_logs : 1;
+  a.size_average = params ? params->size_average : 1;
+  a.grad_scale = grad_scale;
+  a.ws = ws;
+  a.loss_out = loss_out;
+  a.totals_out = totals_out;
+  a.grad = grad;
+  a.met_f64 = nullptr;
+  a.met_f32 = nullptr;
+  a.n_img = n_img;
+  return a;
+}
+}  // namespace
+// kind dispatch for one metric-group mask (instantiated in losses.cu for MG = 0 and in
+// losses_fused.cu for the fused variants)
+template <unsigned MG>
+int launch_loss_kind(int kind, LossArgs& a, int dtype, cudaStream_t st) {
+  switch (kind) {
+    case MDE_LOSS_L1: return launch_loss_dtype<MDE_LOSS_L1, MG>(a, dtype, st);
+    case MDE_LOSS_MSE: return launch_loss_dtype<MDE_LOSS_MSE, MG>(a, dtype, st);
+    case MDE_LOSS_BERHU: return launch_loss_dtype<MDE_LOSS_BERHU, MG>(a, dtype, st);
+    case MDE_LOSS_LAINA_BERHU: return launch_loss_dtype<MDE_LOSS_LAINA_BERHU, MG>(a, dtype, st);
+    case MDE_LOSS_SILOG: return launch_loss_dtype<MDE_LOSS_SILOG, MG>(a, dtype, st);
+    default: set_error("mde_masked_loss: unknown kind %d", kind); return MDE_EINVAL;
+  }
+}
+}  // namespace mde

@@ -50,6 +50,25 @@ __device__ __forceinline__ float rcp_nr(float x) {
   return fmaf(y, fmaf(-x, y, 1.0f), y);
 }
 
+// ln(x) for any x: polynomial path for normal positive x, libdevice for the rest (0, negatives,
+// denormals, inf, NaN) so that the reference's -inf / NaN results are reproduced
+__device__ __forceinline__ float ln_any(float x) {
+  if (x >= 1.17549435e-38f && x < __int_as_float(0x7f800000)) return ln_pos(x);
+  return logf(x);
+}
+
+// out-of-line slow path of log_ratio (rare: non-positive, denormal, inf or NaN operands)
+static __device__ __noinline__ float log_ratio_slow(float p, float t) { return logf(p) - logf(t); }
+
+// ln(p) - ln(t) with ONE logarithm: ln(p * (1/t)). |error| <= ~2e-7 absolute for normal operands
+// (the reference's own two logf calls carry ~1e-7 * |ln| each); anything else takes the slow path.
+__device__ __forceinline__ float log_ratio(float p, float t) {
+  const float q = p * rcp_nr(t);
+  float d = ln_pos(q);
+  if (!(q >= 1.17549435e-38f && q < __int_as_float(0x7f800000) && p > 0.f && t > 0.f)) d = log_ratio_slow(p, t);
+  return d;
+}
+
 // fp32 tile accumulators of one thread: 8 float sums + 4 integer counts
 struct MetricTile {
   float s_abs, s_sq, s_log10, s_sle, s_absrel, s_sqrel, s_rsq, s_lnsq;
@@ -62,25 +81,32 @@ struct MetricCounts {
   __device__ __forceinline__ void zero() { n = c1 = c2 = c3 = 0; }
 };
 
+// One pixel of the metric suite. Besides accumulating, returns through `L_out` the value
+// |ln p - ln t| = ln(max/min) (fast mode with kGrpLog only; 0 otherwise) so that a fused loss can
+// reuse the logarithm, and through `d_out` the difference p - t on the clamped prediction.
 template <unsigned G, bool Ref>
-__device__ __forceinline__ void metric_px(float p, float t, MetricTile& a, MetricCounts& c) {
+__device__ __forceinline__ void metric_px_ex(float p, float t, MetricTile& a, MetricCounts& c, float& L_out,
+                                             float& d_out) {
   const bool v = t > 0.f;                         // metrics.py:60
   p = (p < 1e-7f) ? 1e-7f : p;                    // clamp_min(pred, 1e-7), NaN preserved (metrics.py:59)
   // invalid pixels are replaced by p = t = 1: every float contribution below is then exactly 0
   const float pp = v ? p : 1.0f;
   const float tt = v ? t : 1.0f;
-  float hi = fmaxf(pp, tt), lo = fminf(pp, tt);
-  if (pp != pp) hi = lo = pp;                     // torch.max propagates NaN; fmaxf/fminf drop it
-  const float r = __fdiv_rn(hi, lo);              // == max(fl(p/t), fl(t/p))   (metrics.py:76)
+  const float d = pp - tt;
+  const float hi = fmaxf(pp, tt), lo = fminf(pp, tt);
+  // == max(fl(p/t), fl(t/p)) (metrics.py:76); the fma adds 0*d so that a NaN prediction, which
+  // fmaxf/fminf drop, still poisons r as torch.max would (exact no-op for finite d)
+  const float r = fmaf(d, 0.0f, __fdiv_rn(hi, lo));
   c.n += v ? 1 : 0;
   c.c1 += (v && r < 1.25f) ? 1 : 0;               // strict '<' (metrics.py:77,82,87)
   c.c2 += (v && r < 1.5625f) ? 1 : 0;
   c.c3 += (v && r < 1.953125f) ? 1 : 0;
-  const float d = pp - tt;
   const float ad = fabsf(d);
   const float sq = d * d;
   a.s_abs += ad;
   a.s_sq += sq;
+  L_out = 0.f;
+  d_out = d;
   if (Ref) {
     if (G & kGrpLog) {
       a.s_log10 += fabsf(log10f(pp) - log10f(tt));            // metrics.py:90-91
@@ -100,12 +126,13 @@ __device__ __forceinline__ void metric_px(float p, float t, MetricTile& a, Metri
   } else {
     if (G & kGrpLog) {
       const float L = ln_pos(r);                              // |ln p - ln t| = ln(hi/lo)
+      L_out = L;
       a.s_log10 = fmaf(L, 0.43429448190325182f, a.s_log10);
       a.s_lnsq = fmaf(L, L, a.s_lnsq);
     }
     if (G & kGrpLog1p) {
       // |log1p p - log1p t| = ln((1+hi)/(1+lo))
-      const float s = (1.0f + hi) * rcp_nr(1.0f + lo);
+      const float s = fmaf(d, 0.0f, (1.0f + hi) * rcp_nr(1.0f + lo));
       const float L = ln_pos(s < 1.0f ? 1.0f : s);        // NaN stays NaN
       a.s_sle = fmaf(L, L, a.s_sle);
     }
@@ -114,9 +141,17 @@ __device__ __forceinline__ void metric_px(float p, float t, MetricTile& a, Metri
       const float ar = ad * it;
       a.s_absrel += ar;
       a.s_sqrel = fmaf(ar, ad, a.s_sqrel);
-      a.s_rsq = fmaf(ad, rsqrtf(tt), a.s_rsq);                // sqrt((p-t)^2/t) = |p-t| / sqrt(t)
+      float rs;
+      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(tt));
+      a.s_rsq = fmaf(ad, rs, a.s_rsq);                        // sqrt((p-t)^2/t) = |p-t| / sqrt(t)
     }
   }
+}
+
+template <unsigned G, bool Ref>
+__device__ __forceinline__ void metric_px(float p, float t, MetricTile& a, MetricCounts& c) {
+  float L, d;
+  metric_px_ex<G, Ref>(p, t, a, c, L, d);
 }
 
 // finished values from raw sums (shared by the device finaliser and mde_metrics_finalize_host)

@@ -50,77 +50,85 @@ struct MetricThread {
 __constant__ int kRunToQ[8] = {MDE_Q_ABS, MDE_Q_SQ, MDE_Q_LOG10, MDE_Q_SLE,
                                MDE_Q_ABSREL, MDE_Q_SQREL, MDE_Q_RSQ, MDE_Q_LNSQ};
 
-// Run by the LAST CTA only: per-image values, pooled values, mean over images; re-zero the
-// per-image accumulators so the workspace is clean for the next call. Kept out of line so its
-// fp64 register arrays do not constrain the streaming loop's register allocation.
+// Numerator quantity of metric value m (value = raw[num] / n, sqrt for the last two)
+__constant__ int kValNum[kNM] = {MDE_Q_D1, MDE_Q_D2, MDE_Q_D3, MDE_Q_ABS, MDE_Q_SQ, MDE_Q_LOG10, MDE_Q_SLE,
+                                 MDE_Q_ABSREL, MDE_Q_SQREL, MDE_Q_RSQ, MDE_Q_SQ, MDE_Q_LNSQ};
+
+// Run by the LAST CTA only. One WARP per image: lane q < 12 owns raw quantity q and metric value q,
+// so an image costs one coalesced L2 read, two shuffles and one fp64 divide per lane; warps stride
+// over the images, then one shared-memory pass combines the warps. Also re-zeroes the per-image
+// accumulators so the workspace is clean for the next call.
 __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __restrict__ out_f64,
                                               float* __restrict__ out_f32, double* __restrict__ per_image_values,
                                               double* __restrict__ per_image_raw, double* sm_d) {
   double* iacc = ws.iacc;
-  double pooled[kNQ];
-  double vsum[kNM];
-  double nimg_valid = 0.0;
-#pragma unroll
-  for (int q = 0; q < kNQ; ++q) pooled[q] = 0.0;
-#pragma unroll
-  for (int m = 0; m < kNM; ++m) vsum[m] = 0.0;
-
-  for (int64_t b = threadIdx.x; b < n_img; b += kBlock) {
-    double raw[kNQ], val[kNM];
-#pragma unroll
-    for (int q = 0; q < kNQ; ++q) {
-      raw[q] = __ldcg(&iacc[b * kIacc + q]);
-      iacc[b * kIacc + q] = 0.0;  // leave the workspace clean for the next call
-      pooled[q] += raw[q];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool own = lane < kNM;  // kNM == kNQ == 12
+  const int num_idx = own ? kValNum[lane] : 0;
+  double pooled = 0.0, vsum = 0.0, nvalid = 0.0;
+  for (int64_t b = warp; b < n_img; b += kWarps) {
+    double raw = 0.0;
+    if (own) {
+      raw = __ldcg(&iacc[b * kIacc + lane]);
+      iacc[b * kIacc + lane] = 0.0;
     }
-    metric_values(raw, val);
-    if (raw[MDE_Q_NVALID] > 0.0) {
-      nimg_valid += 1.0;
-#pragma unroll
-      for (int m = 0; m < kNM; ++m) vsum[m] += val[m];
+    const double n = __shfl_sync(0xffffffffu, raw, MDE_Q_NVALID);
+    const double num = __shfl_sync(0xffffffffu, raw, num_idx);
+    double val = num / n;
+    if (lane >= MDE_M_RMSE_TRUE) val = sqrt(val);
+    pooled += raw;
+    if (n > 0.0) {
+      vsum += val;
+      nvalid += 1.0;
     }
-    if (per_image_values) {
-#pragma unroll
-      for (int m = 0; m < kNM; ++m) per_image_values[b * kNM + m] = val[m];
-    }
-    if (per_image_raw) {
-#pragma unroll
-      for (int q = 0; q < kNQ; ++q) per_image_raw[b * kNQ + q] = raw[q];
+    if (own) {
+      if (per_image_values) per_image_values[b * kNM + lane] = val;
+      if (per_image_raw) per_image_raw[b * kNQ + lane] = raw;
     }
   }
-  const double p_tot = block_sum<kNQ>(pooled, sm_d);   // thread q holds pooled total q
-  __shared__ double sm_pooled[kNQ];
-  if (threadIdx.x < kNQ) sm_pooled[threadIdx.x] = p_tot;
-  const double v_tot = block_sum<kNM>(vsum, sm_d);     // thread m holds sum of per-image value m
-  double one[1] = {nimg_valid};
-  const double n_valid_img = block_sum<1>(one, sm_d);  // thread 0
-  __shared__ double sm_nimg;
-  if (threadIdx.x == 0) sm_nimg = n_valid_img;
+  // sm_d: [kWarps][12] pooled | [kWarps][12] vsum | [kWarps] nvalid
+  if (own) {
+    sm_d[warp * kNM + lane] = pooled;
+    sm_d[kWarps * kNM + warp * kNM + lane] = vsum;
+  }
+  if (lane == 0) sm_d[2 * kWarps * kNM + warp] = nvalid;
   __syncthreads();
-  if (threadIdx.x < kNM) {
-    const double mean_v = v_tot / sm_nimg;
-    out_f64[kNM + threadIdx.x] = mean_v;
-    if (out_f32) out_f32[kNM + threadIdx.x] = static_cast<float>(mean_v);
-  }
-  if (threadIdx.x < kNQ) out_f64[2 * kNM + threadIdx.x] = sm_pooled[threadIdx.x];
-  if (threadIdx.x == 0) {
-    double val[kNM];
-    metric_values(sm_pooled, val);
-    for (int m = 0; m < kNM; ++m) {
-      out_f64[m] = val[m];
-      if (out_f32) out_f32[m] = static_cast<float>(val[m]);
+  if (warp == 0) {
+    double P = 0.0, V = 0.0, N = 0.0;
+    if (own) {
+      for (int w = 0; w < kWarps; ++w) {
+        P += sm_d[w * kNM + lane];
+        V += sm_d[kWarps * kNM + w * kNM + lane];
+      }
     }
-    out_f64[2 * kNM + kNQ] = sm_nimg;
-    ws.hdr->ticket = 0;
+    for (int w = 0; w < kWarps; ++w) N += sm_d[2 * kWarps * kNM + w];
+    const double n = __shfl_sync(0xffffffffu, P, MDE_Q_NVALID);
+    const double num = __shfl_sync(0xffffffffu, P, num_idx);
+    double val = num / n;
+    if (lane >= MDE_M_RMSE_TRUE) val = sqrt(val);
+    if (own) {
+      const double mean_v = V / N;
+      out_f64[lane] = val;
+      out_f64[kNM + lane] = mean_v;
+      out_f64[2 * kNM + lane] = P;
+      if (out_f32) {
+        out_f32[lane] = static_cast<float>(val);
+        out_f32[kNM + lane] = static_cast<float>(mean_v);
+      }
+    }
+    if (lane == 0) {
+      out_f64[2 * kNM + kNQ] = N;
+      ws.hdr->ticket = 0;
+    }
   }
 }
 
 template <typename PT, int VEC, unsigned G, bool Ref>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm)
-metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_t n_img, int64_t hw,
+metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_t n_img, int64_t hw, Chunking chunk,
                void* ws_raw, double* __restrict__ out_f64, float* __restrict__ out_f32,
                double* __restrict__ per_image_values, double* __restrict__ per_image_raw) {
-  __shared__ double sm_d[12 * kWarps];
+  __shared__ double sm_d[2 * kNM * kWarps + kWarps];
   __shared__ int sm_i[4 * kWarps];
   __shared__ bool sm_last;
 
@@ -129,9 +137,8 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t units_per_img = hw / VEC;  // VEC == 4 requires hw % 4 == 0 (checked on the host)
-  const int64_t total_units = n_img * units_per_img;
   int64_t ub, ue;
-  cta_chunk(total_units, 32 / VEC, blockIdx.x, gridDim.x, ub, ue);
+  cta_chunk(chunk, blockIdx.x, ub, ue);
 
   MetricThread<G, Ref> th;
   int64_t u = ub;
@@ -189,10 +196,15 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
         sm_i[2 * kWarps + warp] = c2;
         sm_i[3 * kWarps + warp] = c3;
       }
+      // per-thread sums are fp64; the 32-lane tree is done in fp32 (5 levels, <= 4e-7 relative) and
+      // widened again before the cross-warp and cross-CTA accumulation
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const double s = warp_sum(th.run[q]);
-        if (lane == 0) sm_d[q * kWarps + warp] = s;
+        const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
+                          ((G & kGrpRel) && (q >= 4 && q <= 6));
+        if (!used) continue;
+        const float s = warp_sum(static_cast<float>(th.run[q]));
+        if (lane == 0) sm_d[q * kWarps + warp] = static_cast<double>(s);
       }
       __syncthreads();
       if (threadIdx.x < 12) {
@@ -205,7 +217,10 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
           qidx = threadIdx.x;  // MDE_Q_NVALID, D1, D2, D3
         } else {
           const int q = threadIdx.x - 4;
-          for (int w = 0; w < kWarps; ++w) tot += sm_d[q * kWarps + w];
+          const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
+                            ((G & kGrpRel) && (q >= 4 && q <= 6));
+          if (used)
+            for (int w = 0; w < kWarps; ++w) tot += sm_d[q * kWarps + w];
           qidx = kRunToQ[q];
         }
         if (tot != 0.0) atomicAdd(&iacc[img * kIacc + qidx], tot);
@@ -237,8 +252,9 @@ int launch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t hw,
   const int64_t cap = static_cast<int64_t>(sm_count()) * kCtasPerSm;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
+  const Chunking chunk = make_chunking(units, 32 / VEC, static_cast<int>(grid));
   metrics_kernel<PT, VEC, G, Ref><<<static_cast<unsigned>(grid), kBlock, 0, st>>>(
-      static_cast<const PT*>(pred), gt, n_img, hw, ws, out_f64, out_f32, piv, pir);
+      static_cast<const PT*>(pred), gt, n_img, hw, chunk, ws, out_f64, out_f32, piv, pir);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;

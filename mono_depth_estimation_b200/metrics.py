@@ -118,7 +118,26 @@ class MetricComputation(object):
         self.strict = strict
         self.reference_math = reference_math
         self._fused_names = [m for m in metrics if m != "ssim"]
+        self._prefetched = None
+        self.last_f64 = None   # float64 result vector of the last compute() (layout of mde_metrics' out_f64)
         self.reset()
+
+    # ---- hand-over from a criterion that computed the pooled metrics in its own launch -----------------
+    def group_flags(self):
+        g = 0
+        for n in self._fused_names:
+            g |= _lib.METRIC_GROUP.get(n, 0)
+        return g if g else _lib.METRICS_NEED_LOG
+
+    def offer(self, key, values32, f64):
+        self._prefetched = (key, values32, f64)
+
+    def _take_prefetched(self, pred, target):
+        pf, self._prefetched = self._prefetched, None
+        if pf is None:
+            return None
+        key = (pred.data_ptr(), pred._version, tuple(pred.shape), pred.dtype, target.data_ptr(), target._version)
+        return {"values": pf[1], "f64": pf[2]} if pf[0] == key else None
 
     def reset(self):
         self.count = 0
@@ -139,7 +158,10 @@ class MetricComputation(object):
     def compute(self, pred, target):
         """One mean per metric over the valid pixels of the WHOLE call tensor (metrics.py:58-67)."""
         with torch.no_grad():
-            res = fused_metrics(pred, target, names=self._fused_names, reference_math=self.reference_math)
+            res = self._take_prefetched(pred, target)
+            if res is None:
+                res = fused_metrics(pred, target, names=self._fused_names, reference_math=self.reference_math)
+            self.last_f64 = res["f64"]
             if self.strict:
                 # the reference's `assert torch.sum(valid_mask) > 0` (metrics.py:61) reads the device too
                 assert float(res["f64"][2 * _lib.METRIC_NM + _lib.RAW_INDEX["n_valid"]]) > 0, "invalid target!"
@@ -149,6 +171,7 @@ class MetricComputation(object):
         """Mean over images of per-image means for a [B,...,H,W] batch in one launch (extension)."""
         with torch.no_grad():
             res = fused_metrics(pred, target, names=self._fused_names, reference_math=self.reference_math)
+            self.last_f64 = res["f64"]
             if self.strict:
                 assert float(res["f64"][2 * _lib.METRIC_NM + _lib.METRIC_NQ]) > 0, "invalid target!"
             return self._collect(res["image_mean"], pred, target)

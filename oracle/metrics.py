@@ -99,3 +99,19 @@ class RunningMetrics:
         if isinstance(metric, str):
             return self.sum[self.names.index(metric)] / self.count
         assert False, "metric must be int or str"
+
+
+RAW_NAMES = ("n_valid", "d1", "d2", "d3", "abs", "sq", "log10", "sle", "absrel", "sqrel", "rsq", "lnsq")
+
+
+def raw_sums(pred, target):
+    """The 12 raw per-call sums of include/mde_b200.h (MDE_Q_*) in the input dtype: counts from the
+    reference's fp32 ratio test when given fp32 tensors, float sums as plain sums of the reference terms."""
+    p, t = gather_valid(pred, target)
+    r = _max_ratio(p, t)
+    d = p - t
+    out = [p.numel(), int((r < DELTA_THRESHOLDS[0]).sum()), int((r < DELTA_THRESHOLDS[1]).sum()),
+           int((r < DELTA_THRESHOLDS[2]).sum()), d.abs().sum(), (d * d).sum(),
+           (torch.log10(p) - torch.log10(t)).abs().sum(), ((torch.log1p(p) - torch.log1p(t)) ** 2).sum(),
+           (d.abs() / t).sum(), (d * d / t).sum(), torch.sqrt(d * d / t).sum(), ((torch.log(p) - torch.log(t)) ** 2).sum()]
+    return torch.tensor([float(v) for v in out], dtype=torch.float64)

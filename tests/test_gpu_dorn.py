@@ -22,6 +22,16 @@ def Cr():
     return criteria
 
 
+def _gradx_ref(g):
+    """fp64 reference gradient, except on knife-edge logits where the fp32 and fp64 evaluations of the
+    reference are different functions: a logit equal to fp32(1e-8) passes clamp(min=1e-8) in fp32
+    (x >= min) but not after widening to fp64 (fp32(1e-8) < 1e-8). The kernel follows fp32."""
+    g32, g64 = g["ordloss_gradx32"].astype(np.float64), g["ordloss_gradx64"]
+    knife = np.abs(g32 - g64) > 1e-4 * np.abs(g64).max()
+    assert knife.sum() <= 2
+    return np.where(knife, g32, g64)
+
+
 def test_small_golden_layer_and_ordloss(D, Cr, golden):
     g = golden("dorn_small.npz")
     x, gt = T(g["logits"]).cuda(), T(g["gt"]).cuda()
@@ -43,7 +53,7 @@ def test_small_golden_layer_and_ordloss(D, Cr, golden):
     loss = Cr.ordLoss()(P, y)                                                   # the reference's two-module path
     loss.backward()
     close(loss, g["ordloss64"], LOSS_RTOL)
-    grad_close(xr.grad, g["ordloss_gradx64"])
+    grad_close(xr.grad, _gradx_ref(g))
     Pl = T(g["P"]).cuda().requires_grad_(True)
     lp = Cr.ordLoss()(Pl, T(g["y_sid"]).cuda())
     lp.backward()
@@ -62,7 +72,7 @@ def test_small_golden_fused(D, golden):
     close(depth, g["depth"], 1e-5)
     close(P, g["P64"], 1e-5, 1e-7)
     close(loss, g["ordloss64"], LOSS_RTOL)
-    grad_close(xr.grad, g["ordloss_gradx64"])
+    grad_close(xr.grad, _gradx_ref(g))
     head = D.DornOrdinalHead(K, 0.001, 1.0)
     l2, d2, dec2 = head(x, gt)                                                   # no grad requested
     close(l2, g["ordloss64"], LOSS_RTOL)

@@ -171,3 +171,36 @@ def test_shift_property_at_scale(Cr):
     with torch.no_grad():
         l2 = Cr.MaskedMSELoss()(pred + h * grad, gt)
     close(float(l2) - float(loss), h * g2 + h * h * g2 / n_valid, 1e-3)
+
+
+@pytest.mark.parametrize("name", ["silog", "l1", "mse", "berhu", "laina_berhu"])
+@pytest.mark.parametrize("names", [["delta1", "delta2", "delta3", "mse", "mae", "log10", "rmse"],
+                                   ["delta1", "absrel", "sqrel", "msle", "rmse_log", "rmse_true"]])
+def test_loss_with_fused_metrics(Cr, name, names):
+    """criterion.fuse_metrics(mc): ONE launch gives loss, gradient and the pooled metric suite; the following
+    mc.compute(pred, gt) is served from it (no second pass) and equals the stand-alone results."""
+    from mono_depth_estimation_b200 import metrics as M, _lib
+    from oracle import metrics as ometrics
+    for shape, seed in (((3, 1, 40, 56), 71), ((2, 1, 33, 41), 72)):
+        pred, gt = synth.depth_pair(shape, seed, border=2)
+        pred[0, 0, 5, 5] = 1e-9                       # below the metrics' clamp: SILog must not use the clamped value
+        l64, g64 = olosses.loss_and_grad(olosses.LOSSES[name], pred.double(), gt.double())
+        v64 = [float(v) for v in ometrics.compute(pred.double(), gt.double(), names)]
+        mc = M.MetricComputation(names)
+        crit = make(Cr, name).fuse_metrics(mc)
+        p = pred.cuda().requires_grad_(True)
+        g = gt.cuda()
+        _lib.workspace(p.device, shape[0])             # first use initialises the workspace (one tiny launch)
+        n0 = _lib.launch_count()
+        loss = crit(p, g)
+        vals = mc.compute(p.detach(), g)
+        assert _lib.launch_count() - n0 == 1, "metrics must come from the loss launch"
+        loss.backward()
+        close(loss, l64, LOSS_RTOL, msg=name)
+        grad_close(p.grad, g64, msg=name)
+        close(torch.stack(vals), v64, 1e-5, msg=name)
+        assert mc.count == 1
+        # a different tensor is NOT served from the cache
+        vals2 = mc.compute((p.detach() * 1.0), g)
+        assert _lib.launch_count() - n0 >= 3
+        close(torch.stack(vals2), v64, 1e-5)
