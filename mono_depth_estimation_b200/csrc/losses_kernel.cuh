@@ -34,7 +34,7 @@ constexpr unsigned kStashInvalid = 0xffc0dead;  // quiet-NaN payload marking "pi
 // forward: body(idx, p, t) for every element of this CTA's chunk; fold() after every batch of <= 8
 // (VEC) / 4 (scalar) elements per thread. If STASH, body returns a float that is written to `stash`
 // (same layout as pred) with 128-bit stores.
-template <typename PT, bool VEC, bool STASH, typename Body, typename Fold>
+template <typename PT, bool VEC, bool STASH, bool PIPE, typename Body, typename Fold>
 __device__ __forceinline__ void chunk_forward(const PT* __restrict__ pred, const float* __restrict__ gt,
                                               float* stash, const LossArgs& a, Body&& body, Fold&& fold) {
   const int64_t n = a.n;
@@ -43,6 +43,51 @@ __device__ __forceinline__ void chunk_forward(const PT* __restrict__ pred, const
   if constexpr (VEC) {
     const int64_t nq = n >> 2;
     int64_t q = cb + threadIdx.x;
+    if constexpr (PIPE) {
+      // software pipeline: the next iteration's 4 x 16 B are requested before the current 8 pixels are
+      // evaluated (short per-thread runs cannot rely on warps drifting apart to overlap loads and math)
+      float4 p0, t0, p1, t1;
+      bool has0 = q < ce, has1 = q + kBlock < ce;
+      if (has0) {
+        p0 = Elem<PT>::template ld4<true>(pred + 4 * q);
+        t0 = Elem<float>::template ld4<true>(gt + 4 * q);
+      }
+      if (has1) {
+        p1 = Elem<PT>::template ld4<true>(pred + 4 * (q + kBlock));
+        t1 = Elem<float>::template ld4<true>(gt + 4 * (q + kBlock));
+      }
+      while (has0) {
+        const int64_t qn = q + 2 * kBlock, q1 = q + kBlock;
+        const bool n0 = qn < ce, n1 = qn + kBlock < ce;
+        float4 np0, nt0, np1, nt1;
+        if (n0) {
+          np0 = Elem<PT>::template ld4<true>(pred + 4 * qn);
+          nt0 = Elem<float>::template ld4<true>(gt + 4 * qn);
+        }
+        if (n1) {
+          np1 = Elem<PT>::template ld4<true>(pred + 4 * (qn + kBlock));
+          nt1 = Elem<float>::template ld4<true>(gt + 4 * (qn + kBlock));
+        }
+        float4 s0;
+        s0.x = body(4 * q + 0, p0.x, t0.x); s0.y = body(4 * q + 1, p0.y, t0.y);
+        s0.z = body(4 * q + 2, p0.z, t0.z); s0.w = body(4 * q + 3, p0.w, t0.w);
+        if constexpr (STASH) {
+          if (stash) *reinterpret_cast<float4*>(stash + 4 * q) = s0;
+        }
+        if (has1) {
+          float4 s1;
+          s1.x = body(4 * q1 + 0, p1.x, t1.x); s1.y = body(4 * q1 + 1, p1.y, t1.y);
+          s1.z = body(4 * q1 + 2, p1.z, t1.z); s1.w = body(4 * q1 + 3, p1.w, t1.w);
+          if constexpr (STASH) {
+            if (stash) *reinterpret_cast<float4*>(stash + 4 * q1) = s1;
+          }
+        }
+        fold();
+        p0 = np0; t0 = nt0; p1 = np1; t1 = nt1;
+        has0 = n0; has1 = n1;
+        q = qn;
+      }
+    }
     for (; q + kBlock < ce; q += 2 * kBlock) {
       const int64_t q1 = q + kBlock;
       const float4 p0 = Elem<PT>::template ld4<true>(pred + 4 * q);
@@ -222,7 +267,9 @@ __constant__ int kValNumL[MDE_METRIC_NM] = {MDE_Q_D1, MDE_Q_D2, MDE_Q_D3, MDE_Q_
                                             MDE_Q_ABSREL, MDE_Q_SQREL, MDE_Q_RSQ, MDE_Q_SQ, MDE_Q_LNSQ};
 constexpr int kMetBase = 16;  // gacc[kMetBase + q] = pooled raw metric sum q
 
-template <int KIND, typename PT, bool VEC, unsigned MG>
+// LONG = false (a thread sees <= 96 pixels): sums stay in fp32 registers until the end of the chunk and
+// the loads are software-pipelined; LONG = true folds every 8 pixels into fp64 running sums.
+template <int KIND, typename PT, bool VEC, unsigned MG, bool LONG>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm_d[(MG ? 12 : 4) * kWarps];
@@ -245,7 +292,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   if constexpr (KIND == MDE_LOSS_BERHU || KIND == MDE_LOSS_LAINA_BERHU) {
     float mx = -INFINITY;
     bool saw_nan = false;
-    chunk_forward<PT, VEC, false>(
+    chunk_forward<PT, VEC, false, !LONG>(
         pred, gt, nullptr, a,
         [&](int64_t i, float p, float t) -> float {
           float x;
@@ -281,7 +328,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
 #pragma unroll
       for (int q = 0; q < 8; ++q) mrun[q] = 0.0;
     }
-    auto fold = [&] {
+    auto fold_now = [&] {
       run[0] += s0;
       run[1] += s1;
       s0 = 0.f;
@@ -292,10 +339,14 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
         if (MG & kGrpLog1p) mrun[3] += mt.s_sle;
         if (MG & kGrpRel) { mrun[4] += mt.s_absrel; mrun[5] += mt.s_sqrel; mrun[6] += mt.s_rsq; }
         mt.zero();
+        mc.unpack();
       }
     };
+    auto fold = [&] {
+      if constexpr (LONG) fold_now();
+    };
     float* stash = kCanStash ? reinterpret_cast<float*>(grad) : nullptr;
-    chunk_forward<PT, VEC, kCanStash>(
+    chunk_forward<PT, VEC, kCanStash, !LONG>(
         pred, gt, stash, a,
         [&](int64_t i, float p, float t) -> float {
           float mL = 0.f, md = 0.f;
@@ -352,6 +403,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
           }
         },
         fold);
+    fold_now();
     run[2] = static_cast<double>(c0);
     run[3] = static_cast<double>(c1);
     publish_sums<4>(run, gacc, sm_d);
@@ -491,9 +543,9 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   }
 }
 
-template <int KIND, typename PT, bool VEC, unsigned MG>
-int launch_loss(LossArgs& a, cudaStream_t st) {
-  const void* fn = reinterpret_cast<const void*>(&masked_loss_kernel<KIND, PT, VEC, MG>);
+template <int KIND, typename PT, bool VEC, unsigned MG, bool LONG>
+int launch_loss_l(LossArgs& a, cudaStream_t st) {
+  const void* fn = reinterpret_cast<const void*>(&masked_loss_kernel<KIND, PT, VEC, MG, LONG>);
   const int64_t units = VEC ? (a.n >> 2) : a.n;
   int64_t grid = (units + kBlock - 1) / kBlock;
   const int cap = coop_grid(fn, kBlock, 0);
@@ -505,6 +557,13 @@ int launch_loss(LossArgs& a, cudaStream_t st) {
   MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, 0, st));
   count_launch();
   return MDE_OK;
+}
+
+template <int KIND, typename PT, bool VEC, unsigned MG>
+int launch_loss(LossArgs& a, cudaStream_t st) {
+  const int64_t threads = static_cast<int64_t>(sm_count()) * kCtasPerSm * kBlock;
+  const bool is_long = (a.n + threads - 1) / threads > 96;
+  return is_long ? launch_loss_l<KIND, PT, VEC, MG, true>(a, st) : launch_loss_l<KIND, PT, VEC, MG, false>(a, st);
 }
 
 template <int KIND, typename PT, unsigned MG>

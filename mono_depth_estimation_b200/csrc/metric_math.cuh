@@ -3,12 +3,16 @@
 // Two evaluation modes of the SAME quantities (include/mde_b200.h, MDE_Q_*):
 //   Ref  : the reference's own op sequence (metrics.py:75-109 + torchmetrics closed forms):
 //          log10f(p)-log10f(t), log1pf(p)-log1pf(t), IEEE divides everywhere.
-//   Fast : algebraically equal forms that need ONE IEEE divide and at most two logarithms per
-//          pixel; used by default because the full suite in Ref form is issue-bound, not
-//          HBM-bound, on B200 ("metrics kernel").
-// In BOTH modes the delta counts come from r = fl(max(p,t)/min(p,t)) with an IEEE divide, which
-// equals max(fl(p/t), fl(t/p)) bit for bit (round-to-nearest is monotone), so the integer counts
-// are bit-exact against the reference.
+//   Fast : algebraically equal forms built on the SFU (MUFU.RCP / LG2 / RSQ); used by default
+//          because the suite in Ref form is issue-bound, not HBM-bound, on B200.
+//
+// Bit-exact delta counts in BOTH modes. The reference counts max(fl(p/t), fl(t/p)) < 1.25^k, which
+// equals r = fl(max(p,t)/min(p,t)) < 1.25^k (round-to-nearest is monotone). Ref mode evaluates r
+// with an IEEE divide. Fast mode evaluates u = log_1.25(q), q = hi * rcp.approx(lo): |u - log_1.25(x)|
+// <= 2.5e-6 for the true quotient x (rcp.approx: 1 ulp, lg2.approx: <= 3.3e-7 absolute, both bounds
+// measured on B200 by tools/mathlab.cu and documented in the PTX ISA), so u < k decides r < 1.25^k
+// whenever u is farther than 1e-5 from the integers 1, 2, 3; inside that window (6e-5 of the pixels)
+// the pixel takes the exact IEEE divide. The integer counts are therefore identical to the reference.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -76,10 +80,34 @@ struct MetricTile {
     s_abs = s_sq = s_log10 = s_sle = s_absrel = s_sqrel = s_rsq = s_lnsq = 0.f;
   }
 };
+// n / c1 / c2 / c3 plus (fast mode) a packed 4 x 8-bit histogram of the threshold level of the
+// valid pixels since the last unpack(): byte 0 = ratio < 1.25, byte 1 = [1.25, 1.5625),
+// byte 2 = [1.5625, 1.953125), byte 3 = the rest. At most 255 pixels may be packed between unpacks.
 struct MetricCounts {
   int n, c1, c2, c3;
-  __device__ __forceinline__ void zero() { n = c1 = c2 = c3 = 0; }
+  unsigned pk;
+  __device__ __forceinline__ void zero() { n = c1 = c2 = c3 = 0; pk = 0u; }
+  __device__ __forceinline__ void unpack() {
+    const int b0 = pk & 0xffu, b1 = (pk >> 8) & 0xffu, b2 = (pk >> 16) & 0xffu, b3 = pk >> 24;
+    c1 += b0;
+    c2 += b0 + b1;
+    c3 += b0 + b1 + b2;
+    n += b0 + b1 + b2 + b3;
+    pk = 0u;
+  }
 };
+
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rsq(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// ln(q) for q >= 1 (NaN passes through): the SFU log2 away from 1, a 4-term series of ln(1+f) below
+// 1 + 2^-5 where lg2.approx's +4e-8 absolute bias would otherwise dominate a small result.
+__device__ __forceinline__ float ln_ge1_fast(float q, float l2) {
+  const float f = q - 1.0f;
+  const float ser = f * fmaf(f, fmaf(f, fmaf(f, -0.25f, 0.33333333f), -0.5f), 1.0f);
+  return (f < 0.03125f) ? ser : l2 * 0.69314718055994531f;
+}
 
 // One pixel of the metric suite. Besides accumulating, returns through `L_out` the value
 // |ln p - ln t| = ln(max/min) (fast mode with kGrpLog only; 0 otherwise) so that a fused loss can
@@ -94,20 +122,19 @@ __device__ __forceinline__ void metric_px_ex(float p, float t, MetricTile& a, Me
   const float tt = v ? t : 1.0f;
   const float d = pp - tt;
   const float hi = fmaxf(pp, tt), lo = fminf(pp, tt);
-  // == max(fl(p/t), fl(t/p)) (metrics.py:76); the fma adds 0*d so that a NaN prediction, which
-  // fmaxf/fminf drop, still poisons r as torch.max would (exact no-op for finite d)
-  const float r = fmaf(d, 0.0f, __fdiv_rn(hi, lo));
-  c.n += v ? 1 : 0;
-  c.c1 += (v && r < 1.25f) ? 1 : 0;               // strict '<' (metrics.py:77,82,87)
-  c.c2 += (v && r < 1.5625f) ? 1 : 0;
-  c.c3 += (v && r < 1.953125f) ? 1 : 0;
   const float ad = fabsf(d);
-  const float sq = d * d;
   a.s_abs += ad;
-  a.s_sq += sq;
+  a.s_sq = fmaf(d, d, a.s_sq);
   L_out = 0.f;
   d_out = d;
   if (Ref) {
+    // == max(fl(p/t), fl(t/p)) (metrics.py:76); the fma adds 0*d so that a NaN prediction, which
+    // fmaxf/fminf drop, still poisons r as torch.max would (exact no-op for finite d)
+    const float r = fmaf(d, 0.0f, __fdiv_rn(hi, lo));
+    c.n += v ? 1 : 0;
+    c.c1 += (v && r < 1.25f) ? 1 : 0;             // strict '<' (metrics.py:77,82,87)
+    c.c2 += (v && r < 1.5625f) ? 1 : 0;
+    c.c3 += (v && r < 1.953125f) ? 1 : 0;
     if (G & kGrpLog) {
       a.s_log10 += fabsf(log10f(pp) - log10f(tt));            // metrics.py:90-91
       const float dl = logf(pp) - logf(tt);
@@ -118,32 +145,45 @@ __device__ __forceinline__ void metric_px_ex(float p, float t, MetricTile& a, Me
       a.s_sle = fmaf(dl, dl, a.s_sle);
     }
     if (G & kGrpRel) {
+      const float sq = d * d;
       a.s_absrel += __fdiv_rn(ad, tt);                        // metrics.py:97
       const float sr = __fdiv_rn(sq, tt);                     // metrics.py:103
       a.s_sqrel += sr;
       a.s_rsq += __fsqrt_rn(sr);                              // metrics.py:109
     }
   } else {
+    // q ~ max/min (1.5 ulp), NaN predictions propagate through the 0*d term
+    const float q = fmaf(d, 0.0f, hi * mufu_rcp(lo));
+    const float l2 = mufu_lg2(q);
+    // threshold level in the log domain: u = log_1.25(q); NaN -> 4 (beyond every threshold)
+    const float u = fminf(l2 * 3.1062837195f, 4.0f);
+    bool lt1 = u < 1.0f, lt2 = u < 2.0f, lt3 = u < 3.0f;
+    const float kf = (u + 12582912.0f) - 12582912.0f;        // rint(u) via the 1.5*2^23 trick
+    if (fabsf(u - kf) < 1e-5f && u > 0.5f && u < 3.5f) {      // within 1e-5 of a threshold: decide exactly
+      const float r = __fdiv_rn(hi, lo);
+      lt1 = r < 1.25f;
+      lt2 = r < 1.5625f;
+      lt3 = r < 1.953125f;
+    }
+    const unsigned inc = lt1 ? 1u : (lt2 ? 0x100u : (lt3 ? 0x10000u : 0x1000000u));
+    c.pk += v ? inc : 0u;
     if (G & kGrpLog) {
-      const float L = ln_pos(r);                              // |ln p - ln t| = ln(hi/lo)
+      const float L = ln_ge1_fast(q, l2);                     // |ln p - ln t| = ln(max/min)
       L_out = L;
       a.s_log10 = fmaf(L, 0.43429448190325182f, a.s_log10);
       a.s_lnsq = fmaf(L, L, a.s_lnsq);
     }
     if (G & kGrpLog1p) {
       // |log1p p - log1p t| = ln((1+hi)/(1+lo))
-      const float s = fmaf(d, 0.0f, (1.0f + hi) * rcp_nr(1.0f + lo));
-      const float L = ln_pos(s < 1.0f ? 1.0f : s);        // NaN stays NaN
+      const float s1 = fmaf(d, 0.0f, (1.0f + hi) * mufu_rcp(1.0f + lo));
+      const float L = ln_ge1_fast(s1 < 1.0f ? 1.0f : s1, mufu_lg2(s1));   // NaN stays NaN
       a.s_sle = fmaf(L, L, a.s_sle);
     }
     if (G & kGrpRel) {
-      const float it = rcp_nr(tt);
-      const float ar = ad * it;
+      const float ar = ad * mufu_rcp(tt);
       a.s_absrel += ar;
       a.s_sqrel = fmaf(ar, ad, a.s_sqrel);
-      float rs;
-      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(tt));
-      a.s_rsq = fmaf(ad, rs, a.s_rsq);                        // sqrt((p-t)^2/t) = |p-t| / sqrt(t)
+      a.s_rsq = fmaf(ad, mufu_rsq(tt), a.s_rsq);              // sqrt((p-t)^2/t) = |p-t| / sqrt(t)
     }
   }
 }

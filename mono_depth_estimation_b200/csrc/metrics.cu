@@ -16,17 +16,20 @@ namespace {
 constexpr int kNQ = MDE_METRIC_NQ;
 constexpr int kNM = MDE_METRIC_NM;
 
-template <unsigned G, bool Ref>
+// LONG = false: a thread sees at most 128 pixels of an image, so its sums stay in fp32 registers
+// until the flush (error <= ~4e-7 relative) and the fp64 running sums (16 registers) are not needed;
+// that frees the registers for the software-pipelined loads. LONG = true folds every 8 pixels into fp64.
+template <unsigned G, bool Ref, bool LONG>
 struct MetricThread {
   MetricTile tile;
   MetricCounts cnt;
-  double run[8];
+  double run[LONG ? 8 : 1];
 
   __device__ __forceinline__ void reset() {
     tile.zero();
     cnt.zero();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) run[i] = 0.0;
+    for (int i = 0; i < (LONG ? 8 : 1); ++i) run[i] = 0.0;
   }
   __device__ __forceinline__ void px(float p, float t) { metric_px<G, Ref>(p, t, tile, cnt); }
   __device__ __forceinline__ void quad(const float4& p, const float4& t) {
@@ -35,14 +38,23 @@ struct MetricThread {
     px(p.z, t.z);
     px(p.w, t.w);
   }
+  // value of running sum q at flush time
+  __device__ __forceinline__ float total(int q) const {
+    const float t = (q == 0) ? tile.s_abs : (q == 1) ? tile.s_sq : (q == 2) ? tile.s_log10 : (q == 3) ? tile.s_sle
+                  : (q == 4) ? tile.s_absrel : (q == 5) ? tile.s_sqrel : (q == 6) ? tile.s_rsq : tile.s_lnsq;
+    if constexpr (LONG) return static_cast<float>(run[q] + static_cast<double>(t));
+    return t;
+  }
   // fold the fp32 tile sums into the fp64 running sums
   __device__ __forceinline__ void fold() {
+    if constexpr (!LONG) return;
     run[0] += tile.s_abs;
     run[1] += tile.s_sq;
     if (G & kGrpLog) { run[2] += tile.s_log10; run[7] += tile.s_lnsq; }
     if (G & kGrpLog1p) run[3] += tile.s_sle;
     if (G & kGrpRel) { run[4] += tile.s_absrel; run[5] += tile.s_sqrel; run[6] += tile.s_rsq; }
     tile.zero();
+    cnt.unpack();
   }
 };
 
@@ -123,7 +135,7 @@ __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __re
   }
 }
 
-template <typename PT, int VEC, unsigned G, bool Ref>
+template <typename PT, int VEC, unsigned G, bool Ref, bool LONG>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm)
 metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_t n_img, int64_t hw, Chunking chunk,
                void* ws_raw, double* __restrict__ out_f64, float* __restrict__ out_f32,
@@ -140,7 +152,7 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
   int64_t ub, ue;
   cta_chunk(chunk, blockIdx.x, ub, ue);
 
-  MetricThread<G, Ref> th;
+  MetricThread<G, Ref, LONG> th;
   int64_t u = ub;
   while (u < ue) {
     const int64_t img = u / units_per_img;
@@ -149,8 +161,9 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
     th.reset();
 
     int64_t i = u + threadIdx.x;
-    if (VEC == 4) {
-      // 2 quads of pred and of target in flight per thread (4 x 16 B)
+    if (VEC == 4 && LONG) {
+      // long per-thread runs: 2 quads of pred and of target in flight (4 x 16 B); the warps of an SM
+      // drift apart over the many iterations, which overlaps loads and arithmetic across warps
       for (; i + kBlock < seg_end; i += 2 * kBlock) {
         const float4 p0 = Elem<PT>::template ld4<false>(pred + 4 * i);
         const float4 t0 = Elem<float>::template ld4<false>(gt + 4 * i);
@@ -165,6 +178,38 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
         const float4 t0 = Elem<float>::template ld4<false>(gt + 4 * i);
         th.quad(p0, t0);
         th.fold();
+      }
+    } else if (VEC == 4) {
+      // software pipeline: the 2 quads of pred and of target (4 x 16 B) of the NEXT iteration are
+      // requested before the current 8 pixels are evaluated, so the loads overlap the arithmetic
+      float4 p0, t0, p1, t1;
+      bool has0 = i < seg_end, has1 = i + kBlock < seg_end;
+      if (has0) {
+        p0 = Elem<PT>::template ld4<false>(pred + 4 * i);
+        t0 = Elem<float>::template ld4<false>(gt + 4 * i);
+      }
+      if (has1) {
+        p1 = Elem<PT>::template ld4<false>(pred + 4 * (i + kBlock));
+        t1 = Elem<float>::template ld4<false>(gt + 4 * (i + kBlock));
+      }
+      while (has0) {
+        const int64_t in = i + 2 * kBlock;
+        const bool n0 = in < seg_end, n1 = in + kBlock < seg_end;
+        float4 np0, nt0, np1, nt1;
+        if (n0) {
+          np0 = Elem<PT>::template ld4<false>(pred + 4 * in);
+          nt0 = Elem<float>::template ld4<false>(gt + 4 * in);
+        }
+        if (n1) {
+          np1 = Elem<PT>::template ld4<false>(pred + 4 * (in + kBlock));
+          nt1 = Elem<float>::template ld4<false>(gt + 4 * (in + kBlock));
+        }
+        th.quad(p0, t0);
+        if (has1) th.quad(p1, t1);
+        th.fold();
+        p0 = np0; t0 = nt0; p1 = np1; t1 = nt1;
+        has0 = n0; has1 = n1;
+        i = in;
       }
     } else {
       for (; i + 3 * kBlock < seg_end; i += 4 * kBlock) {
@@ -186,6 +231,7 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
 
     // ---- flush this image's partial sums: warp shuffle -> shared memory -> 12 fp64 atomics ----
     {
+      th.cnt.unpack();
       const int c0 = __reduce_add_sync(0xffffffffu, th.cnt.n);
       const int c1 = __reduce_add_sync(0xffffffffu, th.cnt.c1);
       const int c2 = __reduce_add_sync(0xffffffffu, th.cnt.c2);
@@ -203,7 +249,7 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
         const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
                           ((G & kGrpRel) && (q >= 4 && q <= 6));
         if (!used) continue;
-        const float s = warp_sum(static_cast<float>(th.run[q]));
+        const float s = warp_sum(th.total(q));
         if (lane == 0) sm_d[q * kWarps + warp] = static_cast<double>(s);
       }
       __syncthreads();
@@ -243,8 +289,8 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
   metrics_finalize(ws, n_img, out_f64, out_f32, per_image_values, per_image_raw, sm_d);
 }
 
-template <typename PT, int VEC, unsigned G, bool Ref>
-int launch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t hw, void* ws, double* out_f64,
+template <typename PT, int VEC, unsigned G, bool Ref, bool LONG>
+int launch_metrics_l(const void* pred, const float* gt, int64_t n_img, int64_t hw, void* ws, double* out_f64,
                    float* out_f32, double* piv, double* pir, cudaStream_t st) {
   const int64_t units = n_img * (hw / VEC);
   const int64_t per_cta_min = static_cast<int64_t>(kBlock);  // at least one unit per thread
@@ -253,11 +299,22 @@ int launch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t hw,
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   const Chunking chunk = make_chunking(units, 32 / VEC, static_cast<int>(grid));
-  metrics_kernel<PT, VEC, G, Ref><<<static_cast<unsigned>(grid), kBlock, 0, st>>>(
+  metrics_kernel<PT, VEC, G, Ref, LONG><<<static_cast<unsigned>(grid), kBlock, 0, st>>>(
       static_cast<const PT*>(pred), gt, n_img, hw, chunk, ws, out_f64, out_f32, piv, pir);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
+}
+
+template <typename PT, int VEC, unsigned G, bool Ref>
+int launch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t hw, void* ws, double* out_f64,
+                   float* out_f32, double* piv, double* pir, cudaStream_t st) {
+  // pixels one thread sees of one image: the whole batch is spread over <= 2 CTAs per SM
+  const int64_t px = n_img * hw;
+  const int64_t threads = static_cast<int64_t>(sm_count()) * kCtasPerSm * kBlock;
+  const bool is_long = (px + threads - 1) / threads > 96;
+  if (is_long) return launch_metrics_l<PT, VEC, G, Ref, true>(pred, gt, n_img, hw, ws, out_f64, out_f32, piv, pir, st);
+  return launch_metrics_l<PT, VEC, G, Ref, false>(pred, gt, n_img, hw, ws, out_f64, out_f32, piv, pir, st);
 }
 
 template <typename PT>

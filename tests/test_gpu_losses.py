@@ -183,7 +183,7 @@ def test_loss_with_fused_metrics(Cr, name, names):
     from oracle import metrics as ometrics
     for shape, seed in (((3, 1, 40, 56), 71), ((2, 1, 33, 41), 72)):
         pred, gt = synth.depth_pair(shape, seed, border=2)
-        pred[0, 0, 5, 5] = 1e-9                       # below the metrics' clamp: SILog must not use the clamped value
+        pred[0, 0, 5, 5] = 1e-8                       # below the metrics clamp (1e-7), above Laina clamp (1e-9)
         l64, g64 = olosses.loss_and_grad(olosses.LOSSES[name], pred.double(), gt.double())
         v64 = [float(v) for v in ometrics.compute(pred.double(), gt.double(), names)]
         mc = M.MetricComputation(names)

@@ -140,3 +140,28 @@ def test_batch_linearity_at_scale(M):
     sl = slice(5, 8)
     v64 = ometrics.compute_per_image_mean(pred[sl].cpu().double(), gt[sl].cpu().double(), ALL)
     close(full["per_image"][sl].mean(0), v64, METRIC_RTOL)
+
+
+def test_delta_counts_bit_exact_near_thresholds(M):
+    """Adversarial: ratios within a few ulp of 1.25^k in both orientations (p/t and t/p), where the fast
+    path must fall back to the exact IEEE divide. Counts must equal the reference's, pixel for pixel."""
+    g = torch.Generator().manual_seed(77)
+    n = 1 << 20
+    t = (torch.rand(n, generator=g, dtype=torch.float64) * 9.5 + 0.5).float()
+    k = torch.randint(1, 4, (n,), generator=g)
+    thr = torch.tensor([1.25, 1.5625, 1.953125], dtype=torch.float64)[k - 1]
+    ulps = torch.randint(-8, 9, (n,), generator=g).double()
+    flip = torch.rand(n, generator=g) < 0.5
+    ratio = thr * (1.0 + ulps * 2.0 ** -24)
+    p = torch.where(flip, t.double() / ratio, t.double() * ratio).float()
+    p[::97] = t[::97] * 1.25                       # exact-threshold products
+    pred, gt = p.view(4, 1, 512, 512), t.view(4, 1, 512, 512)
+    ref = ometrics.delta_counts(pred, gt)
+    for ref_math in (False, True):
+        res = M.fused_metrics(pred.cuda(), gt.cuda(), per_image=True, reference_math=ref_math)
+        assert _counts(res) == list(ref)
+        for b in range(4):
+            rb = ometrics.delta_counts(pred[b:b + 1], gt[b:b + 1])
+            assert [int(round(v)) for v in res["per_image_raw"][b, :4].tolist()] == list(rb)
+    # half of the sampled ratios sit within 1e-5 (log_1.25 units) of a threshold: the slow path is exercised
+    assert 0.05 < ref[1] / ref[0] < 0.95
