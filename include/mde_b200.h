@@ -246,6 +246,10 @@ const char* mde_last_error(void);
 const char* mde_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t mde_launch_count(void);
+/* Profiling aid: device buffer of 8 x uint64 per CTA (>= 8 * 2 * SM count entries) that the masked-loss
+ * kernels fill with GPU global-timer stamps at their phase boundaries (0 start, 1 reduce loop done,
+ * 2 sums published, 3 grid barrier passed, 4 totals read, 5 gradient written); NULL disarms it. */
+int mde_debug_set_trace(void* device_buf);
 /* SM count / max co-resident CTAs the cooperative kernels use on the current device */
 int mde_device_info(int* sm_count, int* coop_ctas);
 

@@ -68,6 +68,7 @@ SIGNATURES = {
     "mde_version": (C.c_char_p, []),
     "mde_launch_count": (C.c_uint64, []),
     "mde_device_info": (_i32, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mde_debug_set_trace": (_i32, [_vp]),
 }
 
 _lib = None

@@ -100,24 +100,49 @@ __host__ __device__ inline Ws ws_view(void* base) {
 // parity set (used by the previous cooperative launch, which has completed) for the next one.
 // Must run before the first grid barrier; the matching epilogue (epoch + 1) after the last one.
 __device__ __forceinline__ int coop_prologue(const Ws& ws, unsigned& epoch_out) {
-  const unsigned epoch = __ldcg(&ws.hdr->epoch);
+  // one thread per CTA reads the epoch (a hot line if every warp of the grid fetched it) and shares it
+  __shared__ unsigned sm_epoch;
+  if (threadIdx.x == 0) sm_epoch = __ldcg(&ws.hdr->epoch);
+  __syncthreads();
+  const unsigned epoch = sm_epoch;
   const int par = static_cast<int>(epoch & 1u);
   epoch_out = epoch;
   if (blockIdx.x == 0) {
     const int o = par ^ 1;
     for (int i = threadIdx.x; i < kGacc; i += blockDim.x) ws.gacc[o * kGacc + i] = 0.0;
     for (int i = threadIdx.x; i < kUkey; i += blockDim.x) ws.ukey[o * kUkey + i] = 0u;
-    const unsigned dirty = __ldcg(&ws.hdr->dirty[o]);
-    if (dirty) {
-      const unsigned cap = __ldcg(&ws.hdr->max_images);
-      double* rows = ws.iacc + static_cast<size_t>(1 + o) * cap * kIacc;
-      for (size_t i = threadIdx.x; i < static_cast<size_t>(dirty) * kIacc; i += blockDim.x) rows[i] = 0.0;
-      __syncthreads();
-      if (threadIdx.x == 0) ws.hdr->dirty[o] = 0u;
+    if (threadIdx.x == 0) {
+      const unsigned dirty = __ldcg(&ws.hdr->dirty[o]);
+      if (dirty) {
+        const unsigned cap = __ldcg(&ws.hdr->max_images);
+        double* rows = ws.iacc + static_cast<size_t>(1 + o) * cap * kIacc;
+        for (size_t i = 0; i < static_cast<size_t>(dirty) * kIacc; ++i) rows[i] = 0.0;
+        ws.hdr->dirty[o] = 0u;
+      }
     }
   }
   return par;
 }
+#endif
+
+// ---- optional per-CTA phase trace (debug / profiling aid) -------------------------------------------
+// mde_debug_set_trace(buf) arms it: slot k of CTA b receives the GPU global timer (ns) when the CTA
+// passes trace point k. One pointer per translation unit (no relocatable device code in this build).
+#ifdef __CUDACC__
+static __device__ unsigned long long* g_mde_trace = nullptr;
+constexpr int kTraceSlots = 8;
+__device__ __forceinline__ void trace_point(int k) {
+  unsigned long long* t = g_mde_trace;
+  if (t != nullptr && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    t[static_cast<size_t>(blockIdx.x) * kTraceSlots + k] = ns;
+  }
+}
+#define MDE_DEFINE_TRACE_SETTER(name)                                                        \
+  int name(unsigned long long* buf) {                                                        \
+    return cudaMemcpyToSymbol(g_mde_trace, &buf, sizeof(buf)) == cudaSuccess ? MDE_OK : MDE_ECUDA; \
+  }
 #endif
 
 // ---- typed 4-element loads / stores ----------------------------------------------------------

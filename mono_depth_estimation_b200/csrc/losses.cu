@@ -23,6 +23,10 @@
 #include "losses_kernel.cuh"
 
 namespace mde {
+MDE_DEFINE_TRACE_SETTER(set_trace_losses)
+}  // namespace mde
+
+namespace mde {
 
 int eigen_loss_launch(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t h, int64_t w,
                       float grad_scale, void* ws, float* loss_out, double* totals_out, void* grad,

@@ -5,6 +5,10 @@
 // fused step costs one IEEE divide and one logarithm per pixel.
 #include "losses_kernel.cuh"
 
+namespace mde {
+MDE_DEFINE_TRACE_SETTER(set_trace_losses_fused)
+}  // namespace mde
+
 extern "C" int mde_masked_loss_metrics(int kind, const void* pred, int pred_dtype, const float* target,
                                        const uint8_t* mask_u8, int64_t n_img, int64_t h, int64_t w,
                                        const mde_loss_params* params, float grad_scale, unsigned metric_flags,

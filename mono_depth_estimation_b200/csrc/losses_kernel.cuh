@@ -2,6 +2,7 @@
 // Included by losses.cu (plain losses) and losses_fused.cu (losses with the pooled metric suite
 // fused into the reduce phase), which instantiate it for different metric-group masks MG.
 #pragma once
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -23,6 +24,7 @@ struct LossArgs {
   float* loss_out;
   double* totals_out;
   void* grad;
+  int sched;        // 0: tiles claimed from an atomic counter; 1: static interleaved tiles (tile = k*grid + cta)
   double* met_f64;  // fused metrics (MG != 0): same layout as mde_metrics' out_f64
   float* met_f32;
   int64_t n_img;
@@ -207,6 +209,173 @@ __device__ __forceinline__ void chunk_map_reverse(const PT* __restrict__ pred, c
   }
 }
 
+// ---- dynamic tile scheduling (128-bit path) ----------------------------------------------------------
+// HBM/L2 bandwidth is not shared fairly between SMs: with one static chunk per CTA the reduce phase
+// of the slowest CTA takes ~1.7x the fastest one (measured with mde_debug_set_trace) and everybody
+// waits for it at the grid barrier. Instead the CTAs pull tiles of kBlock quads (8 KB of each tensor)
+// from an atomic counter, so fast CTAs simply process more tiles and all CTAs reach the barrier within
+// one tile time. The tile id after next is fetched while the current tile is evaluated, and the next
+// tile's 2 x 16 B per thread are already in flight (software pipeline, ping-pong register buffers).
+struct TileSched {
+  unsigned* ctr;   // zero at launch (parity set of the workspace)
+  int* slot;       // 2 ints of shared memory
+  bool dynamic;    // false: static interleaved tiles (tile = k * grid + cta), no atomics, no CTA barriers
+};
+
+template <typename PT, bool STASH, typename Body, typename Fold>
+__device__ __forceinline__ void tiles_forward(const PT* __restrict__ pred, const float* __restrict__ gt, float* stash,
+                                              const LossArgs& a, TileSched ts, Body&& body, Fold&& fold) {
+  const int64_t nq = a.n >> 2;
+  const int64_t nt = (nq + kBlock - 1) / kBlock;
+  const unsigned G = gridDim.x;
+  auto fetch = [&]() -> unsigned { return (threadIdx.x == 0) ? atomicAdd(ts.ctr, 1u) : 0u; };
+  auto publish = [&](int sl, unsigned c) {
+    if (threadIdx.x == 0) ts.slot[sl] = static_cast<int>(G + c);
+  };
+  auto load = [&](int64_t tile, float4& p, float4& t) -> bool {
+    const int64_t q = tile * kBlock + threadIdx.x;
+    const bool ok = q < nq;
+    if (ok) {
+      p = Elem<PT>::template ld4<true>(pred + 4 * q);
+      t = Elem<float>::template ld4<true>(gt + 4 * q);
+    }
+    return ok;
+  };
+  auto compute = [&](int64_t tile, const float4& p, const float4& t) {
+    const int64_t q = tile * kBlock + threadIdx.x;
+    float4 s;
+    s.x = body(4 * q + 0, p.x, t.x); s.y = body(4 * q + 1, p.y, t.y);
+    s.z = body(4 * q + 2, p.z, t.z); s.w = body(4 * q + 3, p.w, t.w);
+    if constexpr (STASH) {
+      if (stash) *reinterpret_cast<float4*>(stash + 4 * q) = s;
+    }
+  };
+  // The atomic that claims a tile is ISSUED before the loads and the arithmetic of the current step and
+  // its result is only stored to shared memory afterwards, so its L2 round trip is off the critical path.
+  int64_t tA = blockIdx.x, tB;
+  float4 pA, gA, pB, gB;
+  bool okA = false, okB = false;
+  unsigned claim = 0;
+  if (ts.dynamic) {
+    claim = fetch();
+    if (tA < nt) okA = load(tA, pA, gA);
+    publish(0, claim);
+    __syncthreads();
+    tB = ts.slot[0];
+    while (tA < nt) {
+      claim = fetch();
+      okB = (tB < nt) && load(tB, pB, gB);
+      if (okA) compute(tA, pA, gA);
+      publish(1, claim);
+      __syncthreads();
+      tA = ts.slot[1];
+      if (tB >= nt) break;
+      claim = fetch();
+      okA = (tA < nt) && load(tA, pA, gA);
+      if (okB) compute(tB, pB, gB);
+      fold();
+      publish(0, claim);
+      __syncthreads();
+      tB = ts.slot[0];
+    }
+  } else {
+    if (tA < nt) okA = load(tA, pA, gA);
+    tB = tA + G;
+    while (tA < nt) {
+      okB = (tB < nt) && load(tB, pB, gB);
+      if (okA) compute(tA, pA, gA);
+      tA = tB + G;
+      if (tB >= nt) break;
+      okA = (tA < nt) && load(tA, pA, gA);
+      if (okB) compute(tB, pB, gB);
+      fold();
+      tB = tA + G;
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1) {  // n % 4 tail
+    const int64_t i = (nq << 2) + threadIdx.x;
+    if (i < a.n) {
+      const float sv = body(i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
+      if constexpr (STASH) {
+        if (stash) stash[i] = sv;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// gradient phase over dynamically scheduled tiles, highest tile first (the lines touched last are still in L2)
+template <typename PT, bool INPLACE, typename Body>
+__device__ __forceinline__ void tiles_map(const PT* __restrict__ pred, const float* second, PT* out, const LossArgs& a,
+                                          TileSched ts, Body&& body) {
+  const int64_t nq = a.n >> 2;
+  const int64_t nt = (nq + kBlock - 1) / kBlock;
+  const unsigned G = gridDim.x;
+  auto fetch = [&]() -> unsigned { return (threadIdx.x == 0) ? atomicAdd(ts.ctr, 1u) : 0u; };
+  auto publish = [&](int sl, unsigned c) {
+    if (threadIdx.x == 0) ts.slot[sl] = static_cast<int>(G + c);
+  };
+  auto load = [&](int64_t tile, float4& p, float4& t) -> bool {
+    const int64_t q = (nt - 1 - tile) * kBlock + threadIdx.x;
+    const bool ok = q < nq;
+    if (ok) {
+      p = Elem<PT>::template ld4<false>(pred + 4 * q);
+      if constexpr (INPLACE) t = *reinterpret_cast<const float4*>(second + 4 * q);
+      else t = Elem<float>::template ld4<false>(second + 4 * q);
+    }
+    return ok;
+  };
+  auto compute = [&](int64_t tile, const float4& p, const float4& t) {
+    const int64_t q = (nt - 1 - tile) * kBlock + threadIdx.x;
+    float4 g;
+    g.x = body(4 * q + 0, p.x, t.x); g.y = body(4 * q + 1, p.y, t.y);
+    g.z = body(4 * q + 2, p.z, t.z); g.w = body(4 * q + 3, p.w, t.w);
+    Elem<PT>::st4(out + 4 * q, g);
+  };
+  if (blockIdx.x == gridDim.x - 1) {
+    const int64_t i = (nq << 2) + threadIdx.x;
+    if (i < a.n) Elem<PT>::st1(out + i, body(i, Elem<PT>::ld1(pred + i), INPLACE ? second[i] : __ldg(second + i)));
+  }
+  int64_t tA = blockIdx.x, tB;
+  float4 pA, gA, pB, gB;
+  bool okA = false, okB = false;
+  unsigned claim = 0;
+  if (ts.dynamic) {
+    claim = fetch();
+    if (tA < nt) okA = load(tA, pA, gA);
+    publish(0, claim);
+    __syncthreads();
+    tB = ts.slot[0];
+    while (tA < nt) {
+      claim = fetch();
+      okB = (tB < nt) && load(tB, pB, gB);
+      if (okA) compute(tA, pA, gA);
+      publish(1, claim);
+      __syncthreads();
+      tA = ts.slot[1];
+      if (tB >= nt) break;
+      claim = fetch();
+      okA = (tA < nt) && load(tA, pA, gA);
+      if (okB) compute(tB, pB, gB);
+      publish(0, claim);
+      __syncthreads();
+      tB = ts.slot[0];
+    }
+  } else {
+    if (tA < nt) okA = load(tA, pA, gA);
+    tB = tA + G;
+    while (tA < nt) {
+      okB = (tB < nt) && load(tB, pB, gB);
+      if (okA) compute(tA, pA, gA);
+      tA = tB + G;
+      if (tB >= nt) break;
+      okA = (tA < nt) && load(tA, pA, gA);
+      if (okB) compute(tB, pB, gB);
+      tB = tA + G;
+    }
+  }
+}
+
 // block-reduce N doubles and add them to gacc[0..N)
 template <int N>
 __device__ __forceinline__ void publish_sums(const double (&v)[N], double* gacc, double* sm) {
@@ -274,6 +443,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm_d[(MG ? 12 : 4) * kWarps];
   __shared__ float sm_f[kWarps];
+  __shared__ int sm_tile[2];
   constexpr bool kCanStash = (KIND == MDE_LOSS_SILOG) && std::is_same<PT, float>::value;
 
   const PT* __restrict__ pred = static_cast<const PT*>(a.pred);
@@ -281,6 +451,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   const uint8_t* __restrict__ mask = a.mask;
   PT* grad = static_cast<PT*>(a.grad);
 
+  trace_point(0);
   Ws ws = ws_view(a.ws);
   unsigned epoch;
   const int par = coop_prologue(ws, epoch);
@@ -292,9 +463,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   if constexpr (KIND == MDE_LOSS_BERHU || KIND == MDE_LOSS_LAINA_BERHU) {
     float mx = -INFINITY;
     bool saw_nan = false;
-    chunk_forward<PT, VEC, false, !LONG>(
-        pred, gt, nullptr, a,
-        [&](int64_t i, float p, float t) -> float {
+    auto body_max = [&](int64_t i, float p, float t) -> float {
           float x;
           if constexpr (KIND == MDE_LOSS_BERHU) {
             x = p - t;  // criteria.py:118 - signed, unmasked
@@ -306,11 +475,15 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
           saw_nan |= (x != x);
           mx = fmaxf(mx, x);
           return 0.f;
-        },
-        [] {});
+        };
+    if constexpr (VEC) tiles_forward<PT, false>(pred, gt, nullptr, a, TileSched{ukey + 4, sm_tile, a.sched == 0}, body_max, [] {});
+    else chunk_forward<PT, VEC, false, false>(pred, gt, nullptr, a, body_max, [] {});
     publish_max(mx, saw_nan, ukey, sm_f);
     grid.sync();
-    gmax = read_max(ukey);
+    if (threadIdx.x == 0) sm_f[0] = read_max(ukey);   // one L2 read per CTA, shared with the rest
+    __syncthreads();
+    gmax = sm_f[0];
+    __syncthreads();
     cthr = 0.2f * gmax;  // criteria.py:119 / :496 (fp32 product)
   }
 
@@ -346,9 +519,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       if constexpr (LONG) fold_now();
     };
     float* stash = kCanStash ? reinterpret_cast<float*>(grad) : nullptr;
-    chunk_forward<PT, VEC, kCanStash, !LONG>(
-        pred, gt, stash, a,
-        [&](int64_t i, float p, float t) -> float {
+    auto body_sum = [&](int64_t i, float p, float t) -> float {
           float mL = 0.f, md = 0.f;
           if constexpr (MG != 0) metric_px_ex<MG, false>(p, t, mt, mc, mL, md);
           if constexpr (KIND == MDE_LOSS_L1) {
@@ -401,8 +572,10 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
             c1 += (ni == gmax) ? 1 : 0;
             return 0.f;
           }
-        },
-        fold);
+        };
+    if constexpr (VEC) tiles_forward<PT, kCanStash>(pred, gt, stash, a, TileSched{ukey + 2, sm_tile, a.sched == 0}, body_sum, fold);
+    else chunk_forward<PT, VEC, kCanStash, false>(pred, gt, stash, a, body_sum, fold);
+    trace_point(1);
     fold_now();
     run[2] = static_cast<double>(c0);
     run[3] = static_cast<double>(c1);
@@ -431,12 +604,71 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       __syncthreads();
     }
   }
+  trace_point(2);
   grid.sync();
+  trace_point(3);
+
+  // ---------------- totals -> loss value and gradient coefficients ------------------------------------
+  // Warp 0 of every CTA reads the four totals (one request per CTA instead of one per warp: the totals
+  // sit in a single L2 line), lane 0 forms the coefficients and shared memory hands them to the CTA.
+  // Only ONE fp64 divide is on this path; the rest is fp32 (the sums themselves stay fp64).
+  __shared__ float sm_k[4];
+  __shared__ double sm_tot[4];
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const double tv = (lane < 4) ? __ldcg(&gacc[lane]) : 0.0;
+    const double S0 = __shfl_sync(0xffffffffu, tv, 0), S1 = __shfl_sync(0xffffffffu, tv, 1);
+    const double N0 = __shfl_sync(0xffffffffu, tv, 2), N1 = __shfl_sync(0xffffffffu, tv, 3);
+    if (lane == 0) {
+      double loss;
+      float k1 = 0.f, k2 = 0.f, k3 = 0.f;
+      const float gs = a.grad_scale;
+      if constexpr (KIND == MDE_LOSS_L1) {
+        const double inv = 1.0 / N0;
+        loss = S0 * inv;
+        k1 = gs * static_cast<float>(inv);
+      } else if constexpr (KIND == MDE_LOSS_MSE) {
+        const double inv = 1.0 / N0;
+        loss = S0 * inv;
+        k1 = 2.0f * gs * static_cast<float>(inv);
+      } else if constexpr (KIND == MDE_LOSS_SILOG) {
+        const double inv = 1.0 / N0;
+        const double dm = S0 * inv, q = S1 * inv;
+        const double var = q - static_cast<double>(a.vf) * dm * dm;   // the cancellation stays in fp64
+        const float s = sqrtf(static_cast<float>(var));
+        loss = 10.0 * static_cast<double>(s);
+        k1 = 10.0f * gs * static_cast<float>(inv) / s;                 // dL/dd_i = k1 * (d_i - k2)
+        k2 = a.vf * static_cast<float>(dm);
+      } else if constexpr (KIND == MDE_LOSS_BERHU) {
+        const double inv = 1.0 / (N0 + N1);
+        loss = (S0 + S1) * inv;                                         // mean of the concatenation (criteria.py:131)
+        k1 = gs * static_cast<float>(inv);
+      } else {
+        const double inv = a.size_average ? 1.0 / N0 : 1.0;
+        loss = S0 * inv;
+        k1 = gs * static_cast<float>(inv);
+        k2 = gs * 0.2f * static_cast<float>(S1 * inv) / static_cast<float>(N1);  // share of dL/dc per tied maximum
+        k3 = 2.f * cthr + 1e-9f;
+      }
+      sm_k[0] = k1; sm_k[1] = k2; sm_k[2] = k3;
+      if (blockIdx.x == 0) {
+        *a.loss_out = static_cast<float>(loss);
+        if (a.totals_out) {
+          a.totals_out[0] = S0; a.totals_out[1] = S1; a.totals_out[2] = N0; a.totals_out[3] = N1;
+          a.totals_out[4] = static_cast<double>(gmax); a.totals_out[5] = loss;
+        }
+        ws.hdr->epoch = epoch + 1u;
+      }
+    }
+  }
+  __syncthreads();
+  const float k1 = sm_k[0], k2 = sm_k[1], k3 = sm_k[2];
 
   if constexpr (MG != 0) {
-    // CTA 0, warp 0: pooled metric values (one mean over all valid pixels of the call, metrics.py:58-67)
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-      const int lane = threadIdx.x;
+    // pooled metric values (one mean over all valid pixels of the call, metrics.py:58-67): the LAST warp of
+    // the LAST CTA forms them while everybody else already writes gradients (off the critical path)
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= kBlock - 32) {
+      const int lane = threadIdx.x & 31;
       const bool own = lane < MDE_METRIC_NM;
       const double P = own ? __ldcg(&gacc[kMetBase + lane]) : 0.0;
       const double nn = __shfl_sync(0xffffffffu, P, MDE_Q_NVALID);
@@ -456,61 +688,20 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       if (lane == 0) a.met_f64[2 * MDE_METRIC_NM + MDE_METRIC_NQ] = (a.n_img == 1 && nn > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
     }
   }
-
-  const double S0 = __ldcg(&gacc[0]), S1 = __ldcg(&gacc[1]);
-  const double N0 = __ldcg(&gacc[2]), N1 = __ldcg(&gacc[3]);
-
-  // ---------------- loss value and gradient coefficients (every thread, fp64) --------------------
-  double loss;
-  float k1 = 0.f, k2 = 0.f, k3 = 0.f;
-  const double gs = static_cast<double>(a.grad_scale);
-  if constexpr (KIND == MDE_LOSS_L1) {
-    loss = S0 / N0;
-    k1 = static_cast<float>(gs / N0);
-  } else if constexpr (KIND == MDE_LOSS_MSE) {
-    loss = S0 / N0;
-    k1 = static_cast<float>(2.0 * gs / N0);
-  } else if constexpr (KIND == MDE_LOSS_SILOG) {
-    const double dm = S0 / N0, q = S1 / N0;
-    const double s = sqrt(q - static_cast<double>(a.vf) * dm * dm);
-    loss = 10.0 * s;
-    k1 = static_cast<float>(10.0 * gs / (s * N0));     // dL/dd_i = k1 * (d_i - k2)
-    k2 = static_cast<float>(static_cast<double>(a.vf) * dm);
-  } else if constexpr (KIND == MDE_LOSS_BERHU) {
-    loss = (S0 + S1) / (N0 + N1);                        // mean of the concatenation (criteria.py:131)
-    k1 = static_cast<float>(gs / (N0 + N1));
-  } else {
-    const double Mdiv = a.size_average ? N0 : 1.0;
-    loss = S0 / Mdiv;
-    k1 = static_cast<float>(gs / Mdiv);
-    k2 = static_cast<float>(gs * 0.2 * S1 / (N1 * Mdiv));  // share of dL/dc per tied maximum
-    k3 = 2.f * cthr + 1e-9f;
-  }
-
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *a.loss_out = static_cast<float>(loss);
-    if (a.totals_out) {
-      a.totals_out[0] = S0;
-      a.totals_out[1] = S1;
-      a.totals_out[2] = N0;
-      a.totals_out[3] = N1;
-      a.totals_out[4] = static_cast<double>(gmax);
-      a.totals_out[5] = loss;
-    }
-    ws.hdr->epoch = epoch + 1u;
-  }
   if (grad == nullptr) return;
+  trace_point(4);
 
   // ---------------- phase B: gradient, chunk walked backwards ----------------------------------------
   if constexpr (kCanStash) {
     // grad[i] holds d_i (or the off-mask marker): g = k1 (d - k2) / p
-    chunk_map_reverse<PT, VEC, true>(pred, reinterpret_cast<const float*>(grad), grad, a,
-                                     [&](int64_t, float p, float d) -> float {
-                                       const bool v = __float_as_uint(d) != kStashInvalid;
-                                       return v ? k1 * (d - k2) * rcp_nr(p) : 0.f;
-                                     });
+    auto body_g = [&](int64_t, float p, float d) -> float {
+      const bool v = __float_as_uint(d) != kStashInvalid;
+      return v ? k1 * (d - k2) * rcp_nr(p) : 0.f;
+    };
+    if constexpr (VEC) tiles_map<PT, true>(pred, reinterpret_cast<const float*>(grad), grad, a, TileSched{ukey + 3, sm_tile, a.sched == 0}, body_g);
+    else chunk_map_reverse<PT, VEC, true>(pred, reinterpret_cast<const float*>(grad), grad, a, body_g);
   } else {
-    chunk_map_reverse<PT, VEC, false>(pred, gt, grad, a, [&](int64_t i, float p, float t) -> float {
+    auto body_g = [&](int64_t i, float p, float t) -> float {
       if constexpr (KIND == MDE_LOSS_L1) {
         const bool v = t > 0.f;
         return v ? -sgn(t - p) * k1 : 0.f;
@@ -539,8 +730,11 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
         if (a.use_logs) dp = (p >= a.clamp_val) ? dp / p : 0.f;
         return dn * dp;
       }
-    });
+    };
+    if constexpr (VEC) tiles_map<PT, false>(pred, gt, grad, a, TileSched{ukey + 3, sm_tile, a.sched == 0}, body_g);
+    else chunk_map_reverse<PT, VEC, false>(pred, gt, grad, a, body_g);
   }
+  trace_point(5);
 }
 
 template <int KIND, typename PT, bool VEC, unsigned MG, bool LONG>
@@ -605,6 +799,8 @@ inline LossArgs make_loss_args(const void* pred, const float* target, const uint
   a.loss_out = loss_out;
   a.totals_out = totals_out;
   a.grad = grad;
+  static const int sched_env = [] { const char* e = getenv("MDE_SCHED"); return e ? atoi(e) : 0; }();
+  a.sched = sched_env;
   a.met_f64 = nullptr;
   a.met_f32 = nullptr;
   a.n_img = n_img;
