@@ -70,7 +70,8 @@ struct WsHeader {
   unsigned error;
   unsigned pad0[2];
   double tacc[16];
-  unsigned pad1[24];
+  unsigned long long bcast[8];  // grid_barrier_bcast words {seq:32 | payload:32}; never need zeroing
+  unsigned pad1[8];
 };
 static_assert(sizeof(WsHeader) == 256, "workspace header must be 256 bytes");
 constexpr int kGacc = 64;
@@ -122,6 +123,63 @@ __device__ __forceinline__ int coop_prologue(const Ws& ws, unsigned& epoch_out) 
     }
   }
   return par;
+}
+#endif
+
+// ---- grid barrier that also broadcasts what everybody needs next -------------------------------------
+// A cooperative-groups grid.sync() followed by "every CTA reads the totals and derives its
+// coefficients" costs three dependent L2 round trips after the last CTA arrives (barrier counter,
+// totals, then the first data load) plus a hot-spot of ~4700 warps fetching one line. Here the LAST
+// CTA to arrive (ticket == grid-1) reads the totals, computes up to four fp32 values once and stores
+// them as four self-validating 8-byte words {seq | value}; the other CTAs spin on exactly those words,
+// so leaving the barrier and receiving the coefficients is one and the same L2 read. `seq` is unique
+// per launch and stage, so the words never need clearing. Release/acquire through the ticket and the
+// words orders every CTA's earlier global writes before every CTA's later reads (read such data with
+// ld.global.cg: the L1 of this SM is not invalidated). Needs a cooperative launch (co-residency).
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// last_fn(v, post): fills v[0..3]; anything it wants to write besides (loss value, ...) goes into the
+// `post` callable it returns control to AFTER the words are out, i.e. off the other CTAs' critical path.
+template <typename LastFn, typename PostFn>
+__device__ __forceinline__ void grid_barrier_bcast(unsigned* ticket, unsigned long long* words, unsigned seq,
+                                                   float* out_smem4, LastFn&& last_fn, PostFn&& post_fn) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                       // release: this CTA's global writes before its ticket
+    const unsigned t = atomicAdd(ticket, 1u);
+    const bool last = (t == gridDim.x - 1);
+    if (last) {
+      __threadfence();                     // acquire every CTA's writes; also orders them before the words
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      last_fn(v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        st_relaxed_u64(words + i, (static_cast<unsigned long long>(seq) << 32) | __float_as_uint(v[i]));
+      post_fn();
+    }
+    unsigned long long w0, w1, w2, w3;
+    do {
+      w0 = ld_relaxed_u64(words + 0);
+      w1 = ld_relaxed_u64(words + 1);
+      w2 = ld_relaxed_u64(words + 2);
+      w3 = ld_relaxed_u64(words + 3);
+    } while (static_cast<unsigned>(w0 >> 32) != seq || static_cast<unsigned>(w1 >> 32) != seq ||
+             static_cast<unsigned>(w2 >> 32) != seq || static_cast<unsigned>(w3 >> 32) != seq);
+    __threadfence();                       // acquire
+    out_smem4[0] = __uint_as_float(static_cast<unsigned>(w0));
+    out_smem4[1] = __uint_as_float(static_cast<unsigned>(w1));
+    out_smem4[2] = __uint_as_float(static_cast<unsigned>(w2));
+    out_smem4[3] = __uint_as_float(static_cast<unsigned>(w3));
+  }
+  __syncthreads();
 }
 #endif
 

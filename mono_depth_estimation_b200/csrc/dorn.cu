@@ -12,6 +12,11 @@
 // loss term and both logit gradients - is produced from that single read of the logits:
 // 8K (logits) + 4 (gt) + 8K (grad) + 8 (decode) + 4 (depth) = 1104 B/px at K = 68.
 //
+// Per pair the kernel issues ~45 instructions: P through MUFU.EX2 + MUFU.RCP (one Newton step), the
+// log of the clamped probability through MUFU.LG2 accumulated in the log2 domain (one multiply by
+// ln 2 per pixel), predicated selects instead of branches. Accuracy of these forms on B200 is in
+// profiles/r01_mathlab_sfu_accuracy.jsonl (relative error ~1e-7, far inside the 1e-5 tolerance).
+//
 // Bit-exact decode. The reference decides on softmax(clamp(a), clamp(b))[1] > 0.5 evaluated in
 // fp32: with d = fl(b' - a') > 0, P = 1/fl(1 + e), e = fl(exp(-d)). P > 0.5 <=> fl(1+e) < 2 <=>
 // e <= 1 - 2^-23 <=> exp(-d) <= 1 - 1.5*2^-24 (ties-to-even at the midpoint) <=> d > 1.5*2^-24
@@ -34,12 +39,13 @@ __device__ __forceinline__ float clamp_logit(float v) {
 }
 __device__ __forceinline__ bool logit_passes(float v) { return v >= 1e-8f && v <= 1e4f; }
 
-// P = softmax(a', b')[1] exactly as softmax evaluates it: exp(x - max) / sum
-__device__ __forceinline__ float pair_prob(float ac, float bc) {
-  const float d = bc - ac;
-  const float e = expf(-fabsf(d));
-  const float s = 1.0f + e;
-  return (d >= 0.f) ? __fdiv_rn(1.0f, s) : __fdiv_rn(e, s);
+// P = softmax(a', b')[1] = sigmoid(b' - a'), evaluated as softmax does (exp(x - max) / sum) on the SFU:
+// e = 2^(-|d| log2 e), P = 1/(1+e) or e/(1+e). Relative error ~2e-7.
+__device__ __forceinline__ float pair_prob(float d) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(d) * 1.4426950408889634f));
+  const float rs = rcp_nr(1.0f + e);
+  return (d >= 0.f) ? rs : e * rs;
 }
 
 // SID / UD label of a metric depth, op for op as modules/dorn.py:102-107 evaluates it in fp32
@@ -101,7 +107,8 @@ struct DornArgs {
 };
 
 // One kernel for: layer forward only (gt == null), fused supervision step (gt != null).
-template <typename XT>
+// Compile-time switches (which outputs exist) keep the inner loop free of branches.
+template <typename XT, bool HAS_PROB, bool WANT_LOSS, bool HAS_GRAD>
 __global__ void __launch_bounds__(kDBlock, 4) dorn_kernel(DornArgs a) {
   __shared__ double sm[kDWarps];
   const XT* __restrict__ x = static_cast<const XT*>(a.x);
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(kDBlock, 4) dorn_kernel(DornArgs a) {
   const int K = a.K;
   const int64_t hw = a.hw;
   const int64_t npx = a.n * hw;
-  const bool want_loss = (a.gt != nullptr);
+  constexpr bool want_loss = WANT_LOSS;
   const float inv_nhw = a.grad_scale / static_cast<float>(npx);
 
   double loss_acc = 0.0;
@@ -117,24 +124,24 @@ __global__ void __launch_bounds__(kDBlock, 4) dorn_kernel(DornArgs a) {
        px += static_cast<int64_t>(gridDim.x) * kDBlock) {
     const int64_t img = px / hw;
     const int64_t off = px - img * hw;
-    const int64_t base = img * (2 * static_cast<int64_t>(K)) * hw + off;  // channel 0 of this pixel
-    const int64_t pbase = img * static_cast<int64_t>(K) * hw + off;
+    const XT* pa = x + img * (2 * static_cast<int64_t>(K)) * hw + off;   // channel 0 of this pixel
+    XT* ga = HAS_GRAD ? gx + img * (2 * static_cast<int64_t>(K)) * hw + off : nullptr;
+    float* pp = HAS_PROB ? a.prob + img * static_cast<int64_t>(K) * hw + off : nullptr;
 
     float y = 0.f;
-    if (want_loss) {
+    if constexpr (want_loss) {
       const float t = __ldg(a.gt + px);
       y = a.label_mode ? t : depth_label(t, a.alpha, a.beta, K, a.disc);
     }
     int cnt = 0;
-    float lsum = 0.f;
+    float l2sum = 0.f;   // sum of log2(clamped probability); times ln 2 at the end
     for (int k0 = 0; k0 < K; k0 += 4) {
       float av[4], bv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int k = k0 + u;
-        if (k < K) {
-          av[u] = Elem<XT>::ld1(x + base + static_cast<int64_t>(2 * k) * hw);
-          bv[u] = Elem<XT>::ld1(x + base + static_cast<int64_t>(2 * k + 1) * hw);
+        if (k0 + u < K) {
+          av[u] = Elem<XT>::ld1(pa + static_cast<int64_t>(2 * u) * hw);
+          bv[u] = Elem<XT>::ld1(pa + static_cast<int64_t>(2 * u + 1) * hw);
         } else {
           av[u] = 0.f;
           bv[u] = 0.f;
@@ -144,41 +151,43 @@ __global__ void __launch_bounds__(kDBlock, 4) dorn_kernel(DornArgs a) {
       for (int u = 0; u < 4; ++u) {
         const int k = k0 + u;
         if (k >= K) break;
-        const float ac = clamp_logit(av[u]), bc = clamp_logit(bv[u]);
-        const float P = pair_prob(ac, bc);
-        cnt += ((bc - ac) > kTieMargin) ? 1 : 0;  // == (P > 0.5) of the reference, see header
-        if (a.prob) __stcs(a.prob + pbase + static_cast<int64_t>(k) * hw, P);
-        if (want_loss) {
+        const float d = clamp_logit(bv[u]) - clamp_logit(av[u]);
+        const float P = pair_prob(d);
+        cnt += (d > kTieMargin) ? 1 : 0;  // == (P > 0.5) of the reference, see header
+        if constexpr (HAS_PROB) __stcs(pp + static_cast<int64_t>(u) * hw, P);
+        if constexpr (want_loss) {
           const float kf = static_cast<float>(k);
-          float gz = 0.f;  // dloss/d(b' - a')
-          if (kf <= y) {   // criteria.py:769,777: ln clamp(P, 1e-8, 1e8)
-            const bool pass = P >= 1e-8f;  // P <= 1 < 1e8 always
-            lsum += ln_any(pass ? P : 1e-8f);
-            gz = pass ? -(1.0f - P) * inv_nhw : 0.f;
-          } else if (kf > y) {  // criteria.py:770,778: ln clamp(1 - P, 1e-8, 1e8)
-            const float q = 1.0f - P;
-            const bool pass = q >= 1e-8f;
-            lsum += ln_any(pass ? q : 1e-8f);
-            gz = pass ? P * inv_nhw : 0.f;
-          }
-          if (gx) {
-            Elem<XT>::st1(gx + base + static_cast<int64_t>(2 * k) * hw, logit_passes(av[u]) ? -gz : 0.f);
-            Elem<XT>::st1(gx + base + static_cast<int64_t>(2 * k + 1) * hw, logit_passes(bv[u]) ? gz : 0.f);
+          const bool le = kf <= y, gt = kf > y;          // both false for a NaN label (criteria.py:769-770)
+          const float q = 1.0f - P;
+          const float xsel = le ? P : q;                   // criteria.py:777-778
+          const bool clamped = xsel < 1e-8f;               // clamp(., 1e-8, 1e8); the upper bound cannot bind
+          const float xc = clamped ? 1e-8f : xsel;         // NaN stays NaN
+          const float l2 = mufu_lg2(xc);
+          l2sum += (le || gt) ? l2 : 0.f;
+          // dloss/d(b'-a') = -(1-P)/NHW for k <= y, +P/NHW for k > y, zero where the clamp binds
+          float gz = le ? -q : P;
+          gz = (clamped || !(le || gt)) ? 0.f : gz * inv_nhw;
+          if constexpr (HAS_GRAD) {
+            Elem<XT>::st1(ga + static_cast<int64_t>(2 * u) * hw, logit_passes(av[u]) ? -gz : 0.f);
+            Elem<XT>::st1(ga + static_cast<int64_t>(2 * u + 1) * hw, logit_passes(bv[u]) ? gz : 0.f);
           }
         }
       }
+      pa += 8 * hw;
+      if constexpr (HAS_GRAD) ga += 8 * hw;
+      if constexpr (HAS_PROB) pp += 4 * hw;
     }
     if (a.decode) a.decode[px] = static_cast<int64_t>(cnt);
     if (a.depth) a.depth[px] = label_depth(static_cast<float>(cnt), a.alpha, a.beta, K, a.disc);
-    loss_acc += static_cast<double>(lsum);
+    loss_acc += static_cast<double>(l2sum);
   }
 
-  if (!want_loss) return;
+  if constexpr (!want_loss) return;
   Ws ws = ws_view(a.ws);
   publish_one(loss_acc, &ws.hdr->tacc[0], sm);
   if (last_cta(&ws.hdr->ticket)) {
     if (threadIdx.x == 0) {
-      const double s = __ldcg(&ws.hdr->tacc[0]);
+      const double s = __ldcg(&ws.hdr->tacc[0]) * 0.69314718055994531;   // log2 -> ln
       *a.loss_out = static_cast<float>(-s / static_cast<double>(npx));  // criteria.py:784-785
       ws.hdr->tacc[0] = 0.0;
       ws.hdr->ticket = 0u;
@@ -197,40 +206,41 @@ ord_loss_kernel(const float* __restrict__ prob, const float* __restrict__ label,
   for (int64_t px = static_cast<int64_t>(blockIdx.x) * kDBlock + threadIdx.x; px < npx;
        px += static_cast<int64_t>(gridDim.x) * kDBlock) {
     const int64_t img = px / hw;
-    const int64_t pbase = img * static_cast<int64_t>(K) * hw + (px - img * hw);
+    const float* pp = prob + img * static_cast<int64_t>(K) * hw + (px - img * hw);
+    float* gp = grad ? grad + img * static_cast<int64_t>(K) * hw + (px - img * hw) : nullptr;
     const float y = __ldg(label + px);
-    float lsum = 0.f;
+    float l2sum = 0.f;
     for (int k0 = 0; k0 < K; k0 += 8) {
       float pv[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) pv[u] = (k0 + u < K) ? __ldcs(prob + pbase + static_cast<int64_t>(k0 + u) * hw) : 0.5f;
+      for (int u = 0; u < 8; ++u) pv[u] = (k0 + u < K) ? __ldcs(pp + static_cast<int64_t>(u) * hw) : 0.5f;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int k = k0 + u;
         if (k >= K) break;
         const float P = pv[u];
         const float kf = static_cast<float>(k);
-        float g = 0.f;
-        if (kf <= y) {
-          const float c = fminf(fmaxf(P, 1e-8f), 1e8f);
-          lsum += ln_any(P != P ? P : c);
-          g = (P >= 1e-8f && P <= 1e8f) ? -inv_nhw / P : 0.f;
-        } else if (kf > y) {
-          const float q = 1.0f - P;
-          const float c = fminf(fmaxf(q, 1e-8f), 1e8f);
-          lsum += ln_any(q != q ? q : c);
-          g = (q >= 1e-8f && q <= 1e8f) ? inv_nhw / q : 0.f;
-        }
-        if (grad) __stcs(grad + pbase + static_cast<int64_t>(k) * hw, g);
+        const bool le = kf <= y, gt = kf > y;
+        const float xsel = le ? P : 1.0f - P;
+        // clamp(x, 1e-8, 1e8) with NaN kept; the gradient passes inside the closed interval
+        const bool lo = xsel < 1e-8f, hi = xsel > 1e8f;
+        const float xc = lo ? 1e-8f : (hi ? 1e8f : xsel);
+        l2sum += (le || gt) ? mufu_lg2(xc) : 0.f;
+        // d/dP: -1/(P NHW) for k <= y, +1/((1-P) NHW) for k > y
+        float g = (le ? -inv_nhw : inv_nhw) * rcp_nr(xc);
+        g = (lo || hi || !(le || gt)) ? 0.f : g;
+        if (gp) __stcs(gp + static_cast<int64_t>(u) * hw, g);
       }
+      pp += 8 * hw;
+      if (gp) gp += 8 * hw;
     }
-    loss_acc += static_cast<double>(lsum);
+    loss_acc += static_cast<double>(l2sum);
   }
   Ws ws = ws_view(ws_raw);
   publish_one(loss_acc, &ws.hdr->tacc[0], sm);
   if (last_cta(&ws.hdr->ticket)) {
     if (threadIdx.x == 0) {
-      const double s = __ldcg(&ws.hdr->tacc[0]);
+      const double s = __ldcg(&ws.hdr->tacc[0]) * 0.69314718055994531;
       *loss_out = static_cast<float>(-s / static_cast<double>(npx));
       ws.hdr->tacc[0] = 0.0;
       ws.hdr->ticket = 0u;
@@ -254,7 +264,7 @@ ordinal_layer_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ gp,
       const float av = Elem<XT>::ld1(x + base + static_cast<int64_t>(2 * k) * hw);
       const float bv = Elem<XT>::ld1(x + base + static_cast<int64_t>(2 * k + 1) * hw);
       const float g = __ldcs(gp + pbase + static_cast<int64_t>(k) * hw);
-      const float P = pair_prob(clamp_logit(av), clamp_logit(bv));
+      const float P = pair_prob(clamp_logit(bv) - clamp_logit(av));
       const float gz = g * P * (1.0f - P);  // softmax backward for the 2-way case
       Elem<XT>::st1(gx + base + static_cast<int64_t>(2 * k) * hw, logit_passes(av) ? -gz : 0.f);
       Elem<XT>::st1(gx + base + static_cast<int64_t>(2 * k + 1) * hw, logit_passes(bv) ? gz : 0.f);
@@ -338,17 +348,27 @@ inline unsigned px_grid(int64_t npx, int ctas_per_sm) {
   return static_cast<unsigned>(g);
 }
 
-int launch_dorn(DornArgs& a, int x_dtype, cudaStream_t st) {
+template <typename XT>
+int launch_dorn_t(DornArgs& a, cudaStream_t st) {
   const unsigned grid = px_grid(a.n * a.hw, 4);
-  switch (x_dtype) {
-    case MDE_F32: dorn_kernel<float><<<grid, kDBlock, 0, st>>>(a); break;
-    case MDE_F16: dorn_kernel<__half><<<grid, kDBlock, 0, st>>>(a); break;
-    case MDE_BF16: dorn_kernel<__nv_bfloat16><<<grid, kDBlock, 0, st>>>(a); break;
-    default: set_error("dorn: unknown x_dtype %d", x_dtype); return MDE_EINVAL;
-  }
+  const bool p = a.prob != nullptr, l = a.gt != nullptr, g = a.grad_x != nullptr && l;
+#define MDE_DORN(P, L, G) dorn_kernel<XT, P, L, G><<<grid, kDBlock, 0, st>>>(a)
+  if (!l) { if (p) MDE_DORN(true, false, false); else MDE_DORN(false, false, false); }
+  else if (g) { if (p) MDE_DORN(true, true, true); else MDE_DORN(false, true, true); }
+  else { if (p) MDE_DORN(true, true, false); else MDE_DORN(false, true, false); }
+#undef MDE_DORN
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
+}
+
+int launch_dorn(DornArgs& a, int x_dtype, cudaStream_t st) {
+  switch (x_dtype) {
+    case MDE_F32: return launch_dorn_t<float>(a, st);
+    case MDE_F16: return launch_dorn_t<__half>(a, st);
+    case MDE_BF16: return launch_dorn_t<__nv_bfloat16>(a, st);
+    default: set_error("dorn: unknown x_dtype %d", x_dtype); return MDE_EINVAL;
+  }
 }
 
 }  // namespace

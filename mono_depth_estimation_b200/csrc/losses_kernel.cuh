@@ -170,7 +170,7 @@ __device__ __forceinline__ void chunk_map_reverse(const PT* __restrict__ pred, c
     const int64_t nq = n >> 2;
     if (blockIdx.x == gridDim.x - 1) {
       const int64_t i = (nq << 2) + threadIdx.x;
-      if (i < n) Elem<PT>::st1(out + i, body(i, Elem<PT>::ld1(pred + i), INPLACE ? second[i] : __ldg(second + i)));
+      if (i < n) Elem<PT>::st1(out + i, body(i, Elem<PT>::ld1(pred + i), INPLACE ? __ldcg(second + i) : __ldg(second + i)));
     }
     int64_t q = ce - 1 - threadIdx.x;
     for (; q - kBlock >= cb; q -= 2 * kBlock) {
@@ -179,8 +179,8 @@ __device__ __forceinline__ void chunk_map_reverse(const PT* __restrict__ pred, c
       const float4 p1 = Elem<PT>::template ld4<false>(pred + 4 * q1);
       float4 t0, t1;
       if constexpr (INPLACE) {
-        t0 = *reinterpret_cast<const float4*>(second + 4 * q);
-        t1 = *reinterpret_cast<const float4*>(second + 4 * q1);
+        t0 = __ldcg(reinterpret_cast<const float4*>(second + 4 * q));
+        t1 = __ldcg(reinterpret_cast<const float4*>(second + 4 * q1));
       } else {
         t0 = Elem<float>::template ld4<false>(second + 4 * q);
         t1 = Elem<float>::template ld4<false>(second + 4 * q1);
@@ -196,7 +196,7 @@ __device__ __forceinline__ void chunk_map_reverse(const PT* __restrict__ pred, c
     if (q >= cb) {
       const float4 p0 = Elem<PT>::template ld4<false>(pred + 4 * q);
       float4 t0;
-      if constexpr (INPLACE) t0 = *reinterpret_cast<const float4*>(second + 4 * q);
+      if constexpr (INPLACE) t0 = __ldcg(reinterpret_cast<const float4*>(second + 4 * q));
       else t0 = Elem<float>::template ld4<false>(second + 4 * q);
       float4 g0;
       g0.x = body(4 * q + 0, p0.x, t0.x); g0.y = body(4 * q + 1, p0.y, t0.y);
@@ -205,7 +205,7 @@ __device__ __forceinline__ void chunk_map_reverse(const PT* __restrict__ pred, c
     }
   } else {
     for (int64_t i = ce - 1 - threadIdx.x; i >= cb; i -= kBlock)
-      Elem<PT>::st1(out + i, body(i, Elem<PT>::ld1(pred + i), INPLACE ? second[i] : __ldg(second + i)));
+      Elem<PT>::st1(out + i, body(i, Elem<PT>::ld1(pred + i), INPLACE ? __ldcg(second + i) : __ldg(second + i)));
   }
 }
 
@@ -320,7 +320,7 @@ __device__ __forceinline__ void tiles_map(const PT* __restrict__ pred, const flo
     const bool ok = q < nq;
     if (ok) {
       p = Elem<PT>::template ld4<false>(pred + 4 * q);
-      if constexpr (INPLACE) t = *reinterpret_cast<const float4*>(second + 4 * q);
+      if constexpr (INPLACE) t = __ldcg(reinterpret_cast<const float4*>(second + 4 * q));
       else t = Elem<float>::template ld4<false>(second + 4 * q);
     }
     return ok;
@@ -334,7 +334,7 @@ __device__ __forceinline__ void tiles_map(const PT* __restrict__ pred, const flo
   };
   if (blockIdx.x == gridDim.x - 1) {
     const int64_t i = (nq << 2) + threadIdx.x;
-    if (i < a.n) Elem<PT>::st1(out + i, body(i, Elem<PT>::ld1(pred + i), INPLACE ? second[i] : __ldg(second + i)));
+    if (i < a.n) Elem<PT>::st1(out + i, body(i, Elem<PT>::ld1(pred + i), INPLACE ? __ldcg(second + i) : __ldg(second + i)));
   }
   int64_t tA = blockIdx.x, tB;
   float4 pA, gA, pB, gB;
@@ -440,8 +440,8 @@ constexpr int kMetBase = 16;  // gacc[kMetBase + q] = pooled raw metric sum q
 // the loads are software-pipelined; LONG = true folds every 8 pixels into fp64 running sums.
 template <int KIND, typename PT, bool VEC, unsigned MG, bool LONG>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArgs a) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ double sm_d[(MG ? 12 : 4) * kWarps];
+  __shared__ float sm_k[4];
   __shared__ float sm_f[kWarps];
   __shared__ int sm_tile[2];
   constexpr bool kCanStash = (KIND == MDE_LOSS_SILOG) && std::is_same<PT, float>::value;
@@ -479,10 +479,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     if constexpr (VEC) tiles_forward<PT, false>(pred, gt, nullptr, a, TileSched{ukey + 4, sm_tile, a.sched == 0}, body_max, [] {});
     else chunk_forward<PT, VEC, false, false>(pred, gt, nullptr, a, body_max, [] {});
     publish_max(mx, saw_nan, ukey, sm_f);
-    grid.sync();
-    if (threadIdx.x == 0) sm_f[0] = read_max(ukey);   // one L2 read per CTA, shared with the rest
-    __syncthreads();
-    gmax = sm_f[0];
+    grid_barrier_bcast(ukey + 5, ws.hdr->bcast, epoch * 4u + 1u, sm_k, [&](float (&v)[4]) { v[0] = read_max(ukey); }, [] {});
+    gmax = sm_k[0];
     __syncthreads();
     cthr = 0.2f * gmax;  // criteria.py:119 / :496 (fp32 product)
   }
@@ -605,63 +603,52 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     }
   }
   trace_point(2);
-  grid.sync();
-  trace_point(3);
-
-  // ---------------- totals -> loss value and gradient coefficients ------------------------------------
-  // Warp 0 of every CTA reads the four totals (one request per CTA instead of one per warp: the totals
-  // sit in a single L2 line), lane 0 forms the coefficients and shared memory hands them to the CTA.
-  // Only ONE fp64 divide is on this path; the rest is fp32 (the sums themselves stay fp64).
-  __shared__ float sm_k[4];
-  __shared__ double sm_tot[4];
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    const double tv = (lane < 4) ? __ldcg(&gacc[lane]) : 0.0;
-    const double S0 = __shfl_sync(0xffffffffu, tv, 0), S1 = __shfl_sync(0xffffffffu, tv, 1);
-    const double N0 = __shfl_sync(0xffffffffu, tv, 2), N1 = __shfl_sync(0xffffffffu, tv, 3);
-    if (lane == 0) {
-      double loss;
-      float k1 = 0.f, k2 = 0.f, k3 = 0.f;
-      const float gs = a.grad_scale;
-      if constexpr (KIND == MDE_LOSS_L1) {
-        const double inv = 1.0 / N0;
-        loss = S0 * inv;
-        k1 = gs * static_cast<float>(inv);
-      } else if constexpr (KIND == MDE_LOSS_MSE) {
-        const double inv = 1.0 / N0;
-        loss = S0 * inv;
-        k1 = 2.0f * gs * static_cast<float>(inv);
-      } else if constexpr (KIND == MDE_LOSS_SILOG) {
-        const double inv = 1.0 / N0;
-        const double dm = S0 * inv, q = S1 * inv;
-        const double var = q - static_cast<double>(a.vf) * dm * dm;   // the cancellation stays in fp64
-        const float s = sqrtf(static_cast<float>(var));
-        loss = 10.0 * static_cast<double>(s);
-        k1 = 10.0f * gs * static_cast<float>(inv) / s;                 // dL/dd_i = k1 * (d_i - k2)
-        k2 = a.vf * static_cast<float>(dm);
-      } else if constexpr (KIND == MDE_LOSS_BERHU) {
-        const double inv = 1.0 / (N0 + N1);
-        loss = (S0 + S1) * inv;                                         // mean of the concatenation (criteria.py:131)
-        k1 = gs * static_cast<float>(inv);
-      } else {
-        const double inv = a.size_average ? 1.0 / N0 : 1.0;
-        loss = S0 * inv;
-        k1 = gs * static_cast<float>(inv);
-        k2 = gs * 0.2f * static_cast<float>(S1 * inv) / static_cast<float>(N1);  // share of dL/dc per tied maximum
-        k3 = 2.f * cthr + 1e-9f;
-      }
-      sm_k[0] = k1; sm_k[1] = k2; sm_k[2] = k3;
-      if (blockIdx.x == 0) {
-        *a.loss_out = static_cast<float>(loss);
-        if (a.totals_out) {
-          a.totals_out[0] = S0; a.totals_out[1] = S1; a.totals_out[2] = N0; a.totals_out[3] = N1;
-          a.totals_out[4] = static_cast<double>(gmax); a.totals_out[5] = loss;
-        }
-        ws.hdr->epoch = epoch + 1u;
-      }
+  // ---------------- grid barrier; its last arriver turns the totals into loss + coefficients ------------
+  double tS0 = 0.0, tS1 = 0.0, tN0 = 0.0, tN1 = 0.0, tloss = 0.0;   // only meaningful in the last arriver
+  grid_barrier_bcast(ukey + 6, ws.hdr->bcast, epoch * 4u + 2u, sm_k, [&](float (&v)[4]) {
+    const double S0 = __ldcg(&gacc[0]), S1 = __ldcg(&gacc[1]);
+    const double N0 = __ldcg(&gacc[2]), N1 = __ldcg(&gacc[3]);
+    double loss;
+    float k1 = 0.f, k2 = 0.f, k3 = 0.f;
+    const float gs = a.grad_scale;
+    if constexpr (KIND == MDE_LOSS_L1) {
+      const double inv = 1.0 / N0;
+      loss = S0 * inv;
+      k1 = gs * static_cast<float>(inv);
+    } else if constexpr (KIND == MDE_LOSS_MSE) {
+      const double inv = 1.0 / N0;
+      loss = S0 * inv;
+      k1 = 2.0f * gs * static_cast<float>(inv);
+    } else if constexpr (KIND == MDE_LOSS_SILOG) {
+      const double inv = 1.0 / N0;
+      const double dm = S0 * inv, q = S1 * inv;
+      const double var = q - static_cast<double>(a.vf) * dm * dm;   // the cancellation stays in fp64
+      const float s = sqrtf(static_cast<float>(var));
+      loss = 10.0 * static_cast<double>(s);
+      k1 = 10.0f * gs * static_cast<float>(inv) / s;                 // dL/dd_i = k1 * (d_i - k2)
+      k2 = a.vf * static_cast<float>(dm);
+    } else if constexpr (KIND == MDE_LOSS_BERHU) {
+      const double inv = 1.0 / (N0 + N1);
+      loss = (S0 + S1) * inv;                                         // mean of the concatenation (criteria.py:131)
+      k1 = gs * static_cast<float>(inv);
+    } else {
+      const double inv = a.size_average ? 1.0 / N0 : 1.0;
+      loss = S0 * inv;
+      k1 = gs * static_cast<float>(inv);
+      k2 = gs * 0.2f * static_cast<float>(S1 * inv) / static_cast<float>(N1);  // share of dL/dc per tied maximum
+      k3 = 2.f * cthr + 1e-9f;
     }
-  }
-  __syncthreads();
+    v[0] = k1; v[1] = k2; v[2] = k3;
+    tS0 = S0; tS1 = S1; tN0 = N0; tN1 = N1; tloss = loss;
+  }, [&] {
+    *a.loss_out = static_cast<float>(tloss);
+    if (a.totals_out) {
+      a.totals_out[0] = tS0; a.totals_out[1] = tS1; a.totals_out[2] = tN0; a.totals_out[3] = tN1;
+      a.totals_out[4] = static_cast<double>(gmax); a.totals_out[5] = tloss;
+    }
+    ws.hdr->epoch = epoch + 1u;
+  });
+  trace_point(3);
   const float k1 = sm_k[0], k2 = sm_k[1], k3 = sm_k[2];
 
   if constexpr (MG != 0) {
