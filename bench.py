@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--ring", type=int, default=8, help="distinct batches cycled through (ring > L2)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="separate loss and metrics launches (20 B/px)")
+    ap.add_argument("--sync-every", type=int, default=50, help="N>1: all-reduce the metric sums every this many steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     shape = (args.batch, 1, 480, 640)
@@ -181,7 +182,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     W = max(args.warmup, 3)
     K = args.steps
     npx = shape[0] * shape[2] * shape[3]
@@ -191,17 +195,25 @@ def main():
     mcomp = metrics.MetricComputation(TRAIN_METRICS, strict=False)
     # the criterion's launch also produces the metric suite (one read of pred/gt for the whole step)
     crit = criteria.silog_loss(0.85).fuse_metrics(None if args.unfused else mcomp)
-    raw_buf = torch.zeros(_lib.METRIC_NQ, dtype=torch.float64, device=dev)
+    raw_acc = torch.zeros(_lib.METRIC_NQ, dtype=torch.float64, device=dev)
 
     def step(pred, gt):
         p = pred.detach().requires_grad_(True)
         loss = crit(p, gt)                       # reference modules/bts.py:106
         loss.backward()
         vals = mcomp.compute(p.detach(), gt)     # reference metrics.py:16-17 (log_train)
-        if world > 1:  # the only exchange: 12 doubles of pooled raw sums -> global-batch metric values
-            raw_buf.copy_(mcomp.last_f64[2 * _lib.METRIC_NM:2 * _lib.METRIC_NM + _lib.METRIC_NQ])
-            dist.all_reduce(raw_buf)
+        if world > 1:  # pooled raw sums of this rank, accumulated on the device between exchanges
+            raw_acc.add_(mcomp.last_f64[2 * _lib.METRIC_NM:2 * _lib.METRIC_NM + _lib.METRIC_NQ])
         return loss, vals, p.grad
+
+    def exchange():
+        # The ONLY inter-GPU traffic of the path: 12 doubles (pooled metric sums and exact counts) summed
+        # over the ranks, once per logging interval. The loss itself is local, as under the reference's
+        # DDP (pl.Trainer(gpus=N), train.py:137) - which never synchronises metrics at all (no sync_dist,
+        # metrics.py:19-39). Issued eagerly, outside the CUDA graphs.
+        if world > 1:
+            dist.all_reduce(raw_acc)
+            raw_acc.zero_()
 
     side = torch.cuda.Stream(device=dev)
     graphs = None
@@ -214,7 +226,7 @@ def main():
         out = step(*ring[0])
         side.synchronize()
         launches_per_step = _lib.launch_count() - n0
-        if not args.no_graph and world == 1:
+        if not args.no_graph:
             try:
                 graphs = []
                 for i in range(args.ring):
@@ -222,10 +234,15 @@ def main():
                     with torch.cuda.graph(g, stream=side):
                         o = step(*ring[i])
                     graphs.append((g, o))
-            except Exception as e:  # cooperative launches inside capture unsupported -> eager steps
+            except Exception as e:  # capture unsupported (e.g. a collective that cannot be captured) -> eager steps
                 sys.stderr.write("graph capture failed (%s); timing eager steps\n" % (str(e).splitlines()[0],))
                 graphs = None
                 torch.cuda.synchronize()
+        if world > 1:  # every rank must take the same path
+            flag = torch.tensor([1 if graphs is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag) == 0:
+                graphs = None
 
     def run_steps(n, first=0):
         for i in range(n):
@@ -234,6 +251,9 @@ def main():
                 graphs[j][0].replay()
             else:
                 step(*ring[j])
+            if (i + 1) % args.sync_every == 0:
+                exchange()
+        exchange()
 
     def barrier():
         if world > 1:
@@ -377,7 +397,8 @@ def main():
                            "metrics": TRAIN_METRICS, "variance_focus": 0.85,
                            "l2_policy": "ring of %d distinct batches (%.0f MB) larger than the 126 MB L2" %
                                         (args.ring, args.ring * 2 * 4 * npx / 1e6),
-                           "cuda_graph": graphs is not None, "parallelism": "image-sharded x%d" % world},
+                           "cuda_graph": graphs is not None, "parallelism": "image-sharded x%d" % world,
+                           "collective": None if world == 1 else "all-reduce of 12 doubles every %d steps (NCCL)" % args.sync_every},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step) * K,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))

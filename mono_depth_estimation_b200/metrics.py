@@ -141,18 +141,43 @@ class MetricComputation(object):
 
     def reset(self):
         self.count = 0
-        self.sum = [0.0 for _ in self.metrics]
+        self._sum_vec = None                 # running sums of the fused metrics: ONE device vector
+        self._sum_other = {}                 # running sums of anything else ('ssim')
+        self._sum_assigned = None            # a caller may assign .sum directly, as with the reference's plain list
+
+    @property
+    def sum(self):
+        """Running sums in `names` order (reference metrics.py:56,65-66), as 0-dim views of one vector."""
+        if self._sum_assigned is not None:
+            return self._sum_assigned
+        out = []
+        for n in self.metric_names:
+            if n in _lib.METRIC_INDEX:
+                out.append(0.0 if self._sum_vec is None else self._sum_vec[_lib.METRIC_INDEX[n]])
+            else:
+                out.append(self._sum_other.get(n, 0.0))
+        return out
+
+    @sum.setter
+    def sum(self, value):
+        self._sum_assigned = value
 
     def _collect(self, res_vec, pred, target):
+        self._sum_assigned = None
         vals = []
         for n in self.metric_names:
             if n == "ssim":
-                vals.append(_ssim(torch.clamp_min(pred, 1e-07).cpu(), target.cpu()))  # metrics.py:63
+                v = _ssim(torch.clamp_min(pred, 1e-07).cpu(), target.cpu())  # metrics.py:63
+                self._sum_other[n] = self._sum_other.get(n, 0.0) + v
+                vals.append(v)
             else:
                 vals.append(res_vec[_lib.METRIC_INDEX[n]])
         self.count += 1
-        for i, v in enumerate(vals):
-            self.sum[i] = self.sum[i] + v
+        # one 12-float add instead of one launch per metric
+        if self._sum_vec is None:
+            self._sum_vec = res_vec.clone()
+        else:
+            self._sum_vec += res_vec
         return vals
 
     def compute(self, pred, target):

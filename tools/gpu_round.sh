@@ -11,6 +11,6 @@ for f in tests/test_gpu_metrics.py tests/test_gpu_losses.py tests/test_gpu_dorn.
 done
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 || rc=1
 tail -n 2 gpurun_out/smoke.log
-timeout 600 python bench.py --steps ${BENCH_STEPS:-100} --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err || rc=1
+timeout 400 python bench.py --steps ${BENCH_STEPS:-100} --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err || rc=1
 cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
 exit $rc
