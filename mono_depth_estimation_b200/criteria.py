@@ -131,7 +131,7 @@ def masked_loss(kind, pred, target, mask=None, params=None, totals=False, metric
                                                        metrics.group_flags(), _lib.ptr(ws), _lib.ptr(loss),
                                                        _lib.ptr(tot), _lib.ptr(grad), _lib.ptr(m64), _lib.ptr(m32),
                                                        _lib.stream_ptr(dev)))
-                metrics.offer(key, m32, m64)
+                metrics.offer(key, m32[:_lib.METRIC_NM], m64)
             else:
                 _lib.check(lib.mde_masked_loss(kind, _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(tgt), _lib.ptr(mk),
                                                n_img, h, w, C.byref(lp), 1.0, _lib.ptr(ws), _lib.ptr(loss),

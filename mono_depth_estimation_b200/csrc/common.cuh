@@ -195,6 +195,11 @@ __device__ __forceinline__ void trace_point(int k) {
     unsigned long long ns;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
     t[static_cast<size_t>(blockIdx.x) * kTraceSlots + k] = ns;
+    if (k == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      t[static_cast<size_t>(blockIdx.x) * kTraceSlots + 7] = smid;
+    }
   }
 }
 #define MDE_DEFINE_TRACE_SETTER(name)                                                        \

@@ -24,6 +24,7 @@ struct LossArgs {
   float* loss_out;
   double* totals_out;
   void* grad;
+  int use_stash;    // SILog/fp32: keep d_i in the gradient buffer between the phases (only pays while it stays in L2)
   int sched;        // 0: tiles claimed from an atomic counter; 1: static interleaved tiles (tile = k*grid + cta)
   double* met_f64;  // fused metrics (MG != 0): same layout as mde_metrics' out_f64
   float* met_f32;
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
           mx = fmaxf(mx, x);
           return 0.f;
         };
-    if constexpr (VEC) tiles_forward<PT, false>(pred, gt, nullptr, a, TileSched{ukey + 4, sm_tile, a.sched == 0}, body_max, [] {});
+    if constexpr (VEC && !LONG) tiles_forward<PT, false>(pred, gt, nullptr, a, TileSched{ukey + 4, sm_tile, a.sched == 0}, body_max, [] {});
     else chunk_forward<PT, VEC, false, false>(pred, gt, nullptr, a, body_max, [] {});
     publish_max(mx, saw_nan, ukey, sm_f);
     grid_barrier_bcast(ukey + 5, ws.hdr->bcast, epoch * 4u + 1u, sm_k, [&](float (&v)[4]) { v[0] = read_max(ukey); }, [] {});
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     auto fold = [&] {
       if constexpr (LONG) fold_now();
     };
-    float* stash = kCanStash ? reinterpret_cast<float*>(grad) : nullptr;
+    float* stash = (kCanStash && a.use_stash) ? reinterpret_cast<float*>(grad) : nullptr;
     auto body_sum = [&](int64_t i, float p, float t) -> float {
           float mL = 0.f, md = 0.f;
           if constexpr (MG != 0) metric_px_ex<MG, false>(p, t, mt, mc, mL, md);
@@ -571,7 +572,9 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
             return 0.f;
           }
         };
-    if constexpr (VEC) tiles_forward<PT, kCanStash>(pred, gt, stash, a, TileSched{ukey + 2, sm_tile, a.sched == 0}, body_sum, fold);
+    // short runs: dynamically claimed tiles (balance matters, fixed costs dominate); long runs: one static
+    // contiguous chunk per CTA with two quads per iteration (more independent work per instruction stream)
+    if constexpr (VEC && !LONG) tiles_forward<PT, kCanStash>(pred, gt, stash, a, TileSched{ukey + 2, sm_tile, a.sched == 0}, body_sum, fold);
     else chunk_forward<PT, VEC, kCanStash, false>(pred, gt, stash, a, body_sum, fold);
     trace_point(1);
     fold_now();
@@ -680,14 +683,19 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
 
   // ---------------- phase B: gradient, chunk walked backwards ----------------------------------------
   if constexpr (kCanStash) {
-    // grad[i] holds d_i (or the off-mask marker): g = k1 (d - k2) / p
-    auto body_g = [&](int64_t, float p, float d) -> float {
-      const bool v = __float_as_uint(d) != kStashInvalid;
-      return v ? k1 * (d - k2) * rcp_nr(p) : 0.f;
-    };
-    if constexpr (VEC) tiles_map<PT, true>(pred, reinterpret_cast<const float*>(grad), grad, a, TileSched{ukey + 3, sm_tile, a.sched == 0}, body_g);
-    else chunk_map_reverse<PT, VEC, true>(pred, reinterpret_cast<const float*>(grad), grad, a, body_g);
-  } else {
+    if (a.use_stash) {
+      // grad[i] holds d_i (or the off-mask marker): g = k1 (d - k2) / p
+      auto body_s = [&](int64_t, float p, float d) -> float {
+        const bool v = __float_as_uint(d) != kStashInvalid;
+        return v ? k1 * (d - k2) * rcp_nr(p) : 0.f;
+      };
+      if constexpr (VEC && !LONG) tiles_map<PT, true>(pred, reinterpret_cast<const float*>(grad), grad, a, TileSched{ukey + 3, sm_tile, a.sched == 0}, body_s);
+      else chunk_map_reverse<PT, VEC, true>(pred, reinterpret_cast<const float*>(grad), grad, a, body_s);
+      trace_point(5);
+      return;
+    }
+  }
+  {
     auto body_g = [&](int64_t i, float p, float t) -> float {
       if constexpr (KIND == MDE_LOSS_L1) {
         const bool v = t > 0.f;
@@ -718,7 +726,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
         return dn * dp;
       }
     };
-    if constexpr (VEC) tiles_map<PT, false>(pred, gt, grad, a, TileSched{ukey + 3, sm_tile, a.sched == 0}, body_g);
+    if constexpr (VEC && !LONG) tiles_map<PT, false>(pred, gt, grad, a, TileSched{ukey + 3, sm_tile, a.sched == 0}, body_g);
     else chunk_map_reverse<PT, VEC, false>(pred, gt, grad, a, body_g);
   }
   trace_point(5);
@@ -788,6 +796,9 @@ inline LossArgs make_loss_args(const void* pred, const float* target, const uint
   a.grad = grad;
   static const int sched_env = [] { const char* e = getenv("MDE_SCHED"); return e ? atoi(e) : 0; }();
   a.sched = sched_env;
+  // pred + target + gradient/stash must fit in L2 (126 MB) for the stash to save traffic: beyond that the
+  // gradient phase re-reads from HBM either way and the stash would ADD 4 B/px of writes (24 vs 20 B/px)
+  a.use_stash = (a.n * 12 <= (int64_t(96) << 20)) ? 1 : 0;
   a.met_f64 = nullptr;
   a.met_f32 = nullptr;
   a.n_img = n_img;

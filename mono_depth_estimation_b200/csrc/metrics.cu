@@ -17,19 +17,24 @@ constexpr int kNQ = MDE_METRIC_NQ;
 constexpr int kNM = MDE_METRIC_NM;
 
 // LONG = false: a thread sees at most 128 pixels of an image, so its sums stay in fp32 registers
-// until the flush (error <= ~4e-7 relative) and the fp64 running sums (16 registers) are not needed;
-// that frees the registers for the software-pipelined loads. LONG = true folds every 8 pixels into fp64.
+// until the flush (error <= ~4e-7 relative). LONG = true: every 16 iterations (128 pixels) the fp32
+// tile sums are folded into fp64 running sums that live in SHARED memory (one column per thread), so
+// the hot loop carries no fp64 registers and the software-pipelined loads fit without spilling.
 template <unsigned G, bool Ref, bool LONG>
 struct MetricThread {
   MetricTile tile;
   MetricCounts cnt;
-  double run[LONG ? 8 : 1];
+  double* srun;   // LONG: &sm_run[0][threadIdx.x], element q at srun[q * kBlock]
+  int it;
 
   __device__ __forceinline__ void reset() {
     tile.zero();
     cnt.zero();
+    it = 0;
+    if constexpr (LONG) {
 #pragma unroll
-    for (int i = 0; i < (LONG ? 8 : 1); ++i) run[i] = 0.0;
+      for (int q = 0; q < 8; ++q) srun[q * kBlock] = 0.0;
+    }
   }
   __device__ __forceinline__ void px(float p, float t) { metric_px<G, Ref>(p, t, tile, cnt); }
   __device__ __forceinline__ void quad(const float4& p, const float4& t) {
@@ -38,21 +43,25 @@ struct MetricThread {
     px(p.z, t.z);
     px(p.w, t.w);
   }
+  __device__ __forceinline__ float tile_q(int q) const {
+    return (q == 0) ? tile.s_abs : (q == 1) ? tile.s_sq : (q == 2) ? tile.s_log10 : (q == 3) ? tile.s_sle
+         : (q == 4) ? tile.s_absrel : (q == 5) ? tile.s_sqrel : (q == 6) ? tile.s_rsq : tile.s_lnsq;
+  }
   // value of running sum q at flush time
   __device__ __forceinline__ float total(int q) const {
-    const float t = (q == 0) ? tile.s_abs : (q == 1) ? tile.s_sq : (q == 2) ? tile.s_log10 : (q == 3) ? tile.s_sle
-                  : (q == 4) ? tile.s_absrel : (q == 5) ? tile.s_sqrel : (q == 6) ? tile.s_rsq : tile.s_lnsq;
-    if constexpr (LONG) return static_cast<float>(run[q] + static_cast<double>(t));
-    return t;
+    if constexpr (LONG) return static_cast<float>(srun[q * kBlock] + static_cast<double>(tile_q(q)));
+    return tile_q(q);
   }
-  // fold the fp32 tile sums into the fp64 running sums
+  // called once per loop iteration (<= 8 pixels)
   __device__ __forceinline__ void fold() {
     if constexpr (!LONG) return;
-    run[0] += tile.s_abs;
-    run[1] += tile.s_sq;
-    if (G & kGrpLog) { run[2] += tile.s_log10; run[7] += tile.s_lnsq; }
-    if (G & kGrpLog1p) run[3] += tile.s_sle;
-    if (G & kGrpRel) { run[4] += tile.s_absrel; run[5] += tile.s_sqrel; run[6] += tile.s_rsq; }
+    if ((++it & 15) != 0) return;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
+                        ((G & kGrpRel) && (q >= 4 && q <= 6));
+      if (used) srun[q * kBlock] += static_cast<double>(tile_q(q));
+    }
     tile.zero();
     cnt.unpack();
   }
@@ -152,7 +161,9 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
   int64_t ub, ue;
   cta_chunk(chunk, blockIdx.x, ub, ue);
 
+  __shared__ double sm_run[LONG ? 8 * kBlock : 1];
   MetricThread<G, Ref, LONG> th;
+  th.srun = LONG ? &sm_run[threadIdx.x] : nullptr;
   int64_t u = ub;
   while (u < ue) {
     const int64_t img = u / units_per_img;
@@ -161,25 +172,7 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
     th.reset();
 
     int64_t i = u + threadIdx.x;
-    if (VEC == 4 && LONG) {
-      // long per-thread runs: 2 quads of pred and of target in flight (4 x 16 B); the warps of an SM
-      // drift apart over the many iterations, which overlaps loads and arithmetic across warps
-      for (; i + kBlock < seg_end; i += 2 * kBlock) {
-        const float4 p0 = Elem<PT>::template ld4<false>(pred + 4 * i);
-        const float4 t0 = Elem<float>::template ld4<false>(gt + 4 * i);
-        const float4 p1 = Elem<PT>::template ld4<false>(pred + 4 * (i + kBlock));
-        const float4 t1 = Elem<float>::template ld4<false>(gt + 4 * (i + kBlock));
-        th.quad(p0, t0);
-        th.quad(p1, t1);
-        th.fold();
-      }
-      if (i < seg_end) {
-        const float4 p0 = Elem<PT>::template ld4<false>(pred + 4 * i);
-        const float4 t0 = Elem<float>::template ld4<false>(gt + 4 * i);
-        th.quad(p0, t0);
-        th.fold();
-      }
-    } else if (VEC == 4) {
+    if (VEC == 4) {
       // software pipeline: the 2 quads of pred and of target (4 x 16 B) of the NEXT iteration are
       // requested before the current 8 pixels are evaluated, so the loads overlap the arithmetic
       float4 p0, t0, p1, t1;

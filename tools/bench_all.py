@@ -66,6 +66,9 @@ def timed(fns, reps, use_graph=True):
     return 1e3 * a.elapsed_time(b) / (reps * len(fns)), g is not None
 
 
+ONLY = os.environ.get("BENCH_ONLY", "")
+
+
 def report(config, kernel, px, us, bytes_per_px, graph, extra=None):
     gbs = bytes_per_px * px / (us * 1e-6) / 1e9
     d = {"config": config, "kernel": kernel, "px": px, "us": round(us, 2), "mpix_s": round(px / us, 1),

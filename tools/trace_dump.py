@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Dump per-CTA phase times + SM id of the SILog kernel at C2 (static interleaved tiles) for imbalance analysis."""
+import ctypes as C, os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import torch
+from mono_depth_estimation_b200 import _lib, synth
+lib = _lib.load(); dev = torch.device("cuda", 0)
+shape = (16, 1, 480, 640)
+ring = [synth.depth_pair(shape, 500 + i, device=dev) for i in range(8)]
+ws = _lib.workspace(dev, 16)
+loss_t = torch.empty((), device=dev); grad_t = torch.empty(shape, device=dev)
+lp = _lib.LossParams(0.85, 1e-9, 1, 1)
+trace = torch.zeros(296 * 8, dtype=torch.int64, device=dev)
+def run(i):
+    pr, g = ring[i % 8]
+    _lib.check(lib.mde_masked_loss(_lib.LOSS_SILOG, _lib.ptr(pr), 0, _lib.ptr(g), None, 16, 480, 640, C.byref(lp), 1.0,
+               _lib.ptr(ws), _lib.ptr(loss_t), None, _lib.ptr(grad_t), _lib.stream_ptr(dev)))
+for i in range(5): run(i)
+torch.cuda.synchronize()
+_lib.check(lib.mde_debug_set_trace(_lib.ptr(trace)))
+out = []
+for rep in range(4):
+    trace.zero_(); torch.cuda.synchronize(); run(5 + rep); torch.cuda.synchronize()
+    t = trace.view(296, 8).cpu()
+    t0 = int(t[:, 0].min())
+    out.append({"smid": t[:, 7].tolist(), "a_done": [round((int(v) - t0) / 1e3, 2) for v in t[:, 1]],
+                "end": [round((int(v) - t0) / 1e3, 2) for v in t[:, 5]], "b_start": [round((int(v) - t0) / 1e3, 2) for v in t[:, 4]]})
+_lib.check(lib.mde_debug_set_trace(None))
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "trace_dump_%s.json" % os.environ.get("MDE_SCHED", "0")), "w"))
+print("ok")
