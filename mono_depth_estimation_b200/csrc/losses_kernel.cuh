@@ -33,13 +33,34 @@ struct LossArgs {
 
 constexpr unsigned kStashInvalid = 0xffc0dead;  // quiet-NaN payload marking "pixel outside the mask"
 
+// ---- quad evaluation with a rare-case switch ---------------------------------------------------------
+// body(tag, idx, p, t): tag = std::true_type selects the exact (slow) arithmetic. pre(p4, t4) decides
+// once per quad, so the common path carries one predicate per four pixels and no per-pixel branch.
+template <typename Body, typename Pre>
+__device__ __forceinline__ float4 eval_quad(Body& body, Pre& pre, int64_t i0, const float4& p, const float4& t) {
+  float4 s;
+  if (pre(p, t)) {
+    s.x = body(std::true_type{}, i0 + 0, p.x, t.x); s.y = body(std::true_type{}, i0 + 1, p.y, t.y);
+    s.z = body(std::true_type{}, i0 + 2, p.z, t.z); s.w = body(std::true_type{}, i0 + 3, p.w, t.w);
+  } else {
+    s.x = body(std::false_type{}, i0 + 0, p.x, t.x); s.y = body(std::false_type{}, i0 + 1, p.y, t.y);
+    s.z = body(std::false_type{}, i0 + 2, p.z, t.z); s.w = body(std::false_type{}, i0 + 3, p.w, t.w);
+  }
+  return s;
+}
+template <typename Body, typename Pre>
+__device__ __forceinline__ float eval_one(Body& body, Pre& pre, int64_t i, float p, float t) {
+  if (pre(make_float4(p, p, p, p), make_float4(t, t, t, t))) return body(std::true_type{}, i, p, t);
+  return body(std::false_type{}, i, p, t);
+}
+
 // ---- chunk iteration ----------------------------------------------------------------------------
 // forward: body(idx, p, t) for every element of this CTA's chunk; fold() after every batch of <= 8
 // (VEC) / 4 (scalar) elements per thread. If STASH, body returns a float that is written to `stash`
 // (same layout as pred) with 128-bit stores.
-template <typename PT, bool VEC, bool STASH, bool PIPE, typename Body, typename Fold>
+template <typename PT, bool VEC, bool STASH, bool PIPE, typename Body, typename Pre, typename Fold>
 __device__ __forceinline__ void chunk_forward(const PT* __restrict__ pred, const float* __restrict__ gt,
-                                              float* stash, const LossArgs& a, Body&& body, Fold&& fold) {
+                                              float* stash, const LossArgs& a, Body&& body, Pre&& pre, Fold&& fold) {
   const int64_t n = a.n;
   int64_t cb, ce;
   cta_chunk(a.chunk, blockIdx.x, cb, ce);
@@ -72,15 +93,13 @@ __device__ __forceinline__ void chunk_forward(const PT* __restrict__ pred, const
           nt1 = Elem<float>::template ld4<true>(gt + 4 * (qn + kBlock));
         }
         float4 s0;
-        s0.x = body(4 * q + 0, p0.x, t0.x); s0.y = body(4 * q + 1, p0.y, t0.y);
-        s0.z = body(4 * q + 2, p0.z, t0.z); s0.w = body(4 * q + 3, p0.w, t0.w);
+        s0 = eval_quad(body, pre, 4 * q, p0, t0);
         if constexpr (STASH) {
           if (stash) *reinterpret_cast<float4*>(stash + 4 * q) = s0;
         }
         if (has1) {
           float4 s1;
-          s1.x = body(4 * q1 + 0, p1.x, t1.x); s1.y = body(4 * q1 + 1, p1.y, t1.y);
-          s1.z = body(4 * q1 + 2, p1.z, t1.z); s1.w = body(4 * q1 + 3, p1.w, t1.w);
+          s1 = eval_quad(body, pre, 4 * q1, p1, t1);
           if constexpr (STASH) {
             if (stash) *reinterpret_cast<float4*>(stash + 4 * q1) = s1;
           }
@@ -98,10 +117,8 @@ __device__ __forceinline__ void chunk_forward(const PT* __restrict__ pred, const
       const float4 p1 = Elem<PT>::template ld4<true>(pred + 4 * q1);
       const float4 t1 = Elem<float>::template ld4<true>(gt + 4 * q1);
       float4 s0, s1;
-      s0.x = body(4 * q + 0, p0.x, t0.x); s0.y = body(4 * q + 1, p0.y, t0.y);
-      s0.z = body(4 * q + 2, p0.z, t0.z); s0.w = body(4 * q + 3, p0.w, t0.w);
-      s1.x = body(4 * q1 + 0, p1.x, t1.x); s1.y = body(4 * q1 + 1, p1.y, t1.y);
-      s1.z = body(4 * q1 + 2, p1.z, t1.z); s1.w = body(4 * q1 + 3, p1.w, t1.w);
+      s0 = eval_quad(body, pre, 4 * q, p0, t0);
+      s1 = eval_quad(body, pre, 4 * q1, p1, t1);
       if constexpr (STASH) {
         if (stash) {
           *reinterpret_cast<float4*>(stash + 4 * q) = s0;
@@ -114,8 +131,7 @@ __device__ __forceinline__ void chunk_forward(const PT* __restrict__ pred, const
       const float4 p0 = Elem<PT>::template ld4<true>(pred + 4 * q);
       const float4 t0 = Elem<float>::template ld4<true>(gt + 4 * q);
       float4 s0;
-      s0.x = body(4 * q + 0, p0.x, t0.x); s0.y = body(4 * q + 1, p0.y, t0.y);
-      s0.z = body(4 * q + 2, p0.z, t0.z); s0.w = body(4 * q + 3, p0.w, t0.w);
+      s0 = eval_quad(body, pre, 4 * q, p0, t0);
       if constexpr (STASH) {
         if (stash) *reinterpret_cast<float4*>(stash + 4 * q) = s0;
       }
@@ -124,7 +140,7 @@ __device__ __forceinline__ void chunk_forward(const PT* __restrict__ pred, const
     if (blockIdx.x == gridDim.x - 1) {  // n % 4 tail
       const int64_t i = (nq << 2) + threadIdx.x;
       if (i < n) {
-        const float s = body(i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
+        const float s = eval_one(body, pre, i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
         if constexpr (STASH) {
           if (stash) stash[i] = s;
         }
@@ -142,7 +158,7 @@ __device__ __forceinline__ void chunk_forward(const PT* __restrict__ pred, const
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float s = body(i + k * kBlock, p[k], t[k]);
+        const float s = eval_one(body, pre, i + k * kBlock, p[k], t[k]);
         if constexpr (STASH) {
           if (stash) stash[i + k * kBlock] = s;
         }
@@ -150,7 +166,7 @@ __device__ __forceinline__ void chunk_forward(const PT* __restrict__ pred, const
       fold();
     }
     for (; i < ce; i += kBlock) {
-      const float s = body(i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
+      const float s = eval_one(body, pre, i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
       if constexpr (STASH) {
         if (stash) stash[i] = s;
       }
@@ -223,9 +239,9 @@ struct TileSched {
   bool dynamic;    // false: static interleaved tiles (tile = k * grid + cta), no atomics, no CTA barriers
 };
 
-template <typename PT, bool STASH, typename Body, typename Fold>
+template <typename PT, bool STASH, typename Body, typename Pre, typename Fold>
 __device__ __forceinline__ void tiles_forward(const PT* __restrict__ pred, const float* __restrict__ gt, float* stash,
-                                              const LossArgs& a, TileSched ts, Body&& body, Fold&& fold) {
+                                              const LossArgs& a, TileSched ts, Body&& body, Pre&& pre, Fold&& fold) {
   const int64_t nq = a.n >> 2;
   const int64_t nt = (nq + kBlock - 1) / kBlock;
   const unsigned G = gridDim.x;
@@ -245,8 +261,7 @@ __device__ __forceinline__ void tiles_forward(const PT* __restrict__ pred, const
   auto compute = [&](int64_t tile, const float4& p, const float4& t) {
     const int64_t q = tile * kBlock + threadIdx.x;
     float4 s;
-    s.x = body(4 * q + 0, p.x, t.x); s.y = body(4 * q + 1, p.y, t.y);
-    s.z = body(4 * q + 2, p.z, t.z); s.w = body(4 * q + 3, p.w, t.w);
+    s = eval_quad(body, pre, 4 * q, p, t);
     if constexpr (STASH) {
       if (stash) *reinterpret_cast<float4*>(stash + 4 * q) = s;
     }
@@ -296,7 +311,7 @@ __device__ __forceinline__ void tiles_forward(const PT* __restrict__ pred, const
   if (blockIdx.x == gridDim.x - 1) {  // n % 4 tail
     const int64_t i = (nq << 2) + threadIdx.x;
     if (i < a.n) {
-      const float sv = body(i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
+      const float sv = eval_one(body, pre, i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
       if constexpr (STASH) {
         if (stash) stash[i] = sv;
       }
@@ -446,6 +461,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   __shared__ float sm_f[kWarps];
   __shared__ int sm_tile[2];
   constexpr bool kCanStash = (KIND == MDE_LOSS_SILOG) && std::is_same<PT, float>::value;
+  constexpr bool kSilogLog2 = (KIND == MDE_LOSS_SILOG) && (MG & kGrpLog) != 0;
 
   const PT* __restrict__ pred = static_cast<const PT*>(a.pred);
   const float* __restrict__ gt = a.gt;
@@ -464,7 +480,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   if constexpr (KIND == MDE_LOSS_BERHU || KIND == MDE_LOSS_LAINA_BERHU) {
     float mx = -INFINITY;
     bool saw_nan = false;
-    auto body_max = [&](int64_t i, float p, float t) -> float {
+    auto no_pre = [](const float4&, const float4&) { return false; };
+    auto body_max = [&](auto, int64_t i, float p, float t) -> float {
           float x;
           if constexpr (KIND == MDE_LOSS_BERHU) {
             x = p - t;  // criteria.py:118 - signed, unmasked
@@ -477,8 +494,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
           mx = fmaxf(mx, x);
           return 0.f;
         };
-    if constexpr (VEC && !LONG) tiles_forward<PT, false>(pred, gt, nullptr, a, TileSched{ukey + 4, sm_tile, a.sched == 0}, body_max, [] {});
-    else chunk_forward<PT, VEC, false, false>(pred, gt, nullptr, a, body_max, [] {});
+    if constexpr (VEC && !LONG) tiles_forward<PT, false>(pred, gt, nullptr, a, TileSched{ukey + 4, sm_tile, a.sched == 0}, body_max, no_pre, [] {});
+    else chunk_forward<PT, VEC, false, false>(pred, gt, nullptr, a, body_max, no_pre, [] {});
     publish_max(mx, saw_nan, ukey, sm_f);
     grid_barrier_bcast(ukey + 5, ws.hdr->bcast, epoch * 4u + 1u, sm_k, [&](float (&v)[4]) { v[0] = read_max(ukey); }, [] {});
     gmax = sm_k[0];
@@ -518,9 +535,46 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       if constexpr (LONG) fold_now();
     };
     float* stash = (kCanStash && a.use_stash) ? reinterpret_cast<float*>(grad) : nullptr;
-    auto body_sum = [&](int64_t i, float p, float t) -> float {
+    // Rare quads take the exact arithmetic. For the metric suite that is a valid subnormal target (the SFU
+    // forms flush it). The fused SILog widens the test to "a valid target <= 0.01 or a prediction < 1e-7":
+    // everywhere else its mask (t > 0.01, criteria.py:730) equals the metric mask (t > 0) and its residual
+    // equals the metrics' log2 p - log2 t, so the common path adds ONE accumulation (sum d) to the suite -
+    // sum d^2 is the suite's s_lnsq, n its valid count - and the rare path books the differences in s1 / c0.
+    auto pre_sum = [&](const float4& p4, const float4& t4) -> bool {
+      if constexpr (MG == 0) {
+        return false;
+      } else if constexpr (kSilogLog2) {
+        const float ta = (t4.x > 0.f) ? t4.x : 1.0f, tb = (t4.y > 0.f) ? t4.y : 1.0f;
+        const float tc = (t4.z > 0.f) ? t4.z : 1.0f, td = (t4.w > 0.f) ? t4.w : 1.0f;
+        return !(fminf(fminf(ta, tb), fminf(tc, td)) > 0.01f) ||
+               !(fminf(fminf(p4.x, p4.y), fminf(p4.z, p4.w)) >= 1e-7f);
+      } else {
+        return metric_quad_needs_ref(t4);
+      }
+    };
+    auto body_sum = [&](auto slow_tag, int64_t i, float p, float t) -> float {
+          constexpr bool kSlow = decltype(slow_tag)::value;
           float mL = 0.f, md = 0.f;
-          if constexpr (MG != 0) metric_px_ex<MG, false>(p, t, mt, mc, mL, md);
+          if constexpr (MG != 0) {
+            if constexpr (kSlow) {
+              const MetricContrib r = metric_px_ref_contrib<MG>(p, t);
+              metric_add_contrib(r, mt, mc);
+              if constexpr (kSilogLog2) {
+                const bool v2 = t > 0.01f;
+                const float d2 = v2 ? log_ratio_slow(p, t) * 1.4426950408889634f : 0.f;
+                s0 += d2;
+                s1 += d2 * d2 - r.s.s_lnsq * (1.0f / tile_scale<false>(7));
+                c0 += (v2 ? 1 : 0) - r.c.n;
+                return v2 ? d2 : __uint_as_float(kStashInvalid);
+              }
+            } else {
+              metric_px_ex<MG, false>(p, t, mt, mc, mL, md);
+              if constexpr (kSilogLog2) {
+                s0 += mL;
+                return (t > 0.f) ? mL : __uint_as_float(kStashInvalid);
+              }
+            }
+          }
           if constexpr (KIND == MDE_LOSS_L1) {
             const bool v = t > 0.f;
             s0 += v ? fabsf(t - p) : 0.f;
@@ -535,16 +589,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
           } else if constexpr (KIND == MDE_LOSS_SILOG) {
             bool v;
             float d;
-            if constexpr ((MG & kGrpLog) != 0) {
-              // the metric suite already has |ln p - ln t| = ln(max/min): reuse it, signed by p - t.
-              // Only predictions below the metrics' clamp (1e-7) need their own logarithm.
-              v = t > 0.01f;
-              d = (md >= 0.f) ? mL : -mL;
-              if (v && !(p >= 1e-7f)) d = log_ratio_slow(p, t);
-              d = v ? d : 0.f;
-            } else {
-              d = silog_resid(p, t, v);
-            }
+            d = silog_resid(p, t, v);
             s0 += d;
             s1 = fmaf(d, d, s1);
             c0 += v ? 1 : 0;
@@ -574,8 +619,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
         };
     // short runs: dynamically claimed tiles (balance matters, fixed costs dominate); long runs: one static
     // contiguous chunk per CTA with two quads per iteration (more independent work per instruction stream)
-    if constexpr (VEC && !LONG) tiles_forward<PT, kCanStash>(pred, gt, stash, a, TileSched{ukey + 2, sm_tile, a.sched == 0}, body_sum, fold);
-    else chunk_forward<PT, VEC, kCanStash, false>(pred, gt, stash, a, body_sum, fold);
+    if constexpr (VEC && !LONG) tiles_forward<PT, kCanStash>(pred, gt, stash, a, TileSched{ukey + 2, sm_tile, a.sched == 0}, body_sum, pre_sum, fold);
+    else chunk_forward<PT, VEC, kCanStash, false>(pred, gt, stash, a, body_sum, pre_sum, fold);
     trace_point(1);
     fold_now();
     run[2] = static_cast<double>(c0);
@@ -592,7 +637,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float sq = warp_sum(static_cast<float>(mrun[q]));
+        const float sq = warp_sum(static_cast<float>(mrun[q])) * tile_scale<false>(q);
         if (lane == 0) sm_d[(4 + q) * kWarps + warp] = static_cast<double>(sq);
       }
       __syncthreads();
@@ -609,10 +654,16 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   // ---------------- grid barrier; its last arriver turns the totals into loss + coefficients ------------
   double tS0 = 0.0, tS1 = 0.0, tN0 = 0.0, tN1 = 0.0, tloss = 0.0;   // only meaningful in the last arriver
   grid_barrier_bcast(ukey + 6, ws.hdr->bcast, epoch * 4u + 2u, sm_k, [&](float (&v)[4]) {
-    const double S0 = __ldcg(&gacc[0]), S1 = __ldcg(&gacc[1]);
-    const double N0 = __ldcg(&gacc[2]), N1 = __ldcg(&gacc[3]);
+    double S0 = __ldcg(&gacc[0]), S1 = __ldcg(&gacc[1]);
+    double N0 = __ldcg(&gacc[2]), N1 = __ldcg(&gacc[3]);
+    if constexpr (kSilogLog2) {
+      // natural-log totals from the log2 sums, the suite's sum of squares / valid count and the rare-path differences
+      S0 *= 0.69314718055994531;
+      S1 = __ldcg(&gacc[kMetBase + MDE_Q_LNSQ]) + S1 * 0.48045301391820142;
+      N0 += __ldcg(&gacc[kMetBase + MDE_Q_NVALID]);
+    }
     double loss;
-    float k1 = 0.f, k2 = 0.f, k3 = 0.f;
+    float k1 = 0.f, k2 = 0.f, k3 = 0.f, k4 = 0.f;
     const float gs = a.grad_scale;
     if constexpr (KIND == MDE_LOSS_L1) {
       const double inv = 1.0 / N0;
@@ -630,6 +681,10 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       loss = 10.0 * static_cast<double>(s);
       k1 = 10.0f * gs * static_cast<float>(inv) / s;                 // dL/dd_i = k1 * (d_i - k2)
       k2 = a.vf * static_cast<float>(dm);
+      if constexpr (kSilogLog2) {                                    // same, for a stash held in log2 units
+        k3 = k1 * 0.69314718055994531f;
+        k4 = a.vf * static_cast<float>(dm * 1.4426950408889634);
+      }
     } else if constexpr (KIND == MDE_LOSS_BERHU) {
       const double inv = 1.0 / (N0 + N1);
       loss = (S0 + S1) * inv;                                         // mean of the concatenation (criteria.py:131)
@@ -641,7 +696,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       k2 = gs * 0.2f * static_cast<float>(S1 * inv) / static_cast<float>(N1);  // share of dL/dc per tied maximum
       k3 = 2.f * cthr + 1e-9f;
     }
-    v[0] = k1; v[1] = k2; v[2] = k3;
+    v[0] = k1; v[1] = k2; v[2] = k3; v[3] = k4;
     tS0 = S0; tS1 = S1; tN0 = N0; tN1 = N1; tloss = loss;
   }, [&] {
     *a.loss_out = static_cast<float>(tloss);
@@ -685,9 +740,10 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   if constexpr (kCanStash) {
     if (a.use_stash) {
       // grad[i] holds d_i (or the off-mask marker): g = k1 (d - k2) / p
+      const float ks1 = kSilogLog2 ? k3 : k1, ks2 = kSilogLog2 ? sm_k[3] : k2;
       auto body_s = [&](int64_t, float p, float d) -> float {
         const bool v = __float_as_uint(d) != kStashInvalid;
-        return v ? k1 * (d - k2) * rcp_nr(p) : 0.f;
+        return v ? ks1 * (d - ks2) * rcp_nr(p) : 0.f;
       };
       if constexpr (VEC && !LONG) tiles_map<PT, true>(pred, reinterpret_cast<const float*>(grad), grad, a, TileSched{ukey + 3, sm_tile, a.sched == 0}, body_s);
       else chunk_map_reverse<PT, VEC, true>(pred, reinterpret_cast<const float*>(grad), grad, a, body_s);

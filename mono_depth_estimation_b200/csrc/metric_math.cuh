@@ -3,16 +3,19 @@
 // Two evaluation modes of the SAME quantities (include/mde_b200.h, MDE_Q_*):
 //   Ref  : the reference's own op sequence (metrics.py:75-109 + torchmetrics closed forms):
 //          log10f(p)-log10f(t), log1pf(p)-log1pf(t), IEEE divides everywhere.
-//   Fast : algebraically equal forms built on the SFU (MUFU.RCP / LG2 / RSQ); used by default
-//          because the suite in Ref form is issue-bound, not HBM-bound, on B200.
+//   Fast : algebraically equal forms built on the SFU (MUFU.LG2 / RSQ), ~35 issue slots per pixel; used
+//          by default because the suite in Ref form is issue-bound, not HBM-bound, on B200.
+//          Logarithmic sums are carried in log2 units and scaled once per flush (tile_scale()).
 //
-// Bit-exact delta counts in BOTH modes. The reference counts max(fl(p/t), fl(t/p)) < 1.25^k, which
-// equals r = fl(max(p,t)/min(p,t)) < 1.25^k (round-to-nearest is monotone). Ref mode evaluates r
-// with an IEEE divide. Fast mode evaluates u = log_1.25(q), q = hi * rcp.approx(lo): |u - log_1.25(x)|
-// <= 2.5e-6 for the true quotient x (rcp.approx: 1 ulp, lg2.approx: <= 3.3e-7 absolute, both bounds
-// measured on B200 by tools/mathlab.cu and documented in the PTX ISA), so u < k decides r < 1.25^k
-// whenever u is farther than 1e-5 from the integers 1, 2, 3; inside that window (6e-5 of the pixels)
-// the pixel takes the exact IEEE divide. The integer counts are therefore identical to the reference.
+// Bit-exact delta counts in BOTH modes, and in Fast mode without a divide or a branch. The reference
+// counts max(fl(p/t), fl(t/p)) < T for T = 1.25^k, which equals RN(hi/lo) < T with hi = max, lo = min
+// (round-to-nearest is monotone). All three T lie in (1,2) and have an even last mantissa bit, so
+//     RN(x) < T   <=>   x < T - 2^-24   <=>   lo*T - hi > lo * 2^-24            (x = hi/lo >= 1, lo > 0)
+// (the midpoint between T and its predecessor rounds to T). fmaf(lo, T, -hi) rounds lo*T - hi once; that
+// value is a multiple of 2^-6 ulp(lo), hence exactly representable whenever it is within 2^18 ulp(lo) of
+// the right-hand side, and lo*2^-24 is exact - so the fp32 comparison decides the real inequality for
+// every input (tiny lo with hi/lo astronomically large cannot be near a threshold). NaN predictions make
+// hi NaN (max.NaN) and fail every comparison, as NaN < T does in the reference.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -101,27 +104,41 @@ __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ft
 __device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_rsq(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// ln(q) for q >= 1 (NaN passes through): the SFU log2 away from 1, a 4-term series of ln(1+f) below
-// 1 + 2^-5 where lg2.approx's +4e-8 absolute bias would otherwise dominate a small result.
-__device__ __forceinline__ float ln_ge1_fast(float q, float l2) {
-  const float f = q - 1.0f;
-  const float ser = f * fmaf(f, fmaf(f, fmaf(f, -0.25f, 0.33333333f), -0.5f), 1.0f);
-  return (f < 0.03125f) ? ser : l2 * 0.69314718055994531f;
+__device__ __forceinline__ float fmax_nan(float x, float y) {   // NaN if either operand is NaN
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(y));
+  return r;
 }
 
-// One pixel of the metric suite. Besides accumulating, returns through `L_out` the value
-// |ln p - ln t| = ln(max/min) (fast mode with kGrpLog only; 0 otherwise) so that a fused loss can
-// reuse the logarithm, and through `d_out` the difference p - t on the clamped prediction.
+// Factor that turns fp32 tile sum q (MetricTile order: abs, sq, log10, sle, absrel, sqrel, rsq, lnsq)
+// into the unit of the raw quantity: Fast mode carries its logarithms in log2 units.
+template <bool Ref>
+__host__ __device__ constexpr float tile_scale(int q) {
+  return Ref ? 1.0f : (q == 2 ? 0.30102999566398120f : ((q == 3 || q == 7) ? 0.48045301391820142f : 1.0f));
+}
+
+// Fast mode relies on MUFU.LG2/RSQ with flush-to-zero: a quad that holds a valid SUBNORMAL target must
+// be evaluated in Ref mode instead (one predicate per quad: 3 FMNMX + 1 FSETP). Never true for depth
+// in metres; kept so that the fast path has no input it silently gets wrong.
+__device__ __forceinline__ bool metric_quad_needs_ref(const float4& t) {
+  const float a = (t.x > 0.f) ? t.x : 1.0f, b = (t.y > 0.f) ? t.y : 1.0f;
+  const float c = (t.z > 0.f) ? t.z : 1.0f, d = (t.w > 0.f) ? t.w : 1.0f;
+  return fminf(fminf(a, b), fminf(c, d)) < 1.17549435e-38f;
+}
+
+// One pixel of the metric suite. Besides accumulating, returns through `L_out` (fast mode with kGrpLog
+// only; 0 otherwise) the signed value log2(p) - log2(t) of the clamped prediction, so that a fused loss
+// can reuse the logarithms, and through `d_out` the difference p - t on the clamped prediction.
 template <unsigned G, bool Ref>
 __device__ __forceinline__ void metric_px_ex(float p, float t, MetricTile& a, MetricCounts& c, float& L_out,
                                              float& d_out) {
   const bool v = t > 0.f;                         // metrics.py:60
-  p = (p < 1e-7f) ? 1e-7f : p;                    // clamp_min(pred, 1e-7), NaN preserved (metrics.py:59)
   // invalid pixels are replaced by p = t = 1: every float contribution below is then exactly 0
-  const float pp = v ? p : 1.0f;
+  const float ps = v ? p : 1.0f;
   const float tt = v ? t : 1.0f;
+  const float pp = (ps < 1e-7f) ? 1e-7f : ps;     // clamp_min(pred, 1e-7), NaN preserved (metrics.py:59)
   const float d = pp - tt;
-  const float hi = fmaxf(pp, tt), lo = fminf(pp, tt);
+  const float hi = Ref ? fmaxf(pp, tt) : fmax_nan(pp, tt), lo = fminf(pp, tt);
   const float ad = fabsf(d);
   a.s_abs += ad;
   a.s_sq = fmaf(d, d, a.s_sq);
@@ -152,40 +169,59 @@ __device__ __forceinline__ void metric_px_ex(float p, float t, MetricTile& a, Me
       a.s_rsq += __fsqrt_rn(sr);                              // metrics.py:109
     }
   } else {
-    // q ~ max/min (1.5 ulp), NaN predictions propagate through the 0*d term
-    const float q = fmaf(d, 0.0f, hi * mufu_rcp(lo));
-    const float l2 = mufu_lg2(q);
-    // threshold level in the log domain: u = log_1.25(q); NaN -> 4 (beyond every threshold)
-    const float u = fminf(l2 * 3.1062837195f, 4.0f);
-    bool lt1 = u < 1.0f, lt2 = u < 2.0f, lt3 = u < 3.0f;
-    const float kf = (u + 12582912.0f) - 12582912.0f;        // rint(u) via the 1.5*2^23 trick
-    if (fabsf(u - kf) < 1e-5f && u > 0.5f && u < 3.5f) {      // within 1e-5 of a threshold: decide exactly
-      const float r = __fdiv_rn(hi, lo);
-      lt1 = r < 1.25f;
-      lt2 = r < 1.5625f;
-      lt3 = r < 1.953125f;
-    }
+    // level of the ratio among the thresholds, exact (see the header): 1 FMUL + 3 FFMA + 3 FSETP
+    const float e = lo * 5.9604644775390625e-08f;
+    const bool lt1 = fmaf(lo, 1.25f, -hi) > e;                 // strict '<' (metrics.py:77,82,87)
+    const bool lt2 = fmaf(lo, 1.5625f, -hi) > e;
+    const bool lt3 = fmaf(lo, 1.953125f, -hi) > e;
     const unsigned inc = lt1 ? 1u : (lt2 ? 0x100u : (lt3 ? 0x10000u : 0x1000000u));
     c.pk += v ? inc : 0u;
     if (G & kGrpLog) {
-      const float L = ln_ge1_fast(q, l2);                     // |ln p - ln t| = ln(max/min)
-      L_out = L;
-      a.s_log10 = fmaf(L, 0.43429448190325182f, a.s_log10);
-      a.s_lnsq = fmaf(L, L, a.s_lnsq);
+      const float dl = mufu_lg2(pp) - mufu_lg2(tt);           // log2 p - log2 t, signed
+      L_out = dl;
+      a.s_log10 += fabsf(dl);                                 // x log10(2) at the flush
+      a.s_lnsq = fmaf(dl, dl, a.s_lnsq);                      // x ln(2)^2 at the flush
     }
     if (G & kGrpLog1p) {
-      // |log1p p - log1p t| = ln((1+hi)/(1+lo))
-      const float s1 = fmaf(d, 0.0f, (1.0f + hi) * mufu_rcp(1.0f + lo));
-      const float L = ln_ge1_fast(s1 < 1.0f ? 1.0f : s1, mufu_lg2(s1));   // NaN stays NaN
-      a.s_sle = fmaf(L, L, a.s_sle);
+      const float d1 = mufu_lg2(1.0f + pp) - mufu_lg2(1.0f + tt);
+      a.s_sle = fmaf(d1, d1, a.s_sle);                        // x ln(2)^2 at the flush
     }
     if (G & kGrpRel) {
-      const float ar = ad * mufu_rcp(tt);
+      const float rs = mufu_rsq(tt);
+      const float ar = ad * (rs * rs);                        // |p-t| / t
       a.s_absrel += ar;
       a.s_sqrel = fmaf(ar, ad, a.s_sqrel);
-      a.s_rsq = fmaf(ad, mufu_rsq(tt), a.s_rsq);              // sqrt((p-t)^2/t) = |p-t| / sqrt(t)
+      a.s_rsq = fmaf(ad, rs, a.s_rsq);                        // sqrt((p-t)^2/t) = |p-t| / sqrt(t)
     }
   }
+}
+
+// Rare-quad path of the fast kernels: one pixel in Ref arithmetic, returned by value (nothing of the
+// caller's register-resident accumulators has its address taken) and added in the fast tile's units.
+struct MetricContrib {
+  MetricTile s;
+  MetricCounts c;
+};
+template <unsigned G>
+static __device__ __noinline__ MetricContrib metric_px_ref_contrib(float p, float t) {
+  MetricContrib r;
+  r.s.zero();
+  r.c.zero();
+  float L, d;
+  metric_px_ex<G, true>(p, t, r.s, r.c, L, d);
+  return r;
+}
+__device__ __forceinline__ void metric_add_contrib(const MetricContrib& r, MetricTile& a, MetricCounts& c) {
+  a.s_abs += r.s.s_abs; a.s_sq += r.s.s_sq;
+  a.s_log10 += r.s.s_log10 * (1.0f / tile_scale<false>(2));
+  a.s_sle += r.s.s_sle * (1.0f / tile_scale<false>(3));
+  a.s_absrel += r.s.s_absrel; a.s_sqrel += r.s.s_sqrel; a.s_rsq += r.s.s_rsq;
+  a.s_lnsq += r.s.s_lnsq * (1.0f / tile_scale<false>(7));
+  c.n += r.c.n; c.c1 += r.c.c1; c.c2 += r.c.c2; c.c3 += r.c.c3;
+}
+template <unsigned G>
+__device__ __forceinline__ void metric_px_ref_into_fast(float p, float t, MetricTile& a, MetricCounts& c) {
+  metric_add_contrib(metric_px_ref_contrib<G>(p, t), a, c);
 }
 
 template <unsigned G, bool Ref>

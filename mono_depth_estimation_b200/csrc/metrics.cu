@@ -36,16 +36,29 @@ struct MetricThread {
       for (int q = 0; q < 8; ++q) srun[q * kBlock] = 0.0;
     }
   }
-  __device__ __forceinline__ void px(float p, float t) { metric_px<G, Ref>(p, t, tile, cnt); }
-  __device__ __forceinline__ void quad(const float4& p, const float4& t) {
-    px(p.x, t.x);
-    px(p.y, t.y);
-    px(p.z, t.z);
-    px(p.w, t.w);
+  // scalar path: the rare-case test (valid subnormal target, see metric_quad_needs_ref) per pixel
+  __device__ __forceinline__ void px(float p, float t) {
+    if (!Ref && t > 0.f && t < 1.17549435e-38f) metric_px_ref_into_fast<G>(p, t, tile, cnt);
+    else metric_px<G, Ref>(p, t, tile, cnt);
   }
+  __device__ __forceinline__ void quad(const float4& p, const float4& t) {
+    if (!Ref && metric_quad_needs_ref(t)) {
+      metric_px_ref_into_fast<G>(p.x, t.x, tile, cnt);
+      metric_px_ref_into_fast<G>(p.y, t.y, tile, cnt);
+      metric_px_ref_into_fast<G>(p.z, t.z, tile, cnt);
+      metric_px_ref_into_fast<G>(p.w, t.w, tile, cnt);
+    } else {
+      metric_px<G, Ref>(p.x, t.x, tile, cnt);
+      metric_px<G, Ref>(p.y, t.y, tile, cnt);
+      metric_px<G, Ref>(p.z, t.z, tile, cnt);
+      metric_px<G, Ref>(p.w, t.w, tile, cnt);
+    }
+  }
+  // tile sum q in the unit of its raw quantity (the fast forms carry logarithms in log2 units)
   __device__ __forceinline__ float tile_q(int q) const {
-    return (q == 0) ? tile.s_abs : (q == 1) ? tile.s_sq : (q == 2) ? tile.s_log10 : (q == 3) ? tile.s_sle
-         : (q == 4) ? tile.s_absrel : (q == 5) ? tile.s_sqrel : (q == 6) ? tile.s_rsq : tile.s_lnsq;
+    const float s = (q == 0) ? tile.s_abs : (q == 1) ? tile.s_sq : (q == 2) ? tile.s_log10 : (q == 3) ? tile.s_sle
+                  : (q == 4) ? tile.s_absrel : (q == 5) ? tile.s_sqrel : (q == 6) ? tile.s_rsq : tile.s_lnsq;
+    return s * tile_scale<Ref>(q);
   }
   // value of running sum q at flush time
   __device__ __forceinline__ float total(int q) const {
