@@ -52,7 +52,9 @@ int coop_grid(const void* func, int block, size_t smem) {
     if (it != g_coop_grid.end()) return it->second;
   }
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, block, smem);
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024) e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, block, smem);
   if (e != cudaSuccess || per_sm <= 0) {
     set_error("occupancy query failed: %s", cudaGetErrorString(e));
     return -1;

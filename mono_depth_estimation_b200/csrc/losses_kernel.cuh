@@ -392,6 +392,105 @@ __device__ __forceinline__ void tiles_map(const PT* __restrict__ pred, const flo
   }
 }
 
+// ---- SILog with the residuals parked in SHARED memory between the phases (SS variant) -----------------
+// Up to kSsSlots tiles per CTA (2 CTAs x 13 x 8 KB = 208 KB of the SM's shared memory): the reduce phase
+// writes d_i of every tile it claimed into its own slot and remembers the tile id; the gradient phase
+// walks the CTA's slots backwards, reading d_i from shared memory and p_i through L2. Compared with the
+// stash in the gradient buffer this removes 4 B/px of L2 writes from the reduce phase and 4 B/px of L2
+// reads from the gradient phase, and the gradient phase needs no tile counter. A CTA stops claiming when
+// its slots are committed; the launch guarantees grid x kSsSlots >= number of tiles.
+constexpr int kSsSlots = 13;
+constexpr size_t kSsBytes = static_cast<size_t>(kSsSlots) * kBlock * sizeof(float4);
+
+template <typename PT, typename Body, typename Pre, typename Fold>
+__device__ __forceinline__ int tiles_forward_ss(const PT* __restrict__ pred, const float* __restrict__ gt, float4* ss,
+                                                int* list, const LossArgs& a, TileSched ts, Body&& body, Pre&& pre,
+                                                Fold&& fold) {
+  const int64_t nq = a.n >> 2;
+  const int64_t nt = (nq + kBlock - 1) / kBlock;
+  const unsigned G = gridDim.x;
+  int ns = 0;  // slots filled so far (uniform over the CTA)
+  // a claim is only issued while the CTA can still house the tile: ns done + current + prefetched + this one
+  auto fetch = [&]() -> unsigned {
+    if (threadIdx.x != 0) return 0u;
+    return (ns + 3 <= kSsSlots) ? atomicAdd(ts.ctr, 1u) : 0x7fffffffu - G;
+  };
+  auto publish = [&](int sl, unsigned c) {
+    if (threadIdx.x == 0) ts.slot[sl] = static_cast<int>(G + c);
+  };
+  auto load = [&](int64_t tile, float4& p, float4& t) -> bool {
+    const int64_t q = tile * kBlock + threadIdx.x;
+    const bool ok = q < nq;
+    if (ok) {
+      p = Elem<PT>::template ld4<true>(pred + 4 * q);
+      t = __ldcs(reinterpret_cast<const float4*>(gt + 4 * q));   // the target is not needed again
+    }
+    return ok;
+  };
+  auto compute = [&](int64_t tile, bool ok, const float4& p, const float4& t) {
+    if (ok) ss[ns * kBlock + threadIdx.x] = eval_quad(body, pre, 4 * (tile * kBlock + threadIdx.x), p, t);
+    if (threadIdx.x == 0) list[ns] = static_cast<int>(tile);
+    ++ns;
+  };
+  int64_t tA = blockIdx.x, tB;
+  float4 pA, gA, pB, gB;
+  bool okA = false, okB = false;
+  unsigned claim = fetch();
+  if (tA < nt) okA = load(tA, pA, gA);
+  publish(0, claim);
+  __syncthreads();
+  tB = ts.slot[0];
+  while (tA < nt) {
+    claim = fetch();
+    okB = (tB < nt) && load(tB, pB, gB);
+    compute(tA, okA, pA, gA);
+    publish(1, claim);
+    __syncthreads();
+    tA = ts.slot[1];
+    if (tB >= nt) break;
+    claim = fetch();
+    okA = (tA < nt) && load(tA, pA, gA);
+    compute(tB, okB, pB, gB);
+    fold();
+    publish(0, claim);
+    __syncthreads();
+    tB = ts.slot[0];
+  }
+  if (blockIdx.x == gridDim.x - 1) {  // n % 4 tail: summed here, its gradient is recomputed in the map phase
+    const int64_t i = (nq << 2) + threadIdx.x;
+    if (i < a.n) eval_one(body, pre, i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
+  }
+  __syncthreads();
+  return ns;
+}
+
+// gradient phase of the SS variant: own slots, last one first; body(p, d) -> gradient
+template <typename PT, typename Body>
+__device__ __forceinline__ void tiles_map_ss(const PT* __restrict__ pred, const float4* ss, const int* list, int ns,
+                                             PT* out, const LossArgs& a, Body&& body) {
+  const int64_t nq = a.n >> 2;
+  auto quad_of = [&](int sl) -> int64_t { return static_cast<int64_t>(list[sl]) * kBlock + threadIdx.x; };
+  auto emit = [&](int64_t q, const float4& p, const float4& d) {
+    float4 g;
+    g.x = body(p.x, d.x); g.y = body(p.y, d.y); g.z = body(p.z, d.z); g.w = body(p.w, d.w);
+    Elem<PT>::st4(out + 4 * q, g);
+  };
+  int sl = ns - 1;
+  for (; sl >= 1; sl -= 2) {
+    const int64_t q0 = quad_of(sl), q1 = quad_of(sl - 1);
+    const bool ok0 = q0 < nq, ok1 = q1 < nq;
+    float4 p0, p1;
+    if (ok0) p0 = Elem<PT>::template ld4<false>(pred + 4 * q0);
+    if (ok1) p1 = Elem<PT>::template ld4<false>(pred + 4 * q1);
+    if (ok0) emit(q0, p0, ss[sl * kBlock + threadIdx.x]);
+    if (ok1) emit(q1, p1, ss[(sl - 1) * kBlock + threadIdx.x]);
+  }
+  if (sl == 0) {
+    const int64_t q0 = quad_of(0);
+    if (q0 < nq) emit(q0, Elem<PT>::template ld4<false>(pred + 4 * q0), ss[threadIdx.x]);
+  }
+}
+
 // block-reduce N doubles and add them to gacc[0..N)
 template <int N>
 __device__ __forceinline__ void publish_sums(const double (&v)[N], double* gacc, double* sm) {
@@ -454,14 +553,21 @@ constexpr int kMetBase = 16;  // gacc[kMetBase + q] = pooled raw metric sum q
 
 // LONG = false (a thread sees <= 96 pixels): sums stay in fp32 registers until the end of the chunk and
 // the loads are software-pipelined; LONG = true folds every 8 pixels into fp64 running sums.
-template <int KIND, typename PT, bool VEC, unsigned MG, bool LONG>
+// SS = true: the shared-memory stash variant of SILog (fp32, 128-bit path, short runs, gradient requested)
+template <int KIND, typename PT, bool VEC, unsigned MG, bool LONG, bool SS = false>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArgs a) {
   __shared__ double sm_d[(MG ? 12 : 4) * kWarps];
   __shared__ float sm_k[4];
   __shared__ float sm_f[kWarps];
   __shared__ int sm_tile[2];
+  __shared__ int sm_list[SS ? kSsSlots : 1];
+  extern __shared__ float4 sm_ss[];  // SS: [kSsSlots][kBlock] residual quads
+  static_assert(!SS || (KIND == MDE_LOSS_SILOG && std::is_same<PT, float>::value && VEC && !LONG), "SS is a SILog/fp32 variant");
   constexpr bool kCanStash = (KIND == MDE_LOSS_SILOG) && std::is_same<PT, float>::value;
-  constexpr bool kSilogLog2 = (KIND == MDE_LOSS_SILOG) && (MG & kGrpLog) != 0;
+  // residuals in log2 units: whenever they come from MUFU.LG2 (shared with the metric suite, or the SS variant)
+  constexpr bool kSilogShare = (KIND == MDE_LOSS_SILOG) && (MG & kGrpLog) != 0;
+  constexpr bool kSilogLog2 = kSilogShare || SS;
+  int ss_n = 0;
 
   const PT* __restrict__ pred = static_cast<const PT*>(a.pred);
   const float* __restrict__ gt = a.gt;
@@ -542,8 +648,9 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     // sum d^2 is the suite's s_lnsq, n its valid count - and the rare path books the differences in s1 / c0.
     auto pre_sum = [&](const float4& p4, const float4& t4) -> bool {
       if constexpr (MG == 0) {
+        if constexpr (SS) return !(fminf(fminf(p4.x, p4.y), fminf(p4.z, p4.w)) >= 1.17549435e-38f);
         return false;
-      } else if constexpr (kSilogLog2) {
+      } else if constexpr (kSilogShare) {
         const float ta = (t4.x > 0.f) ? t4.x : 1.0f, tb = (t4.y > 0.f) ? t4.y : 1.0f;
         const float tc = (t4.z > 0.f) ? t4.z : 1.0f, td = (t4.w > 0.f) ? t4.w : 1.0f;
         return !(fminf(fminf(ta, tb), fminf(tc, td)) > 0.01f) ||
@@ -559,7 +666,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
             if constexpr (kSlow) {
               const MetricContrib r = metric_px_ref_contrib<MG>(p, t);
               metric_add_contrib(r, mt, mc);
-              if constexpr (kSilogLog2) {
+              if constexpr (kSilogShare) {
                 const bool v2 = t > 0.01f;
                 const float d2 = v2 ? log_ratio_slow(p, t) * 1.4426950408889634f : 0.f;
                 s0 += d2;
@@ -569,7 +676,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
               }
             } else {
               metric_px_ex<MG, false>(p, t, mt, mc, mL, md);
-              if constexpr (kSilogLog2) {
+              if constexpr (kSilogShare) {
                 s0 += mL;
                 return (t > 0.f) ? mL : __uint_as_float(kStashInvalid);
               }
@@ -589,7 +696,13 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
           } else if constexpr (KIND == MDE_LOSS_SILOG) {
             bool v;
             float d;
-            d = silog_resid(p, t, v);
+            if constexpr (SS) {   // MG == 0 here: log2 units, MUFU.LG2 on the common path
+              v = t > 0.01f;
+              if constexpr (kSlow) d = v ? log_ratio_slow(p, t) * 1.4426950408889634f : 0.f;
+              else d = mufu_lg2(v ? p : 1.0f) - mufu_lg2(v ? t : 1.0f);
+            } else {
+              d = silog_resid(p, t, v);
+            }
             s0 += d;
             s1 = fmaf(d, d, s1);
             c0 += v ? 1 : 0;
@@ -619,7 +732,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
         };
     // short runs: dynamically claimed tiles (balance matters, fixed costs dominate); long runs: one static
     // contiguous chunk per CTA with two quads per iteration (more independent work per instruction stream)
-    if constexpr (VEC && !LONG) tiles_forward<PT, kCanStash>(pred, gt, stash, a, TileSched{ukey + 2, sm_tile, a.sched == 0}, body_sum, pre_sum, fold);
+    if constexpr (SS) ss_n = tiles_forward_ss<PT>(pred, gt, sm_ss, sm_list, a, TileSched{ukey + 2, sm_tile, true}, body_sum, pre_sum, fold);
+    else if constexpr (VEC && !LONG) tiles_forward<PT, kCanStash>(pred, gt, stash, a, TileSched{ukey + 2, sm_tile, a.sched == 0}, body_sum, pre_sum, fold);
     else chunk_forward<PT, VEC, kCanStash, false>(pred, gt, stash, a, body_sum, pre_sum, fold);
     trace_point(1);
     fold_now();
@@ -656,10 +770,12 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   grid_barrier_bcast(ukey + 6, ws.hdr->bcast, epoch * 4u + 2u, sm_k, [&](float (&v)[4]) {
     double S0 = __ldcg(&gacc[0]), S1 = __ldcg(&gacc[1]);
     double N0 = __ldcg(&gacc[2]), N1 = __ldcg(&gacc[3]);
-    if constexpr (kSilogLog2) {
-      // natural-log totals from the log2 sums, the suite's sum of squares / valid count and the rare-path differences
+    if constexpr (kSilogLog2) {   // natural-log totals from the log2 sums
       S0 *= 0.69314718055994531;
-      S1 = __ldcg(&gacc[kMetBase + MDE_Q_LNSQ]) + S1 * 0.48045301391820142;
+      S1 *= 0.48045301391820142;
+    }
+    if constexpr (kSilogShare) {  // + the suite's sum of squares / valid count (S1, N0 held the rare-path differences)
+      S1 += __ldcg(&gacc[kMetBase + MDE_Q_LNSQ]);
       N0 += __ldcg(&gacc[kMetBase + MDE_Q_NVALID]);
     }
     double loss;
@@ -737,6 +853,24 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   trace_point(4);
 
   // ---------------- phase B: gradient, chunk walked backwards ----------------------------------------
+  if constexpr (SS) {
+    const float ks1 = k3, ks2 = sm_k[3];
+    tiles_map_ss<PT>(pred, sm_ss, sm_list, ss_n, grad, a, [&](float p, float d) -> float {
+      const bool v = __float_as_uint(d) != kStashInvalid;
+      return v ? ks1 * (d - ks2) * rcp_nr(p) : 0.f;
+    });
+    if (blockIdx.x == gridDim.x - 1) {   // n % 4 tail, recomputed
+      const int64_t i = ((a.n >> 2) << 2) + threadIdx.x;
+      if (i < a.n) {
+        bool v;
+        const float p = Elem<PT>::ld1(pred + i);
+        const float d = silog_resid(p, __ldg(gt + i), v);
+        Elem<PT>::st1(grad + i, v ? k1 * (d - k2) * rcp_nr(p) : 0.f);
+      }
+    }
+    trace_point(5);
+    return;
+  }
   if constexpr (kCanStash) {
     if (a.use_stash) {
       // grad[i] holds d_i (or the off-mask marker): g = k1 (d - k2) / p
@@ -804,10 +938,39 @@ int launch_loss_l(LossArgs& a, cudaStream_t st) {
   return MDE_OK;
 }
 
+// SILog / fp32 / 128-bit path with a gradient and few enough tiles: residuals parked in shared memory
+template <unsigned MG>
+int launch_loss_ss(LossArgs& a, cudaStream_t st, bool& taken) {
+  taken = false;
+  static const bool off = [] { const char* e = getenv("MDE_NO_SMEM_STASH"); return e && atoi(e) != 0; }();
+  if (off) return MDE_OK;
+  const void* fn = reinterpret_cast<const void*>(&masked_loss_kernel<MDE_LOSS_SILOG, float, true, MG, false, true>);
+  const int cap = coop_grid(fn, kBlock, kSsBytes);
+  if (cap <= 0) return MDE_OK;   // (e.g. the carve-out is not available) -> generic path
+  const int64_t nq = a.n >> 2;
+  const int64_t nt = (nq + kBlock - 1) / kBlock;
+  int64_t grid = nt < cap ? nt : cap;
+  if (grid < 1) grid = 1;
+  if (nt > grid * kSsSlots) return MDE_OK;
+  a.chunk = make_chunking(nq, 8, static_cast<int>(grid));
+  void* args[] = {&a};
+  MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, kSsBytes, st));
+  count_launch();
+  taken = true;
+  return MDE_OK;
+}
+
 template <int KIND, typename PT, bool VEC, unsigned MG>
 int launch_loss(LossArgs& a, cudaStream_t st) {
   const int64_t threads = static_cast<int64_t>(sm_count()) * kCtasPerSm * kBlock;
   const bool is_long = (a.n + threads - 1) / threads > 96;
+  if constexpr (KIND == MDE_LOSS_SILOG && std::is_same<PT, float>::value && VEC) {
+    if (!is_long && a.grad != nullptr) {
+      bool taken = false;
+      const int rc = launch_loss_ss<MG>(a, st, taken);
+      if (rc != MDE_OK || taken) return rc;
+    }
+  }
   return is_long ? launch_loss_l<KIND, PT, VEC, MG, true>(a, st) : launch_loss_l<KIND, PT, VEC, MG, false>(a, st);
 }
 
