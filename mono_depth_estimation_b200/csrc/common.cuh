@@ -77,13 +77,19 @@ static_assert(sizeof(WsHeader) == 256, "workspace header must be 256 bytes");
 constexpr int kGacc = 64;
 constexpr int kUkey = 16;
 constexpr int kIacc = 16;
-constexpr size_t kWsFixedBytes = 256 + 2 * kGacc * 8 + 2 * kUkey * 4 + 128;  // 1536
+// [1536, +32768) slots[512][4][2] words {seq:32 | half of a double:32}: per-CTA partial totals of
+//              grid_sum4_bcast (self-validating, unique seq per launch and stage: never need zeroing)
+constexpr int kSlotCtas = 512;                       // >= resident CTAs of any cooperative launch here
+constexpr size_t kSlotBytes = static_cast<size_t>(kSlotCtas) * 4 * 2 * 8;
+constexpr size_t kWsHeadBytes = 256 + 2 * kGacc * 8 + 2 * kUkey * 4 + 128;  // 1536
+constexpr size_t kWsFixedBytes = kWsHeadBytes + kSlotBytes;
 
 struct Ws {
   WsHeader* hdr;
   double* gacc;     // [2][kGacc]
   unsigned* ukey;   // [2][kUkey]
   double* iacc;     // [3][max_images][kIacc]
+  unsigned long long* slots;  // [kSlotCtas][4][2]
 };
 
 __host__ __device__ inline Ws ws_view(void* base) {
@@ -92,6 +98,7 @@ __host__ __device__ inline Ws ws_view(void* base) {
   w.hdr = reinterpret_cast<WsHeader*>(b);
   w.gacc = reinterpret_cast<double*>(b + 256);
   w.ukey = reinterpret_cast<unsigned*>(b + 256 + 2 * kGacc * 8);
+  w.slots = reinterpret_cast<unsigned long long*>(b + kWsHeadBytes);
   w.iacc = reinterpret_cast<double*>(b + kWsFixedBytes);
   return w;
 }
@@ -148,13 +155,19 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 
 // last_fn(v, post): fills v[0..3]; anything it wants to write besides (loss value, ...) goes into the
 // `post` callable it returns control to AFTER the words are out, i.e. off the other CTAs' critical path.
-template <typename LastFn, typename PostFn>
+// mid_fn() runs on every thread after the CTA's ticket has been ISSUED and before anybody waits: loads
+// started there overlap the barrier's round trips instead of delaying the release fence.
+template <typename LastFn, typename PostFn, typename MidFn>
 __device__ __forceinline__ void grid_barrier_bcast(unsigned* ticket, unsigned long long* words, unsigned seq,
-                                                   float* out_smem4, LastFn&& last_fn, PostFn&& post_fn) {
+                                                   float* out_smem4, LastFn&& last_fn, PostFn&& post_fn, MidFn&& mid_fn) {
   __syncthreads();
+  unsigned t = 0u;
   if (threadIdx.x == 0) {
     __threadfence();                       // release: this CTA's global writes before its ticket
-    const unsigned t = atomicAdd(ticket, 1u);
+    t = atomicAdd(ticket, 1u);
+  }
+  mid_fn();
+  if (threadIdx.x == 0) {
     const bool last = (t == gridDim.x - 1);
     if (last) {
       __threadfence();                     // acquire every CTA's writes; also orders them before the words
@@ -178,6 +191,61 @@ __device__ __forceinline__ void grid_barrier_bcast(unsigned* ticket, unsigned lo
     out_smem4[1] = __uint_as_float(static_cast<unsigned>(w1));
     out_smem4[2] = __uint_as_float(static_cast<unsigned>(w2));
     out_smem4[3] = __uint_as_float(static_cast<unsigned>(w3));
+  }
+  __syncthreads();
+}
+template <typename LastFn, typename PostFn>
+__device__ __forceinline__ void grid_barrier_bcast(unsigned* ticket, unsigned long long* words, unsigned seq,
+                                                   float* out_smem4, LastFn&& last_fn, PostFn&& post_fn) {
+  grid_barrier_bcast(ticket, words, seq, out_smem4, last_fn, post_fn, [] {});
+}
+#endif
+
+// ---- grid-wide sum of four doubles without a ticket ---------------------------------------------------
+// The ticket barrier above costs four dependent L2 round trips after the last CTA is ready (its atomics,
+// the fence, the ticket, the totals read, the broadcast). Here every CTA stores its four partial totals
+// into its OWN slot as self-validating words {seq | 32 bits of the double} and then every CTA gathers
+// all slots itself (<= 3 doubles per thread), spinning only on words whose seq is not there yet: after
+// the last CTA's store the critical path is one store, one load and a block reduction. No fence is
+// needed because the data travels inside the words that are waited for; consequently this is NOT a
+// memory barrier for anything else (use the ticket barrier when one CTA must see another's buffers).
+// The summation order is fixed by the grid size, so the totals are bit-reproducible run to run.
+// `mine`: thread q < 4 passes this CTA's total q (as returned by block_sum<4>). Totals -> sm_tot[0..3].
+#ifdef __CUDACC__
+template <typename MidFn>
+__device__ __forceinline__ void grid_sum4_bcast(unsigned long long* slots, unsigned seq, double mine, double* sm_tot,
+                                                double* sm_scratch, MidFn&& mid_fn) {
+  const unsigned long long tag = static_cast<unsigned long long>(seq) << 32;
+  if (threadIdx.x < 4) {
+    const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine));
+    unsigned long long* w = slots + (static_cast<size_t>(blockIdx.x) * 4 + threadIdx.x) * 2;
+    st_relaxed_u64(w, tag | (b >> 32));
+    st_relaxed_u64(w + 1, tag | (b & 0xffffffffull));
+  }
+  mid_fn();
+  const int n = static_cast<int>(gridDim.x) * 4;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += kBlock) {   // i & 3 == threadIdx.x & 3: one quantity per thread
+    const unsigned long long* w = slots + static_cast<size_t>(i) * 2;
+    unsigned long long hi, lo;
+    do {
+      hi = ld_relaxed_u64(w);
+      lo = ld_relaxed_u64(w + 1);
+    } while ((hi >> 32) != seq || (lo >> 32) != seq);
+    acc += __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffull)));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o >= 4; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane < 4) sm_scratch[warp * 4 + lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double x = 0.0;
+#pragma unroll
+    for (int i = 0; i < (kWarps * 4) / 32; ++i) x += sm_scratch[lane + 32 * i];
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane < 4) sm_tot[lane] = x;
   }
   __syncthreads();
 }

@@ -393,101 +393,143 @@ __device__ __forceinline__ void tiles_map(const PT* __restrict__ pred, const flo
 }
 
 // ---- SILog with the residuals parked in SHARED memory between the phases (SS variant) -----------------
-// Up to kSsSlots tiles per CTA (2 CTAs x 13 x 8 KB = 208 KB of the SM's shared memory): the reduce phase
-// writes d_i of every tile it claimed into its own slot and remembers the tile id; the gradient phase
-// walks the CTA's slots backwards, reading d_i from shared memory and p_i through L2. Compared with the
-// stash in the gradient buffer this removes 4 B/px of L2 writes from the reduce phase and 4 B/px of L2
-// reads from the gradient phase, and the gradient phase needs no tile counter. A CTA stops claiming when
-// its slots are committed; the launch guarantees grid x kSsSlots >= number of tiles.
-constexpr int kSsSlots = 13;
-constexpr size_t kSsBytes = static_cast<size_t>(kSsSlots) * kBlock * sizeof(float4);
+// Per CTA: kSsSlots tile slots of 8 KB + a ring of kSsRing target tiles (2 CTAs x 13 x 8 KB = 208 KB of the
+// SM's shared memory). The reduce phase is fed by the bulk-copy engine (cp.async.bulk + one mbarrier per
+// slot): the prediction tile lands directly in the slot that will hold its residuals (each thread replaces
+// its own quad in place), the target tile in the ring; copies run kSsRing tiles ahead of the arithmetic
+// without costing a register, which is what the 1 us of loaded HBM latency needs at ~0.7 us of issue time
+// per tile. The gradient phase walks the CTA's slots backwards, d_i from shared memory and p_i through L2.
+// Compared with the stash in the gradient buffer this removes 4 B/px of L2 writes from the reduce phase and
+// 4 B/px of L2 reads from the gradient phase, and the gradient phase needs no tile counter. The first
+// kSsRing tiles of a CTA are static (cta + j x grid), the rest are claimed from an atomic counter (HBM/L2
+// bandwidth is not shared fairly between SMs); a CTA stops claiming when its slots are committed and the
+// launch guarantees grid x kSsSlots >= number of tiles.
+constexpr int kSsSlots = 10;
+constexpr int kSsRing = 3;
+constexpr size_t kSsBytes = static_cast<size_t>(kSsSlots + kSsRing) * kBlock * sizeof(float4);
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// contiguous global -> shared copy by the bulk-copy engine; completion is counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ss: [kSsSlots + kSsRing][kBlock] float4 (slots, then the target ring); bars: kSsSlots mbarriers, used once each
 template <typename PT, typename Body, typename Pre, typename Fold>
 __device__ __forceinline__ int tiles_forward_ss(const PT* __restrict__ pred, const float* __restrict__ gt, float4* ss,
-                                                int* list, const LossArgs& a, TileSched ts, Body&& body, Pre&& pre,
-                                                Fold&& fold) {
+                                                int* list, unsigned long long* bars, const LossArgs& a, TileSched ts,
+                                                Body&& body, Pre&& pre, Fold&& fold) {
+  static_assert(sizeof(PT) == 4, "the SS variant is fp32 only");
   const int64_t nq = a.n >> 2;
   const int64_t nt = (nq + kBlock - 1) / kBlock;
   const unsigned G = gridDim.x;
-  int ns = 0;  // slots filled so far (uniform over the CTA)
-  // a claim is only issued while the CTA can still house the tile: ns done + current + prefetched + this one
-  auto fetch = [&]() -> unsigned {
-    if (threadIdx.x != 0) return 0u;
-    return (ns + 3 <= kSsSlots) ? atomicAdd(ts.ctr, 1u) : 0x7fffffffu - G;
+  float4* ring = ss + kSsSlots * kBlock;
+  // thread 0 is the producer: arm slot k's barrier and start both copies of tile `tile`
+  auto issue = [&](int k, int64_t tile) {
+    const int64_t q0 = tile * kBlock;
+    const unsigned bytes = static_cast<unsigned>(((nq - q0 < kBlock) ? (nq - q0) : kBlock) * sizeof(float4));
+    mbar_expect_tx(&bars[k], 2u * bytes);
+    bulk_g2s(ss + k * kBlock, pred + 4 * q0, bytes, &bars[k]);
+    bulk_g2s(ring + (k % kSsRing) * kBlock, gt + 4 * q0, bytes, &bars[k]);
   };
-  auto publish = [&](int sl, unsigned c) {
-    if (threadIdx.x == 0) ts.slot[sl] = static_cast<int>(G + c);
-  };
-  auto load = [&](int64_t tile, float4& p, float4& t) -> bool {
-    const int64_t q = tile * kBlock + threadIdx.x;
-    const bool ok = q < nq;
-    if (ok) {
-      p = Elem<PT>::template ld4<true>(pred + 4 * q);
-      t = __ldcs(reinterpret_cast<const float4*>(gt + 4 * q));   // the target is not needed again
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kSsSlots; ++k) mbar_init(&bars[k], 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int k = 0; k < kSsRing; ++k) {   // static head of the CTA's tile sequence
+      const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(k) * G;
+      list[k] = (tile < nt) ? static_cast<int>(tile) : -1;
+      if (tile < nt) issue(k, tile);
     }
-    return ok;
-  };
-  auto compute = [&](int64_t tile, bool ok, const float4& p, const float4& t) {
-    if (ok) ss[ns * kBlock + threadIdx.x] = eval_quad(body, pre, 4 * (tile * kBlock + threadIdx.x), p, t);
-    if (threadIdx.x == 0) list[ns] = static_cast<int>(tile);
-    ++ns;
-  };
-  int64_t tA = blockIdx.x, tB;
-  float4 pA, gA, pB, gB;
-  bool okA = false, okB = false;
-  unsigned claim = fetch();
-  if (tA < nt) okA = load(tA, pA, gA);
-  publish(0, claim);
+    for (int k = kSsRing; k < kSsSlots; ++k) list[k] = -1;
+  }
   __syncthreads();
-  tB = ts.slot[0];
-  while (tA < nt) {
-    claim = fetch();
-    okB = (tB < nt) && load(tB, pB, gB);
-    compute(tA, okA, pA, gA);
-    publish(1, claim);
-    __syncthreads();
-    tA = ts.slot[1];
-    if (tB >= nt) break;
-    claim = fetch();
-    okA = (tA < nt) && load(tA, pA, gA);
-    compute(tB, okB, pB, gB);
+  int k = 0;
+  for (; k < kSsSlots; ++k) {
+    const int tile = list[k];
+    if (tile < 0) break;
+    // claim the tile that will use slot k + kSsRing; its id is only needed after this tile's arithmetic
+    unsigned claim = 0u;
+    const bool want = (threadIdx.x == 0) && (k + kSsRing < kSsSlots);
+    if (want) claim = atomicAdd(ts.ctr, 1u);
+    mbar_wait(&bars[k], 0u);
+    const int64_t q = static_cast<int64_t>(tile) * kBlock + threadIdx.x;
+    if (q < nq) {
+      const float4 p = ss[k * kBlock + threadIdx.x];
+      const float4 t = ring[(k % kSsRing) * kBlock + threadIdx.x];
+      ss[k * kBlock + threadIdx.x] = eval_quad(body, pre, 4 * q, p, t);
+    }
     fold();
-    publish(0, claim);
-    __syncthreads();
-    tB = ts.slot[0];
+    __syncthreads();   // every thread is done with ring slot k % kSsRing: it may be refilled
+    if (want) {
+      const int64_t nxt = static_cast<int64_t>(kSsRing) * G + claim;
+      if (nxt < nt) {
+        list[k + kSsRing] = static_cast<int>(nxt);
+        issue(k + kSsRing, nxt);
+      }
+    }
+    // list[k + kSsRing] is read kSsRing - 1 iterations (and barriers) later
   }
   if (blockIdx.x == gridDim.x - 1) {  // n % 4 tail: summed here, its gradient is recomputed in the map phase
     const int64_t i = (nq << 2) + threadIdx.x;
     if (i < a.n) eval_one(body, pre, i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
   }
   __syncthreads();
-  return ns;
+  return k;
 }
 
-// gradient phase of the SS variant: own slots, last one first; body(p, d) -> gradient
-template <typename PT, typename Body>
-__device__ __forceinline__ void tiles_map_ss(const PT* __restrict__ pred, const float4* ss, const int* list, int ns,
-                                             PT* out, const LossArgs& a, Body&& body) {
+// Gradient phase of the SS variant. The predictions of the CTA's own tiles are requested (through L2)
+// BEFORE the grid barrier into registers - the reduce loop's registers are free by then - so their
+// latency is spent inside the barrier wait; after the barrier the phase is d_i from shared memory,
+// arithmetic and streaming stores, last slot first.
+template <typename PT>
+struct SsPred {
+  float4 p[kSsSlots];
+};
+template <typename PT>
+__device__ __forceinline__ void tiles_prefetch_ss(const PT* __restrict__ pred, const int* list, int ns, const LossArgs& a,
+                                                  SsPred<PT>& r) {
   const int64_t nq = a.n >> 2;
-  auto quad_of = [&](int sl) -> int64_t { return static_cast<int64_t>(list[sl]) * kBlock + threadIdx.x; };
-  auto emit = [&](int64_t q, const float4& p, const float4& d) {
-    float4 g;
-    g.x = body(p.x, d.x); g.y = body(p.y, d.y); g.z = body(p.z, d.z); g.w = body(p.w, d.w);
-    Elem<PT>::st4(out + 4 * q, g);
-  };
-  int sl = ns - 1;
-  for (; sl >= 1; sl -= 2) {
-    const int64_t q0 = quad_of(sl), q1 = quad_of(sl - 1);
-    const bool ok0 = q0 < nq, ok1 = q1 < nq;
-    float4 p0, p1;
-    if (ok0) p0 = Elem<PT>::template ld4<false>(pred + 4 * q0);
-    if (ok1) p1 = Elem<PT>::template ld4<false>(pred + 4 * q1);
-    if (ok0) emit(q0, p0, ss[sl * kBlock + threadIdx.x]);
-    if (ok1) emit(q1, p1, ss[(sl - 1) * kBlock + threadIdx.x]);
+#pragma unroll
+  for (int sl = 0; sl < kSsSlots; ++sl) {
+    if (sl < ns) {
+      const int64_t q = static_cast<int64_t>(list[sl]) * kBlock + threadIdx.x;
+      if (q < nq) r.p[sl] = Elem<PT>::template ld4<false>(pred + 4 * q);
+    }
   }
-  if (sl == 0) {
-    const int64_t q0 = quad_of(0);
-    if (q0 < nq) emit(q0, Elem<PT>::template ld4<false>(pred + 4 * q0), ss[threadIdx.x]);
+}
+template <typename PT, typename Body>
+__device__ __forceinline__ void tiles_map_ss(const SsPred<PT>& r, const float4* ss, const int* list, int ns, PT* out,
+                                             const LossArgs& a, Body&& body) {
+  const int64_t nq = a.n >> 2;
+#pragma unroll
+  for (int sl = kSsSlots - 1; sl >= 0; --sl) {
+    if (sl < ns) {
+      const int64_t q = static_cast<int64_t>(list[sl]) * kBlock + threadIdx.x;
+      if (q < nq) {
+        const float4 d = ss[sl * kBlock + threadIdx.x];
+        const float4 p = r.p[sl];
+        float4 g;
+        g.x = body(p.x, d.x); g.y = body(p.y, d.y); g.z = body(p.z, d.z); g.w = body(p.w, d.w);
+        Elem<PT>::st4(out + 4 * q, g);
+      }
+    }
   }
 }
 
@@ -561,7 +603,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   __shared__ float sm_f[kWarps];
   __shared__ int sm_tile[2];
   __shared__ int sm_list[SS ? kSsSlots : 1];
-  extern __shared__ float4 sm_ss[];  // SS: [kSsSlots][kBlock] residual quads
+  __shared__ __align__(8) unsigned long long sm_bars[SS ? kSsSlots : 1];
+  extern __shared__ float4 sm_ss[];  // SS: [kSsSlots + kSsRing][kBlock] quads (residual slots, target ring)
   static_assert(!SS || (KIND == MDE_LOSS_SILOG && std::is_same<PT, float>::value && VEC && !LONG), "SS is a SILog/fp32 variant");
   constexpr bool kCanStash = (KIND == MDE_LOSS_SILOG) && std::is_same<PT, float>::value;
   // residuals in log2 units: whenever they come from MUFU.LG2 (shared with the metric suite, or the SS variant)
@@ -610,6 +653,9 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   }
 
   // ---------------- phase A1: masked sums and counts ------------------------------------------------
+  double ss_mine = 0.0;                 // SS: this CTA's total q in thread q < 4
+  float met_run[MG ? 8 : 1];            // per-thread metric sums / counts handed to flush_metrics()
+  int met_cnt[MG ? 4 : 1];
   {
     float s0 = 0.f, s1 = 0.f;
     int c0 = 0, c1 = 0;
@@ -732,26 +778,39 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
         };
     // short runs: dynamically claimed tiles (balance matters, fixed costs dominate); long runs: one static
     // contiguous chunk per CTA with two quads per iteration (more independent work per instruction stream)
-    if constexpr (SS) ss_n = tiles_forward_ss<PT>(pred, gt, sm_ss, sm_list, a, TileSched{ukey + 2, sm_tile, true}, body_sum, pre_sum, fold);
+    if constexpr (SS) ss_n = tiles_forward_ss<PT>(pred, gt, sm_ss, sm_list, sm_bars, a, TileSched{ukey + 2, sm_tile, true}, body_sum, pre_sum, fold);
     else if constexpr (VEC && !LONG) tiles_forward<PT, kCanStash>(pred, gt, stash, a, TileSched{ukey + 2, sm_tile, a.sched == 0}, body_sum, pre_sum, fold);
     else chunk_forward<PT, VEC, kCanStash, false>(pred, gt, stash, a, body_sum, pre_sum, fold);
     trace_point(1);
     fold_now();
     run[2] = static_cast<double>(c0);
     run[3] = static_cast<double>(c1);
-    publish_sums<4>(run, gacc, sm_d);
+    if constexpr (SS && kSilogShare) {   // the suite's sum of squares / valid count complete the loss totals
+      run[1] += mrun[7];
+      run[2] += static_cast<double>(mc.n);
+    }
+    if constexpr (SS) ss_mine = block_sum<4>(run, sm_d);
+    else publish_sums<4>(run, gacc, sm_d);
     if constexpr (MG != 0) {
-      // 4 counts + 8 float sums: 32-lane tree in fp32 / REDUX, widened before crossing warps and CTAs
+#pragma unroll
+      for (int q = 0; q < 8; ++q) met_run[q] = static_cast<float>(mrun[q]);
+      met_cnt[0] = mc.n; met_cnt[1] = mc.c1; met_cnt[2] = mc.c2; met_cnt[3] = mc.c3;
+    }
+  }
+  // pooled metric sums of this CTA -> 12 fp64 atomics (4 counts + 8 float sums: 32-lane tree in fp32 /
+  // REDUX, widened before crossing warps and CTAs)
+  auto flush_metrics = [&] {
+    if constexpr (MG != 0) {
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-      const int r0 = __reduce_add_sync(0xffffffffu, mc.n), r1 = __reduce_add_sync(0xffffffffu, mc.c1);
-      const int r2 = __reduce_add_sync(0xffffffffu, mc.c2), r3 = __reduce_add_sync(0xffffffffu, mc.c3);
+      const int r0 = __reduce_add_sync(0xffffffffu, met_cnt[0]), r1 = __reduce_add_sync(0xffffffffu, met_cnt[1]);
+      const int r2 = __reduce_add_sync(0xffffffffu, met_cnt[2]), r3 = __reduce_add_sync(0xffffffffu, met_cnt[3]);
       if (lane == 0) {
         sm_d[0 * kWarps + warp] = r0; sm_d[1 * kWarps + warp] = r1;
         sm_d[2 * kWarps + warp] = r2; sm_d[3 * kWarps + warp] = r3;
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float sq = warp_sum(static_cast<float>(mrun[q])) * tile_scale<false>(q);
+        const float sq = warp_sum(met_run[q]) * tile_scale<false>(q);
         if (lane == 0) sm_d[(4 + q) * kWarps + warp] = static_cast<double>(sq);
       }
       __syncthreads();
@@ -763,18 +822,19 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       }
       __syncthreads();
     }
-  }
+  };
+  if constexpr (!SS) flush_metrics();
   trace_point(2);
+  SsPred<PT> ss_pred;
   // ---------------- grid barrier; its last arriver turns the totals into loss + coefficients ------------
-  double tS0 = 0.0, tS1 = 0.0, tN0 = 0.0, tN1 = 0.0, tloss = 0.0;   // only meaningful in the last arriver
-  grid_barrier_bcast(ukey + 6, ws.hdr->bcast, epoch * 4u + 2u, sm_k, [&](float (&v)[4]) {
-    double S0 = __ldcg(&gacc[0]), S1 = __ldcg(&gacc[1]);
-    double N0 = __ldcg(&gacc[2]), N1 = __ldcg(&gacc[3]);
+  double tS0 = 0.0, tS1 = 0.0, tN0 = 0.0, tN1 = 0.0, tloss = 0.0;   // only meaningful where coefficients() ran
+  // totals -> loss value and the fp32 gradient coefficients
+  auto coefficients = [&](double S0, double S1, double N0, double N1, float (&v)[4]) {
     if constexpr (kSilogLog2) {   // natural-log totals from the log2 sums
       S0 *= 0.69314718055994531;
       S1 *= 0.48045301391820142;
     }
-    if constexpr (kSilogShare) {  // + the suite's sum of squares / valid count (S1, N0 held the rare-path differences)
+    if constexpr (kSilogShare && !SS) {  // + the suite's sum of squares / valid count (S1, N0 held the rare-path differences)
       S1 += __ldcg(&gacc[kMetBase + MDE_Q_LNSQ]);
       N0 += __ldcg(&gacc[kMetBase + MDE_Q_NVALID]);
     }
@@ -814,14 +874,42 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     }
     v[0] = k1; v[1] = k2; v[2] = k3; v[3] = k4;
     tS0 = S0; tS1 = S1; tN0 = N0; tN1 = N1; tloss = loss;
-  }, [&] {
+  };
+  auto write_results = [&] {
     *a.loss_out = static_cast<float>(tloss);
     if (a.totals_out) {
       a.totals_out[0] = tS0; a.totals_out[1] = tS1; a.totals_out[2] = tN0; a.totals_out[3] = tN1;
       a.totals_out[4] = static_cast<double>(gmax); a.totals_out[5] = tloss;
     }
     ws.hdr->epoch = epoch + 1u;
-  });
+  };
+  if constexpr (SS) {
+    // ticket-free all-reduce of the four totals (common.cuh); every CTA derives the coefficients itself.
+    // While the slots travel: flush the metric sums (arrival counted on ukey[6] for the finaliser below)
+    // and request this CTA's predictions for the gradient phase.
+    __shared__ double sm_tot[4];
+    grid_sum4_bcast(ws.slots, epoch * 4u + 2u, ss_mine, sm_tot, sm_d, [&] {
+      flush_metrics();
+      if constexpr (MG != 0) {
+        if (threadIdx.x == kBlock - 32) {
+          __threadfence();               // the CTA's metric atomics (ordered by the __syncthreads above) before its arrival
+          atomicAdd(ukey + 6, 1u);
+        }
+      }
+      if (grad != nullptr) tiles_prefetch_ss<PT>(pred, sm_list, ss_n, a, ss_pred);
+    });
+    if (threadIdx.x == 0) {
+      float v[4];
+      coefficients(sm_tot[0], sm_tot[1], sm_tot[2], sm_tot[3], v);
+      sm_k[0] = v[0]; sm_k[1] = v[1]; sm_k[2] = v[2]; sm_k[3] = v[3];
+      if (blockIdx.x == 0) write_results();
+    }
+    __syncthreads();
+  } else {
+    grid_barrier_bcast(ukey + 6, ws.hdr->bcast, epoch * 4u + 2u, sm_k, [&](float (&v)[4]) {
+      coefficients(__ldcg(&gacc[0]), __ldcg(&gacc[1]), __ldcg(&gacc[2]), __ldcg(&gacc[3]), v);
+    }, write_results);
+  }
   trace_point(3);
   const float k1 = sm_k[0], k2 = sm_k[1], k3 = sm_k[2];
 
@@ -830,6 +918,13 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     // the LAST CTA forms them while everybody else already writes gradients (off the critical path)
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= kBlock - 32) {
       const int lane = threadIdx.x & 31;
+      if constexpr (SS) {   // the all-reduce above is no memory barrier: wait for every CTA's metric atomics
+        if (lane == 0) {
+          while (*reinterpret_cast<volatile unsigned*>(ukey + 6) < gridDim.x) {}
+          __threadfence();
+        }
+        __syncwarp();
+      }
       const bool own = lane < MDE_METRIC_NM;
       const double P = own ? __ldcg(&gacc[kMetBase + lane]) : 0.0;
       const double nn = __shfl_sync(0xffffffffu, P, MDE_Q_NVALID);
@@ -855,7 +950,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   // ---------------- phase B: gradient, chunk walked backwards ----------------------------------------
   if constexpr (SS) {
     const float ks1 = k3, ks2 = sm_k[3];
-    tiles_map_ss<PT>(pred, sm_ss, sm_list, ss_n, grad, a, [&](float p, float d) -> float {
+    tiles_map_ss<PT>(ss_pred, sm_ss, sm_list, ss_n, grad, a, [&](float p, float d) -> float {
       const bool v = __float_as_uint(d) != kStashInvalid;
       return v ? ks1 * (d - ks2) * rcp_nr(p) : 0.f;
     });
