@@ -77,9 +77,9 @@ static_assert(sizeof(WsHeader) == 256, "workspace header must be 256 bytes");
 constexpr int kGacc = 64;
 constexpr int kUkey = 16;
 constexpr int kIacc = 16;
-// [1536, +32768) slots[512][4][2] words {seq:32 | half of a double:32}: per-CTA partial totals of
+// [1536, +24576) slots[384][4][2] words {seq:32 | half of a double:32}: per-CTA partial totals of
 //              grid_sum4_bcast (self-validating, unique seq per launch and stage: never need zeroing)
-constexpr int kSlotCtas = 512;                       // >= resident CTAs of any cooperative launch here
+constexpr int kSlotCtas = 384;                       // >= resident CTAs of any cooperative launch here (2 x 148)
 constexpr size_t kSlotBytes = static_cast<size_t>(kSlotCtas) * 4 * 2 * 8;
 constexpr size_t kWsHeadBytes = 256 + 2 * kGacc * 8 + 2 * kUkey * 4 + 128;  // 1536
 constexpr size_t kWsFixedBytes = kWsHeadBytes + kSlotBytes;
@@ -212,9 +212,12 @@ __device__ __forceinline__ void grid_barrier_bcast(unsigned* ticket, unsigned lo
 // The summation order is fixed by the grid size, so the totals are bit-reproducible run to run.
 // `mine`: thread q < 4 passes this CTA's total q (as returned by block_sum<4>). Totals -> sm_tot[0..3].
 #ifdef __CUDACC__
-template <typename MidFn>
+// own_fn(q): this CTA's total q again, from shared memory - the thread that would poll the CTA's own slot
+// takes it from there (a load issued right behind another thread's store may still see the old word and
+// would cost the last arriver one more round trip).
+template <typename OwnFn, typename MidFn>
 __device__ __forceinline__ void grid_sum4_bcast(unsigned long long* slots, unsigned seq, double mine, double* sm_tot,
-                                                double* sm_scratch, MidFn&& mid_fn) {
+                                                double* sm_scratch, OwnFn&& own_fn, MidFn&& mid_fn) {
   const unsigned long long tag = static_cast<unsigned long long>(seq) << 32;
   if (threadIdx.x < 4) {
     const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine));
@@ -223,9 +226,14 @@ __device__ __forceinline__ void grid_sum4_bcast(unsigned long long* slots, unsig
     st_relaxed_u64(w + 1, tag | (b & 0xffffffffull));
   }
   mid_fn();
+  // (Measured: looking at the slots BEFORE mid_fn's loads are issued makes the barrier slower, not faster.)
   const int n = static_cast<int>(gridDim.x) * 4;
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += kBlock) {   // i & 3 == threadIdx.x & 3: one quantity per thread
+    if ((i >> 2) == static_cast<int>(blockIdx.x)) {
+      acc += own_fn(i & 3);
+      continue;
+    }
     const unsigned long long* w = slots + static_cast<size_t>(i) * 2;
     unsigned long long hi, lo;
     do {

@@ -494,37 +494,49 @@ __device__ __forceinline__ int tiles_forward_ss(const PT* __restrict__ pred, con
   return k;
 }
 
-// Gradient phase of the SS variant. The predictions of the CTA's own tiles are requested (through L2)
-// BEFORE the grid barrier into registers - the reduce loop's registers are free by then - so their
-// latency is spent inside the barrier wait; after the barrier the phase is d_i from shared memory,
-// arithmetic and streaming stores, last slot first.
-template <typename PT>
+// Gradient phase of the SS variant, last slot first. The predictions of the kSsPre slots that are consumed
+// first are requested (through L2) BEFORE the grid barrier into registers - the reduce loop's registers
+// are free by then - so their latency is spent inside the barrier wait; the remaining slots are requested
+// right after the barrier and consumed behind those. After the barrier the phase is d_i from shared memory,
+// arithmetic and streaming stores.
+template <typename PT, int kSsPre>
 struct SsPred {
-  float4 p[kSsSlots];
+  float4 p[kSsPre];
 };
-template <typename PT>
+template <typename PT, int kSsPre>
 __device__ __forceinline__ void tiles_prefetch_ss(const PT* __restrict__ pred, const int* list, int ns, const LossArgs& a,
-                                                  SsPred<PT>& r) {
+                                                  SsPred<PT, kSsPre>& r) {
   const int64_t nq = a.n >> 2;
 #pragma unroll
-  for (int sl = 0; sl < kSsSlots; ++sl) {
-    if (sl < ns) {
+  for (int j = 0; j < kSsPre; ++j) {
+    const int sl = ns - 1 - j;
+    if (sl >= 0) {
       const int64_t q = static_cast<int64_t>(list[sl]) * kBlock + threadIdx.x;
-      if (q < nq) r.p[sl] = Elem<PT>::template ld4<false>(pred + 4 * q);
+      if (q < nq) r.p[j] = Elem<PT>::template ld4<false>(pred + 4 * q);
     }
   }
 }
-template <typename PT, typename Body>
-__device__ __forceinline__ void tiles_map_ss(const SsPred<PT>& r, const float4* ss, const int* list, int ns, PT* out,
-                                             const LossArgs& a, Body&& body) {
+template <typename PT, int kSsPre, typename Body>
+__device__ __forceinline__ void tiles_map_ss(const PT* __restrict__ pred, const SsPred<PT, kSsPre>& r, const float4* ss,
+                                             const int* list, int ns, PT* out, const LossArgs& a, Body&& body) {
   const int64_t nq = a.n >> 2;
+  float4 late[(kSsSlots - kSsPre) > 0 ? (kSsSlots - kSsPre) : 1];
 #pragma unroll
-  for (int sl = kSsSlots - 1; sl >= 0; --sl) {
-    if (sl < ns) {
+  for (int j = kSsPre; j < kSsSlots; ++j) {
+    const int sl = ns - 1 - j;
+    if (sl >= 0) {
+      const int64_t q = static_cast<int64_t>(list[sl]) * kBlock + threadIdx.x;
+      if (q < nq) late[j - kSsPre] = Elem<PT>::template ld4<false>(pred + 4 * q);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kSsSlots; ++j) {
+    const int sl = ns - 1 - j;
+    if (sl >= 0) {
       const int64_t q = static_cast<int64_t>(list[sl]) * kBlock + threadIdx.x;
       if (q < nq) {
         const float4 d = ss[sl * kBlock + threadIdx.x];
-        const float4 p = r.p[sl];
+        const float4 p = (j < kSsPre) ? r.p[j < kSsPre ? j : 0] : late[j < kSsPre ? 0 : j - kSsPre];
         float4 g;
         g.x = body(p.x, d.x); g.y = body(p.y, d.y); g.z = body(p.z, d.z); g.w = body(p.w, d.w);
         Elem<PT>::st4(out + 4 * q, g);
@@ -599,6 +611,7 @@ constexpr int kMetBase = 16;  // gacc[kMetBase + q] = pooled raw metric sum q
 template <int KIND, typename PT, bool VEC, unsigned MG, bool LONG, bool SS = false>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArgs a) {
   __shared__ double sm_d[(MG ? 12 : 4) * kWarps];
+  __shared__ double sm_own[SS ? 4 * kWarps : 1];
   __shared__ float sm_k[4];
   __shared__ float sm_f[kWarps];
   __shared__ int sm_tile[2];
@@ -789,12 +802,27 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       run[1] += mrun[7];
       run[2] += static_cast<double>(mc.n);
     }
-    if constexpr (SS) ss_mine = block_sum<4>(run, sm_d);
-    else publish_sums<4>(run, gacc, sm_d);
     if constexpr (MG != 0) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) met_run[q] = static_cast<float>(mrun[q]);
       met_cnt[0] = mc.n; met_cnt[1] = mc.c1; met_cnt[2] = mc.c2; met_cnt[3] = mc.c3;
+    }
+    if constexpr (SS) {
+      // loss totals only (rows 0-3 of sm_own stay valid for the all-reduce below); the metric sums are
+      // flushed while the slots travel
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double sq = warp_sum(run[q]);
+        if (lane == 0) sm_own[q * kWarps + warp] = sq;
+      }
+      __syncthreads();
+      if (threadIdx.x < 4) {
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) ss_mine += sm_own[threadIdx.x * kWarps + w];
+      }
+    } else {
+      publish_sums<4>(run, gacc, sm_d);
     }
   }
   // pooled metric sums of this CTA -> 12 fp64 atomics (4 counts + 8 float sums: 32-lane tree in fp32 /
@@ -825,11 +853,13 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   };
   if constexpr (!SS) flush_metrics();
   trace_point(2);
-  SsPred<PT> ss_pred;
+  // slots requested before the barrier: all of them, or what fits beside the fused suite's live registers
+  constexpr int kSsPre = (MG != 0) ? 6 : kSsSlots;
+  SsPred<PT, kSsPre> ss_pred;
   // ---------------- grid barrier; its last arriver turns the totals into loss + coefficients ------------
-  double tS0 = 0.0, tS1 = 0.0, tN0 = 0.0, tN1 = 0.0, tloss = 0.0;   // only meaningful where coefficients() ran
+  struct Totals { double S0, S1, N0, N1, loss; };
   // totals -> loss value and the fp32 gradient coefficients
-  auto coefficients = [&](double S0, double S1, double N0, double N1, float (&v)[4]) {
+  auto coefficients = [&](double S0, double S1, double N0, double N1, float (&v)[4]) -> Totals {
     if constexpr (kSilogLog2) {   // natural-log totals from the log2 sums
       S0 *= 0.69314718055994531;
       S1 *= 0.48045301391820142;
@@ -873,13 +903,13 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       k3 = 2.f * cthr + 1e-9f;
     }
     v[0] = k1; v[1] = k2; v[2] = k3; v[3] = k4;
-    tS0 = S0; tS1 = S1; tN0 = N0; tN1 = N1; tloss = loss;
+    return Totals{S0, S1, N0, N1, loss};
   };
-  auto write_results = [&] {
-    *a.loss_out = static_cast<float>(tloss);
+  auto write_results = [&](const Totals& t) {
+    *a.loss_out = static_cast<float>(t.loss);
     if (a.totals_out) {
-      a.totals_out[0] = tS0; a.totals_out[1] = tS1; a.totals_out[2] = tN0; a.totals_out[3] = tN1;
-      a.totals_out[4] = static_cast<double>(gmax); a.totals_out[5] = tloss;
+      a.totals_out[0] = t.S0; a.totals_out[1] = t.S1; a.totals_out[2] = t.N0; a.totals_out[3] = t.N1;
+      a.totals_out[4] = static_cast<double>(gmax); a.totals_out[5] = t.loss;
     }
     ws.hdr->epoch = epoch + 1u;
   };
@@ -888,34 +918,45 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     // While the slots travel: flush the metric sums (arrival counted on ukey[6] for the finaliser below)
     // and request this CTA's predictions for the gradient phase.
     __shared__ double sm_tot[4];
-    grid_sum4_bcast(ws.slots, epoch * 4u + 2u, ss_mine, sm_tot, sm_d, [&] {
+    __shared__ double sm_gather[kWarps * 4];
+    grid_sum4_bcast(ws.slots, epoch * 4u + 2u, ss_mine, sm_tot, sm_gather, [&](int q) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) tot += sm_own[q * kWarps + w];
+      return tot;
+    }, [&] {
       flush_metrics();
-      if constexpr (MG != 0) {
-        if (threadIdx.x == kBlock - 32) {
-          __threadfence();               // the CTA's metric atomics (ordered by the __syncthreads above) before its arrival
-          atomicAdd(ukey + 6, 1u);
-        }
-      }
-      if (grad != nullptr) tiles_prefetch_ss<PT>(pred, sm_list, ss_n, a, ss_pred);
+      if (grad != nullptr) tiles_prefetch_ss<PT, kSsPre>(pred, sm_list, ss_n, a, ss_pred);
     });
     if (threadIdx.x == 0) {
       float v[4];
-      coefficients(sm_tot[0], sm_tot[1], sm_tot[2], sm_tot[3], v);
+      const Totals t = coefficients(sm_tot[0], sm_tot[1], sm_tot[2], sm_tot[3], v);
       sm_k[0] = v[0]; sm_k[1] = v[1]; sm_k[2] = v[2]; sm_k[3] = v[3];
-      if (blockIdx.x == 0) write_results();
+      if (blockIdx.x == 0) write_results(t);
     }
     __syncthreads();
+    if constexpr (MG != 0) {
+      // arrival for the metric finaliser (end of the kernel), off everybody's critical path: the CTA's
+      // metric atomics (flush_metrics) were issued before the __syncthreads above, so this fence orders them
+      if (threadIdx.x == kBlock - 32) {
+        __threadfence();
+        atomicAdd(ukey + 6, 1u);
+      }
+    }
   } else {
+    Totals tt{0.0, 0.0, 0.0, 0.0, 0.0};   // only meaningful in the last arriver
     grid_barrier_bcast(ukey + 6, ws.hdr->bcast, epoch * 4u + 2u, sm_k, [&](float (&v)[4]) {
-      coefficients(__ldcg(&gacc[0]), __ldcg(&gacc[1]), __ldcg(&gacc[2]), __ldcg(&gacc[3]), v);
-    }, write_results);
+      tt = coefficients(__ldcg(&gacc[0]), __ldcg(&gacc[1]), __ldcg(&gacc[2]), __ldcg(&gacc[3]), v);
+    }, [&] { write_results(tt); });
   }
   trace_point(3);
   const float k1 = sm_k[0], k2 = sm_k[1], k3 = sm_k[2];
 
+  // pooled metric values (one mean over all valid pixels of the call, metrics.py:58-67), formed by the LAST
+  // warp of the LAST CTA: right after the ticket barrier, or (SS) at the very end of the kernel, when every
+  // CTA's arrival has long been counted
+  auto finalize_metrics = [&] {
   if constexpr (MG != 0) {
-    // pooled metric values (one mean over all valid pixels of the call, metrics.py:58-67): the LAST warp of
-    // the LAST CTA forms them while everybody else already writes gradients (off the critical path)
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= kBlock - 32) {
       const int lane = threadIdx.x & 31;
       if constexpr (SS) {   // the all-reduce above is no memory barrier: wait for every CTA's metric atomics
@@ -944,13 +985,18 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       if (lane == 0) a.met_f64[2 * MDE_METRIC_NM + MDE_METRIC_NQ] = (a.n_img == 1 && nn > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
     }
   }
-  if (grad == nullptr) return;
+  };
+  if constexpr (!SS) finalize_metrics();
+  if (grad == nullptr) {
+    if constexpr (SS) finalize_metrics();
+    return;
+  }
   trace_point(4);
 
   // ---------------- phase B: gradient, chunk walked backwards ----------------------------------------
   if constexpr (SS) {
     const float ks1 = k3, ks2 = sm_k[3];
-    tiles_map_ss<PT>(ss_pred, sm_ss, sm_list, ss_n, grad, a, [&](float p, float d) -> float {
+    tiles_map_ss<PT, kSsPre>(pred, ss_pred, sm_ss, sm_list, ss_n, grad, a, [&](float p, float d) -> float {
       const bool v = __float_as_uint(d) != kStashInvalid;
       return v ? ks1 * (d - ks2) * rcp_nr(p) : 0.f;
     });
@@ -964,6 +1010,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       }
     }
     trace_point(5);
+    finalize_metrics();
     return;
   }
   if constexpr (kCanStash) {
