@@ -345,10 +345,17 @@ def main():
             kern[name] = {"us_per_launch": us, "algorithmic_bytes": BYTES_PER_PX[name] * npx, "achieved_gbs": gbs,
                           "frac_of_peak": gbs / peak, "launches_timed": reps * args.ring, "graph": kg is not None}
     dom = "silog_fwd_bwd" if args.unfused else "silog_metrics_fused"   # the kernel the timed step launches
+    traffic = None   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (C2 batch only)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if dom in tj and args.batch == 16:
+            traffic = float(tj[dom]["dram_read_bytes"] + tj[dom]["dram_write_bytes"])
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                "frac": kern[dom]["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
                 "frac_of_nominal_8000": kern[dom]["achieved_gbs"] / 8000.0, "kernels": kern,
-                "note": "launches replayed from a CUDA graph (no host launch cost); per-launch ncu times are in profiles/"}
+                "note": "launches replayed from a CUDA graph (no host launch cost); per-launch ncu times and the traffic capture are in profiles/r01_ncu_summary_final.md"}
 
     # ---- e2e: public API, host (pinned) inputs, H2D + D2H inside the timed region -----------------------
     hp, hg = [], []

@@ -84,3 +84,27 @@ def test_point_cloud(Cr):
     batch = torch.from_numpy(np.stack([depth, depth * 0.5])).cuda()
     ob = PC.point_cloud(batch, cam)
     np.testing.assert_allclose(np.nan_to_num(ob[0].cpu().numpy()), np.nan_to_num(ref), rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("shape", [(48, 64), (30, 1028), (480, 640)])
+def test_point_cloud_tiled_path(Cr, shape):
+    """w % 4 == 0 takes the 128-bit tiled kernel (shared-memory staged stores, reciprocal + residual divide):
+    same values as the fp64 oracle to the last bits, partial last tile, batch, world transform."""
+    from mono_depth_estimation_b200 import pointcloud as PC
+    rs = np.random.RandomState(11)
+    depth = (rs.rand(3, *shape) * 12).astype(np.float32)
+    depth[:, 0, :7] = 0.05; depth[1, 3, 3] = 200.0
+    cam = PC.Camera(angle_x=0.8575560450553894, clip_start=0.1, clip_end=100.0,
+                    matrix_world=[[0.68, -0.32, 0.65, 7.35], [0.73, 0.31, -0.61, -6.92], [-0.01, 0.89, 0.45, 4.95], [0, 0, 0, 1]])
+    out = PC.point_cloud(torch.from_numpy(depth).cuda(), cam).cpu().numpy()
+    assert out.dtype == np.float64 and out.shape == (3, *shape, 3)
+    for b in range(3):
+        ref = opc.point_cloud(depth[b], cam.angle_x, cam.clip_start, cam.clip_end)
+        assert np.array_equal(np.isnan(out[b]), np.isnan(ref))
+        np.testing.assert_allclose(np.nan_to_num(out[b]), np.nan_to_num(ref), rtol=1e-15, atol=0)
+        assert np.array_equal(np.signbit(out[b][..., 0]), np.signbit(ref[..., 0]))      # -0.0 at invalid pixels
+    ref0 = opc.point_cloud(depth[0], cam.angle_x, cam.clip_start, cam.clip_end)
+    out32 = PC.point_cloud(torch.from_numpy(depth[0]).cuda(), cam, dtype=torch.float32).cpu().numpy()
+    np.testing.assert_array_equal(np.nan_to_num(out32), np.nan_to_num(ref0.astype(np.float32)))
+    outw = PC.point_cloud_world(depth[0], cam)
+    np.testing.assert_allclose(np.nan_to_num(outw), np.nan_to_num(opc.to_world(ref0, cam.matrix_world)), rtol=1e-6, atol=1e-6)
