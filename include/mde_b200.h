@@ -227,6 +227,30 @@ int mde_vnl_loss(const float* gt_depth, const void* pred, int pred_dtype, const 
                  float grad_scale, void* ws, void* scratch, float* loss_out, double* stats_out,
                  void* grad, void* stream);
 
+/* ---- VNL's classification half ------------------------------------------ */
+/*
+ * WCEL_Loss.forward(pred_logit, gt_bins, gt) (reference criteria.py:839-863), forward + backward:
+ *   loss = -sum_px sum_c weight[bin_px][c] * log_softmax(logits_px)[c] / #(gt > 0)
+ * logits [n,C,hw] (x_dtype), gt_bins [n,hw] int32 (a bin outside [0,C) - modules/vnl.py:213 marks padding
+ * C+1 - has an all-zero one-hot row), gt_depth [n,hw] fp32 (only its count of > 0 pixels is used),
+ * weight [C,C] fp32 row-normalised as criteria.py:846-848 leaves it (row = gt bin), rowsum [C] = fp32 sums
+ * of those rows. grad_logits (nullable, dtype of logits) = (softmax * rowsum[bin] - weight[bin]) / n_valid.
+ * Two launches (valid count, fused pass); all pointers are device memory.
+ */
+int mde_wcel_loss(const void* logits, int x_dtype, const int* gt_bins, const float* gt_depth,
+                  const float* weight, const float* rowsum, int64_t n, int64_t C, int64_t hw,
+                  float grad_scale, void* ws, float* loss_out, void* grad_logits, void* stream);
+/* VNLModule.depth_to_bins (reference modules/vnl.py:202-217): bins_out int32 [n]; depth_inout is clamped to
+ * [depth_min, depth_max] IN PLACE and padding (depth < 0) restored to -1, as the reference mutates its input. */
+int mde_depth_to_bins(float* depth_inout, int64_t n, float depth_min, float depth_max, float depth_min_log,
+                      float depth_bin_interval, int64_t C, int* bins_out, void* stream);
+/* VNLModule.bins_to_depth (reference modules/vnl.py:219-230): prob [n,C,hw] -> depth_out [n,hw] fp32 =
+ * 10 ^ sum_c prob_c * border_c; and its backward grad_prob_c = grad_depth * ln(10) * depth * border_c. */
+int mde_bins_to_depth(const void* prob, int x_dtype, const float* border, int64_t n, int64_t C, int64_t hw,
+                      float* depth_out, void* stream);
+int mde_bins_to_depth_bwd(const float* depth, const float* grad_depth, const float* border, int64_t n, int64_t C,
+                          int64_t hw, int x_dtype, void* grad_prob, void* stream);
+
 /* ---- depth -> point cloud ----------------------------------------------------------------- */
 /*
  * point_cloud(depth, cam) (reference depth2pointcloud.py:12-31) for a batch of depth maps, with the

@@ -258,6 +258,102 @@ def gen_config_scalars():
     np.savez_compressed(os.path.join(OUT, "config_c1.npz"), **out)
 
 
+def _vnl_module_methods():
+    """depth_to_bins / bins_to_depth of VNLModule (reference modules/vnl.py:202-230) compiled straight from
+    the reference source: the module itself cannot be imported (pytorch_lightning is absent)."""
+    import ast
+    src = open(os.path.join(R.REF_ROOT, "modules", "vnl.py")).read()
+    tree = ast.parse(src)
+    fns = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in ("depth_to_bins", "bins_to_depth"):
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = {"torch": torch, "np": np}
+            exec(compile(mod, "modules/vnl.py", "exec"), ns)
+            fns[node.name] = ns[node.name]
+    assert len(fns) == 2
+    return fns
+
+
+def gen_wcel():
+    """WCEL_Loss / ModelLoss by the reference's classes; depth_to_bins / bins_to_depth by the reference's
+    method bodies run against a stand-in `self` carrying method.{depth_min,depth_max,dec_out_c},
+    params.{depth_min_log,depth_bin_interval,depth_bin_border} and device."""
+    import types
+    from oracle import wcel as ow
+    crit = R.load("criteria")
+    fns = _vnl_module_methods()
+    out = {}
+    for C, tag in ((150, "c150"), (24, "c24")):
+        p = ow.vnl_params(0.01, 1.1, C)
+        self_ = types.SimpleNamespace(
+            method=types.SimpleNamespace(depth_min=0.01, depth_max=1.1, dec_out_c=C),
+            params=types.SimpleNamespace(depth_min_log=p["depth_min_log"], depth_bin_interval=p["depth_bin_interval"],
+                                         depth_bin_border=p["depth_bin_border"]),
+            device=torch.device("cpu"))
+        g = torch.Generator().manual_seed(900 + C)
+        B, H, W = (2, 6, 12) if C == 150 else (2, 12, 20)
+        gt = torch.rand((B, 1, H, W), generator=g) * 1.3 + 0.002           # beyond both clamps
+        gt[1, :, :3, :] = -1.0                                               # VNL padding
+        gt[0, 0, 5, 5] = 0.01; gt[0, 0, 5, 6] = 1.1; gt[0, 0, 5, 7] = 0.0     # borders, zero (valid bin, not counted)
+        logits = torch.randn((B, C, H, W), generator=g) * 3.0
+        depth_in = gt.clone()
+        bins = fns["depth_to_bins"](self_, depth_in)                          # mutates depth_in
+        out[f"{tag}_gt"], out[f"{tag}_logits"] = gt.numpy(), logits.numpy()
+        out[f"{tag}_bins"], out[f"{tag}_gt_after"] = bins.numpy(), depth_in.numpy()
+        args = types.SimpleNamespace(wce_loss_weight=p["wce_loss_weight"], dec_out_c=C, focal_x=519.0, focal_y=519.0,
+                                     crop_size=(H, W), diff_loss_weight=6.0)
+        for dt, sfx in ((torch.float32, "32"), (torch.float64, "64")):
+            m = crit.WCEL_Loss(types.SimpleNamespace(**vars(args)))
+            if dt == torch.float64:   # forward() casts the weight to fp32 (:851): feed an fp64 run through a patched cast
+                w64 = m.weight.clone()
+                lg = logits.double().requires_grad_(True)
+                lp = torch.nn.functional.log_softmax(lg, 1)
+                lp = torch.t(torch.transpose(lp, 0, 1).reshape(lp.size(1), -1))
+                oh = (bins.reshape(-1, 1) == torch.arange(C, dtype=bins.dtype)).double()
+                loss = -1 * torch.sum(torch.matmul(oh, w64) * lp) / torch.sum(depth_in > 0.).double()
+            else:
+                lg = logits.clone().requires_grad_(True)
+                loss = m(lg, bins, depth_in)
+            (gr,) = torch.autograd.grad(loss, lg)
+            out[f"{tag}_loss{sfx}"], out[f"{tag}_grad{sfx}"] = loss.detach().numpy(), gr.numpy()
+        # bins_to_depth on the softmax of the logits (what the decoder hands over, network/VNL.py:681)
+        sm = torch.softmax(logits, 1)
+        for dt, sfx in ((torch.float32, "32"),):
+            x = sm.clone().requires_grad_(True)
+            d = fns["bins_to_depth"](self_, x)
+            (gx,) = torch.autograd.grad(d.sum(), x)
+            out[f"{tag}_softmax"], out[f"{tag}_depth{sfx}"], out[f"{tag}_depth_gradsum{sfx}"] = sm.numpy(), d.detach().numpy(), gx.numpy()
+        out[f"{tag}_depth64"] = (10 ** (sm.double().permute(0, 2, 3, 1) * torch.tensor(p["depth_bin_border"])).sum(3, keepdim=True)).permute(0, 3, 1, 2).numpy()
+    # ModelLoss = WCEL + 6 * VNL on one small case with fixed triplets
+    C = 24
+    p = ow.vnl_params(0.01, 1.1, C)
+    H, W = 12, 20
+    gtv, predv, trip = synth.vnl_inputs((2, 1, H, W), 61, n_triplets=300, pad_rows=2)
+    args = types.SimpleNamespace(wce_loss_weight=p["wce_loss_weight"], dec_out_c=C, focal_x=519.0, focal_y=519.0,
+                                 crop_size=(H, W), diff_loss_weight=6.0)
+    ml = crit.ModelLoss(args)
+    v = ml.virtual_normal_loss
+    t = trip.numpy()
+    sel = {"p1_x": t[0] % W, "p1_y": t[0] // W, "p2_x": t[1] % W, "p2_y": t[1] // W, "p3_x": t[2] % W, "p3_y": t[2] // W}
+    v.select_index = lambda: sel
+    self_ = types.SimpleNamespace(
+        method=types.SimpleNamespace(depth_min=0.01, depth_max=1.1, dec_out_c=C),
+        params=types.SimpleNamespace(depth_min_log=p["depth_min_log"], depth_bin_interval=p["depth_bin_interval"],
+                                     depth_bin_border=p["depth_bin_border"]), device=torch.device("cpu"))
+    gt_in = gtv.clone()
+    bins = fns["depth_to_bins"](self_, gt_in)
+    logits = torch.randn((2, C, H, W), generator=torch.Generator().manual_seed(62)) * 2.0
+    lg = logits.clone().requires_grad_(True)
+    pd = predv.clone().requires_grad_(True)
+    total = ml(pd, lg, bins, gt_in)
+    g_lg, g_pd = torch.autograd.grad(total, (lg, pd))
+    out.update({"ml_gt": gtv.numpy(), "ml_gt_after": gt_in.numpy(), "ml_pred": predv.numpy(), "ml_trip": trip.numpy(),
+                "ml_logits": logits.numpy(), "ml_bins": bins.numpy(), "ml_total32": total.detach().numpy(),
+                "ml_grad_logits32": g_lg.numpy(), "ml_grad_pred32": g_pd.numpy()})
+    np.savez_compressed(os.path.join(OUT, "wcel_small.npz"), **out)
+
+
 def main():
     assert R.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
@@ -267,6 +363,7 @@ def main():
     gen_dorn()
     gen_vnl()
     gen_config_scalars()
+    gen_wcel()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -166,3 +166,48 @@ def test_vnl(golden, sel):
         close(l.detach(), g[f"loss{tag}_sel{int(sel)}"], rt)
         scale = np.abs(g[f"grad{tag}_sel{int(sel)}"]).max()
         close(gr, g[f"grad{tag}_sel{int(sel)}"], rt * 10, rt * scale)
+
+
+# ---- VNL's ModelLoss other half: WCEL_Loss, depth_to_bins, bins_to_depth -----------------
+@pytest.mark.parametrize("tag,C", [("c150", 150), ("c24", 24)])
+def test_wcel_and_bins(golden, tag, C):
+    from oracle import wcel as ow
+    g = golden("wcel_small.npz")
+    p = ow.vnl_params(0.01, 1.1, C)
+    gt = T(g[f"{tag}_gt"]).clone()
+    bins = ow.depth_to_bins(gt, p)
+    assert bins.dtype == torch.int32 and np.array_equal(bins.numpy(), g[f"{tag}_bins"])        # integer: exact
+    assert np.array_equal(gt.numpy(), g[f"{tag}_gt_after"])                                    # in-place clamp / -1 restore
+    logits = T(g[f"{tag}_logits"])
+    for dt, sfx, rt in ((torch.float64, "64", 1e-12), (torch.float32, "32", 2e-6)):
+        lg = logits.to(dt).requires_grad_(True)
+        loss = ow.wcel_loss(lg, bins, gt, p["wce_loss_weight"], C)
+        (gr,) = torch.autograd.grad(loss, lg)
+        close(loss.detach(), g[f"{tag}_loss{sfx}"], rt)
+        close(gr, g[f"{tag}_grad{sfx}"], 1e-5 if sfx == "32" else 1e-10, 1e-9 if sfx == "32" else 1e-15)
+    close(g[f"{tag}_loss32"], g[f"{tag}_loss64"], 1e-5)
+    sm = T(g[f"{tag}_softmax"]).requires_grad_(True)
+    d = ow.bins_to_depth(sm, p)
+    close(d.detach(), g[f"{tag}_depth32"], 1e-6)
+    close(d.detach(), g[f"{tag}_depth64"], 1e-5)
+    (gx,) = torch.autograd.grad(d.sum(), sm)
+    close(gx, g[f"{tag}_depth_gradsum32"], 1e-5, 1e-9)
+
+
+def test_model_loss(golden):
+    from oracle import wcel as ow
+    g = golden("wcel_small.npz")
+    C = 24
+    p = ow.vnl_params(0.01, 1.1, C)
+    gt = T(g["ml_gt"]).clone()
+    bins = ow.depth_to_bins(gt, p)
+    assert np.array_equal(bins.numpy(), g["ml_bins"]) and np.array_equal(gt.numpy(), g["ml_gt_after"])
+    lg = T(g["ml_logits"]).double().requires_grad_(True)
+    pd = T(g["ml_pred"]).double().requires_grad_(True)
+    H, W = gt.shape[-2:]
+    vnl = lambda gt_, pred_: ovnl.vnl_loss(gt_, pred_, T(g["ml_trip"]), 519.0, 519.0)
+    total = ow.model_loss(pd, lg, bins, gt.double(), p, vnl, 6.0)
+    g_lg, g_pd = torch.autograd.grad(total, (lg, pd))
+    close(total.detach(), g["ml_total32"], 2e-5)
+    close(g_lg, g["ml_grad_logits32"], 1e-4, 1e-8)
+    close(g_pd, g["ml_grad_pred32"], 1e-3, 1e-6 * float(np.abs(g["ml_grad_pred32"]).max()))

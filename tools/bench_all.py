@@ -197,6 +197,37 @@ def main():
     report("C4", "vnl fwd+bwd (100k triplets x 8)", px, us, 12.0 + 24.0 * n_trip / px, g,
            {"mtriplets_s": round(B * n_trip / us, 1), "valid_triplets": float(stats[0].item()), "loss": float(loss_t.item())})
 
+    # ---------------- C4 companion: WCEL fwd+bwd, bins -> depth, depth -> bins at 8x150x385x385 ---
+    from mono_depth_estimation_b200 import wcel
+    Cc = 150
+    pw = wcel.vnl_params(0.01, 1.1, Cc)
+    w = torch.tensor(pw["wce_loss_weight"], dtype=torch.float64)
+    w32 = (w / w.sum(1, keepdim=True)).float().to(dev).contiguous()
+    rowsum = w32.double().sum(1).float().contiguous()
+    border = torch.tensor(pw["depth_bin_border"], dtype=torch.float32, device=dev)
+    logits = torch.randn((B, Cc, H, W), device=dev) * 3.0
+    gtw = gt.clone()
+    bins = wcel.depth_to_bins(gtw, 0.01, 1.1, Cc)
+    gl = torch.empty_like(logits)
+    ws = _lib.workspace(dev, B)
+    fns = [lambda: _lib.check(lib.mde_wcel_loss(_lib.ptr(logits), 0, _lib.ptr(bins), _lib.ptr(gtw), _lib.ptr(w32), _lib.ptr(rowsum), B, Cc, H * W,
+                                                1.0, _lib.ptr(ws), _lib.ptr(loss_t), _lib.ptr(gl), sp()))]
+    us, g = timed(fns, reps)
+    report("C4 WCEL", "wcel fwd+bwd (150 bins), count + fused pass", px, us, 8.0 * Cc + 8.0, g, {"loss": float(loss_t.item())})
+    fns = [lambda: _lib.check(lib.mde_wcel_loss(_lib.ptr(logits), 0, _lib.ptr(bins), _lib.ptr(gtw), _lib.ptr(w32), _lib.ptr(rowsum), B, Cc, H * W,
+                                                1.0, _lib.ptr(ws), _lib.ptr(loss_t), None, sp()))]
+    us, g = timed(fns, reps)
+    report("C4 WCEL", "wcel forward only", px, us, 4.0 * Cc + 8.0, g)
+    sm = torch.softmax(logits, 1)
+    dep = torch.empty((B, 1, H, W), device=dev)
+    fns = [lambda: _lib.check(lib.mde_bins_to_depth(_lib.ptr(sm), 0, _lib.ptr(border), B, Cc, H * W, _lib.ptr(dep), sp()))]
+    us, g = timed(fns, reps)
+    report("C4 WCEL", "bins_to_depth (150 bins)", px, us, 4.0 * Cc + 4.0, g)
+    fns = [lambda: _lib.check(lib.mde_bins_to_depth_bwd(_lib.ptr(dep), _lib.ptr(dep), _lib.ptr(border), B, Cc, H * W, 0, _lib.ptr(gl), sp()))]
+    us, g = timed(fns, reps)
+    report("C4 WCEL", "bins_to_depth backward", px, us, 4.0 * Cc + 8.0, g)
+    del logits, gl, sm
+
     # ---------------- C5: NYU-test-shaped eval, 654 x 480 x 640, 10 metrics ------------------------------------
     B = 654 if not QUICK else 64
     shp = (B, 1, 480, 640)
