@@ -151,11 +151,33 @@ def run_reference_arm(args, shape):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
+
+
+# The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner to
+# stdout at init): file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved one.
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -408,7 +430,7 @@ def main():
                            "collective": None if world == 1 else "all-reduce of 12 doubles every %d steps (NCCL)" % args.sync_every},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step) * K,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
