@@ -204,3 +204,68 @@ def test_loss_with_fused_metrics(Cr, name, names):
         vals2 = mc.compute((p.detach() * 1.0), g)
         assert _lib.launch_count() - n0 >= 3
         close(torch.stack(vals2), v64, 1e-5)
+
+
+def _silog_both(Cr, pred, gt, names=("delta1", "delta2", "delta3", "mse", "mae", "log10", "rmse")):
+    """(plain loss, grad), (fused loss, grad, metric values) of SILog on the same tensors."""
+    from mono_depth_estimation_b200 import metrics as M
+    loss, grad = run_loss(Cr.silog_loss(0.85), pred.cuda(), gt.cuda())
+    mc = M.MetricComputation(list(names), strict=False)
+    crit = Cr.silog_loss(0.85).fuse_metrics(mc)
+    p = pred.cuda().requires_grad_(True)
+    lf = crit(p, gt.cuda())
+    vals = mc.compute(p.detach(), gt.cuda())
+    lf.backward()
+    return (loss, grad), (lf.detach(), p.grad.detach(), torch.stack(vals))
+
+
+def test_silog_shared_memory_variant_rare_quads(Cr):
+    """The fast path of the SS kernels assumes valid targets > 0.01 and predictions >= 1e-7 per QUAD and sends
+    every other quad through the exact arithmetic: targets in (0, 0.01] (valid for the metrics, masked for the
+    loss, criteria.py:730), exactly 0.01, a subnormal target, predictions below the metrics' clamp."""
+    from oracle import metrics as ometrics
+    names = ["delta1", "delta2", "delta3", "mse", "mae", "log10", "rmse"]
+    pred, gt = synth.depth_pair((2, 1, 40, 64), 81, border=2)
+    gt[0, 0, 10, 8:20] = torch.linspace(1e-4, 0.0099, 12)
+    gt[0, 0, 11, 8] = 0.01
+    gt[0, 0, 12, 9] = 0.010001
+    pred[1, 0, 21, 31] = 3e-8                          # below the metrics clamp, a legal SILog operand
+    l64, g64 = olosses.loss_and_grad(olosses.silog, pred.double(), gt.double())
+    v64 = [float(v) for v in ometrics.compute(pred.double(), gt.double(), names)]
+    (lp, gp), (lf, gf, vf) = _silog_both(Cr, pred, gt, names)
+    close(lp, l64, LOSS_RTOL); grad_close(gp, g64)
+    close(lf, l64, LOSS_RTOL); grad_close(gf, g64)
+    close(vf, v64, 1e-5)
+    # a subnormal (valid) target: masked for the loss, still a pixel of the metric suite ('rmse' would overflow
+    # fp32 there in the reference as well, so it is left out of this list)
+    names2 = ["delta1", "delta2", "delta3", "mae", "log10"]
+    gt2 = gt.clone(); gt2[1, 0, 20, 30] = 1e-39
+    l64b, g64b = olosses.loss_and_grad(olosses.silog, pred.double(), gt2.double())
+    v64b = [float(v) for v in ometrics.compute(pred.double(), gt2.double(), names2)]
+    (lp, gp), (lf, gf, vf) = _silog_both(Cr, pred, gt2, names2)
+    close(lp, l64b, LOSS_RTOL); grad_close(gp, g64b)
+    close(lf, l64b, LOSS_RTOL); grad_close(gf, g64b)
+    close(vf, v64b, 1e-5)
+    # non-positive predictions under the mask poison the loss exactly as the reference's log does
+    for bad in (0.0, -1.0, float("nan")):
+        p2 = pred.clone(); p2[0, 0, 30, 40] = bad
+        assert gt[0, 0, 30, 40] > 0.01
+        (lp, _), (lf, _, _) = _silog_both(Cr, p2, gt, names)
+        assert torch.isnan(lp) and torch.isnan(lf), bad
+
+
+@pytest.mark.parametrize("extra_tiles", [0, 1])
+def test_silog_shared_memory_variant_capacity_boundary(Cr, extra_tiles):
+    """The SS kernels hold at most 10 tiles of 2048 px per CTA: a batch of exactly grid x 10 tiles runs there,
+    one tile more takes the generic kernel; both must agree with the oracle (and with each other)."""
+    from mono_depth_estimation_b200 import _lib
+    import ctypes as C
+    sm, coop = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.load().mde_device_info(C.byref(sm), C.byref(coop)))
+    tiles = coop.value * 10 + extra_tiles
+    shape = (1, 1, tiles, 2048)
+    pred, gt = synth.depth_pair(shape, 82, border=0)
+    l64, g64 = olosses.loss_and_grad(olosses.silog, pred.double(), gt.double())
+    (lp, gp), (lf, gf, _) = _silog_both(Cr, pred, gt)
+    close(lp, l64, LOSS_RTOL); grad_close(gp, g64)
+    close(lf, l64, LOSS_RTOL); grad_close(gf, g64)
