@@ -404,8 +404,8 @@ __device__ __forceinline__ void tiles_map(const PT* __restrict__ pred, const flo
 // kSsRing tiles of a CTA are static (cta + j x grid), the rest are claimed from an atomic counter (HBM/L2
 // bandwidth is not shared fairly between SMs); a CTA stops claiming when its slots are committed and the
 // launch guarantees grid x kSsSlots >= number of tiles.
-constexpr int kSsSlots = 10;
-constexpr int kSsRing = 3;
+constexpr int kSsSlots = 11;
+constexpr int kSsRing = 2;
 constexpr size_t kSsBytes = static_cast<size_t>(kSsSlots + kSsRing) * kBlock * sizeof(float4);
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
