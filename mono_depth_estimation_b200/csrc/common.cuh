@@ -201,6 +201,37 @@ __device__ __forceinline__ void grid_barrier_bcast(unsigned* ticket, unsigned lo
 }
 #endif
 
+// ---- bulk-copy engine (cp.async.bulk, SASS UBLKCP) + mbarrier -------------------------------------------
+// One thread arms an mbarrier with the byte count and starts a contiguous global -> shared copy; the
+// consumers wait on the barrier's phase parity. Copies cost no registers and run arbitrarily far ahead.
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// contiguous global -> shared copy by the bulk-copy engine; completion is counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+#endif
+
 // ---- grid-wide sum of four doubles without a ticket ---------------------------------------------------
 // The ticket barrier above costs four dependent L2 round trips after the last CTA is ready (its atomics,
 // the fence, the ticket, the totals read, the broadcast). Here every CTA stores its four partial totals

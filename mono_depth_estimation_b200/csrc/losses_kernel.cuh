@@ -408,28 +408,6 @@ constexpr int kSsSlots = 11;
 constexpr int kSsRing = 2;
 constexpr size_t kSsBytes = static_cast<size_t>(kSsSlots + kSsRing) * kBlock * sizeof(float4);
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// contiguous global -> shared copy by the bulk-copy engine; completion is counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 // ss: [kSsSlots + kSsRing][kBlock] float4 (slots, then the target ring); bars: kSsSlots mbarriers, used once each
 template <typename PT, typename Body, typename Pre, typename Fold>
 __device__ __forceinline__ int tiles_forward_ss(const PT* __restrict__ pred, const float* __restrict__ gt, float4* ss,

@@ -6,6 +6,9 @@
 // (fp32 over <= 16 pixels, fp64 across tiles), flushes with one warp-shuffle/shared-memory block
 // reduction per image it touched and one fp64 atomic per quantity, and the last CTA to finish
 // turns the per-image sums into pooled values, per-image values and the mean over images.
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 #include "metric_math.cuh"
 
@@ -69,6 +72,11 @@ struct MetricThread {
   __device__ __forceinline__ void fold() {
     if constexpr (!LONG) return;
     if ((++it & 15) != 0) return;
+    fold_now();
+  }
+  // fp32 tile sums -> fp64 running sums (LONG); callers keep <= 128 pixels between two calls
+  __device__ __forceinline__ void fold_now() {
+    if constexpr (!LONG) return;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
@@ -186,36 +194,38 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
 
     int64_t i = u + threadIdx.x;
     if (VEC == 4) {
-      // software pipeline: the 2 quads of pred and of target (4 x 16 B) of the NEXT iteration are
-      // requested before the current 8 pixels are evaluated, so the loads overlap the arithmetic
-      float4 p0, t0, p1, t1;
-      bool has0 = i < seg_end, has1 = i + kBlock < seg_end;
-      if (has0) {
-        p0 = Elem<PT>::template ld4<false>(pred + 4 * i);
-        t0 = Elem<float>::template ld4<false>(gt + 4 * i);
-      }
-      if (has1) {
-        p1 = Elem<PT>::template ld4<false>(pred + 4 * (i + kBlock));
-        t1 = Elem<float>::template ld4<false>(gt + 4 * (i + kBlock));
-      }
-      while (has0) {
-        const int64_t in = i + 2 * kBlock;
-        const bool n0 = in < seg_end, n1 = in + kBlock < seg_end;
-        float4 np0, nt0, np1, nt1;
-        if (n0) {
-          np0 = Elem<PT>::template ld4<false>(pred + 4 * in);
-          nt0 = Elem<float>::template ld4<false>(gt + 4 * in);
+      // Software pipeline over three register buffers (A, B, C) of one quad x {pred, target} each: while one
+      // buffer is evaluated the other two are in flight (64 B per thread, 64 KB per SM). The loop is unrolled
+      // over the buffer triple so that nothing is ever moved between registers (the rotating form spent 16
+      // MOVs per 8 pixels and spilled), its counters are 32-bit offsets from the segment start, and the fp64
+      // fold (LONG) runs after every 8 triples = 96 pixels.
+      // (Feeding this loop from shared memory with cp.async.bulk + one __syncthreads per tile was measured:
+      // 392 us instead of 325 us at C5 - the per-tile CTA barrier costs more than the plumbing it removes.)
+      const PT* __restrict__ pbase = pred + 4 * u;
+      const float* __restrict__ gbase = gt + 4 * u;
+      const int nseg = static_cast<int>(seg_end - u);          // quads in this segment (< 2^31: one image at most)
+      int j = threadIdx.x;                                       // quad offset of buffer A
+      float4 pa, ta, pb, tb, pc, tc;
+      auto load1 = [&](int jj, float4& p0, float4& t0) {
+        if (jj < nseg) {
+          p0 = Elem<PT>::template ld4<false>(pbase + 4 * static_cast<int64_t>(jj));
+          t0 = Elem<float>::template ld4<false>(gbase + 4 * static_cast<int64_t>(jj));
         }
-        if (n1) {
-          np1 = Elem<PT>::template ld4<false>(pred + 4 * (in + kBlock));
-          nt1 = Elem<float>::template ld4<false>(gt + 4 * (in + kBlock));
+      };
+      load1(j, pa, ta);
+      load1(j + kBlock, pb, tb);
+      while (j < nseg) {
+#pragma unroll 1
+        for (int r = 0; r < 8 && j < nseg; ++r) {
+          load1(j + 2 * kBlock, pc, tc);
+          th.quad(pa, ta);
+          load1(j + 3 * kBlock, pa, ta);
+          if (j + kBlock < nseg) th.quad(pb, tb);
+          load1(j + 4 * kBlock, pb, tb);
+          if (j + 2 * kBlock < nseg) th.quad(pc, tc);
+          j += 3 * kBlock;
         }
-        th.quad(p0, t0);
-        if (has1) th.quad(p1, t1);
-        th.fold();
-        p0 = np0; t0 = nt0; p1 = np1; t1 = nt1;
-        has0 = n0; has1 = n1;
-        i = in;
+        th.fold_now();
       }
     } else {
       for (; i + 3 * kBlock < seg_end; i += 4 * kBlock) {
