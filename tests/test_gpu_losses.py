@@ -269,3 +269,34 @@ def test_silog_shared_memory_variant_capacity_boundary(Cr, extra_tiles):
     (lp, gp), (lf, gf, _) = _silog_both(Cr, pred, gt)
     close(lp, l64, LOSS_RTOL); grad_close(gp, g64)
     close(lf, l64, LOSS_RTOL); grad_close(gf, g64)
+
+
+def test_silog_shared_memory_variant_is_bit_reproducible(Cr):
+    """compute-sanitizer is not available on the GPU pool, so races in the SS kernels (bulk-copy ring, in-place
+    residual slots, dynamic tile claims, the ticket-free all-reduce) are hunted by determinism: its loss totals are
+    summed in a fixed order and every gradient element is a pure function of (p_i, t_i, totals), so 40 launches on
+    the same C2 batch - interleaved with launches on other data that recycle the workspace parity sets and the
+    slot words - must give bit-identical loss and gradient, for the plain and the fused kernel."""
+    from mono_depth_estimation_b200 import metrics as M
+    pred, gt = synth.depth_pair((16, 1, 480, 640), 91, device="cuda")
+    other_p, other_g = synth.depth_pair((8, 1, 228, 304), 92, device="cuda")
+    for fused in (False, True):
+        ref_loss = ref_grad = ref_vals = None
+        for it in range(40):
+            mc = M.MetricComputation(["delta1", "delta2", "delta3", "mse", "mae", "log10", "rmse"], strict=False)
+            crit = Cr.silog_loss(0.85)
+            if fused:
+                crit = crit.fuse_metrics(mc)
+            p = pred.detach().requires_grad_(True)
+            loss = crit(p, gt)
+            vals = torch.stack(mc.compute(p.detach(), gt)) if fused else None
+            loss.backward()
+            if ref_loss is None:
+                ref_loss, ref_grad, ref_vals = loss.detach().clone(), p.grad.clone(), vals
+            else:
+                assert torch.equal(loss.detach(), ref_loss), (fused, it)
+                assert torch.equal(p.grad, ref_grad), (fused, it)
+                if fused:   # the metric sums go through fp64 atomics: equal to ~1e-15, the integer counts exactly
+                    close(vals, ref_vals, 1e-12)
+            if it % 3 == 0:
+                run_loss(Cr.silog_loss(0.85), other_p, other_g)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run ONE hot-path call a few times (for ncu / compute-sanitizer).  python tools/run_one.py <name> [reps]
-names: c5_metrics, c2_metrics, c2_fused, dorn_fused, dorn_decode, ord_loss, vnl, c1_berhu, pointcloud"""
+names: c5_metrics, c2_metrics, c2_fused, dorn_fused, dorn_decode, ord_loss, vnl, c1_berhu, pointcloud, wcel"""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
@@ -45,6 +45,18 @@ elif name == "vnl":
     grad = torch.empty_like(pred)
     f = lambda: _lib.check(lib.mde_vnl_loss(_lib.ptr(gt), _lib.ptr(pred), 0, _lib.ptr(trip), 8, 385, 385, 100000, 519.0, 519.0, 1, 1.0, _lib.ptr(ws), _lib.ptr(scratch),
                                             _lib.ptr(loss_t), None, _lib.ptr(grad), sp()))
+elif name == "wcel":
+    from mono_depth_estimation_b200 import wcel
+    B, Cc, H, W = 2, 150, 97, 131
+    pw = wcel.vnl_params(0.01, 1.1, Cc)
+    w = torch.tensor(pw["wce_loss_weight"], dtype=torch.float64)
+    w32 = (w / w.sum(1, keepdim=True)).float().to(dev).contiguous(); rowsum = w32.double().sum(1).float().contiguous()
+    gt = torch.rand((B, 1, H, W), device=dev) * 1.2 + 0.005; gt[1, :, :9, :] = -1.0
+    bins = wcel.depth_to_bins(gt, 0.01, 1.1, Cc)
+    logits = torch.randn((B, Cc, H, W), device=dev) * 3.0; gl = torch.empty_like(logits)
+    ws = _lib.workspace(dev, B)
+    f = lambda: _lib.check(lib.mde_wcel_loss(_lib.ptr(logits), 0, _lib.ptr(bins), _lib.ptr(gt), _lib.ptr(w32), _lib.ptr(rowsum), B, Cc, H * W,
+                                             1.0, _lib.ptr(ws), _lib.ptr(loss_t), _lib.ptr(gl), sp()))
 elif name == "pointcloud":
     d = torch.rand((64, 480, 640), device=dev) * 12; out = torch.empty((64, 480, 640, 3), device=dev)
     f = lambda: _lib.check(lib.mde_point_cloud(_lib.ptr(d), 64, 480, 640, 0.8575, 0.1, 100.0, None, 0, _lib.ptr(out), sp()))
