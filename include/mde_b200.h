@@ -251,6 +251,19 @@ int mde_bins_to_depth(const void* prob, int x_dtype, const float* border, int64_
 int mde_bins_to_depth_bwd(const float* depth, const float* grad_depth, const float* border, int64_t n, int64_t C,
                           int64_t hw, int x_dtype, void* grad_prob, void* stream);
 
+/* ---- MiDaS scale-and-shift alignment (evaluation side) ------------------- */
+/*
+ * compute_scale_and_shift(prediction, target, mask) (reference criteria.py:154-176): per image the least-squares
+ * (scale, shift) that aligns pred to target over the mask (mask_u8 nullable: target > 0, :155-156); zeros where the
+ * 2x2 system is singular (:170-174). pred [n_img,hw] (pred_dtype), target [n_img,hw] fp32, outputs fp32 [n_img].
+ * The workspace must have been initialised for >= n_img images.
+ */
+int mde_scale_and_shift(const void* pred, int pred_dtype, const float* target, const uint8_t* mask_u8,
+                        int64_t n_img, int64_t hw, void* ws, float* scale_out, float* shift_out, void* stream);
+/* MidasModule.scale_shift (reference modules/midas.py:56-62): out = scale[img] * pred + shift[img], fp32 out. */
+int mde_apply_scale_shift(const void* pred, int pred_dtype, const float* scale, const float* shift, int64_t n_img,
+                          int64_t hw, float* out, void* stream);
+
 /* ---- depth -> point cloud ----------------------------------------------------------------- */
 /*
  * point_cloud(depth, cam) (reference depth2pointcloud.py:12-31) for a batch of depth maps, with the

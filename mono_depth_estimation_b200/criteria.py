@@ -27,7 +27,8 @@ import torch.nn as nn
 from . import _lib
 
 __all__ = ["MaskedDepthLoss", "MaskedMSELoss", "MaskedL1Loss", "berHuLoss", "LainaBerHuLoss", "silog_loss",
-           "ordLoss", "OrdinalRegressionLoss", "VNL_Loss", "ModelLoss", "masked_loss"]
+           "ordLoss", "OrdinalRegressionLoss", "VNL_Loss", "ModelLoss", "masked_loss",
+           "compute_scale_and_shift", "scale_shift"]
 
 
 def _scale_grad(grad, grad_output):
@@ -370,6 +371,57 @@ class VNL_Loss(nn.Module):
         loss = _FusedLossFn.apply(pred_depth, launch)
         self.last_stats = stats
         return loss
+
+
+def compute_scale_and_shift(prediction, target, mask=None):
+    """reference criteria.py:154-176: per-image least-squares (scale, shift) aligning `prediction` to `target` over
+    the mask (default `target > 0`); zeros where the 2x2 system is singular. prediction/target [B,H,W] (or any
+    [..., H, W]: every leading dim is an image) -> two fp32 tensors of shape [B]. One pass over the inputs
+    (C ABI mde_scale_and_shift). Evaluation-side function: the result is detached (the differentiable use inside
+    MidasLoss, criteria.py:306-332, is a later row of the scope table)."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(prediction, target, mask)
+    assert prediction.shape == target.shape, "inconsistent dimensions"
+    n_img, h, w = _as_images(prediction)
+    p = prediction.detach()
+    if p.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        p = p.float()
+    p = p.contiguous()
+    t = target.detach().to(torch.float32).contiguous()
+    m = None
+    if mask is not None:
+        assert mask.shape == target.shape, "inconsistent dimensions"
+        m = (mask.detach() != 0).to(torch.uint8).contiguous()
+    lead = tuple(prediction.shape[:-2]) if prediction.dim() > 2 else (1,)
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(dev, n_img)
+        scale = torch.empty(n_img, dtype=torch.float32, device=dev)
+        shift = torch.empty(n_img, dtype=torch.float32, device=dev)
+        _lib.check(lib.mde_scale_and_shift(_lib.ptr(p), _lib.dtype_code(p), _lib.ptr(t), _lib.ptr(m), n_img, h * w,
+                                           _lib.ptr(ws), _lib.ptr(scale), _lib.ptr(shift), _lib.stream_ptr(dev)))
+    return scale.view(lead), shift.view(lead)
+
+
+def scale_shift(pred, target):
+    """MidasModule.scale_shift (reference modules/midas.py:56-62): align pred to target per image and return both
+    as [B,1,H,W] (what the MiDaS module feeds to the metric logger in validation/test)."""
+    lib = _lib.load()
+    if pred.ndim == 4:
+        pred = pred.squeeze(1)
+    if target.ndim == 4:
+        target = target.squeeze(1)
+    scale, shift = compute_scale_and_shift(pred, target)
+    dev = pred.device
+    p = pred.detach()
+    if p.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        p = p.float()
+    p = p.contiguous()
+    n_img, h, w = _as_images(p)
+    with torch.cuda.device(dev):
+        out = torch.empty(p.shape, dtype=torch.float32, device=dev)
+        _lib.check(lib.mde_apply_scale_shift(_lib.ptr(p), _lib.dtype_code(p), _lib.ptr(scale.contiguous()),
+                                             _lib.ptr(shift.contiguous()), n_img, h * w, _lib.ptr(out), _lib.stream_ptr(dev)))
+    return out.unsqueeze(1), target.unsqueeze(1)
 
 
 class ModelLoss(nn.Module):

@@ -354,6 +354,27 @@ def gen_wcel():
     np.savez_compressed(os.path.join(OUT, "wcel_small.npz"), **out)
 
 
+def gen_midas():
+    """compute_scale_and_shift by the reference's own function (criteria.py:154-176), fp32 and fp64, default and
+    explicit mask; one image with a single valid pixel and one without any (singular systems -> zeros)."""
+    crit = R.load("criteria")
+    g = torch.Generator().manual_seed(777)
+    B, H, W = 5, 24, 36
+    target = torch.rand((B, H, W), generator=g) * 9.5 + 0.5
+    target[torch.rand((B, H, W), generator=g) < 0.25] = 0.0
+    pred = (1.0 / target.clamp_min(0.3)) * 0.7 + 0.2 + torch.randn((B, H, W), generator=g) * 0.05   # disparity-like
+    target[3] = 0.0; target[3, 4, 5] = 2.0        # one valid pixel: det == 0
+    target[4] = 0.0                                # no valid pixel
+    out = {"pred": pred.numpy(), "target": target.numpy()}
+    for dt, sfx in ((torch.float32, "32"), (torch.float64, "64")):
+        s, t = crit.compute_scale_and_shift(pred.to(dt), target.to(dt))
+        out["scale" + sfx], out["shift" + sfx] = s.numpy(), t.numpy()
+    mask = (target > 1.0).float()
+    s, t = crit.compute_scale_and_shift(pred.double(), target.double(), mask.double())
+    out["mask"], out["scale_mask64"], out["shift_mask64"] = mask.numpy(), s.numpy(), t.numpy()
+    np.savez_compressed(os.path.join(OUT, "midas_small.npz"), **out)
+
+
 def main():
     assert R.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
@@ -364,6 +385,7 @@ def main():
     gen_vnl()
     gen_config_scalars()
     gen_wcel()
+    gen_midas()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

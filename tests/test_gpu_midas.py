@@ -1,0 +1,60 @@
+"""GPU parity of the MiDaS alignment step (evaluation side) against the oracle and the
+reference-made golden vectors: compute_scale_and_shift (criteria.py:154-176), scale_shift (modules/midas.py:56-62)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import midas as om
+from oracle import metrics as ometrics
+from tests.gpu_util import T, close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Cr():
+    from mono_depth_estimation_b200 import criteria
+    return criteria
+
+
+def test_golden(Cr, golden):
+    g = golden("midas_small.npz")
+    pred, target = T(g["pred"]).cuda(), T(g["target"]).cuda()
+    s, t = Cr.compute_scale_and_shift(pred, target)
+    assert s.shape == (5,) and s.dtype == torch.float32 and s.is_cuda
+    close(s, g["scale64"], 1e-5); close(t, g["shift64"], 1e-5, 1e-6)
+    assert float(s[3]) == 0.0 and float(t[3]) == 0.0 and float(s[4]) == 0.0 and float(t[4]) == 0.0   # singular -> zeros
+    sm, tm = Cr.compute_scale_and_shift(pred, target, T(g["mask"]).cuda())
+    close(sm, g["scale_mask64"], 1e-5); close(tm, g["shift_mask64"], 1e-5, 1e-6)
+    # second call on the same workspace (self-cleaning accumulators), then a metrics call sharing that region
+    s2, _ = Cr.compute_scale_and_shift(pred, target)
+    assert torch.equal(s, s2) or bool(torch.allclose(s, s2, rtol=1e-6))
+    from mono_depth_estimation_b200 import metrics as M
+    res = M.fused_metrics(pred[:3].clamp_min(1e-3), target[:3])
+    v64 = [float(v) for v in ometrics.compute(pred[:3].clamp_min(1e-3).cpu().double(), target[:3].cpu().double(), ["mae", "delta1"])]
+    close(res["f64"][[3, 0]], v64, 1e-5)
+
+
+@pytest.mark.parametrize("shape,dtype", [((4, 1, 384, 384), torch.float32), ((3, 33, 41), torch.float32),
+                                         ((64, 1, 96, 128), torch.float32), ((2, 1, 384, 384), torch.float16)])
+def test_scale_shift_vs_oracle(Cr, shape, dtype):
+    g = torch.Generator().manual_seed(5 + shape[0])
+    target = torch.rand(shape, generator=g) * 9.5 + 0.5
+    target[torch.rand(shape, generator=g) < 0.2] = 0.0
+    pred = ((1.0 / target.clamp_min(0.3)) * 0.7 + 0.2 + torch.randn(shape, generator=g) * 0.05).to(dtype)
+    p3 = pred.squeeze(1) if pred.ndim == 4 else pred
+    t3 = target.squeeze(1) if target.ndim == 4 else target
+    s64, t64 = om.compute_scale_and_shift(p3.double(), t3.double())
+    s, t = Cr.compute_scale_and_shift(p3.cuda(), t3.cuda())
+    close(s, s64, 1e-5); close(t, t64, 1e-5, 1e-6)
+    y_hat, y = Cr.scale_shift(pred.cuda(), target.cuda())
+    ref_hat, ref_y = om.scale_shift(pred.double(), target.double())
+    assert y_hat.shape == ref_hat.shape and y.shape == ref_y.shape and y_hat.dtype == torch.float32
+    close(y_hat, ref_hat, 2e-5, 2e-5)
+    assert torch.equal(y.cpu(), ref_y.float())
+    # the aligned prediction then goes to the metric suite (modules/midas.py:77-80)
+    from mono_depth_estimation_b200 import metrics as M
+    names = ["delta1", "absrel", "rmse"]
+    vals = M.MetricComputation(names, strict=False).compute(y_hat, y)
+    v64 = [float(v) for v in ometrics.compute(ref_hat, ref_y, names)]
+    close(torch.stack(vals), v64, 2e-4)   # the metrics see an fp32 alignment of an fp32 (or fp16) prediction

@@ -211,3 +211,18 @@ def test_model_loss(golden):
     close(total.detach(), g["ml_total32"], 2e-5)
     close(g_lg, g["ml_grad_logits32"], 1e-4, 1e-8)
     close(g_pd, g["ml_grad_pred32"], 1e-3, 1e-6 * float(np.abs(g["ml_grad_pred32"]).max()))
+
+
+def test_midas_scale_and_shift(golden):
+    from oracle import midas as om
+    g = golden("midas_small.npz")
+    pred, target = T(g["pred"]), T(g["target"])
+    s64, t64 = om.compute_scale_and_shift(pred.double(), target.double())
+    close(s64, g["scale64"], 1e-12); close(t64, g["shift64"], 1e-12)
+    s32, t32 = om.compute_scale_and_shift(pred, target)
+    close(s32, g["scale32"], 1e-6); close(t32, g["shift32"], 1e-6, 1e-7)
+    assert float(s64[3]) == 0.0 and float(t64[3]) == 0.0 and float(s64[4]) == 0.0      # singular systems
+    sm, tm = om.compute_scale_and_shift(pred.double(), target.double(), T(g["mask"]).double())
+    close(sm, g["scale_mask64"], 1e-12); close(tm, g["shift_mask64"], 1e-12)
+    # the fp32 reference is within the tolerance budget of its fp64 evaluation
+    close(g["scale32"][:3], g["scale64"][:3], 1e-4); close(g["shift32"][:3], g["shift64"][:3], 1e-4, 1e-5)
