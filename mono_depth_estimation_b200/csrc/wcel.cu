@@ -266,7 +266,10 @@ __global__ void __launch_bounds__(256) bins_to_depth_kernel(const XT* __restrict
   }
 }
 
-// backward: grad_p[c] = g * ln(10) * depth * border_c
+// backward: grad_p[c] = g * ln(10) * depth * border_c. Write-only over C planes: a warp owns 128 consecutive
+// pixels (4 per lane, 32 apart) so that every visit of a channel plane writes 512 contiguous bytes - with one
+// pixel per lane (128 B per plane visit, 150 planes 593 KB apart) the stores ran at 3.0 TB/s, in this form at
+// 5.0 TB/s. (The same lockstep applied to the READS of wcel_kernel was measured 10-30 % slower and is not used.)
 template <typename XT>
 __global__ void __launch_bounds__(256) bins_to_depth_bwd_kernel(const float* __restrict__ depth, const float* __restrict__ gdepth,
                                                                 const float* __restrict__ border, int64_t n, int C,
@@ -275,12 +278,27 @@ __global__ void __launch_bounds__(256) bins_to_depth_bwd_kernel(const float* __r
   for (int i = threadIdx.x; i < C; i += 256) sm_b[i] = __ldg(border + i);
   __syncthreads();
   const int64_t npx = n * hw;
-  for (int64_t px = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; px < npx;
-       px += static_cast<int64_t>(gridDim.x) * 256) {
-    const int64_t img = px / hw;
-    const int64_t base = img * static_cast<int64_t>(C) * hw + (px - img * hw);
-    const float k = __ldg(gdepth + px) * (__ldg(depth + px) * 2.302585092994046f);
-    for (int c = 0; c < C; ++c) Elem<XT>::st1(gp + base + static_cast<int64_t>(c) * hw, k * sm_b[c]);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * 256) >> 5;
+  for (int64_t g0 = warp_global * 128; g0 < npx; g0 += n_warps * 128) {
+    float k[4];
+    int64_t base[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t px = g0 + j * 32 + lane;
+      const bool ok = px < npx;
+      const int64_t pc = ok ? px : 0;
+      const int64_t img = pc / hw;
+      base[j] = ok ? img * static_cast<int64_t>(C) * hw + (pc - img * hw) : -1;
+      k[j] = ok ? __ldg(gdepth + pc) * (__ldg(depth + pc) * 2.302585092994046f) : 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      const float bc = sm_b[c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (base[j] >= 0) Elem<XT>::st1(gp + base[j] + static_cast<int64_t>(c) * hw, k[j] * bc);
+    }
   }
 }
 
