@@ -264,6 +264,17 @@ int mde_scale_and_shift(const void* pred, int pred_dtype, const float* target, c
 int mde_apply_scale_shift(const void* pred, int pred_dtype, const float* scale, const float* shift, int64_t n_img,
                           int64_t hw, float* out, void* stream);
 
+/*
+ * MidasLoss.forward WITHOUT the scale/shift alignment (reference criteria.py:306-332 with loss in {'mse','l1','trim'},
+ * reduction='batch-based'; the criterion of the registered method `my`, modules/my.py:39): data term
+ * (mse_loss :219-223 or l1_loss :201-206; 'trim' :208-217 trims nothing as written and equals l1) plus
+ * alpha * GradientLoss over `scales` strided grids (:226-244, :283-303), forward + backward in one cooperative
+ * launch. data_kind: 0 mse, 1 l1/trim. grad nullable (dtype of pred). pred/target [n_img,h,w].
+ */
+int mde_midas_loss(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t h, int64_t w,
+                   int data_kind, float alpha, int scales, float grad_scale, void* ws, float* loss_out,
+                   void* grad, void* stream);
+
 /* ---- depth -> point cloud ----------------------------------------------------------------- */
 /*
  * point_cloud(depth, cam) (reference depth2pointcloud.py:12-31) for a batch of depth maps, with the

@@ -67,6 +67,7 @@ SIGNATURES = {
     "mde_bins_to_depth_bwd": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "mde_scale_and_shift": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mde_apply_scale_shift": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "mde_midas_loss": (_i32, [_vp, _i32, _vp, _i64, _i64, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "mde_point_cloud": (_i32, [_vp, _i64, _i64, _i64, _f32, _f32, _f32, C.POINTER(C.c_float), _i32, _vp, _vp]),
     "mde_workspace_bytes": (C.c_size_t, [_i64]),
     "mde_workspace_init": (_i32, [_vp, _i64, _vp]),

@@ -28,7 +28,7 @@ from . import _lib
 
 __all__ = ["MaskedDepthLoss", "MaskedMSELoss", "MaskedL1Loss", "berHuLoss", "LainaBerHuLoss", "silog_loss",
            "ordLoss", "OrdinalRegressionLoss", "VNL_Loss", "ModelLoss", "masked_loss",
-           "compute_scale_and_shift", "scale_shift"]
+           "compute_scale_and_shift", "scale_shift", "MidasLoss"]
 
 
 def _scale_grad(grad, grad_output):
@@ -422,6 +422,60 @@ def scale_shift(pred, target):
         _lib.check(lib.mde_apply_scale_shift(_lib.ptr(p), _lib.dtype_code(p), _lib.ptr(scale.contiguous()),
                                              _lib.ptr(shift.contiguous()), n_img, h * w, _lib.ptr(out), _lib.stream_ptr(dev)))
     return out.unsqueeze(1), target.unsqueeze(1)
+
+
+class MidasLoss(nn.Module):
+    """reference criteria.py:306-332: data term + alpha * multi-scale gradient matching.
+
+    Built on the kernels: `loss` in {'mse', 'l1', 'trim'} with reduction='batch-based' - 'mse' with alpha=0.5 is the
+    criterion of the registered method `my` (modules/my.py:39); 'trim' (criteria.py:208-217) trims nothing as the
+    reference is written and equals 'l1'. Not built yet: the 'ssi*' variants (they differentiate through
+    compute_scale_and_shift) and reduction='image-based' (which raises inside the reference for 'mse')."""
+
+    def __init__(self, alpha=0.5, scales=4, loss='ssimse', reduction='batch-based'):
+        super().__init__()
+        self.loss = loss
+        if 'trim' in self.loss or 'l1' in self.loss:
+            self._kind = 1
+        elif 'mse' in self.loss:
+            self._kind = 0
+        else:
+            raise ValueError()
+        if 'ssi' in self.loss:
+            raise NotImplementedError("MidasLoss(loss=%r): the scale-and-shift invariant variants differentiate through "
+                                      "compute_scale_and_shift (criteria.py:326-328); only 'mse', 'l1' and 'trim' are on "
+                                      "the kernels so far" % (loss,))
+        if reduction != 'batch-based':
+            raise NotImplementedError("MidasLoss(reduction=%r): only 'batch-based' (the reference default) is built" % (reduction,))
+        self._alpha = float(alpha)
+        self._scales = int(scales)
+
+    def forward(self, prediction, target):
+        lib = _lib.load()
+        dev = _lib.require_cuda(prediction, target)
+        if prediction.ndim == 4:
+            prediction = prediction.squeeze(1)
+        if target.ndim == 4:
+            target = target.squeeze(1)
+        assert prediction.shape == target.shape and prediction.ndim == 3, "prediction/target must be [B,H,W] or [B,1,H,W]"
+        B, H, W = (int(v) for v in prediction.shape)
+        t = target.detach().to(torch.float32).contiguous()
+        kind, alpha, scales = self._kind, self._alpha, self._scales
+
+        def launch(p, need_grad):
+            pc = p.detach()
+            if pc.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                pc = pc.float()
+            pc = pc.contiguous()
+            with torch.cuda.device(dev):
+                ws = _lib.workspace(dev, B)
+                loss = torch.empty((), dtype=torch.float32, device=dev)
+                grad = torch.empty_like(pc) if need_grad else None
+                _lib.check(lib.mde_midas_loss(_lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(t), B, H, W, kind, alpha, scales,
+                                              1.0, _lib.ptr(ws), _lib.ptr(loss), _lib.ptr(grad), _lib.stream_ptr(dev)))
+            return loss, (grad.to(p.dtype) if grad is not None and grad.dtype != p.dtype else grad)
+
+        return _FusedLossFn.apply(prediction, launch)
 
 
 class ModelLoss(nn.Module):

@@ -372,6 +372,21 @@ def gen_midas():
     mask = (target > 1.0).float()
     s, t = crit.compute_scale_and_shift(pred.double(), target.double(), mask.double())
     out["mask"], out["scale_mask64"], out["shift_mask64"] = mask.numpy(), s.numpy(), t.numpy()
+    # MidasLoss without ssi (the `my` method's criterion and its l1 / trim siblings), loss and gradient, fp32 + fp64
+    g2 = torch.Generator().manual_seed(778)
+    Bm, Hm, Wm = 3, 21, 30                       # not multiples of 8: the coarse grids end off the border
+    tg = torch.rand((Bm, 1, Hm, Wm), generator=g2) * 9.5 + 0.5
+    tg[torch.rand((Bm, 1, Hm, Wm), generator=g2) < 0.25] = 0.0
+    pr = tg.clamp_min(0.4) + torch.randn((Bm, 1, Hm, Wm), generator=g2) * 0.3
+    pr[0, 0, 4, 4:8] = tg[0, 0, 4, 4:8]          # exact ties: |0| has a zero subgradient
+    out["ml_pred"], out["ml_target"] = pr.numpy(), tg.numpy()
+    for name, kw in (("mse", dict(alpha=0.5, loss="mse")), ("l1", dict(alpha=0.5, loss="l1")), ("trim", dict(alpha=0.5, loss="trim")),
+                     ("mse_a0", dict(alpha=0.0, loss="mse")), ("mse_s2", dict(alpha=0.25, scales=2, loss="mse"))):
+        for dt, sfx in ((torch.float32, "32"), (torch.float64, "64")):
+            p = pr.to(dt).clone().requires_grad_(True)
+            l = crit.MidasLoss(**kw)(p, tg.to(dt))
+            (gr,) = torch.autograd.grad(l, p)
+            out[f"ml_{name}_loss{sfx}"], out[f"ml_{name}_grad{sfx}"] = l.detach().numpy(), gr.numpy()
     np.savez_compressed(os.path.join(OUT, "midas_small.npz"), **out)
 
 

@@ -37,3 +37,68 @@ def scale_shift(pred, target):
     scale, shift = compute_scale_and_shift(pred, target)
     pred = scale.view(-1, 1, 1) * pred + shift.view(-1, 1, 1)
     return pred.unsqueeze(1), target.unsqueeze(1)
+
+
+# ---- MidasLoss (criteria.py:306-332) and its parts, restated op for op --------------------------------------
+def reduction_batch_based(image_loss, M):
+    """criteria.py:179-188."""
+    divisor = torch.sum(M)
+    if divisor == 0:
+        return 0
+    return torch.sum(image_loss) / divisor
+
+
+def mse_loss(prediction, target, mask):
+    """criteria.py:219-223 (batch-based)."""
+    M = torch.sum(mask, (1, 2))
+    res = prediction - target
+    return reduction_batch_based(mask * res * res, 2 * M)
+
+
+def l1_loss(prediction, target, mask):
+    """criteria.py:201-206 (batch-based)."""
+    M = torch.sum(mask, (1, 2))
+    diff = (target - prediction)[mask.bool()]
+    return reduction_batch_based(diff.abs(), 2 * M)
+
+
+def trimmed_mae_loss(prediction, target, mask, trim=0.2):
+    """criteria.py:208-217 AS WRITTEN: `torch.sort(...)[: k]` slices the (values, indices) tuple, so nothing is
+    trimmed and the value equals the l1 data term (needs k >= 2)."""
+    M = torch.sum(mask, (1, 2))
+    res = (prediction - target)[mask.bool()].abs()
+    trimmed, _ = torch.sort(res.view(-1), descending=False)[: int(len(res) * (1.0 - trim))]
+    return reduction_batch_based(trimmed, 2 * M)
+
+
+def gradient_loss(prediction, target, mask):
+    """criteria.py:226-244 (batch-based)."""
+    M = torch.sum(mask, (1, 2))
+    diff = torch.mul(mask, prediction - target)
+    grad_x = torch.abs(diff[:, :, 1:] - diff[:, :, :-1])
+    grad_x = torch.mul(torch.mul(mask[:, :, 1:], mask[:, :, :-1]), grad_x)
+    grad_y = torch.abs(diff[:, 1:, :] - diff[:, :-1, :])
+    grad_y = torch.mul(torch.mul(mask[:, 1:, :], mask[:, :-1, :]), grad_y)
+    image_loss = torch.sum(grad_x, (1, 2)) + torch.sum(grad_y, (1, 2))
+    return reduction_batch_based(image_loss, M)
+
+
+def midas_loss(prediction, target, alpha=0.5, scales=4, loss="mse"):
+    """MidasLoss.forward (criteria.py:319-332), batch-based reduction; 'ssi' in `loss` adds the alignment."""
+    if prediction.ndim == 4:
+        prediction = prediction.squeeze(1)
+    if target.ndim == 4:
+        target = target.squeeze(1)
+    mask = (target > 0).type(prediction.dtype)
+    if "ssi" in loss:
+        scale, shift = compute_scale_and_shift(prediction, target, mask)
+        prediction = scale.view(-1, 1, 1) * prediction + shift.view(-1, 1, 1)
+    data = trimmed_mae_loss if "trim" in loss else (mse_loss if "mse" in loss else l1_loss)
+    total = data(prediction, target, mask)
+    if alpha > 0:
+        reg = 0
+        for s in range(scales):
+            step = 2 ** s
+            reg = reg + gradient_loss(prediction[:, ::step, ::step], target[:, ::step, ::step], mask[:, ::step, ::step])
+        total = total + alpha * reg
+    return total

@@ -58,3 +58,40 @@ def test_scale_shift_vs_oracle(Cr, shape, dtype):
     vals = M.MetricComputation(names, strict=False).compute(y_hat, y)
     v64 = [float(v) for v in ometrics.compute(ref_hat, ref_y, names)]
     close(torch.stack(vals), v64, 2e-4)   # the metrics see an fp32 alignment of an fp32 (or fp16) prediction
+
+
+@pytest.mark.parametrize("name,kw", [("mse", dict(alpha=0.5, loss="mse")), ("l1", dict(alpha=0.5, loss="l1")),
+                                     ("trim", dict(alpha=0.5, loss="trim")), ("mse_a0", dict(alpha=0.0, loss="mse")),
+                                     ("mse_s2", dict(alpha=0.25, scales=2, loss="mse"))])
+def test_midas_loss_golden(Cr, golden, name, kw):
+    from tests.gpu_util import LOSS_RTOL, grad_close, run_loss
+    g = golden("midas_small.npz")
+    pred, target = T(g["ml_pred"]).cuda(), T(g["ml_target"]).cuda()
+    loss, grad = run_loss(Cr.MidasLoss(**kw), pred, target)
+    assert loss.dim() == 0 and grad.shape == pred.shape
+    close(loss, g[f"ml_{name}_loss64"], LOSS_RTOL)
+    grad_close(grad, g[f"ml_{name}_grad64"])
+    with torch.no_grad():
+        close(Cr.MidasLoss(**kw)(pred, target), g[f"ml_{name}_loss64"], LOSS_RTOL)
+
+
+@pytest.mark.parametrize("shape", [(8, 1, 384, 384), (3, 1, 33, 41), (2, 1, 480, 640)])
+def test_midas_loss_vs_oracle(Cr, shape):
+    """The `my` method's criterion (modules/my.py:39) at its training size and at odd sizes; all-invalid images."""
+    from tests.gpu_util import LOSS_RTOL, grad_close, run_loss
+    g = torch.Generator().manual_seed(17 + shape[0])
+    target = torch.rand(shape, generator=g) * 9.5 + 0.5
+    target[torch.rand(shape, generator=g) < 0.2] = 0.0
+    target[-1, :, : shape[2] // 3] = 0.0
+    pred = target.clamp_min(0.4) + torch.randn(shape, generator=g) * 0.3
+    for kw in (dict(alpha=0.5, loss="mse"), dict(alpha=0.5, loss="l1")):
+        p64 = pred.double().requires_grad_(True)
+        l64 = om.midas_loss(p64, target.double(), **kw)
+        (g64,) = torch.autograd.grad(l64, p64)
+        loss, grad = run_loss(Cr.MidasLoss(**kw), pred.cuda(), target.cuda())
+        close(loss, l64.detach(), LOSS_RTOL)
+        grad_close(grad, g64)
+    z = torch.zeros(2, 1, 16, 24).cuda()
+    assert float(Cr.MidasLoss(alpha=0.5, loss="mse")(torch.ones_like(z), z)) == 0.0      # zero divisors give 0 (criteria.py:185-186)
+    with pytest.raises(NotImplementedError):
+        Cr.MidasLoss()                                                                    # default 'ssimse' is not built yet

@@ -226,3 +226,21 @@ def test_midas_scale_and_shift(golden):
     close(sm, g["scale_mask64"], 1e-12); close(tm, g["shift_mask64"], 1e-12)
     # the fp32 reference is within the tolerance budget of its fp64 evaluation
     close(g["scale32"][:3], g["scale64"][:3], 1e-4); close(g["shift32"][:3], g["shift64"][:3], 1e-4, 1e-5)
+
+
+@pytest.mark.parametrize("name,kw", [("mse", dict(alpha=0.5, loss="mse")), ("l1", dict(alpha=0.5, loss="l1")),
+                                     ("trim", dict(alpha=0.5, loss="trim")), ("mse_a0", dict(alpha=0.0, loss="mse")),
+                                     ("mse_s2", dict(alpha=0.25, scales=2, loss="mse"))])
+def test_midas_loss(golden, name, kw):
+    from oracle import midas as om
+    g = golden("midas_small.npz")
+    pred, target = T(g["ml_pred"]), T(g["ml_target"])
+    p = pred.double().requires_grad_(True)
+    l = om.midas_loss(p, target.double(), **kw)
+    (gr,) = torch.autograd.grad(l, p)
+    close(l.detach(), g[f"ml_{name}_loss64"], 1e-12)
+    close(gr, g[f"ml_{name}_grad64"], 1e-10, 1e-15)
+    close(g[f"ml_{name}_loss32"], g[f"ml_{name}_loss64"], 1e-5)
+    if name == "trim":   # as written the reference trims nothing: same value and gradient as l1
+        close(g["ml_trim_loss64"], g["ml_l1_loss64"], 1e-12)
+        close(g["ml_trim_grad64"], g["ml_l1_grad64"], 1e-12, 1e-15)

@@ -242,7 +242,12 @@ def main():
     fns = [lambda: _lib.check(lib.mde_apply_scale_shift(_lib.ptr(prd), 0, _lib.ptr(sc), _lib.ptr(sh), Bm, Hm * Wm, _lib.ptr(al), sp()))]
     us, g = timed(fns, reps)
     report("MiDaS 64x384x384", "apply scale/shift", pxm, us, 8.0, g)
-    del tgt, prd, al
+    lg = torch.empty_like(prd)
+    tg3 = tgt
+    fns = [lambda: _lib.check(lib.mde_midas_loss(_lib.ptr(prd), 0, _lib.ptr(tg3), Bm, Hm, Wm, 0, 0.5, 4, 1.0, _lib.ptr(ws), _lib.ptr(loss_t), _lib.ptr(lg), sp()))]
+    us, g = timed(fns, reps)
+    report("MiDaS 64x384x384", "MidasLoss('mse', alpha 0.5, 4 scales) fwd+bwd", pxm, us, 12.0, g)
+    del tgt, prd, al, lg
 
     # ---------------- C5: NYU-test-shaped eval, 654 x 480 x 640, 10 metrics ------------------------------------
     B = 654 if not QUICK else 64
