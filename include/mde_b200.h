@@ -259,7 +259,8 @@ int mde_bins_to_depth_bwd(const float* depth, const float* grad_depth, const flo
  * The workspace must have been initialised for >= n_img images.
  */
 int mde_scale_and_shift(const void* pred, int pred_dtype, const float* target, const uint8_t* mask_u8,
-                        int64_t n_img, int64_t hw, void* ws, float* scale_out, float* shift_out, void* stream);
+                        int64_t n_img, int64_t hw, void* ws, float* scale_out, float* shift_out,
+                        double* sums_out /* nullable: [n_img][5] = a00, a01, a11, det, det != 0 */, void* stream);
 /* MidasModule.scale_shift (reference modules/midas.py:56-62): out = scale[img] * pred + shift[img], fp32 out. */
 int mde_apply_scale_shift(const void* pred, int pred_dtype, const float* scale, const float* shift, int64_t n_img,
                           int64_t hw, float* out, void* stream);
@@ -270,10 +271,18 @@ int mde_apply_scale_shift(const void* pred, int pred_dtype, const float* scale, 
  * (mse_loss :219-223 or l1_loss :201-206; 'trim' :208-217 trims nothing as written and equals l1) plus
  * alpha * GradientLoss over `scales` strided grids (:226-244, :283-303), forward + backward in one cooperative
  * launch. data_kind: 0 mse, 1 l1/trim. grad nullable (dtype of pred). pred/target [n_img,h,w].
+ * scale/shift (nullable, [n_img] fp32 from mde_scale_and_shift): the 'ssi' variants (criteria.py:326-328) evaluate the
+ * loss on scale * pred + shift; grad is then dL/d(aligned pred) and mde_midas_ssi_backward finishes the chain rule.
  */
-int mde_midas_loss(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t h, int64_t w,
-                   int data_kind, float alpha, int scales, float grad_scale, void* ws, float* loss_out,
-                   void* grad, void* stream);
+int mde_midas_loss(const void* pred, int pred_dtype, const float* target, const float* scale, const float* shift,
+                   int64_t n_img, int64_t h, int64_t w, int data_kind, float alpha, int scales, float grad_scale,
+                   void* ws, float* loss_out, void* grad, void* stream);
+/* Backward of the 'ssi' variants through compute_scale_and_shift: grad_inout holds g = dL/d(aligned pred) (fp32) on
+ * entry and dL/dpred on exit: s g_i + m_i (U y_i - 2 s U p_i - t U - s V), U, V from the per-image sums of
+ * mde_scale_and_shift and G0 = sum g, G1 = sum g p. coef_scratch: device, n_img * 4 floats, 16-byte aligned. */
+int mde_midas_ssi_backward(const float* pred, const float* target, const float* scale, const float* shift,
+                           const double* sums, int64_t n_img, int64_t hw, void* ws, float* coef_scratch,
+                           float* grad_inout, void* stream);
 
 /* ---- depth -> point cloud ----------------------------------------------------------------- */
 /*

@@ -65,9 +65,10 @@ SIGNATURES = {
     "mde_depth_to_bins": (_i32, [_vp, _i64, _f32, _f32, _f32, _f32, _i64, _vp, _vp]),
     "mde_bins_to_depth": (_i32, [_vp, _i32, _vp, _i64, _i64, _i64, _vp, _vp]),
     "mde_bins_to_depth_bwd": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
-    "mde_scale_and_shift": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "mde_scale_and_shift": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mde_apply_scale_shift": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp]),
-    "mde_midas_loss": (_i32, [_vp, _i32, _vp, _i64, _i64, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
+    "mde_midas_loss": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
+    "mde_midas_ssi_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mde_point_cloud": (_i32, [_vp, _i64, _i64, _i64, _f32, _f32, _f32, C.POINTER(C.c_float), _i32, _vp, _vp]),
     "mde_workspace_bytes": (C.c_size_t, [_i64]),
     "mde_workspace_init": (_i32, [_vp, _i64, _vp]),

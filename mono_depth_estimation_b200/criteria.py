@@ -398,7 +398,7 @@ def compute_scale_and_shift(prediction, target, mask=None):
         scale = torch.empty(n_img, dtype=torch.float32, device=dev)
         shift = torch.empty(n_img, dtype=torch.float32, device=dev)
         _lib.check(lib.mde_scale_and_shift(_lib.ptr(p), _lib.dtype_code(p), _lib.ptr(t), _lib.ptr(m), n_img, h * w,
-                                           _lib.ptr(ws), _lib.ptr(scale), _lib.ptr(shift), _lib.stream_ptr(dev)))
+                                           _lib.ptr(ws), _lib.ptr(scale), _lib.ptr(shift), None, _lib.stream_ptr(dev)))
     return scale.view(lead), shift.view(lead)
 
 
@@ -427,10 +427,12 @@ def scale_shift(pred, target):
 class MidasLoss(nn.Module):
     """reference criteria.py:306-332: data term + alpha * multi-scale gradient matching.
 
-    Built on the kernels: `loss` in {'mse', 'l1', 'trim'} with reduction='batch-based' - 'mse' with alpha=0.5 is the
-    criterion of the registered method `my` (modules/my.py:39); 'trim' (criteria.py:208-217) trims nothing as the
-    reference is written and equals 'l1'. Not built yet: the 'ssi*' variants (they differentiate through
-    compute_scale_and_shift) and reduction='image-based' (which raises inside the reference for 'mse')."""
+    `loss` in {'mse', 'l1', 'trim', 'ssimse', 'ssil1', 'ssitrim'} with reduction='batch-based': 'mse' with alpha=0.5
+    is the criterion of the registered method `my` (modules/my.py:39), the 'ssi*' names those of `midas`
+    (modules/midas.py:30-31). 'trim' (criteria.py:208-217) trims nothing as the reference is written and equals 'l1'.
+    The 'ssi' variants align the prediction per image first (compute_scale_and_shift) and differentiate through
+    that 2x2 solve (C ABI mde_midas_ssi_backward). reduction='image-based' is not built (it raises inside the
+    reference for 'mse')."""
 
     def __init__(self, alpha=0.5, scales=4, loss='ssimse', reduction='batch-based'):
         super().__init__()
@@ -441,10 +443,7 @@ class MidasLoss(nn.Module):
             self._kind = 0
         else:
             raise ValueError()
-        if 'ssi' in self.loss:
-            raise NotImplementedError("MidasLoss(loss=%r): the scale-and-shift invariant variants differentiate through "
-                                      "compute_scale_and_shift (criteria.py:326-328); only 'mse', 'l1' and 'trim' are on "
-                                      "the kernels so far" % (loss,))
+        self._ssi = 'ssi' in self.loss
         if reduction != 'batch-based':
             raise NotImplementedError("MidasLoss(reduction=%r): only 'batch-based' (the reference default) is built" % (reduction,))
         self._alpha = float(alpha)
@@ -460,19 +459,31 @@ class MidasLoss(nn.Module):
         assert prediction.shape == target.shape and prediction.ndim == 3, "prediction/target must be [B,H,W] or [B,1,H,W]"
         B, H, W = (int(v) for v in prediction.shape)
         t = target.detach().to(torch.float32).contiguous()
-        kind, alpha, scales = self._kind, self._alpha, self._scales
+        kind, alpha, scales, ssi = self._kind, self._alpha, self._scales, self._ssi
 
         def launch(p, need_grad):
             pc = p.detach()
-            if pc.dtype not in (torch.float32, torch.float16, torch.bfloat16):
-                pc = pc.float()
+            if pc.dtype not in (torch.float32, torch.float16, torch.bfloat16) or ssi:
+                pc = pc.float()                      # the backward through the solve works on fp32 buffers
             pc = pc.contiguous()
+            sp = _lib.stream_ptr(dev)
             with torch.cuda.device(dev):
                 ws = _lib.workspace(dev, B)
                 loss = torch.empty((), dtype=torch.float32, device=dev)
                 grad = torch.empty_like(pc) if need_grad else None
-                _lib.check(lib.mde_midas_loss(_lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(t), B, H, W, kind, alpha, scales,
-                                              1.0, _lib.ptr(ws), _lib.ptr(loss), _lib.ptr(grad), _lib.stream_ptr(dev)))
+                scale = shift = sums = None
+                if ssi:                              # criteria.py:326-328
+                    scale = torch.empty(B, dtype=torch.float32, device=dev)
+                    shift = torch.empty(B, dtype=torch.float32, device=dev)
+                    sums = torch.empty((B, 5), dtype=torch.float64, device=dev)
+                    _lib.check(lib.mde_scale_and_shift(_lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(t), None, B, H * W,
+                                                       _lib.ptr(ws), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(sums), sp))
+                _lib.check(lib.mde_midas_loss(_lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(t), _lib.ptr(scale), _lib.ptr(shift),
+                                              B, H, W, kind, alpha, scales, 1.0, _lib.ptr(ws), _lib.ptr(loss), _lib.ptr(grad), sp))
+                if ssi and need_grad:
+                    coef = torch.empty((B, 4), dtype=torch.float32, device=dev)
+                    _lib.check(lib.mde_midas_ssi_backward(_lib.ptr(pc), _lib.ptr(t), _lib.ptr(scale), _lib.ptr(shift),
+                                                          _lib.ptr(sums), B, H * W, _lib.ptr(ws), _lib.ptr(coef), _lib.ptr(grad), sp))
             return loss, (grad.to(p.dtype) if grad is not None and grad.dtype != p.dtype else grad)
 
         return _FusedLossFn.apply(prediction, launch)

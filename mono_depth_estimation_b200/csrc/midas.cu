@@ -22,7 +22,7 @@ template <typename PT>
 __global__ void __launch_bounds__(kMBlock) scale_shift_kernel(const PT* __restrict__ pred, const float* __restrict__ gt,
                                                              const uint8_t* __restrict__ mask, int64_t n_img, int64_t hw,
                                                              int chunks_per_img, void* ws_raw, float* __restrict__ scale_out,
-                                                             float* __restrict__ shift_out) {
+                                                             float* __restrict__ shift_out, double* __restrict__ sums_out) {
   __shared__ double sm[5 * kMWarps];
   __shared__ bool sm_last;
   Ws ws = ws_view(ws_raw);
@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(kMBlock) scale_shift_kernel(const PT* __restri
     }
     scale_out[b] = static_cast<float>(x0);
     shift_out[b] = static_cast<float>(x1);
+    if (sums_out) {   // {a00, a01, a11, det, valid} for the backward through the solve (mde_midas_ssi_backward)
+      sums_out[b * 5 + 0] = a00; sums_out[b * 5 + 1] = a01; sums_out[b * 5 + 2] = a11;
+      sums_out[b * 5 + 3] = det; sums_out[b * 5 + 4] = (det != 0.0) ? 1.0 : 0.0;
+    }
 #pragma unroll
     for (int q = 0; q < 5; ++q) r[q] = 0.0;
   }
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(kMBlock) apply_scale_shift_kernel(const PT* __
 
 template <typename PT>
 int launch_scale_shift(const void* pred, const float* gt, const uint8_t* mask, int64_t n_img, int64_t hw, void* ws,
-                       float* scale_out, float* shift_out, cudaStream_t st) {
+                       float* scale_out, float* shift_out, double* sums_out, cudaStream_t st) {
   const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
   int64_t cpi = cap / n_img;
   const int64_t max_cpi = (hw + kMChunk - 1) / kMChunk;
@@ -112,7 +116,7 @@ int launch_scale_shift(const void* pred, const float* gt, const uint8_t* mask, i
   int64_t grid = n_img * cpi;
   if (grid > cap) grid = cap;
   scale_shift_kernel<PT><<<static_cast<unsigned>(grid), kMBlock, 0, st>>>(static_cast<const PT*>(pred), gt, mask, n_img, hw,
-                                                                         static_cast<int>(cpi), ws, scale_out, shift_out);
+                                                                         static_cast<int>(cpi), ws, scale_out, shift_out, sums_out);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
@@ -135,15 +139,16 @@ int launch_apply(const void* pred, const float* scale, const float* shift, int64
 }  // namespace mde
 
 extern "C" int mde_scale_and_shift(const void* pred, int pred_dtype, const float* target, const uint8_t* mask_u8,
-                                   int64_t n_img, int64_t hw, void* ws, float* scale_out, float* shift_out, void* stream) {
+                                   int64_t n_img, int64_t hw, void* ws, float* scale_out, float* shift_out,
+                                   double* sums_out, void* stream) {
   using namespace mde;
   MDE_REQUIRE(pred && target && ws && scale_out && shift_out, MDE_EINVAL, "null pointer");
   MDE_REQUIRE(n_img > 0 && hw > 0, MDE_EINVAL, "empty input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (pred_dtype) {
-    case MDE_F32: return launch_scale_shift<float>(pred, target, mask_u8, n_img, hw, ws, scale_out, shift_out, st);
-    case MDE_F16: return launch_scale_shift<__half>(pred, target, mask_u8, n_img, hw, ws, scale_out, shift_out, st);
-    case MDE_BF16: return launch_scale_shift<__nv_bfloat16>(pred, target, mask_u8, n_img, hw, ws, scale_out, shift_out, st);
+    case MDE_F32: return launch_scale_shift<float>(pred, target, mask_u8, n_img, hw, ws, scale_out, shift_out, sums_out, st);
+    case MDE_F16: return launch_scale_shift<__half>(pred, target, mask_u8, n_img, hw, ws, scale_out, shift_out, sums_out, st);
+    case MDE_BF16: return launch_scale_shift<__nv_bfloat16>(pred, target, mask_u8, n_img, hw, ws, scale_out, shift_out, sums_out, st);
     default: set_error("mde_scale_and_shift: unknown pred_dtype %d", pred_dtype); return MDE_EINVAL;
   }
 }
@@ -186,6 +191,8 @@ struct MidasArgs {
   const void* pred;
   const float* gt;
   int n_img, h, w;
+  const float* scale;   // nullable: per-image alignment p^ = scale * p + shift (the 'ssi' variants)
+  const float* shift;
   int kind;        // 0: mse, 1: l1 (= trim)
   int scales;
   float alpha, grad_scale;
@@ -208,6 +215,12 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
   const unsigned HW = static_cast<unsigned>(H) * static_cast<unsigned>(W);
   const unsigned total = static_cast<unsigned>(a.n_img) * HW;
   const unsigned tid = blockIdx.x * kBlock + threadIdx.x, nthr = gridDim.x * kBlock;
+  const bool ssi = a.scale != nullptr;
+  // prediction as the loss sees it: aligned with two separately rounded ops, as `scale * prediction + shift` is
+  auto ldp = [&](unsigned idx, float sc, float sh) -> float {
+    const float p = Elem<PT>::ld1(pred + idx);
+    return ssi ? __fadd_rn(__fmul_rn(sc, p), sh) : p;
+  };
 
   Ws ws = ws_view(a.ws);
   unsigned epoch;
@@ -220,11 +233,12 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
 #pragma unroll
     for (int q = 0; q < 2 + 2 * kMaxScales; ++q) acc[q] = 0.0;
     for (unsigned idx = tid; idx < total; idx += nthr) {
-      const unsigned rem = idx % HW;
+      const unsigned img = idx / HW, rem = idx - img * HW;
       const unsigned i = rem / W, j = rem - i * W;
+      const float sc = ssi ? __ldg(a.scale + img) : 1.f, sh = ssi ? __ldg(a.shift + img) : 0.f;
       const float t = __ldg(gt + idx);
       const bool v = t > 0.f;
-      const float res = v ? Elem<PT>::ld1(pred + idx) - t : 0.f;
+      const float res = v ? ldp(idx, sc, sh) - t : 0.f;
       acc[0] += static_cast<double>(a.kind == 0 ? res * res : fabsf(res));
       acc[1] += v ? 1.0 : 0.0;
 #pragma unroll
@@ -237,11 +251,11 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
         float e = 0.f;
         if (j + step < static_cast<unsigned>(W)) {
           const float tr = __ldg(gt + idx + step);
-          if (tr > 0.f) e += fabsf((Elem<PT>::ld1(pred + idx + step) - tr) - res);
+          if (tr > 0.f) e += fabsf((ldp(idx + step, sc, sh) - tr) - res);
         }
         if (i + step < static_cast<unsigned>(H)) {
           const float td = __ldg(gt + idx + step * W);
-          if (td > 0.f) e += fabsf((Elem<PT>::ld1(pred + idx + step * W) - td) - res);
+          if (td > 0.f) e += fabsf((ldp(idx + step * W, sc, sh) - td) - res);
         }
         acc[2 + 2 * s] += static_cast<double>(e);
       }
@@ -277,12 +291,13 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
   // ---------------- phase B: gradient -----------------------------------------------------------------------
   const float cd = sm_c[0];
   for (unsigned idx = tid; idx < total; idx += nthr) {
-    const unsigned rem = idx % HW;
+    const unsigned img = idx / HW, rem = idx - img * HW;
     const unsigned i = rem / W, j = rem - i * W;
+    const float sc = ssi ? __ldg(a.scale + img) : 1.f, sh = ssi ? __ldg(a.shift + img) : 0.f;
     const float t = __ldg(gt + idx);
     float g = 0.f;
     if (t > 0.f) {
-      const float res = Elem<PT>::ld1(pred + idx) - t;
+      const float res = ldp(idx, sc, sh) - t;
       g = cd * (a.kind == 0 ? res : sgnf(res));
 #pragma unroll
       for (int s = 0; s < kMaxScales; ++s) {
@@ -293,19 +308,19 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
         float sg = 0.f;   // sum over the four pairs of d|.|/d(res of this pixel)
         if (j + step < static_cast<unsigned>(W)) {
           const float tr = __ldg(gt + idx + step);
-          if (tr > 0.f) sg -= sgnf((Elem<PT>::ld1(pred + idx + step) - tr) - res);
+          if (tr > 0.f) sg -= sgnf((ldp(idx + step, sc, sh) - tr) - res);
         }
         if (j >= step) {
           const float tl = __ldg(gt + idx - step);
-          if (tl > 0.f) sg += sgnf(res - (Elem<PT>::ld1(pred + idx - step) - tl));
+          if (tl > 0.f) sg += sgnf(res - (ldp(idx - step, sc, sh) - tl));
         }
         if (i + step < static_cast<unsigned>(H)) {
           const float td = __ldg(gt + idx + step * W);
-          if (td > 0.f) sg -= sgnf((Elem<PT>::ld1(pred + idx + step * W) - td) - res);
+          if (td > 0.f) sg -= sgnf((ldp(idx + step * W, sc, sh) - td) - res);
         }
         if (i >= step) {
           const float tu = __ldg(gt + idx - step * W);
-          if (tu > 0.f) sg += sgnf(res - (Elem<PT>::ld1(pred + idx - step * W) - tu));
+          if (tu > 0.f) sg += sgnf(res - (ldp(idx - step * W, sc, sh) - tu));
         }
         g = fmaf(cs, sg, g);
       }
@@ -332,16 +347,18 @@ int launch_midas(MidasArgs& a, cudaStream_t st) {
 }  // namespace
 }  // namespace mde
 
-extern "C" int mde_midas_loss(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t h, int64_t w,
-                              int data_kind, float alpha, int scales, float grad_scale, void* ws, float* loss_out,
-                              void* grad, void* stream) {
+extern "C" int mde_midas_loss(const void* pred, int pred_dtype, const float* target, const float* scale, const float* shift,
+                              int64_t n_img, int64_t h, int64_t w, int data_kind, float alpha, int scales, float grad_scale,
+                              void* ws, float* loss_out, void* grad, void* stream) {
   using namespace mde;
   MDE_REQUIRE(pred && target && ws && loss_out, MDE_EINVAL, "null pointer");
   MDE_REQUIRE(n_img > 0 && h > 0 && w > 0, MDE_EINVAL, "empty input");
   MDE_REQUIRE(n_img * h * w < (int64_t(1) << 31), MDE_ETOOBIG, "more than 2^31 pixels");
   MDE_REQUIRE(data_kind == 0 || data_kind == 1, MDE_EINVAL, "data_kind: 0 (mse) or 1 (l1 / trim)");
   MDE_REQUIRE(scales >= 0 && scales <= kMaxScales, MDE_EINVAL, "scales must be in [0, 8]");
+  MDE_REQUIRE((scale == nullptr) == (shift == nullptr), MDE_EINVAL, "scale and shift come together");
   MidasArgs a;
+  a.scale = scale; a.shift = shift;
   a.pred = pred; a.gt = target; a.n_img = static_cast<int>(n_img); a.h = static_cast<int>(h); a.w = static_cast<int>(w);
   a.kind = data_kind; a.scales = scales; a.alpha = alpha; a.grad_scale = grad_scale; a.ws = ws; a.loss_out = loss_out;
   a.grad = grad;
@@ -352,4 +369,115 @@ extern "C" int mde_midas_loss(const void* pred, int pred_dtype, const float* tar
     case MDE_BF16: return launch_midas<__nv_bfloat16>(a, st);
     default: set_error("mde_midas_loss: unknown pred_dtype %d", pred_dtype); return MDE_EINVAL;
   }
+}
+
+// ---- backward through the alignment: dL/dp from g = dL/dp^ ---------------------------------------------------
+// p^_j = s p_j + t with (s, t) the least-squares solution of A [s t]^T = b (A, b: the masked sums above). Perturbing
+// p_i changes a00, a01, b0, hence (s, t):  A [ds dt]^T = m_i [y_i - 2 s p_i - t, -s]^T dp_i. With G0 = sum_j g_j and
+// G1 = sum_j g_j p_j per image,
+//     dL/dp_i = s g_i + m_i (U y_i - 2 s U p_i - t U - s V),   U = (a11 G1 - a01 G0) / det,  V = (a00 G0 - a01 G1) / det
+// (zero correction where det == 0: the reference leaves scale = shift = 0 there as constants). Two launches: the
+// per-image reduction of (g, g p), then the elementwise update in place on g.
+namespace mde {
+namespace {
+
+__global__ void __launch_bounds__(kMBlock) ssi_reduce_kernel(const float* __restrict__ pred, const float* __restrict__ g,
+                                                            int64_t n_img, int64_t hw, int chunks_per_img, void* ws_raw,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            const double* __restrict__ sums, float* __restrict__ coef) {
+  __shared__ double sm[2 * kMWarps];
+  __shared__ bool sm_last;
+  Ws ws = ws_view(ws_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_work = n_img * chunks_per_img;
+  const int64_t per_chunk = ((hw + chunks_per_img - 1) / chunks_per_img + kMBlock - 1) / kMBlock * kMBlock;
+  for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+    const int64_t img = wk / chunks_per_img;
+    const int64_t c0 = (wk - img * chunks_per_img) * per_chunk;
+    int64_t c1 = c0 + per_chunk;
+    if (c1 > hw) c1 = hw;
+    double G0 = 0.0, G1 = 0.0;
+    for (int64_t i = c0 + threadIdx.x; i < c1; i += kMBlock) {
+      const double gv = static_cast<double>(__ldg(g + img * hw + i));
+      G0 += gv;
+      G1 = fma(gv, static_cast<double>(__ldg(pred + img * hw + i)), G1);
+    }
+    const double s0 = warp_sum(G0), s1 = warp_sum(G1);
+    if (lane == 0) { sm[warp] = s0; sm[kMWarps + warp] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double tot = 0.0;
+      for (int w = 0; w < kMWarps; ++w) tot += sm[threadIdx.x * kMWarps + w];
+      if (tot != 0.0) atomicAdd(&ws.iacc[img * kIacc + threadIdx.x], tot);
+    }
+    __syncthreads();
+  }
+  __threadfence();
+  if (threadIdx.x == 0) sm_last = (atomicAdd(&ws.hdr->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!sm_last) return;
+  __threadfence();
+  for (int64_t b = threadIdx.x; b < n_img; b += kMBlock) {
+    double* r = ws.iacc + b * kIacc;
+    const double G0 = __ldcg(r + 0), G1 = __ldcg(r + 1);
+    r[0] = 0.0; r[1] = 0.0;
+    const double a00 = sums[b * 5 + 0], a01 = sums[b * 5 + 1], a11 = sums[b * 5 + 2], det = sums[b * 5 + 3];
+    const double s = static_cast<double>(scale[b]), t = static_cast<double>(shift[b]);
+    double U = 0.0, V = 0.0;
+    if (det != 0.0) {
+      U = (a11 * G1 - a01 * G0) / det;
+      V = (a00 * G0 - a01 * G1) / det;
+    }
+    coef[b * 4 + 0] = static_cast<float>(s);                 // s g_i
+    coef[b * 4 + 1] = static_cast<float>(U);                 // U y_i
+    coef[b * 4 + 2] = static_cast<float>(-2.0 * s * U);      // -2 s U p_i
+    coef[b * 4 + 3] = static_cast<float>(-(t * U + s * V));  // constant
+  }
+  if (threadIdx.x == 0) ws.hdr->ticket = 0u;
+}
+
+__global__ void __launch_bounds__(kMBlock) ssi_update_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                            const float* __restrict__ coef, int64_t n_img, int64_t hw,
+                                                            float* __restrict__ g) {
+  const int64_t total = n_img * hw;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kMBlock + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kMBlock) {
+    const int64_t b = i / hw;
+    const float4 c = __ldg(reinterpret_cast<const float4*>(coef) + b);
+    const float y = __ldg(gt + i);
+    float out = c.x * g[i];
+    if (y > 0.f) out += fmaf(c.y, y, fmaf(c.z, __ldg(pred + i), c.w));
+    g[i] = out;
+  }
+}
+
+}  // namespace
+}  // namespace mde
+
+extern "C" int mde_midas_ssi_backward(const float* pred, const float* target, const float* scale, const float* shift,
+                                      const double* sums, int64_t n_img, int64_t hw, void* ws, float* coef_scratch,
+                                      float* grad_inout, void* stream) {
+  using namespace mde;
+  MDE_REQUIRE(pred && target && scale && shift && sums && ws && coef_scratch && grad_inout, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(n_img > 0 && hw > 0, MDE_EINVAL, "empty input");
+  MDE_REQUIRE(aligned_to(coef_scratch, 16), MDE_EALIGN, "coef_scratch must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  int64_t cpi = cap / n_img;
+  const int64_t max_cpi = (hw + kMChunk - 1) / kMChunk;
+  if (cpi > max_cpi) cpi = max_cpi;
+  if (cpi < 1) cpi = 1;
+  int64_t grid = n_img * cpi;
+  if (grid > cap) grid = cap;
+  ssi_reduce_kernel<<<static_cast<unsigned>(grid), kMBlock, 0, st>>>(pred, grad_inout, n_img, hw, static_cast<int>(cpi), ws, scale,
+                                                                    shift, sums, coef_scratch);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  int64_t g2 = (n_img * hw + kMBlock - 1) / kMBlock;
+  const int64_t cap2 = static_cast<int64_t>(sm_count()) * 8;
+  if (g2 > cap2) g2 = cap2;
+  ssi_update_kernel<<<static_cast<unsigned>(g2), kMBlock, 0, st>>>(pred, target, coef_scratch, n_img, hw, grad_inout);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
 }

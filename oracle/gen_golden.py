@@ -381,9 +381,12 @@ def gen_midas():
     pr[0, 0, 4, 4:8] = tg[0, 0, 4, 4:8]          # exact ties: |0| has a zero subgradient
     out["ml_pred"], out["ml_target"] = pr.numpy(), tg.numpy()
     for name, kw in (("mse", dict(alpha=0.5, loss="mse")), ("l1", dict(alpha=0.5, loss="l1")), ("trim", dict(alpha=0.5, loss="trim")),
-                     ("mse_a0", dict(alpha=0.0, loss="mse")), ("mse_s2", dict(alpha=0.25, scales=2, loss="mse"))):
+                     ("mse_a0", dict(alpha=0.0, loss="mse")), ("mse_s2", dict(alpha=0.25, scales=2, loss="mse")),
+                     ("ssimse", dict(alpha=0.5, loss="ssimse")), ("ssil1", dict(alpha=0.5, loss="ssil1")),
+                     ("ssimse_a0", dict(alpha=0.0, loss="ssimse"))):
         for dt, sfx in ((torch.float32, "32"), (torch.float64, "64")):
-            p = pr.to(dt).clone().requires_grad_(True)
+            src = (0.7 / pr.clamp_min(0.3) + 0.2) if "ssi" in name else pr     # disparity-like input for the aligned variants
+            p = src.to(dt).clone().requires_grad_(True)
             l = crit.MidasLoss(**kw)(p, tg.to(dt))
             (gr,) = torch.autograd.grad(l, p)
             out[f"ml_{name}_loss{sfx}"], out[f"ml_{name}_grad{sfx}"] = l.detach().numpy(), gr.numpy()

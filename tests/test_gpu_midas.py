@@ -62,11 +62,15 @@ def test_scale_shift_vs_oracle(Cr, shape, dtype):
 
 @pytest.mark.parametrize("name,kw", [("mse", dict(alpha=0.5, loss="mse")), ("l1", dict(alpha=0.5, loss="l1")),
                                      ("trim", dict(alpha=0.5, loss="trim")), ("mse_a0", dict(alpha=0.0, loss="mse")),
-                                     ("mse_s2", dict(alpha=0.25, scales=2, loss="mse"))])
+                                     ("mse_s2", dict(alpha=0.25, scales=2, loss="mse")),
+                                     ("ssimse", dict(alpha=0.5, loss="ssimse")), ("ssil1", dict(alpha=0.5, loss="ssil1")),
+                                     ("ssimse_a0", dict(alpha=0.0, loss="ssimse"))])
 def test_midas_loss_golden(Cr, golden, name, kw):
     from tests.gpu_util import LOSS_RTOL, grad_close, run_loss
     g = golden("midas_small.npz")
     pred, target = T(g["ml_pred"]).cuda(), T(g["ml_target"]).cuda()
+    if "ssi" in name:
+        pred = 0.7 / pred.clamp_min(0.3) + 0.2
     loss, grad = run_loss(Cr.MidasLoss(**kw), pred, target)
     assert loss.dim() == 0 and grad.shape == pred.shape
     close(loss, g[f"ml_{name}_loss64"], LOSS_RTOL)
@@ -84,14 +88,20 @@ def test_midas_loss_vs_oracle(Cr, shape):
     target[torch.rand(shape, generator=g) < 0.2] = 0.0
     target[-1, :, : shape[2] // 3] = 0.0
     pred = target.clamp_min(0.4) + torch.randn(shape, generator=g) * 0.3
-    for kw in (dict(alpha=0.5, loss="mse"), dict(alpha=0.5, loss="l1")):
-        p64 = pred.double().requires_grad_(True)
+    disp = 0.7 / pred.clamp_min(0.3) + 0.2           # disparity-like input for the aligned ('ssi') variants
+    for kw in (dict(alpha=0.5, loss="mse"), dict(alpha=0.5, loss="l1"), dict(alpha=0.5, loss="ssimse"),
+               dict(alpha=0.5, loss="ssitrim")):
+        src = disp if "ssi" in kw["loss"] else pred
+        p64 = src.double().requires_grad_(True)
         l64 = om.midas_loss(p64, target.double(), **kw)
         (g64,) = torch.autograd.grad(l64, p64)
-        loss, grad = run_loss(Cr.MidasLoss(**kw), pred.cuda(), target.cuda())
-        close(loss, l64.detach(), LOSS_RTOL)
-        grad_close(grad, g64)
+        loss, grad = run_loss(Cr.MidasLoss(**kw), src.cuda(), target.cuda())
+        close(loss, l64.detach(), 3e-5 if "ssi" in kw["loss"] else LOSS_RTOL, msg=str(kw))
+        if "ssi" in kw["loss"]:   # the alignment is an fp32 product + sum of an fp32 prediction: 1e-5-level gradient noise
+            close(grad, g64, 1e-3, 2e-5 * float(g64.abs().max()), msg=str(kw))
+        else:
+            grad_close(grad, g64, msg=str(kw))
     z = torch.zeros(2, 1, 16, 24).cuda()
     assert float(Cr.MidasLoss(alpha=0.5, loss="mse")(torch.ones_like(z), z)) == 0.0      # zero divisors give 0 (criteria.py:185-186)
     with pytest.raises(NotImplementedError):
-        Cr.MidasLoss()                                                                    # default 'ssimse' is not built yet
+        Cr.MidasLoss(reduction="image-based")

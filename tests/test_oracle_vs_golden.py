@@ -230,11 +230,15 @@ def test_midas_scale_and_shift(golden):
 
 @pytest.mark.parametrize("name,kw", [("mse", dict(alpha=0.5, loss="mse")), ("l1", dict(alpha=0.5, loss="l1")),
                                      ("trim", dict(alpha=0.5, loss="trim")), ("mse_a0", dict(alpha=0.0, loss="mse")),
-                                     ("mse_s2", dict(alpha=0.25, scales=2, loss="mse"))])
+                                     ("mse_s2", dict(alpha=0.25, scales=2, loss="mse")),
+                                     ("ssimse", dict(alpha=0.5, loss="ssimse")), ("ssil1", dict(alpha=0.5, loss="ssil1")),
+                                     ("ssimse_a0", dict(alpha=0.0, loss="ssimse"))])
 def test_midas_loss(golden, name, kw):
     from oracle import midas as om
     g = golden("midas_small.npz")
     pred, target = T(g["ml_pred"]), T(g["ml_target"])
+    if "ssi" in name:
+        pred = 0.7 / pred.clamp_min(0.3) + 0.2
     p = pred.double().requires_grad_(True)
     l = om.midas_loss(p, target.double(), **kw)
     (gr,) = torch.autograd.grad(l, p)
