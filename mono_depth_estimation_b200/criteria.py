@@ -428,8 +428,8 @@ class MidasLoss(nn.Module):
     """reference criteria.py:306-332: data term + alpha * multi-scale gradient matching.
 
     `loss` in {'mse', 'l1', 'trim', 'ssimse', 'ssil1', 'ssitrim'} with reduction='batch-based': 'mse' with alpha=0.5
-    is the criterion of the registered method `my` (modules/my.py:39), the 'ssi*' names those of `midas`
-    (modules/midas.py:30-31). 'trim' (criteria.py:208-217) trims nothing as the reference is written and equals 'l1'.
+    is the criterion of the registered method `my` (modules/my.py:39), 'ssil1' / 'ssimse' / 'l1' / 'mse' / 'trim' those
+    of `midas` (modules/midas.py:30-31; its default 'ssitrim' routes to TrimmedProcrustesLoss, which is not built). 'trim' (criteria.py:208-217) trims nothing as the reference is written and equals 'l1'.
     The 'ssi' variants align the prediction per image first (compute_scale_and_shift) and differentiate through
     that 2x2 solve (C ABI mde_midas_ssi_backward). reduction='image-based' is not built (it raises inside the
     reference for 'mse')."""
