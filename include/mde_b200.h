@@ -295,6 +295,14 @@ int mde_point_cloud(const float* depth, int64_t n_img, int64_t h, int64_t w, flo
                     float clip_start, float clip_end, const float* matrix_world_host, int out_f64,
                     void* out, void* stream);
 
+/* ASCII PLY writer of reference depth2pointcloud.py:131-154 (host code; pointers are HOST memory): for every pixel
+ * the front point then the back point (back_xyz nullable), each skipped when its x is NaN, as
+ * "%f %f %f %d %d %d 0" with the cv2 BGR colour swapped to RGB; header, lines and the template's final newline.
+ * front_xyz/back_xyz [n_points,3] float64 (world coordinates), color_bgr [n_points,3] uint8.
+ * Returns the number of vertices written (>= 0) or a negative MDE_E* code. */
+int64_t mde_write_ply(const char* path, const double* front_xyz, const double* back_xyz, const uint8_t* color_bgr,
+                      int64_t n_points);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 size_t mde_workspace_bytes(int64_t max_images);
 /* zero-fills the workspace and records its capacity (max_images); call once after allocating */

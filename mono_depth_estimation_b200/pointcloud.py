@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["Camera", "point_cloud", "point_cloud_world"]
+__all__ = ["Camera", "point_cloud", "point_cloud_world", "write_ply"]
 
 
 @dataclass
@@ -63,3 +63,31 @@ def point_cloud(depth, cam, dtype=torch.float64):
 def point_cloud_world(depth, cam, dtype=torch.float64):
     """point_cloud followed by `cam.matrix_world @ p` for every point (depth2pointcloud.py:103-108), fused."""
     return _launch(depth, cam, cam.matrix_world, dtype)
+
+
+def write_ply(path, front_points, color_bgr, back_points=None):
+    """The ASCII PLY file of reference depth2pointcloud.py:131-154: for every pixel the front point, then the back
+    point, each skipped when its x is NaN; colours arrive as cv2 gives them (BGR) and are written RGB with alpha 0.
+    front_points / back_points: [..., 3] world coordinates (numpy or tensor), color_bgr: uint8 [..., 3] with the same
+    number of pixels. Host-side writer (C ABI mde_write_ply). Returns the number of vertices written."""
+    lib = _lib.load()
+
+    def host(x, dtype):
+        if isinstance(x, torch.Tensor):
+            x = x.detach().cpu().numpy()
+        return np.ascontiguousarray(np.asarray(x, dtype=dtype).reshape(-1, 3))
+
+    f = host(front_points, np.float64)
+    c = host(color_bgr, np.uint8)
+    if c.shape[0] != f.shape[0]:
+        raise ValueError("color must hold one BGR triple per point")
+    b = None
+    if back_points is not None:
+        b = host(back_points, np.float64)
+        if b.shape[0] != f.shape[0]:
+            raise ValueError("front and back point sets must have the same number of pixels")
+    n = lib.mde_write_ply(str(path).encode(), C.c_void_p(f.ctypes.data), None if b is None else C.c_void_p(b.ctypes.data),
+                          C.c_void_p(c.ctypes.data), f.shape[0])
+    if n < 0:
+        _lib.check(int(n))
+    return int(n)
