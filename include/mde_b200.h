@@ -227,6 +227,17 @@ int mde_vnl_loss(const float* gt_depth, const void* pred, int pred_dtype, const 
                  float grad_scale, void* ws, void* scratch, float* loss_out, double* stats_out,
                  void* grad, void* stream);
 
+/*
+ * Metrics of a prediction and a target that are BOTH bilinearly resized to out_h x out_w first, as the test steps of
+ * the eigen / dorn / my modules do (F.interpolate(mode='bilinear'), align_corners=False: reference
+ * modules/eigen.py:49-51, modules/dorn.py:181-183, modules/my.py:64-66) - sampled on the fly, the resized images are
+ * never materialised. pred [n_img,pred_h,pred_w], target [n_img,target_h,target_w], fp32. Outputs as mde_metrics.
+ */
+int mde_metrics_resized(const float* pred, int64_t pred_h, int64_t pred_w, const float* target, int64_t target_h,
+                        int64_t target_w, int64_t n_img, int64_t out_h, int64_t out_w, unsigned flags, void* ws,
+                        double* out_f64, float* out_f32, double* per_image_values, double* per_image_raw,
+                        void* stream);
+
 /* ---- VNL's classification half ------------------------------------------ */
 /*
  * WCEL_Loss.forward(pred_logit, gt_bins, gt) (reference criteria.py:839-863), forward + backward:

@@ -42,6 +42,7 @@ _vp, _i64, _i32, _u32, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint, C.c_floa
 # name -> (restype, argtypes); every symbol include/mde_b200.h declares
 SIGNATURES = {
     "mde_metrics": (_i32, [_vp, _i32, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mde_metrics_resized": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mde_metrics_finalize_host": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mde_masked_loss": (_i32, [_i32, _vp, _i32, _vp, _vp, _i64, _i64, _i64, C.POINTER(LossParams), _f32,
                                _vp, _vp, _vp, _vp, _vp]),

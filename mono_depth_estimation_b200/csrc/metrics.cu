@@ -92,6 +92,54 @@ struct MetricThread {
 __constant__ int kRunToQ[8] = {MDE_Q_ABS, MDE_Q_SQ, MDE_Q_LOG10, MDE_Q_SLE,
                                MDE_Q_ABSREL, MDE_Q_SQREL, MDE_Q_RSQ, MDE_Q_LNSQ};
 
+// Flush one image's partial sums of this CTA: warp shuffle -> shared memory -> 12 fp64 atomics into the image's
+// accumulator row. Ends with the shared buffers consumed.
+template <unsigned G, bool Ref, bool LONG>
+__device__ __forceinline__ void flush_image(MetricThread<G, Ref, LONG>& th, int64_t img, double* iacc, double* sm_d, int* sm_i) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  th.cnt.unpack();
+  const int c0 = __reduce_add_sync(0xffffffffu, th.cnt.n);
+  const int c1 = __reduce_add_sync(0xffffffffu, th.cnt.c1);
+  const int c2 = __reduce_add_sync(0xffffffffu, th.cnt.c2);
+  const int c3 = __reduce_add_sync(0xffffffffu, th.cnt.c3);
+  if (lane == 0) {
+    sm_i[0 * kWarps + warp] = c0;
+    sm_i[1 * kWarps + warp] = c1;
+    sm_i[2 * kWarps + warp] = c2;
+    sm_i[3 * kWarps + warp] = c3;
+  }
+  // per-thread sums are fp64; the 32-lane tree is done in fp32 (5 levels, <= 4e-7 relative) and
+  // widened again before the cross-warp and cross-CTA accumulation
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
+                      ((G & kGrpRel) && (q >= 4 && q <= 6));
+    if (!used) continue;
+    const float s = warp_sum(th.total(q));
+    if (lane == 0) sm_d[q * kWarps + warp] = static_cast<double>(s);
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    double tot = 0.0;
+    int qidx;
+    if (threadIdx.x < 4) {
+      long long ci = 0;
+      for (int w = 0; w < kWarps; ++w) ci += sm_i[threadIdx.x * kWarps + w];
+      tot = static_cast<double>(ci);
+      qidx = threadIdx.x;  // MDE_Q_NVALID, D1, D2, D3
+    } else {
+      const int q = threadIdx.x - 4;
+      const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
+                        ((G & kGrpRel) && (q >= 4 && q <= 6));
+      if (used)
+        for (int w = 0; w < kWarps; ++w) tot += sm_d[q * kWarps + w];
+      qidx = kRunToQ[q];
+    }
+    if (tot != 0.0) atomicAdd(&iacc[img * kIacc + qidx], tot);
+  }
+  __syncthreads();
+}
+
 // Numerator quantity of metric value m (value = raw[num] / n, sqrt for the last two)
 __constant__ int kValNum[kNM] = {MDE_Q_D1, MDE_Q_D2, MDE_Q_D3, MDE_Q_ABS, MDE_Q_SQ, MDE_Q_LOG10, MDE_Q_SLE,
                                  MDE_Q_ABSREL, MDE_Q_SQREL, MDE_Q_RSQ, MDE_Q_SQ, MDE_Q_LNSQ};
@@ -245,50 +293,7 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
       }
     }
 
-    // ---- flush this image's partial sums: warp shuffle -> shared memory -> 12 fp64 atomics ----
-    {
-      th.cnt.unpack();
-      const int c0 = __reduce_add_sync(0xffffffffu, th.cnt.n);
-      const int c1 = __reduce_add_sync(0xffffffffu, th.cnt.c1);
-      const int c2 = __reduce_add_sync(0xffffffffu, th.cnt.c2);
-      const int c3 = __reduce_add_sync(0xffffffffu, th.cnt.c3);
-      if (lane == 0) {
-        sm_i[0 * kWarps + warp] = c0;
-        sm_i[1 * kWarps + warp] = c1;
-        sm_i[2 * kWarps + warp] = c2;
-        sm_i[3 * kWarps + warp] = c3;
-      }
-      // per-thread sums are fp64; the 32-lane tree is done in fp32 (5 levels, <= 4e-7 relative) and
-      // widened again before the cross-warp and cross-CTA accumulation
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
-                          ((G & kGrpRel) && (q >= 4 && q <= 6));
-        if (!used) continue;
-        const float s = warp_sum(th.total(q));
-        if (lane == 0) sm_d[q * kWarps + warp] = static_cast<double>(s);
-      }
-      __syncthreads();
-      if (threadIdx.x < 12) {
-        double tot = 0.0;
-        int qidx;
-        if (threadIdx.x < 4) {
-          long long ci = 0;
-          for (int w = 0; w < kWarps; ++w) ci += sm_i[threadIdx.x * kWarps + w];
-          tot = static_cast<double>(ci);
-          qidx = threadIdx.x;  // MDE_Q_NVALID, D1, D2, D3
-        } else {
-          const int q = threadIdx.x - 4;
-          const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
-                            ((G & kGrpRel) && (q >= 4 && q <= 6));
-          if (used)
-            for (int w = 0; w < kWarps; ++w) tot += sm_d[q * kWarps + w];
-          qidx = kRunToQ[q];
-        }
-        if (tot != 0.0) atomicAdd(&iacc[img * kIacc + qidx], tot);
-      }
-      __syncthreads();
-    }
+    flush_image<G, Ref, LONG>(th, img, iacc, sm_d, sm_i);
     u = seg_end;
   }
 
@@ -302,6 +307,67 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
   if (!sm_last) return;
   __threadfence();
 
+  metrics_finalize(ws, n_img, out_f64, out_f32, per_image_values, per_image_raw, sm_d);
+}
+
+// ---- metrics on bilinearly resized inputs -----------------------------------------------
+// The test steps of the eigen / dorn / my modules resize BOTH the prediction and the target to 480 x 640 with
+// F.interpolate(mode='bilinear') (align_corners=False) right before log_test (modules/eigen.py:49-51,
+// modules/dorn.py:181-183, modules/my.py:64-66). Here every output pixel samples its two sources on the fly
+// (ATen's rule: src = (dst + 0.5) * in/out - 0.5 clamped at 0, the 4-tap blend in ATen's CUDA op order) and goes
+// straight into the metric accumulators: the two resized images are never written or re-read.
+__device__ __forceinline__ float bilinear_tap(const float* __restrict__ img, int ih, int iw, float sy, float sx, int oy, int ox) {
+  float fy = sy * (static_cast<float>(oy) + 0.5f) - 0.5f, fx = sx * (static_cast<float>(ox) + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  fx = fx < 0.f ? 0.f : fx;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = y0 + (y0 < ih - 1 ? 1 : 0), x1 = x0 + (x0 < iw - 1 ? 1 : 0);
+  const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float v00 = __ldg(img + static_cast<int64_t>(y0) * iw + x0), v01 = __ldg(img + static_cast<int64_t>(y0) * iw + x1);
+  const float v10 = __ldg(img + static_cast<int64_t>(y1) * iw + x0), v11 = __ldg(img + static_cast<int64_t>(y1) * iw + x1);
+  return hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+}
+
+template <unsigned G>
+__global__ void __launch_bounds__(kBlock, kCtasPerSm)
+metrics_resized_kernel(const float* __restrict__ pred, int ph, int pw, const float* __restrict__ gt, int gh, int gw,
+                       int64_t n_img, int oh, int ow, int chunks_per_img, void* ws_raw, double* __restrict__ out_f64,
+                       float* __restrict__ out_f32, double* __restrict__ per_image_values, double* __restrict__ per_image_raw) {
+  __shared__ double sm_d[2 * kNM * kWarps + kWarps];
+  __shared__ int sm_i[4 * kWarps];
+  __shared__ bool sm_last;
+  Ws ws = ws_view(ws_raw);
+  const float spy = static_cast<float>(ph) / static_cast<float>(oh), spx = static_cast<float>(pw) / static_cast<float>(ow);
+  const float sgy = static_cast<float>(gh) / static_cast<float>(oh), sgx = static_cast<float>(gw) / static_cast<float>(ow);
+  const int ohw = oh * ow;
+  const int per_chunk = ((ohw + chunks_per_img - 1) / chunks_per_img + kBlock - 1) / kBlock * kBlock;
+  const int64_t n_work = n_img * chunks_per_img;
+  MetricThread<G, false, false> th;
+  th.srun = nullptr;
+  for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+    const int64_t img = wk / chunks_per_img;
+    const int c0 = static_cast<int>(wk - img * chunks_per_img) * per_chunk;
+    const int c1 = (c0 + per_chunk < ohw) ? c0 + per_chunk : ohw;
+    const float* pimg = pred + img * static_cast<int64_t>(ph) * pw;
+    const float* gimg = gt + img * static_cast<int64_t>(gh) * gw;
+    th.reset();
+    int it = 0;
+    for (int i = c0 + threadIdx.x; i < c1; i += kBlock) {
+      const int oy = i / ow, ox = i - oy * ow;
+      th.px(bilinear_tap(pimg, ph, pw, spy, spx, oy, ox), bilinear_tap(gimg, gh, gw, sgy, sgx, oy, ox));
+      if ((++it & 63) == 0) th.cnt.unpack();   // the packed level histogram holds 255 pixels
+    }
+    flush_image<G, false, false>(th, img, ws.iacc, sm_d, sm_i);
+  }
+  __threadfence();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&ws.hdr->ticket, 1u);
+    sm_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!sm_last) return;
+  __threadfence();
   metrics_finalize(ws, n_img, out_f64, out_f32, per_image_values, per_image_raw, sm_d);
 }
 
@@ -386,3 +452,30 @@ extern "C" int mde_metrics(const void* pred, int pred_dtype, const float* target
 }
 
 extern "C" void mde_metrics_finalize_host(const double* raw, double* values) { mde::metric_values(raw, values); }
+
+extern "C" int mde_metrics_resized(const float* pred, int64_t pred_h, int64_t pred_w, const float* target, int64_t target_h,
+                                   int64_t target_w, int64_t n_img, int64_t out_h, int64_t out_w, unsigned flags, void* ws,
+                                   double* out_f64, float* out_f32, double* per_image_values, double* per_image_raw,
+                                   void* stream) {
+  using namespace mde;
+  MDE_REQUIRE(pred && target && ws && out_f64, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(n_img > 0 && pred_h > 0 && pred_w > 0 && target_h > 0 && target_w > 0 && out_h > 0 && out_w > 0, MDE_EINVAL,
+              "empty input");
+  MDE_REQUIRE(out_h * out_w < (int64_t(1) << 30) && pred_h * pred_w < (int64_t(1) << 30) && target_h * target_w < (int64_t(1) << 30),
+              MDE_ETOOBIG, "image too large");
+  MDE_REQUIRE((flags & MDE_METRICS_REFERENCE_MATH) == 0, MDE_EINVAL, "the resized path uses the fast metric forms");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * kCtasPerSm;
+  int64_t cpi = cap / n_img;
+  const int64_t max_cpi = (out_h * out_w + 4 * kBlock - 1) / (4 * kBlock);
+  if (cpi > max_cpi) cpi = max_cpi;
+  if (cpi < 1) cpi = 1;
+  int64_t grid = n_img * cpi;
+  if (grid > cap) grid = cap;
+  metrics_resized_kernel<kGrpAll><<<static_cast<unsigned>(grid), kBlock, 0, st>>>(
+      pred, static_cast<int>(pred_h), static_cast<int>(pred_w), target, static_cast<int>(target_h), static_cast<int>(target_w), n_img,
+      static_cast<int>(out_h), static_cast<int>(out_w), static_cast<int>(cpi), ws, out_f64, out_f32, per_image_values, per_image_raw);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}

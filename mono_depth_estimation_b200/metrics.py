@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["MetricLogger", "MetricComputation", "METRICS", "fused_metrics"]
+__all__ = ["MetricLogger", "MetricComputation", "METRICS", "fused_metrics", "fused_metrics_resized"]
 
 
 def _prep(pred, target):
@@ -74,6 +74,38 @@ def fused_metrics(pred, target, names=None, per_image=False, reference_math=Fals
         _lib.check(lib.mde_metrics(_lib.ptr(pred), _lib.dtype_code(pred), _lib.ptr(target), n_img, hw, flags,
                                    _lib.ptr(ws), _lib.ptr(out64), _lib.ptr(out32), _lib.ptr(piv), _lib.ptr(pir),
                                    _lib.stream_ptr(dev)))
+    res = {"values": out32[:_lib.METRIC_NM], "image_mean": out32[_lib.METRIC_NM:], "f64": out64}
+    if per_image:
+        res["per_image"] = piv
+        res["per_image_raw"] = pir
+    return res
+
+
+def fused_metrics_resized(pred, target, size=(480, 640), per_image=False):
+    """Metrics of `pred` and `target` after BOTH are bilinearly resized to `size` - what the test steps of the eigen,
+    dorn and my modules do with two F.interpolate(mode='bilinear') calls before log_test (reference
+    modules/eigen.py:49-51, modules/dorn.py:181-183, modules/my.py:64-66) - in one launch that samples the sources on
+    the fly (C ABI mde_metrics_resized). pred [B,1,h,w] / target [B,1,h',w'] (or [B,h,w]); same dict as fused_metrics."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(pred, target)
+    p = pred.detach().to(torch.float32).contiguous()
+    t = target.detach().to(torch.float32).contiguous()
+    ph, pw = int(p.shape[-2]), int(p.shape[-1])
+    th, tw = int(t.shape[-2]), int(t.shape[-1])
+    n_img = p.numel() // (ph * pw)
+    if t.numel() // (th * tw) != n_img:
+        raise AssertionError("inconsistent dimensions")
+    oh, ow = int(size[0]), int(size[1])
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(dev, n_img)
+        out64 = torch.empty(_lib.METRICS_OUT_F64, dtype=torch.float64, device=dev)
+        out32 = torch.empty(2 * _lib.METRIC_NM, dtype=torch.float32, device=dev)
+        piv = pir = None
+        if per_image:
+            piv = torch.empty((n_img, _lib.METRIC_NM), dtype=torch.float64, device=dev)
+            pir = torch.empty((n_img, _lib.METRIC_NQ), dtype=torch.float64, device=dev)
+        _lib.check(lib.mde_metrics_resized(_lib.ptr(p), ph, pw, _lib.ptr(t), th, tw, n_img, oh, ow, 0, _lib.ptr(ws),
+                                           _lib.ptr(out64), _lib.ptr(out32), _lib.ptr(piv), _lib.ptr(pir), _lib.stream_ptr(dev)))
     res = {"values": out32[:_lib.METRIC_NM], "image_mean": out32[_lib.METRIC_NM:], "f64": out64}
     if per_image:
         res["per_image"] = piv
@@ -189,6 +221,16 @@ class MetricComputation(object):
             self.last_f64 = res["f64"]
             if self.strict:
                 # the reference's `assert torch.sum(valid_mask) > 0` (metrics.py:61) reads the device too
+                assert float(res["f64"][2 * _lib.METRIC_NM + _lib.RAW_INDEX["n_valid"]]) > 0, "invalid target!"
+            return self._collect(res["values"], pred, target)
+
+    def compute_resized(self, pred, target, size=(480, 640)):
+        """compute() on pred and target bilinearly resized to `size` first (the test_step pattern of the eigen, dorn
+        and my modules), without materialising the resized tensors (extension; see fused_metrics_resized)."""
+        with torch.no_grad():
+            res = fused_metrics_resized(pred, target, size)
+            self.last_f64 = res["f64"]
+            if self.strict:
                 assert float(res["f64"][2 * _lib.METRIC_NM + _lib.RAW_INDEX["n_valid"]]) > 0, "invalid target!"
             return self._collect(res["values"], pred, target)
 

@@ -165,3 +165,35 @@ def test_delta_counts_bit_exact_near_thresholds(M):
             assert [int(round(v)) for v in res["per_image_raw"][b, :4].tolist()] == list(rb)
     # half of the sampled ratios sit within 1e-5 (log_1.25 units) of a threshold: the slow path is exercised
     assert 0.05 < ref[1] / ref[0] < 0.95
+
+
+@pytest.mark.parametrize("pshape,tshape", [((2, 1, 240, 320), (2, 1, 427, 561)), ((1, 1, 257, 353), (1, 1, 480, 640)),
+                                           ((3, 1, 480, 640), (3, 1, 480, 640)), ((2, 1, 109, 147), (2, 1, 55, 74))])
+def test_metrics_of_bilinearly_resized_inputs(M, pshape, tshape):
+    """the test steps of eigen / dorn / my resize prediction AND target to 480 x 640 with
+    F.interpolate(mode='bilinear') before log_test (modules/eigen.py:49-51). Oracle: those two torch ops on the CPU
+    followed by the metric oracle. Float metrics within 1e-5; the delta counts may move by the few pixels whose
+    interpolated ratio sits within an ulp of a threshold (CPU and GPU blend in a different op order)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(pshape[2] + tshape[3])
+    target = torch.rand(tshape, generator=g) * 9.5 + 0.5
+    target[torch.rand(tshape, generator=g) < 0.2] = 0.0
+    target[:, :, :7, :] = 0.0
+    pred = torch.rand(pshape, generator=g) * 9.0 + 0.6
+    size = (480, 640)
+    y_hat = F.interpolate(pred, size, mode="bilinear")
+    y = F.interpolate(target, size, mode="bilinear")
+    v64 = [float(v) for v in ometrics.compute(y_hat.double(), y.double(), ALL)]
+    ref_counts = list(ometrics.delta_counts(y_hat, y))
+    res = M.fused_metrics_resized(pred.cuda(), target.cuda(), size, per_image=True)
+    close(res["f64"][:12], v64, 2e-5)
+    got = _counts(res)
+    assert got[0] == ref_counts[0] or abs(got[0] - ref_counts[0]) <= 4          # y' > 0 at the same pixels
+    assert all(abs(a - b) <= 8 for a, b in zip(got, ref_counts)), (got, ref_counts)
+    assert res["per_image"].shape == (pshape[0], 12)
+    if pshape == tshape and pshape[-2:] == size:   # identity resize: exactly the plain kernel's numbers
+        plain = M.fused_metrics(pred.cuda(), target.cuda())
+        assert _counts(plain) == got
+        close(res["f64"][:12], plain["f64"][:12], 1e-6)
+    vals = M.MetricComputation(["delta1", "absrel", "rmse"], strict=False).compute_resized(pred.cuda(), target.cuda(), size)
+    close(torch.stack(vals), [v64[ALL.index(n)] for n in ("delta1", "absrel", "rmse")], 2e-5)
