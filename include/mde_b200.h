@@ -295,6 +295,29 @@ int mde_midas_ssi_backward(const float* pred, const float* target, const float* 
                            const double* sums, int64_t n_img, int64_t hw, void* ws, float* coef_scratch,
                            float* grad_inout, void* stream);
 
+/*
+ * TrimmedProcrustesLoss (reference criteria.py:335-363; `midas --loss ssitrim`, modules/midas.py:36-37), three calls:
+ *
+ * mde_robust_normalize = normalize_prediction_robust (criteria.py:135-152) of prediction AND target under the mask
+ * target > 0: x' = (x - m) / s with m the lower median of mask * x over ALL pixels of the image (exact: radix select
+ * on the fp32 bit pattern) and s = clamp(sum mask |x - m| / sum mask, 1e-6); m = 0, s = 1 for an image without a
+ * valid pixel. stats_* [n_img][8] fp32 = {m, s, n_valid, k (bit pattern of the uint32 index that holds the median),
+ * mask_k, Z = sum mask sign(x - m), s_was_clamped, 0}. pred/target/outputs fp32 [n_img, hw].
+ */
+int mde_robust_normalize(const float* pred, const float* target, int64_t n_img, int64_t hw, float* stats_pred,
+                         float* stats_target, float* pred_out, float* target_out, void* stream);
+/* mde_midas_loss on tensors whose validity is NOT target > 0: valid_src > 0 decides (criteria.py:351 takes the mask
+ * from the original target, the loss is evaluated on the normalised one). No scale/shift. Otherwise as mde_midas_loss. */
+int mde_midas_loss_masked(const void* pred, int pred_dtype, const float* target, const float* valid_src,
+                          int64_t n_img, int64_t h, int64_t w, int data_kind, float alpha, int scales,
+                          float grad_scale, void* ws, float* loss_out, void* grad, void* stream);
+/* Backward through the normalisation of the prediction: grad_inout holds g = dL/dx' on entry, dL/dx on exit:
+ * g_j / s - mask_j sign(x'_j) Gx / (s n) + [j == k] mask_k (Gx Z / (s n) - G / s), G = sum g, Gx = sum g x' per image
+ * (median gradient to element k, as torch.median(dim).values back-propagates; Gx terms dropped where s was clamped).
+ * pred_norm: pred_out of mde_robust_normalize; target: the ORIGINAL target; coef_scratch: n_img * 4 floats, 16-byte aligned. */
+int mde_robust_backward(const float* pred_norm, const float* target, const float* stats_pred, int64_t n_img,
+                        int64_t hw, void* ws, float* coef_scratch, float* grad_inout, void* stream);
+
 /* ---- depth -> point cloud ----------------------------------------------------------------- */
 /*
  * point_cloud(depth, cam) (reference depth2pointcloud.py:12-31) for a batch of depth maps, with the

@@ -70,6 +70,9 @@ SIGNATURES = {
     "mde_apply_scale_shift": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp]),
     "mde_midas_loss": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "mde_midas_ssi_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "mde_robust_normalize": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "mde_midas_loss_masked": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
+    "mde_robust_backward": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mde_point_cloud": (_i32, [_vp, _i64, _i64, _i64, _f32, _f32, _f32, C.POINTER(C.c_float), _i32, _vp, _vp]),
     "mde_write_ply": (_i64, [C.c_char_p, _vp, _vp, _vp, _i64]),
     "mde_workspace_bytes": (C.c_size_t, [_i64]),

@@ -28,7 +28,8 @@ from . import _lib
 
 __all__ = ["MaskedDepthLoss", "MaskedMSELoss", "MaskedL1Loss", "berHuLoss", "LainaBerHuLoss", "silog_loss",
            "ordLoss", "OrdinalRegressionLoss", "VNL_Loss", "ModelLoss", "masked_loss",
-           "compute_scale_and_shift", "scale_shift", "MidasLoss"]
+           "compute_scale_and_shift", "scale_shift", "MidasLoss", "TrimmedProcrustesLoss",
+           "normalize_prediction_robust"]
 
 
 def _scale_grad(grad, grad_output):
@@ -429,7 +430,7 @@ class MidasLoss(nn.Module):
 
     `loss` in {'mse', 'l1', 'trim', 'ssimse', 'ssil1', 'ssitrim'} with reduction='batch-based': 'mse' with alpha=0.5
     is the criterion of the registered method `my` (modules/my.py:39), 'ssil1' / 'ssimse' / 'l1' / 'mse' / 'trim' those
-    of `midas` (modules/midas.py:30-31; its default 'ssitrim' routes to TrimmedProcrustesLoss, which is not built). 'trim' (criteria.py:208-217) trims nothing as the reference is written and equals 'l1'.
+    of `midas` (modules/midas.py:30-31; its default 'ssitrim' routes to TrimmedProcrustesLoss below). 'trim' (criteria.py:208-217) trims nothing as the reference is written and equals 'l1'.
     The 'ssi' variants align the prediction per image first (compute_scale_and_shift) and differentiate through
     that 2x2 solve (C ABI mde_midas_ssi_backward). reduction='image-based' is not built (it raises inside the
     reference for 'mse')."""
@@ -484,6 +485,81 @@ class MidasLoss(nn.Module):
                     coef = torch.empty((B, 4), dtype=torch.float32, device=dev)
                     _lib.check(lib.mde_midas_ssi_backward(_lib.ptr(pc), _lib.ptr(t), _lib.ptr(scale), _lib.ptr(shift),
                                                           _lib.ptr(sums), B, H * W, _lib.ptr(ws), _lib.ptr(coef), _lib.ptr(grad), sp))
+            return loss, (grad.to(p.dtype) if grad is not None and grad.dtype != p.dtype else grad)
+
+        return _FusedLossFn.apply(prediction, launch)
+
+
+def normalize_prediction_robust(target, mask=None):
+    """reference criteria.py:135-152: per image (x - median(mask * x)) / clamp(mean_mask |x - median|, 1e-6) with the
+    default mask `target > 0` (the only one TrimmedProcrustesLoss uses). Evaluation-side function, detached result.
+    [B,H,W] fp32 -> [B,H,W] fp32 (C ABI mde_robust_normalize with the tensor as its own mask source)."""
+    lib = _lib.load()
+    dev = _lib.require_cuda(target)
+    if mask is not None:
+        raise NotImplementedError("normalize_prediction_robust: only the default mask (target > 0) is built")
+    n_img, h, w = _as_images(target)
+    x = target.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        st_a = torch.empty((n_img, 8), dtype=torch.float32, device=dev)
+        st_b = torch.empty((n_img, 8), dtype=torch.float32, device=dev)
+        out_a, out_b = torch.empty_like(x), torch.empty_like(x)
+        _lib.check(lib.mde_robust_normalize(_lib.ptr(x), _lib.ptr(x), n_img, h * w, _lib.ptr(st_a), _lib.ptr(st_b),
+                                            _lib.ptr(out_a), _lib.ptr(out_b), _lib.stream_ptr(dev)))
+    return out_b.view(target.shape)
+
+
+class TrimmedProcrustesLoss(nn.Module):
+    """reference criteria.py:335-363, the default criterion of the registered method `midas` (`--loss ssitrim`,
+    modules/midas.py:36-37): both tensors are normalised per image by normalize_prediction_robust (:135-152, median
+    and mean absolute deviation over `target > 0`), then TrimmedMAELoss (= l1 as the reference is written, :208-217)
+    + alpha * GradientLoss (:283-303) on the normalised pair, batch-based. The backward runs through the median
+    (gradient to the element that holds it) and the deviation in closed form (C ABI mde_robust_backward).
+    `prediction_ssi` holds the normalised prediction of the last call, as in the reference (:360-363)."""
+
+    def __init__(self, alpha=0.5, scales=4, reduction="batch-based"):
+        super().__init__()
+        if reduction != 'batch-based':
+            raise NotImplementedError("TrimmedProcrustesLoss(reduction=%r): only 'batch-based' (the reference default) is built" % (reduction,))
+        self._alpha = float(alpha)
+        self._scales = int(scales)
+        self._prediction_ssi = None
+
+    @property
+    def prediction_ssi(self):
+        return self._prediction_ssi
+
+    def forward(self, prediction, target):
+        lib = _lib.load()
+        dev = _lib.require_cuda(prediction, target)
+        if prediction.ndim == 4:
+            prediction = prediction.squeeze(1)
+        if target.ndim == 4:
+            target = target.squeeze(1)
+        assert prediction.shape == target.shape and prediction.ndim == 3, "prediction/target must be [B,H,W] or [B,1,H,W]"
+        B, H, W = (int(v) for v in prediction.shape)
+        t = target.detach().to(torch.float32).contiguous()
+        alpha, scales = self._alpha, self._scales
+
+        def launch(p, need_grad):
+            pc = p.detach().float().contiguous()
+            sp = _lib.stream_ptr(dev)
+            with torch.cuda.device(dev):
+                ws = _lib.workspace(dev, B)
+                loss = torch.empty((), dtype=torch.float32, device=dev)
+                st_p = torch.empty((B, 8), dtype=torch.float32, device=dev)
+                st_t = torch.empty((B, 8), dtype=torch.float32, device=dev)
+                pn, tn = torch.empty_like(pc), torch.empty_like(t)
+                grad = torch.empty_like(pc) if need_grad else None
+                _lib.check(lib.mde_robust_normalize(_lib.ptr(pc), _lib.ptr(t), B, H * W, _lib.ptr(st_p), _lib.ptr(st_t),
+                                                    _lib.ptr(pn), _lib.ptr(tn), sp))
+                _lib.check(lib.mde_midas_loss_masked(_lib.ptr(pn), _lib.dtype_code(pn), _lib.ptr(tn), _lib.ptr(t), B, H, W, 1,
+                                                     alpha, scales, 1.0, _lib.ptr(ws), _lib.ptr(loss), _lib.ptr(grad), sp))
+                if need_grad:
+                    coef = torch.empty((B, 4), dtype=torch.float32, device=dev)
+                    _lib.check(lib.mde_robust_backward(_lib.ptr(pn), _lib.ptr(t), _lib.ptr(st_p), B, H * W, _lib.ptr(ws),
+                                                       _lib.ptr(coef), _lib.ptr(grad), sp))
+            self._prediction_ssi = pn
             return loss, (grad.to(p.dtype) if grad is not None and grad.dtype != p.dtype else grad)
 
         return _FusedLossFn.apply(prediction, launch)

@@ -190,6 +190,7 @@ constexpr int kMaxScales = 8;
 struct MidasArgs {
   const void* pred;
   const float* gt;
+  const float* vsrc;    // nullable: validity comes from vsrc > 0 instead of gt > 0 (TrimmedProcrustesLoss: gt is normalised)
   int n_img, h, w;
   const float* scale;   // nullable: per-image alignment p^ = scale * p + shift (the 'ssi' variants)
   const float* shift;
@@ -203,7 +204,7 @@ struct MidasArgs {
 
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
-template <typename PT>
+template <typename PT, bool VS>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm_d[2 * kWarps];
@@ -216,6 +217,12 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
   const unsigned total = static_cast<unsigned>(a.n_img) * HW;
   const unsigned tid = blockIdx.x * kBlock + threadIdx.x, nthr = gridDim.x * kBlock;
   const bool ssi = a.scale != nullptr;
+  const float* __restrict__ vs = a.vsrc;
+  // target value and validity of one pixel (criteria.py:322: mask = target > 0 on the ORIGINAL target)
+  auto ldt = [&](unsigned idx, float& t) -> bool {
+    t = __ldg(gt + idx);
+    return VS ? (__ldg(vs + idx) > 0.f) : (t > 0.f);
+  };
   // prediction as the loss sees it: aligned with two separately rounded ops, as `scale * prediction + shift` is
   auto ldp = [&](unsigned idx, float sc, float sh) -> float {
     const float p = Elem<PT>::ld1(pred + idx);
@@ -236,8 +243,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
       const unsigned img = idx / HW, rem = idx - img * HW;
       const unsigned i = rem / W, j = rem - i * W;
       const float sc = ssi ? __ldg(a.scale + img) : 1.f, sh = ssi ? __ldg(a.shift + img) : 0.f;
-      const float t = __ldg(gt + idx);
-      const bool v = t > 0.f;
+      float t;
+      const bool v = ldt(idx, t);
       const float res = v ? ldp(idx, sc, sh) - t : 0.f;
       acc[0] += static_cast<double>(a.kind == 0 ? res * res : fabsf(res));
       acc[1] += v ? 1.0 : 0.0;
@@ -250,12 +257,12 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
         if (!v) continue;
         float e = 0.f;
         if (j + step < static_cast<unsigned>(W)) {
-          const float tr = __ldg(gt + idx + step);
-          if (tr > 0.f) e += fabsf((ldp(idx + step, sc, sh) - tr) - res);
+          float tr;
+          if (ldt(idx + step, tr)) e += fabsf((ldp(idx + step, sc, sh) - tr) - res);
         }
         if (i + step < static_cast<unsigned>(H)) {
-          const float td = __ldg(gt + idx + step * W);
-          if (td > 0.f) e += fabsf((ldp(idx + step * W, sc, sh) - td) - res);
+          float td;
+          if (ldt(idx + step * W, td)) e += fabsf((ldp(idx + step * W, sc, sh) - td) - res);
         }
         acc[2 + 2 * s] += static_cast<double>(e);
       }
@@ -294,9 +301,9 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
     const unsigned img = idx / HW, rem = idx - img * HW;
     const unsigned i = rem / W, j = rem - i * W;
     const float sc = ssi ? __ldg(a.scale + img) : 1.f, sh = ssi ? __ldg(a.shift + img) : 0.f;
-    const float t = __ldg(gt + idx);
+    float t;
     float g = 0.f;
-    if (t > 0.f) {
+    if (ldt(idx, t)) {
       const float res = ldp(idx, sc, sh) - t;
       g = cd * (a.kind == 0 ? res : sgnf(res));
 #pragma unroll
@@ -307,20 +314,20 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
         const float cs = sm_c[1 + s];
         float sg = 0.f;   // sum over the four pairs of d|.|/d(res of this pixel)
         if (j + step < static_cast<unsigned>(W)) {
-          const float tr = __ldg(gt + idx + step);
-          if (tr > 0.f) sg -= sgnf((ldp(idx + step, sc, sh) - tr) - res);
+          float tr;
+          if (ldt(idx + step, tr)) sg -= sgnf((ldp(idx + step, sc, sh) - tr) - res);
         }
         if (j >= step) {
-          const float tl = __ldg(gt + idx - step);
-          if (tl > 0.f) sg += sgnf(res - (ldp(idx - step, sc, sh) - tl));
+          float tl;
+          if (ldt(idx - step, tl)) sg += sgnf(res - (ldp(idx - step, sc, sh) - tl));
         }
         if (i + step < static_cast<unsigned>(H)) {
-          const float td = __ldg(gt + idx + step * W);
-          if (td > 0.f) sg -= sgnf((ldp(idx + step * W, sc, sh) - td) - res);
+          float td;
+          if (ldt(idx + step * W, td)) sg -= sgnf((ldp(idx + step * W, sc, sh) - td) - res);
         }
         if (i >= step) {
-          const float tu = __ldg(gt + idx - step * W);
-          if (tu > 0.f) sg += sgnf(res - (ldp(idx - step * W, sc, sh) - tu));
+          float tu;
+          if (ldt(idx - step * W, tu)) sg += sgnf(res - (ldp(idx - step * W, sc, sh) - tu));
         }
         g = fmaf(cs, sg, g);
       }
@@ -331,7 +338,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
 
 template <typename PT>
 int launch_midas(MidasArgs& a, cudaStream_t st) {
-  const void* fn = reinterpret_cast<const void*>(&midas_loss_kernel<PT>);
+  const void* fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true>)
+                          : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false>);
   const int64_t n = static_cast<int64_t>(a.n_img) * a.h * a.w;
   int64_t grid = (n + kBlock - 1) / kBlock;
   const int cap = coop_grid(fn, kBlock, 0);
@@ -347,10 +355,11 @@ int launch_midas(MidasArgs& a, cudaStream_t st) {
 }  // namespace
 }  // namespace mde
 
-extern "C" int mde_midas_loss(const void* pred, int pred_dtype, const float* target, const float* scale, const float* shift,
-                              int64_t n_img, int64_t h, int64_t w, int data_kind, float alpha, int scales, float grad_scale,
-                              void* ws, float* loss_out, void* grad, void* stream) {
-  using namespace mde;
+namespace mde {
+namespace {
+int midas_loss_entry(const void* pred, int pred_dtype, const float* target, const float* vsrc, const float* scale,
+                     const float* shift, int64_t n_img, int64_t h, int64_t w, int data_kind, float alpha, int scales,
+                     float grad_scale, void* ws, float* loss_out, void* grad, void* stream) {
   MDE_REQUIRE(pred && target && ws && loss_out, MDE_EINVAL, "null pointer");
   MDE_REQUIRE(n_img > 0 && h > 0 && w > 0, MDE_EINVAL, "empty input");
   MDE_REQUIRE(n_img * h * w < (int64_t(1) << 31), MDE_ETOOBIG, "more than 2^31 pixels");
@@ -358,7 +367,7 @@ extern "C" int mde_midas_loss(const void* pred, int pred_dtype, const float* tar
   MDE_REQUIRE(scales >= 0 && scales <= kMaxScales, MDE_EINVAL, "scales must be in [0, 8]");
   MDE_REQUIRE((scale == nullptr) == (shift == nullptr), MDE_EINVAL, "scale and shift come together");
   MidasArgs a;
-  a.scale = scale; a.shift = shift;
+  a.scale = scale; a.shift = shift; a.vsrc = vsrc;
   a.pred = pred; a.gt = target; a.n_img = static_cast<int>(n_img); a.h = static_cast<int>(h); a.w = static_cast<int>(w);
   a.kind = data_kind; a.scales = scales; a.alpha = alpha; a.grad_scale = grad_scale; a.ws = ws; a.loss_out = loss_out;
   a.grad = grad;
@@ -369,6 +378,15 @@ extern "C" int mde_midas_loss(const void* pred, int pred_dtype, const float* tar
     case MDE_BF16: return launch_midas<__nv_bfloat16>(a, st);
     default: set_error("mde_midas_loss: unknown pred_dtype %d", pred_dtype); return MDE_EINVAL;
   }
+}
+}  // namespace
+}  // namespace mde
+
+extern "C" int mde_midas_loss(const void* pred, int pred_dtype, const float* target, const float* scale, const float* shift,
+                              int64_t n_img, int64_t h, int64_t w, int data_kind, float alpha, int scales, float grad_scale,
+                              void* ws, float* loss_out, void* grad, void* stream) {
+  return mde::midas_loss_entry(pred, pred_dtype, target, nullptr, scale, shift, n_img, h, w, data_kind, alpha, scales,
+                               grad_scale, ws, loss_out, grad, stream);
 }
 
 // ---- backward through the alignment: dL/dp from g = dL/dp^ ---------------------------------------------------
@@ -477,6 +495,278 @@ extern "C" int mde_midas_ssi_backward(const float* pred, const float* target, co
   const int64_t cap2 = static_cast<int64_t>(sm_count()) * 8;
   if (g2 > cap2) g2 = cap2;
   ssi_update_kernel<<<static_cast<unsigned>(g2), kMBlock, 0, st>>>(pred, target, coef_scratch, n_img, hw, grad_inout);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+
+// ---- TrimmedProcrustesLoss: robust per-image normalisation (median / mean absolute deviation) -----------------
+//
+//   normalize_prediction_robust(x, mask)    reference criteria.py:135-152
+//     m_b = median over ALL pixels of (mask * x)_b (torch.median: the lower median, the zeros of the masked-out
+//           pixels included), 0 for images without a valid pixel;  x' = x - m_b
+//     s_b = clamp(sum mask |x'| / sum mask, min 1e-6), 1 for images without a valid pixel;  result x' / s_b
+//   TrimmedProcrustesLoss.forward            reference criteria.py:335-363 (the `midas` method's default criterion
+//     '--loss ssitrim', modules/midas.py:36-37): trimmed_mae (= l1 as written, :208-217) + alpha * GradientLoss on
+//     the two normalised tensors, the mask still being `target > 0` of the ORIGINAL target (:351).
+//
+// Statistics: one CTA per (image, tensor) finds the median EXACTLY with a 3-round radix select on the
+// order-preserving key of the fp32 bit pattern (11 + 11 + 10 bits, shared-memory histogram), then one more pass
+// finds the first index that holds it (the element the median's gradient goes to), the deviation sum and
+// Z = sum mask sign(x - m). stats row (8 floats): {m, s, n, k as int bits, mask_k, Z, clamped, 0}.
+namespace mde {
+namespace {
+
+constexpr int kStatW = 8;
+constexpr int kRBlock = 1024;
+constexpr int kRWarps = kRBlock / 32;
+
+__device__ __forceinline__ unsigned okey(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float okey_inv(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(kRBlock) robust_stats_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                              int64_t hw, float* __restrict__ stats_pred,
+                                                              float* __restrict__ stats_gt) {
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned sm_u[3];
+  __shared__ double sm_d[3 * kRWarps];
+  const int64_t img = blockIdx.x >> 1;
+  const bool is_gt = (blockIdx.x & 1) != 0;
+  const float* x = (is_gt ? gt : pred) + img * hw;
+  const float* t = gt + img * hw;
+  float* out = (is_gt ? stats_gt : stats_pred) + img * kStatW;
+  const unsigned n = static_cast<unsigned>(hw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // mask * x as the reference forms it (0 * x keeps the sign of x at masked-out pixels; -0 == +0 as a median value)
+  auto masked = [&](unsigned i) -> float { const float xv = __ldg(x + i); return (__ldg(t + i) > 0.f) ? xv : 0.f * xv; };
+
+  unsigned prefix = 0u, rank = (n - 1u) >> 1;   // lower median: sorted[(n - 1) / 2]
+  unsigned fixed = 0u;                           // key bits already decided
+#pragma unroll 1
+  for (int r = 0; r < 3; ++r) {
+    const int shift = (r == 0) ? 21 : ((r == 1) ? 10 : 0);
+    const unsigned bins = (r == 2) ? 1024u : 2048u;
+    for (unsigned i = threadIdx.x; i < 2048u; i += kRBlock) hist[i] = 0u;
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < n; i += kRBlock) {
+      const unsigned k = okey(masked(i));
+      if ((k & fixed) == prefix) atomicAdd(&hist[(k >> shift) & (bins - 1u)], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {   // the bin holding the rank: warp-wide scan over `bins` counters, 64 (or 32) per lane
+      const unsigned per = bins / 32u;
+      unsigned mine = 0u;
+      for (unsigned b = 0; b < per; ++b) mine += hist[lane * per + b];
+      unsigned incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const unsigned excl = incl - mine;
+      if (excl <= rank && rank < incl) {         // exactly one lane
+        unsigned acc = excl, b = lane * per;
+        for (;; ++b) {
+          const unsigned h = hist[b];
+          if (acc + h > rank) break;
+          acc += h;
+        }
+        sm_u[0] = b;
+        sm_u[1] = rank - acc;
+      }
+    }
+    __syncthreads();
+    prefix |= sm_u[0] << shift;
+    rank = sm_u[1];
+    fixed |= (bins - 1u) << shift;
+  }
+  const float med = okey_inv(prefix);
+  if (threadIdx.x == 0) sm_u[2] = 0xffffffffu;
+  __syncthreads();
+  unsigned kmin = 0xffffffffu;
+  double cnt = 0.0, dev = 0.0, zs = 0.0;
+  for (unsigned i = threadIdx.x; i < n; i += kRBlock) {
+    const bool v = __ldg(t + i) > 0.f;
+    const float xv = __ldg(x + i);
+    if (i < kmin && okey(v ? xv : 0.f * xv) == prefix) kmin = i;
+    if (v) {
+      const float d = xv - med;
+      cnt += 1.0;
+      dev += static_cast<double>(fabsf(d));
+      zs += (d > 0.f) ? 1.0 : ((d < 0.f) ? -1.0 : 0.0);
+    }
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  cnt = warp_sum(cnt); dev = warp_sum(dev); zs = warp_sum(zs);
+  if (lane == 0) {
+    atomicMin(&sm_u[2], kmin);
+    sm_d[warp] = cnt; sm_d[kRWarps + warp] = dev; sm_d[2 * kRWarps + warp] = zs;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double nn = 0.0, dv = 0.0, z = 0.0;
+    for (int w = 0; w < kRWarps; ++w) { nn += sm_d[w]; dv += sm_d[kRWarps + w]; z += sm_d[2 * kRWarps + w]; }
+    const unsigned k = sm_u[2];
+    float m = 0.f, s = 1.f, clamped = 1.f, mk = 0.f;
+    if (nn > 0.0) {                                         // criteria.py:139, :144-150
+      m = med;
+      const float raw = static_cast<float>(dv / nn);
+      clamped = (raw < 1e-6f) ? 1.f : 0.f;
+      s = (raw < 1e-6f) ? 1e-6f : raw;
+      mk = (k < n && __ldg(t + k) > 0.f) ? 1.f : 0.f;
+    }
+    out[0] = m; out[1] = s; out[2] = static_cast<float>(nn); out[3] = __uint_as_float(k);
+    out[4] = mk; out[5] = static_cast<float>(z); out[6] = clamped; out[7] = 0.f;
+  }
+}
+
+// x' = (x - m) / s for both tensors: subtraction and IEEE division rounded separately, as the reference's two ops are
+__global__ void __launch_bounds__(kMBlock) robust_apply_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                              const float* __restrict__ stats_pred,
+                                                              const float* __restrict__ stats_gt, int64_t n_img, int64_t hw,
+                                                              float* __restrict__ pred_out, float* __restrict__ gt_out) {
+  const int64_t total = n_img * hw;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kMBlock + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kMBlock) {
+    const int64_t b = i / hw;
+    const float mp = __ldg(stats_pred + b * kStatW), sp = __ldg(stats_pred + b * kStatW + 1);
+    const float mt = __ldg(stats_gt + b * kStatW), st = __ldg(stats_gt + b * kStatW + 1);
+    pred_out[i] = __fdiv_rn(__fsub_rn(__ldg(pred + i), mp), sp);
+    gt_out[i] = __fdiv_rn(__fsub_rn(__ldg(gt + i), mt), st);
+  }
+}
+
+// Backward through the normalisation of the prediction, x' = (x - m) / s with m = x_k mask_k (median element k) and
+// s = sum mask |x - m| / n (constant where clamped). With g = dL/dx', G = sum g, Gx = sum g x' per image:
+//   dL/dx_j = g_j / s - mask_j sign(x_j - m) Gx / (s n)  +  [j == k] mask_k (Gx Z / (s n) - G / s),  Z = sum mask sign(x - m)
+// (the Gx terms vanish where s was clamped, every correction where the image has no valid pixel).
+__global__ void __launch_bounds__(kMBlock) robust_reduce_kernel(const float* __restrict__ xn, const float* __restrict__ g,
+                                                               int64_t n_img, int64_t hw, int chunks_per_img, void* ws_raw,
+                                                               const float* __restrict__ stats, float* __restrict__ coef) {
+  __shared__ double sm[2 * kMWarps];
+  __shared__ bool sm_last;
+  Ws ws = ws_view(ws_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_work = n_img * chunks_per_img;
+  const int64_t per_chunk = ((hw + chunks_per_img - 1) / chunks_per_img + kMBlock - 1) / kMBlock * kMBlock;
+  for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+    const int64_t img = wk / chunks_per_img;
+    const int64_t c0 = (wk - img * chunks_per_img) * per_chunk;
+    int64_t c1 = c0 + per_chunk;
+    if (c1 > hw) c1 = hw;
+    double G0 = 0.0, G1 = 0.0;
+    for (int64_t i = c0 + threadIdx.x; i < c1; i += kMBlock) {
+      const double gv = static_cast<double>(__ldg(g + img * hw + i));
+      G0 += gv;
+      G1 = fma(gv, static_cast<double>(__ldg(xn + img * hw + i)), G1);
+    }
+    const double s0 = warp_sum(G0), s1 = warp_sum(G1);
+    if (lane == 0) { sm[warp] = s0; sm[kMWarps + warp] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double tot = 0.0;
+      for (int w = 0; w < kMWarps; ++w) tot += sm[threadIdx.x * kMWarps + w];
+      if (tot != 0.0) atomicAdd(&ws.iacc[img * kIacc + threadIdx.x], tot);
+    }
+    __syncthreads();
+  }
+  __threadfence();
+  if (threadIdx.x == 0) sm_last = (atomicAdd(&ws.hdr->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!sm_last) return;
+  __threadfence();
+  for (int64_t b = threadIdx.x; b < n_img; b += kMBlock) {
+    double* r = ws.iacc + b * kIacc;
+    const double G = __ldcg(r + 0), Gx = __ldcg(r + 1);
+    r[0] = 0.0; r[1] = 0.0;
+    const float* sr = stats + b * kStatW;
+    const double s = static_cast<double>(sr[1]), n = static_cast<double>(sr[2]), mk = static_cast<double>(sr[4]);
+    const double Z = static_cast<double>(sr[5]);
+    const bool live = (n > 0.0) && (sr[6] == 0.f);
+    const double q = live ? Gx / (s * n) : 0.0;
+    coef[b * 4 + 0] = static_cast<float>(1.0 / s);
+    coef[b * 4 + 1] = static_cast<float>(-q);
+    coef[b * 4 + 2] = (n > 0.0) ? static_cast<float>(mk * (q * Z - G / s)) : 0.f;
+    coef[b * 4 + 3] = sr[3];                                  // k (bit pattern of an unsigned)
+  }
+  if (threadIdx.x == 0) ws.hdr->ticket = 0u;
+}
+
+__global__ void __launch_bounds__(kMBlock) robust_update_kernel(const float* __restrict__ xn, const float* __restrict__ gt,
+                                                               const float* __restrict__ coef, int64_t n_img, int64_t hw,
+                                                               float* __restrict__ g) {
+  const int64_t total = n_img * hw;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kMBlock + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kMBlock) {
+    const int64_t b = i / hw;
+    const float4 c = __ldg(reinterpret_cast<const float4*>(coef) + b);
+    float out = c.x * g[i];
+    if (__ldg(gt + i) > 0.f) out = fmaf(c.y, sgnf(__ldg(xn + i)), out);     // sign(x - m) = sign(x')
+    if (static_cast<unsigned>(i - b * hw) == __float_as_uint(c.w)) out += c.z;
+    g[i] = out;
+  }
+}
+
+}  // namespace
+}  // namespace mde
+
+extern "C" int mde_robust_normalize(const float* pred, const float* target, int64_t n_img, int64_t hw, float* stats_pred,
+                                    float* stats_target, float* pred_out, float* target_out, void* stream) {
+  using namespace mde;
+  MDE_REQUIRE(pred && target && stats_pred && stats_target && pred_out && target_out, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(n_img > 0 && hw > 0, MDE_EINVAL, "empty input");
+  MDE_REQUIRE(hw < (int64_t(1) << 31) && n_img < (int64_t(1) << 30), MDE_ETOOBIG, "image too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  robust_stats_kernel<<<static_cast<unsigned>(2 * n_img), kRBlock, 0, st>>>(pred, target, hw, stats_pred, stats_target);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  int64_t grid = (n_img * hw + kMBlock - 1) / kMBlock;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (grid > cap) grid = cap;
+  robust_apply_kernel<<<static_cast<unsigned>(grid), kMBlock, 0, st>>>(pred, target, stats_pred, stats_target, n_img, hw, pred_out,
+                                                                      target_out);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  return MDE_OK;
+}
+
+extern "C" int mde_midas_loss_masked(const void* pred, int pred_dtype, const float* target, const float* valid_src,
+                                     int64_t n_img, int64_t h, int64_t w, int data_kind, float alpha, int scales,
+                                     float grad_scale, void* ws, float* loss_out, void* grad, void* stream) {
+  using namespace mde;
+  MDE_REQUIRE(valid_src, MDE_EINVAL, "null pointer");
+  return midas_loss_entry(pred, pred_dtype, target, valid_src, nullptr, nullptr, n_img, h, w, data_kind, alpha, scales,
+                          grad_scale, ws, loss_out, grad, stream);
+}
+
+extern "C" int mde_robust_backward(const float* pred_norm, const float* target, const float* stats_pred, int64_t n_img,
+                                   int64_t hw, void* ws, float* coef_scratch, float* grad_inout, void* stream) {
+  using namespace mde;
+  MDE_REQUIRE(pred_norm && target && stats_pred && ws && coef_scratch && grad_inout, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(n_img > 0 && hw > 0, MDE_EINVAL, "empty input");
+  MDE_REQUIRE(aligned_to(coef_scratch, 16), MDE_EALIGN, "coef_scratch must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  int64_t cpi = cap / n_img;
+  const int64_t max_cpi = (hw + kMChunk - 1) / kMChunk;
+  if (cpi > max_cpi) cpi = max_cpi;
+  if (cpi < 1) cpi = 1;
+  int64_t grid = n_img * cpi;
+  if (grid > cap) grid = cap;
+  robust_reduce_kernel<<<static_cast<unsigned>(grid), kMBlock, 0, st>>>(pred_norm, grad_inout, n_img, hw, static_cast<int>(cpi), ws,
+                                                                       stats_pred, coef_scratch);
+  count_launch();
+  MDE_CUDA_TRY(cudaGetLastError());
+  int64_t g2 = (n_img * hw + kMBlock - 1) / kMBlock;
+  const int64_t cap2 = static_cast<int64_t>(sm_count()) * 8;
+  if (g2 > cap2) g2 = cap2;
+  robust_update_kernel<<<static_cast<unsigned>(g2), kMBlock, 0, st>>>(pred_norm, target, coef_scratch, n_img, hw, grad_inout);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;

@@ -390,6 +390,30 @@ def gen_midas():
             l = crit.MidasLoss(**kw)(p, tg.to(dt))
             (gr,) = torch.autograd.grad(l, p)
             out[f"ml_{name}_loss{sfx}"], out[f"ml_{name}_grad{sfx}"] = l.detach().numpy(), gr.numpy()
+    # TrimmedProcrustesLoss (criteria.py:335-363, `midas --loss ssitrim`) and normalize_prediction_robust (:135-152):
+    # two ordinary images, one with > 50 % invalid pixels (median = a masked zero), one with a constant prediction
+    # (deviation 0: the scale is clamped to 1e-6), one without any valid pixel
+    g3 = torch.Generator().manual_seed(779)
+    Bt, Ht, Wt = 5, 22, 31
+    tt = torch.rand((Bt, 1, Ht, Wt), generator=g3) * 9.5 + 0.5
+    tt[torch.rand((Bt, 1, Ht, Wt), generator=g3) < 0.25] = 0.0
+    tt[2][torch.rand((1, Ht, Wt), generator=g3) < 0.5] = 0.0
+    tt[4] = 0.0
+    pt = 0.7 / (tt.clamp_min(0.4) + torch.randn((Bt, 1, Ht, Wt), generator=g3) * 0.3).clamp_min(0.3) + 0.2
+    pt[3] = 0.75
+    out["tp_pred"], out["tp_target"] = pt.numpy(), tt.numpy()
+    for name, kw in (("tp", dict(alpha=0.5)), ("tp_a0", dict(alpha=0.0)), ("tp_s2", dict(alpha=0.25, scales=2))):
+        # fp32 only: the reference builds its mask and statistics as float32 (criteria.py:137,348) and its
+        # `m[valid] = median(...)` refuses a float64 source
+        for dt, sfx in ((torch.float32, "32"),):
+            p = pt.to(dt).clone().requires_grad_(True)
+            mod = crit.TrimmedProcrustesLoss(**kw)
+            l = mod(p, tt.to(dt))
+            (gr,) = torch.autograd.grad(l, p)
+            out[f"{name}_loss{sfx}"], out[f"{name}_grad{sfx}"] = l.detach().numpy(), gr.numpy()
+            if name == "tp":
+                out[f"tp_ssi{sfx}"] = mod.prediction_ssi.detach().numpy()
+                out[f"tp_tnorm{sfx}"] = crit.normalize_prediction_robust(tt.to(dt).squeeze(1)).numpy()
     np.savez_compressed(os.path.join(OUT, "midas_small.npz"), **out)
 
 
@@ -397,6 +421,9 @@ def main():
     assert R.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
+    if sys.argv[1:] == ["midas"]:
+        gen_midas()
+        return
     gen_losses()
     gen_metrics()
     gen_dorn()

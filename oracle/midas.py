@@ -102,3 +102,39 @@ def midas_loss(prediction, target, alpha=0.5, scales=4, loss="mse"):
             reg = reg + gradient_loss(prediction[:, ::step, ::step], target[:, ::step, ::step], mask[:, ::step, ::step])
         total = total + alpha * reg
     return total
+
+
+# ---- TrimmedProcrustesLoss (criteria.py:335-363) ------------------------------------------------------------
+def normalize_prediction_robust(target, mask=None):
+    """criteria.py:135-152, with the mask and the statistics in the dtype of `target` (the reference hard-codes
+    float32 at :137 and therefore only runs in fp32; in fp32 this is the same op sequence)."""
+    if mask is None:
+        mask = (target > 0).type(target.dtype)
+    ssum = torch.sum(mask, (1, 2))
+    valid = ssum > 0
+    m = torch.zeros_like(ssum)
+    s = torch.ones_like(ssum)
+    m[valid] = torch.median((mask[valid] * target[valid]).view(int(valid.sum()), -1), dim=1).values
+    target = target - m.view(-1, 1, 1)
+    sq = torch.sum(mask * target.abs(), (1, 2))
+    s[valid] = torch.clamp(sq[valid] / ssum[valid], min=1e-6)
+    return target / s.view(-1, 1, 1)
+
+
+def trimmed_procrustes_loss(prediction, target, alpha=0.5, scales=4):
+    """TrimmedProcrustesLoss.forward (criteria.py:345-358), batch-based. Returns (loss, normalised prediction)."""
+    if prediction.ndim == 4:
+        prediction = prediction.squeeze(1)
+    if target.ndim == 4:
+        target = target.squeeze(1)
+    mask = (target > 0).type(prediction.dtype)
+    p_ssi = normalize_prediction_robust(prediction, mask)
+    t_ssi = normalize_prediction_robust(target, mask)
+    total = trimmed_mae_loss(p_ssi, t_ssi, mask)
+    if alpha > 0:
+        reg = 0
+        for s in range(scales):
+            step = 2 ** s
+            reg = reg + gradient_loss(p_ssi[:, ::step, ::step], t_ssi[:, ::step, ::step], mask[:, ::step, ::step])
+        total = total + alpha * reg
+    return total, p_ssi

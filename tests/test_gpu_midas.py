@@ -105,3 +105,72 @@ def test_midas_loss_vs_oracle(Cr, shape):
     assert float(Cr.MidasLoss(alpha=0.5, loss="mse")(torch.ones_like(z), z)) == 0.0      # zero divisors give 0 (criteria.py:185-186)
     with pytest.raises(NotImplementedError):
         Cr.MidasLoss(reduction="image-based")
+
+
+def _tp_compare(grad, g_ref, pred, target, msg=""):
+    """Per-image gradient check of TrimmedProcrustesLoss. torch.median hands the median's gradient to ONE of the
+    elements holding the median value; which one is an implementation detail (CPU sort order) when valid pixels
+    tie, so on images whose valid predictions are not distinct the comparison is on the gradient with the
+    element(s) that differ by the median term removed, plus the image sum."""
+    g_ref = g_ref.detach().double().cpu() if torch.is_tensor(g_ref) else torch.from_numpy(np.asarray(g_ref, dtype=np.float64))
+    g = grad.detach().double().cpu()
+    for b in range(g.shape[0]):
+        gb, rb = g[b].reshape(-1), g_ref[b].reshape(-1)
+        scale = float(rb.abs().max())
+        if scale == 0.0:
+            assert float(gb.abs().max()) == 0.0, msg
+            continue
+        pv = pred[b].reshape(-1)[target[b].reshape(-1) > 0]
+        if pv.unique().numel() == pv.numel():
+            close(gb, rb, 2e-4, 1e-5 * scale, msg=msg)
+        else:
+            bad = ((gb - rb).abs() > 1e-4 * scale).nonzero().reshape(-1)
+            assert bad.numel() in (0, 2), msg
+            close(gb.sum(), rb.sum(), 1e-3, 1e-5 * scale, msg=msg)
+
+
+@pytest.mark.parametrize("name,kw", [("tp", dict(alpha=0.5)), ("tp_a0", dict(alpha=0.0)), ("tp_s2", dict(alpha=0.25, scales=2))])
+def test_trimmed_procrustes_golden(Cr, golden, name, kw):
+    from tests.gpu_util import run_loss
+    g = golden("midas_small.npz")
+    pred, target = T(g["tp_pred"]), T(g["tp_target"])
+    mod = Cr.TrimmedProcrustesLoss(**kw)
+    loss, grad = run_loss(mod, pred.cuda(), target.cuda())
+    assert loss.dim() == 0 and grad.shape == pred.shape
+    close(loss, g[f"{name}_loss32"], 1e-5)
+    _tp_compare(grad, g[f"{name}_grad32"], pred, target, msg=name)
+    if name == "tp":
+        close(mod.prediction_ssi, g["tp_ssi32"], 1e-5, 1e-6)
+        close(Cr.normalize_prediction_robust(target.squeeze(1).cuda()), g["tp_tnorm32"], 1e-5, 1e-6)
+    with torch.no_grad():
+        close(Cr.TrimmedProcrustesLoss(**kw)(pred.cuda(), target.cuda()), g[f"{name}_loss32"], 1e-5)
+
+
+@pytest.mark.parametrize("shape", [(8, 1, 384, 384), (3, 1, 33, 41), (2, 1, 480, 640)])
+def test_trimmed_procrustes_vs_oracle(Cr, shape):
+    """`midas --loss ssitrim` (modules/midas.py:36-37) at its training size (384 x 384) and at odd sizes."""
+    from tests.gpu_util import run_loss
+    g = torch.Generator().manual_seed(23 + shape[0])
+    target = torch.rand(shape, generator=g) * 9.5 + 0.5
+    target[torch.rand(shape, generator=g) < 0.2] = 0.0
+    target[-1, :, : shape[2] // 3] = 0.0
+    pred = 0.7 / (target.clamp_min(0.4) + torch.randn(shape, generator=g) * 0.3).clamp_min(0.3) + 0.2
+    pred = pred + torch.rand(shape, generator=g) * 1e-3        # distinct values: the median element is unique
+    for kw in (dict(alpha=0.5), dict(alpha=0.0)):
+        p64 = pred.double().requires_grad_(True)
+        l64, ssi64 = om.trimmed_procrustes_loss(p64, target.double(), **kw)
+        (g64,) = torch.autograd.grad(l64, p64)
+        mod = Cr.TrimmedProcrustesLoss(**kw)
+        loss, grad = run_loss(mod, pred.cuda(), target.cuda())
+        close(loss, l64.detach(), 2e-5, msg=str(kw))
+        close(mod.prediction_ssi, ssi64.detach(), 2e-5, 2e-6, msg=str(kw))
+        _tp_compare(grad, g64, pred, target, msg=str(kw))
+    # the median itself is exact: (x - m) vanishes at the element that holds it
+    ssi = Cr.TrimmedProcrustesLoss()
+    ssi(pred.cuda(), target.cuda())
+    masked = (pred * (target > 0)).reshape(shape[0], -1)
+    med = masked.median(dim=1).values
+    s = ((pred - med.view(-1, 1, 1, 1)).abs() * (target > 0)).reshape(shape[0], -1).sum(1) / (target > 0).reshape(shape[0], -1).sum(1)
+    close(ssi.prediction_ssi.cpu().reshape(shape), (pred - med.view(-1, 1, 1, 1)) / s.view(-1, 1, 1, 1), 1e-5, 1e-6)
+    with pytest.raises(NotImplementedError):
+        Cr.TrimmedProcrustesLoss(reduction="image-based")

@@ -248,3 +248,29 @@ def test_midas_loss(golden, name, kw):
     if name == "trim":   # as written the reference trims nothing: same value and gradient as l1
         close(g["ml_trim_loss64"], g["ml_l1_loss64"], 1e-12)
         close(g["ml_trim_grad64"], g["ml_l1_grad64"], 1e-12, 1e-15)
+
+
+@pytest.mark.parametrize("name,kw", [("tp", dict(alpha=0.5)), ("tp_a0", dict(alpha=0.0)), ("tp_s2", dict(alpha=0.25, scales=2))])
+def test_trimmed_procrustes(golden, name, kw):
+    """TrimmedProcrustesLoss (criteria.py:335-363). The reference only runs in fp32 (its mask and statistics are
+    hard-coded float32, :137 / :348), so the golden vectors are fp32; the oracle reproduces them with the same op
+    sequence and its fp64 evaluation stays within the 1e-5 budget of them."""
+    from oracle import midas as om
+    g = golden("midas_small.npz")
+    pred, target = T(g["tp_pred"]), T(g["tp_target"])
+    p = pred.clone().requires_grad_(True)
+    l, ssi = om.trimmed_procrustes_loss(p, target, **kw)
+    (gr,) = torch.autograd.grad(l, p)
+    close(l.detach(), g[f"{name}_loss32"], 1e-6)
+    close(gr, g[f"{name}_grad32"], 1e-5, 1e-6 * float(np.abs(g[f"{name}_grad32"]).max()))
+    if name == "tp":
+        close(ssi.detach(), g["tp_ssi32"], 1e-6, 1e-7)
+        close(om.normalize_prediction_robust(target.squeeze(1)), g["tp_tnorm32"], 1e-6, 1e-7)
+    p64 = pred.double().requires_grad_(True)
+    l64, _ = om.trimmed_procrustes_loss(p64, target.double(), **kw)
+    (g64,) = torch.autograd.grad(l64, p64)
+    close(l64.detach(), g[f"{name}_loss32"], 1e-5)
+    for b in range(pred.shape[0]):
+        close(g64[b], g[f"{name}_grad32"][b], 1e-4, 2e-6 * float(g64[b].abs().max()))
+    assert float(g64[4].abs().max()) == 0.0                      # image without a valid pixel
+    assert float(g64[3].abs().max()) > 1e3                       # constant prediction: scale clamped to 1e-6
