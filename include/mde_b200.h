@@ -318,6 +318,21 @@ int mde_midas_loss_masked(const void* pred, int pred_dtype, const float* target,
 int mde_robust_backward(const float* pred_norm, const float* target, const float* stats_pred, int64_t n_img,
                         int64_t hw, void* ws, float* coef_scratch, float* grad_inout, void* stream);
 
+/* ---- layered-depth ("stdepth") base criterion -------------------------- */
+/*
+ * The closure BaseModule.setup_criterion returns (reference modules/base_module.py:124-208; the criterion of the
+ * registered methods `bts` and `laina`), forward + backward in one cooperative launch, for the terms that are masked
+ * reductions: flags is a bit set of 1 depth_silog (:157/:160, depth_w * nan_to_num(silog_loss) over targ[D] > 0),
+ * 2 color_mae (:158), 4 color_mse (:161), 8 all_mse (:163-164), 16 all_mae (:166-167), 32 fb_divergence (:184-194).
+ * pred/targ [n_img, C, hw] with C = 10 (single layer, depth channels D = 8:10) or 20 (D = 16:20, :137);
+ * rgba [n_img, rgba_c >= 4, hw] fp32, mask1 = rgba[:, 3] > 0 (:133). out8 (device): {total, depth_silog, colour term,
+ * all_mse, all_mae, fb_divergence, #mask1 pixels, #maskD elements}. grad nullable, dtype of pred, scaled by grad_scale.
+ * The SSIM and compositing terms (:168-183) belong to stdepth_utils.py and are out of scope.
+ */
+int mde_stdepth_loss(const void* pred, int pred_dtype, const float* targ, const float* rgba, int64_t rgba_c,
+                     int64_t n_img, int64_t C, int64_t hw, int flags, float depth_w, float fbdiv_w,
+                     float variance_focus, float grad_scale, void* ws, float* out8, void* grad, void* stream);
+
 /* ---- depth -> point cloud ----------------------------------------------------------------- */
 /*
  * point_cloud(depth, cam) (reference depth2pointcloud.py:12-31) for a batch of depth maps, with the

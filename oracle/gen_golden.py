@@ -417,12 +417,75 @@ def gen_midas():
     np.savez_compressed(os.path.join(OUT, "midas_small.npz"), **out)
 
 
+def _base_module_criterion(method, single_layer):
+    """The closure BaseModule.setup_criterion returns (reference modules/base_module.py:124-208), compiled straight
+    from the reference source (the module itself needs pytorch_lightning) and bound to a stand-in `self`; it calls
+    the reference's own criteria.silog_loss and stdepth_utils functions."""
+    import ast
+    import importlib.util
+    import types
+    import torch.nn.functional as F
+    src = open(os.path.join(R.REF_ROOT, "modules", "base_module.py")).read()
+    node = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "setup_criterion")
+    spec = importlib.util.spec_from_file_location("_mde_ref_stdepth_utils", os.path.join(R.REF_ROOT, "stdepth_utils.py"))
+    su = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(su)
+    ns = {"torch": torch, "F": F, "criteria": R.load("criteria"), "composite_layers": su.composite_layers,
+          "depth_sort": su.depth_sort, "dssim2d": su.dssim2d}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "modules/base_module.py", "exec"), ns)
+    return ns["setup_criterion"](types.SimpleNamespace(method=method, single_layer=single_layer))
+
+
+from oracle.gen_golden_inputs import stdepth_inputs  # noqa: E402
+
+
+def gen_stdepth():
+    import types
+    T = torch.from_numpy
+    out = {}
+    cases = [("silma", "silma", 10), ("silms", "silms", 10), ("mse", "mse", 10), ("mae", "mae", 10),
+             ("silma_fb", "silma+fbdivergence", 10), ("mae_mse_fb", "mae+mse+fbdivergence", 10), ("silma20", "silma", 20),
+             ("mae20_fb", "mae+fbdivergence", 20)]
+    for C in (10, 20):
+        pred, targ, rgba = stdepth_inputs(880 + C, 3, C, 19, 27)
+        rgba[2, 3] = 0.0 if C == 20 else rgba[2, 3]                         # an image without mask1 pixels
+        out[f"pred{C}"], out[f"targ{C}"], out[f"rgba{C}"] = pred.numpy(), targ.numpy(), rgba.numpy()
+    for name, loss_name, C in cases:
+        method = types.SimpleNamespace(loss=loss_name, variance_focus=0.85, depth_loss_weight=0.7, comp_loss_weight=1.0,
+                                       fbdiv_loss_weight=0.3, ssim_loss_weight=1.0)
+        crit = _base_module_criterion(method, single_layer=(C == 10))
+        for dt, sfx in ((torch.float32, "32"), (torch.float64, "64")):
+            p = T(out[f"pred{C}"]).to(dt).requires_grad_(True)
+            loss, ld = crit(p, T(out[f"targ{C}"]).to(dt), T(out[f"rgba{C}"]).to(dt), return_loss_dict=True)
+            (gr,) = torch.autograd.grad(loss, p)
+            out[f"{name}_loss{sfx}"] = loss.detach().numpy()
+            if dt == torch.float64:
+                out[f"{name}_grad{sfx}"] = gr.numpy()
+            else:                                    # fp32 gradient: a strided sample keeps the fixture small
+                out[f"{name}_grad{sfx}_s7"] = gr.numpy().reshape(-1)[::7].copy()
+            for k, v in ld.items():
+                out[f"{name}_{k}{sfx}"] = v.numpy()
+    # empty depth mask: silog -> NaN -> nan_to_num -> 0 (base_module.py:126-127)
+    pred, targ, rgba = stdepth_inputs(899, 2, 10, 8, 9)
+    targ[:, 8:] = 0.0
+    method = types.SimpleNamespace(loss="silma", variance_focus=0.85, depth_loss_weight=0.7, comp_loss_weight=1.0,
+                                   fbdiv_loss_weight=0.3, ssim_loss_weight=1.0)
+    p = pred.clone().requires_grad_(True)
+    loss, ld = _base_module_criterion(method, True)(p, targ, rgba, return_loss_dict=True)
+    out.update({"e_pred": pred.numpy(), "e_targ": targ.numpy(), "e_rgba": rgba.numpy(), "e_loss32": loss.detach().numpy(),
+                "e_depth_silog32": ld["depth_silog"].numpy()})
+    np.savez_compressed(os.path.join(OUT, "stdepth_small.npz"), **out)
+
+
 def main():
     assert R.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     if sys.argv[1:] == ["midas"]:
         gen_midas()
+        return
+    if sys.argv[1:] == ["stdepth"]:
+        gen_stdepth()
         return
     gen_losses()
     gen_metrics()
@@ -431,6 +494,7 @@ def main():
     gen_config_scalars()
     gen_wcel()
     gen_midas()
+    gen_stdepth()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

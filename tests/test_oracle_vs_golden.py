@@ -274,3 +274,38 @@ def test_trimmed_procrustes(golden, name, kw):
         close(g64[b], g[f"{name}_grad32"][b], 1e-4, 2e-6 * float(g64[b].abs().max()))
     assert float(g64[4].abs().max()) == 0.0                      # image without a valid pixel
     assert float(g64[3].abs().max()) > 1e3                       # constant prediction: scale clamped to 1e-6
+
+
+STDEPTH_CASES = [("silma", "silma", 10), ("silms", "silms", 10), ("mse", "mse", 10), ("mae", "mae", 10),
+                 ("silma_fb", "silma+fbdivergence", 10), ("mae_mse_fb", "mae+mse+fbdivergence", 10), ("silma20", "silma", 20),
+                 ("mae20_fb", "mae+fbdivergence", 20)]
+
+
+@pytest.mark.parametrize("name,loss_name,C", STDEPTH_CASES)
+def test_stdepth_base_criterion(golden, name, loss_name, C):
+    """BaseModule.setup_criterion's closure (modules/base_module.py:124-208), masked-reduction terms."""
+    from oracle import stdepth as ost
+    g = golden("stdepth_small.npz")
+    pred, targ, rgba = T(g[f"pred{C}"]), T(g[f"targ{C}"]), T(g[f"rgba{C}"])
+    kw = dict(variance_focus=0.85, depth_w=0.7, fbdiv_w=0.3, single_layer=(C == 10))
+    p = pred.double().requires_grad_(True)
+    l64, d64 = ost.stdepth_loss(p, targ.double(), rgba.double(), loss_name, **kw)
+    (g64,) = torch.autograd.grad(l64, p)
+    close(l64.detach(), g[f"{name}_loss64"], 1e-12)
+    close(g64, g[f"{name}_grad64"], 1e-10, 1e-15)
+    for k, v in d64.items():
+        close(v.detach(), g[f"{name}_{k}64"], 1e-12)
+    p32 = pred.clone().requires_grad_(True)
+    l32, _ = ost.stdepth_loss(p32, targ, rgba, loss_name, **kw)
+    (g32,) = torch.autograd.grad(l32, p32)
+    close(l32.detach(), g[f"{name}_loss32"], 2e-6)
+    close(g32.reshape(-1)[::7], g[f"{name}_grad32_s7"], 1e-5, 1e-9)
+    close(g[f"{name}_loss32"], g[f"{name}_loss64"], 1e-5)
+
+
+def test_stdepth_empty_depth_mask(golden):
+    from oracle import stdepth as ost
+    g = golden("stdepth_small.npz")
+    l, d = ost.stdepth_loss(T(g["e_pred"]), T(g["e_targ"]), T(g["e_rgba"]), "silma", depth_w=0.7)
+    assert float(d["depth_silog"]) == 0.0 and float(g["e_depth_silog32"]) == 0.0       # NaN -> nan_to_num -> 0
+    close(l, g["e_loss32"], 2e-6)
