@@ -192,6 +192,7 @@ struct MidasArgs {
   const float* gt;
   const float* vsrc;    // nullable: validity comes from vsrc > 0 instead of gt > 0 (TrimmedProcrustesLoss: gt is normalised)
   int n_img, h, w;
+  unsigned dj, di, dimg;   // grid stride in (columns, rows, images); filled by launch_midas
   const float* scale;   // nullable: per-image alignment p^ = scale * p + shift (the 'ssi' variants)
   const float* shift;
   int kind;        // 0: mse, 1: l1 (= trim)
@@ -204,7 +205,22 @@ struct MidasArgs {
 
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
-template <typename PT, bool VS>
+// Position of a flat pixel index inside its image, advanced by a constant stride without dividing: the stride's
+// (images, rows, columns) decomposition comes from the host.
+struct PixPos {
+  unsigned img, i, j;
+};
+__device__ __forceinline__ void pos_advance(PixPos& q, const MidasArgs& a) {
+  q.j += a.dj;
+  unsigned carry = 0u;
+  if (q.j >= static_cast<unsigned>(a.w)) { q.j -= a.w; carry = 1u; }
+  q.i += a.di + carry;
+  carry = 0u;
+  if (q.i >= static_cast<unsigned>(a.h)) { q.i -= a.h; carry = 1u; }
+  q.img += a.dimg + carry;
+}
+
+template <typename PT, bool VS, int MAXS>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm_d[2 * kWarps];
@@ -212,21 +228,20 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
   const PT* __restrict__ pred = static_cast<const PT*>(a.pred);
   const float* __restrict__ gt = a.gt;
   PT* __restrict__ grad = static_cast<PT*>(a.grad);
-  const int H = a.h, W = a.w, S = a.scales;
-  const unsigned HW = static_cast<unsigned>(H) * static_cast<unsigned>(W);
+  const unsigned H = a.h, W = a.w;
+  const int S = a.scales;
+  const unsigned HW = H * W;
   const unsigned total = static_cast<unsigned>(a.n_img) * HW;
   const unsigned tid = blockIdx.x * kBlock + threadIdx.x, nthr = gridDim.x * kBlock;
   const bool ssi = a.scale != nullptr;
   const float* __restrict__ vs = a.vsrc;
-  // target value and validity of one pixel (criteria.py:322: mask = target > 0 on the ORIGINAL target)
-  auto ldt = [&](unsigned idx, float& t) -> bool {
-    t = __ldg(gt + idx);
-    return VS ? (__ldg(vs + idx) > 0.f) : (t > 0.f);
-  };
   // prediction as the loss sees it: aligned with two separately rounded ops, as `scale * prediction + shift` is
-  auto ldp = [&](unsigned idx, float sc, float sh) -> float {
-    const float p = Elem<PT>::ld1(pred + idx);
-    return ssi ? __fadd_rn(__fmul_rn(sc, p), sh) : p;
+  auto align = [&](float p, float sc, float sh) -> float { return ssi ? __fadd_rn(__fmul_rn(sc, p), sh) : p; };
+  // residual of one pixel, 0 and invalid where the mask is off (criteria.py:322: mask = target > 0 on the ORIGINAL target)
+  auto residual = [&](unsigned idx, float sc, float sh, bool& v) -> float {
+    const float t = __ldg(gt + idx);
+    v = VS ? (__ldg(vs + idx) > 0.f) : (t > 0.f);
+    return align(Elem<PT>::ld1(pred + idx), sc, sh) - t;
   };
 
   Ws ws = ws_view(a.ws);
@@ -234,43 +249,81 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
   const int par = coop_prologue(ws, epoch);
   double* gacc = ws.gacc + par * kGacc;
 
+  PixPos q0;
+  {
+    const unsigned first = (tid < total) ? tid : 0u;
+    q0.img = first / HW;
+    const unsigned rem = first - q0.img * HW;
+    q0.i = rem / W;
+    q0.j = rem - q0.i * W;
+  }
+
   // ---------------- phase A ---------------------------------------------------------------------------
   {
-    double acc[2 + 2 * kMaxScales];
+    // fp32 within a thread for at most 64 pixels, then fp64; counts are exact integers
+    float f_data = 0.f, f_s[MAXS];
+    unsigned c_data = 0u, c_s[MAXS];
+    double d_data = 0.0, d_s[MAXS];
 #pragma unroll
-    for (int q = 0; q < 2 + 2 * kMaxScales; ++q) acc[q] = 0.0;
-    for (unsigned idx = tid; idx < total; idx += nthr) {
-      const unsigned img = idx / HW, rem = idx - img * HW;
-      const unsigned i = rem / W, j = rem - i * W;
-      const float sc = ssi ? __ldg(a.scale + img) : 1.f, sh = ssi ? __ldg(a.shift + img) : 0.f;
-      float t;
-      const bool v = ldt(idx, t);
-      const float res = v ? ldp(idx, sc, sh) - t : 0.f;
-      acc[0] += static_cast<double>(a.kind == 0 ? res * res : fabsf(res));
-      acc[1] += v ? 1.0 : 0.0;
+    for (int s = 0; s < MAXS; ++s) { f_s[s] = 0.f; c_s[s] = 0u; d_s[s] = 0.0; }
+    PixPos q = q0;
+    unsigned it = 0u;
+    for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
+      const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
+      // scale 0 touches every pixel: centre, right and lower neighbour are requested together
+      const bool has_r = q.j + 1u < W, has_d = q.i + 1u < H;
+      bool v, v_r, v_d;
+      const float res_c = residual(idx, sc, sh, v);
+      const float res_r = residual(has_r ? idx + 1u : idx, sc, sh, v_r);
+      const float res_d = residual(has_d ? idx + W : idx, sc, sh, v_d);
+      const float res = v ? res_c : 0.f;
+      f_data += (a.kind == 0) ? res * res : fabsf(res);
+      c_data += v ? 1u : 0u;
+      if (S > 0) {
+        c_s[0] += v ? 1u : 0u;
+        float e = 0.f;
+        if (v && has_r && v_r) e += fabsf(res_r - res);
+        if (v && has_d && v_d) e += fabsf(res_d - res);
+        f_s[0] += e;
+      }
 #pragma unroll
-      for (int s = 0; s < kMaxScales; ++s) {
+      for (int s = 1; s < MAXS; ++s) {
         if (s >= S) break;
         const unsigned step = 1u << s;
-        if (((i | j) & (step - 1u)) != 0u) break;          // off this grid: off every coarser grid too
-        acc[3 + 2 * s] += v ? 1.0 : 0.0;
+        if (((q.i | q.j) & (step - 1u)) != 0u) break;          // off this grid: off every coarser grid too
+        c_s[s] += v ? 1u : 0u;
         if (!v) continue;
         float e = 0.f;
-        if (j + step < static_cast<unsigned>(W)) {
-          float tr;
-          if (ldt(idx + step, tr)) e += fabsf((ldp(idx + step, sc, sh) - tr) - res);
+        bool vn;
+        if (q.j + step < W) {
+          const float rn = residual(idx + step, sc, sh, vn);
+          if (vn) e += fabsf(rn - res);
         }
-        if (i + step < static_cast<unsigned>(H)) {
-          float td;
-          if (ldt(idx + step * W, td)) e += fabsf((ldp(idx + step * W, sc, sh) - td) - res);
+        if (q.i + step < H) {
+          const float rn = residual(idx + step * W, sc, sh, vn);
+          if (vn) e += fabsf(rn - res);
         }
-        acc[2 + 2 * s] += static_cast<double>(e);
+        f_s[s] += e;
+      }
+      if ((++it & 63u) == 0u) {
+        d_data += static_cast<double>(f_data); f_data = 0.f;
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) { d_s[s] += static_cast<double>(f_s[s]); f_s[s] = 0.f; }
       }
     }
-    for (int q = 0; q < 2 + 2 * S; q += 2) {
-      const double pair[2] = {acc[q], acc[q + 1]};
+    d_data += static_cast<double>(f_data);
+    {
+      const double pair[2] = {d_data, static_cast<double>(c_data)};
       const double tot = block_sum<2>(pair, sm_d);
-      if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[q + threadIdx.x], tot);
+      if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[threadIdx.x], tot);
+    }
+#pragma unroll
+    for (int s = 0; s < MAXS; ++s) {
+      if (s < S) {                                               // uniform over the grid
+        const double pair[2] = {d_s[s] + static_cast<double>(f_s[s]), static_cast<double>(c_s[s])};
+        const double tot = block_sum<2>(pair, sm_d);
+        if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + 2 * s + threadIdx.x], tot);
+      }
     }
   }
   grid.sync();
@@ -281,6 +334,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
     double loss = (N > 0.0) ? Sd / (2.0 * N) : 0.0;                 // reduction_batch_based(image_loss, 2 M)
     const double gs = static_cast<double>(a.grad_scale);
     sm_c[0] = (N > 0.0) ? static_cast<float>(gs * (a.kind == 0 ? 1.0 / N : 0.5 / N)) : 0.f;
+    for (int s = 0; s < kMaxScales; ++s) sm_c[1 + s] = 0.f;
     for (int s = 0; s < S; ++s) {
       const double Ss = __ldcg(&gacc[2 + 2 * s]), Ns = __ldcg(&gacc[3 + 2 * s]);
       const bool on = (a.alpha > 0.f) && (Ns > 0.0);
@@ -296,38 +350,52 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
   if (grad == nullptr) return;
 
   // ---------------- phase B: gradient -----------------------------------------------------------------------
-  const float cd = sm_c[0];
-  for (unsigned idx = tid; idx < total; idx += nthr) {
-    const unsigned img = idx / HW, rem = idx - img * HW;
-    const unsigned i = rem / W, j = rem - i * W;
-    const float sc = ssi ? __ldg(a.scale + img) : 1.f, sh = ssi ? __ldg(a.shift + img) : 0.f;
-    float t;
+  const float cd = sm_c[0], c0 = sm_c[1];
+  PixPos q = q0;
+  for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
+    const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
+    // the five points of the scale-0 stencil are requested together
+    const bool has_r = q.j + 1u < W, has_l = q.j >= 1u, has_d = q.i + 1u < H, has_u = q.i >= 1u;
+    bool v, v_r, v_l, v_d, v_u;
+    const float res = residual(idx, sc, sh, v);
+    const float res_r = residual(has_r ? idx + 1u : idx, sc, sh, v_r);
+    const float res_l = residual(has_l ? idx - 1u : idx, sc, sh, v_l);
+    const float res_d = residual(has_d ? idx + W : idx, sc, sh, v_d);
+    const float res_u = residual(has_u ? idx - W : idx, sc, sh, v_u);
     float g = 0.f;
-    if (ldt(idx, t)) {
-      const float res = ldp(idx, sc, sh) - t;
+    if (v) {
       g = cd * (a.kind == 0 ? res : sgnf(res));
+      if (S > 0) {
+        float sg = 0.f;   // sum over the four pairs of d|.|/d(res of this pixel)
+        if (has_r && v_r) sg -= sgnf(res_r - res);
+        if (has_l && v_l) sg += sgnf(res - res_l);
+        if (has_d && v_d) sg -= sgnf(res_d - res);
+        if (has_u && v_u) sg += sgnf(res - res_u);
+        g = fmaf(c0, sg, g);
+      }
 #pragma unroll
-      for (int s = 0; s < kMaxScales; ++s) {
+      for (int s = 1; s < MAXS; ++s) {
         if (s >= S) break;
         const unsigned step = 1u << s;
-        if (((i | j) & (step - 1u)) != 0u) break;
+        if (((q.i | q.j) & (step - 1u)) != 0u) break;
         const float cs = sm_c[1 + s];
-        float sg = 0.f;   // sum over the four pairs of d|.|/d(res of this pixel)
-        if (j + step < static_cast<unsigned>(W)) {
-          float tr;
-          if (ldt(idx + step, tr)) sg -= sgnf((ldp(idx + step, sc, sh) - tr) - res);
+        float sg = 0.f;
+        bool vn;
+        if (q.j + step < W) {
+          const float rn = residual(idx + step, sc, sh, vn);
+          if (vn) sg -= sgnf(rn - res);
         }
-        if (j >= step) {
-          float tl;
-          if (ldt(idx - step, tl)) sg += sgnf(res - (ldp(idx - step, sc, sh) - tl));
+        if (q.j >= step) {
+          const float rn = residual(idx - step, sc, sh, vn);
+          if (vn) sg += sgnf(res - rn);
         }
-        if (i + step < static_cast<unsigned>(H)) {
-          float td;
-          if (ldt(idx + step * W, td)) sg -= sgnf((ldp(idx + step * W, sc, sh) - td) - res);
+        if (q.i + step < H) {
+          const float rn = residual(idx + step * W, sc, sh, vn);
+          if (vn) sg -= sgnf(rn - res);
         }
-        if (i >= step) {
-          float tu;
-          if (ldt(idx - step * W, tu)) sg += sgnf(res - (ldp(idx - step * W, sc, sh) - tu));
+        if (q.i >= step) {
+          const float rn = residual(idx - step * W, sc, sh, vn);
+          if (vn) sg += sgnf(res - rn);
         }
         g = fmaf(cs, sg, g);
       }
@@ -338,14 +406,24 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
 
 template <typename PT>
 int launch_midas(MidasArgs& a, cudaStream_t st) {
-  const void* fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true>)
-                          : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false>);
+  const void* fn;
+  if (a.scales <= 4) fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true, 4>)
+                                 : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, 4>);
+  else fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true, kMaxScales>)
+                   : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, kMaxScales>);
   const int64_t n = static_cast<int64_t>(a.n_img) * a.h * a.w;
   int64_t grid = (n + kBlock - 1) / kBlock;
   const int cap = coop_grid(fn, kBlock, 0);
   if (cap <= 0) return MDE_ECUDA;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
+  {   // the grid stride as (images, rows, columns), so that the kernel advances its position without dividing
+    const int64_t nthr = grid * kBlock;
+    a.dj = static_cast<unsigned>(nthr % a.w);
+    const int64_t t1 = nthr / a.w;
+    a.di = static_cast<unsigned>(t1 % a.h);
+    a.dimg = static_cast<unsigned>(t1 / a.h);
+  }
   void* args[] = {&a};
   MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, 0, st));
   count_launch();

@@ -29,7 +29,7 @@ struct StdArgs {
   const float* targ;    // [n_img, C, hw]
   const float* alpha;   // plane 3 of image 0 of rgba [n_img, rgba_c, hw]
   int64_t alpha_stride; // rgba_c * hw
-  int n_img, d0, d1, flags;
+  int n_img, flags;
   unsigned hw;
   float depth_w, fbdiv_w, lambda, grad_scale;
   void* ws;
@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
   const unsigned HW = a.hw;
   const unsigned npx = static_cast<unsigned>(a.n_img) * HW;
   const unsigned tid = blockIdx.x * kBlock + threadIdx.x, nthr = gridDim.x * kBlock;
-  const int flags = a.flags, d0 = a.d0, d1 = a.d1;
+  const int flags = a.flags;
+  constexpr int d0 = (C == 10) ? 8 : 16, d1 = C;                // depth channels (base_module.py:137)
 
   Ws ws = ws_view(a.ws);
   unsigned epoch;
@@ -83,10 +84,15 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
       const bool m1 = __ldg(a.alpha + static_cast<size_t>(b) * a.alpha_stride + pix) > 0.f;
       float cabs = 0.f, csq = 0.f, aabs = 0.f, asq = 0.f, dabs = 0.f, dsq = 0.f, sd = 0.f, sdd = 0.f, nd = 0.f, ns = 0.f;
       float pf[3], pb[3], tf[3], tb[3];
+      float pv[C], tv[C];                                        // all 2C loads of the pixel are requested before any use
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float p = Elem<PT>::ld1(pred + base + static_cast<size_t>(c) * HW);
-        const float t = __ldg(targ + base + static_cast<size_t>(c) * HW);
+        pv[c] = Elem<PT>::ld1(pred + base + static_cast<size_t>(c) * HW);
+        tv[c] = __ldg(targ + base + static_cast<size_t>(c) * HW);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float p = pv[c], t = tv[c];
         const float diff = p - t;
         if (c < 3) { pf[c] = p; tf[c] = t; }
         if (c >= 4 && c < 7) { pb[c - 4] = p; tb[c - 4] = t; }
@@ -170,10 +176,15 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
     const bool m1 = __ldg(a.alpha + static_cast<size_t>(b) * a.alpha_stride + pix) > 0.f;
     float g[C];
     float pf[3], pb[3], tf[3], tb[3];
+    float pv[C], tv[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const float p = Elem<PT>::ld1(pred + base + static_cast<size_t>(c) * HW);
-      const float t = __ldg(targ + base + static_cast<size_t>(c) * HW);
+      pv[c] = Elem<PT>::ld1(pred + base + static_cast<size_t>(c) * HW);
+      tv[c] = __ldg(targ + base + static_cast<size_t>(c) * HW);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float p = pv[c], t = tv[c];
       const float diff = p - t;
       if (c < 3) { pf[c] = p; tf[c] = t; }
       if (c >= 4 && c < 7) { pb[c - 4] = p; tb[c - 4] = t; }
@@ -189,7 +200,7 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
       if (c >= d0 && c < d1 && t > 0.f) {
         if (flags & ST_ALLMSE) gc = fmaf(2.f * k_dep, diff, gc);
         if (flags & ST_ALLMAE) gc = fmaf(k_dep, sgn0(diff), gc);
-        if ((flags & ST_SILOG) && t > 1e-2f) gc += k_sil * ((logf(p) - logf(t)) - k_mean) / p;
+        if ((flags & ST_SILOG) && t > 1e-2f) gc += __fdividef(k_sil * ((logf(p) - logf(t)) - k_mean), p);
       }
       g[c] = gc;
     }
@@ -244,7 +255,6 @@ extern "C" int mde_stdepth_loss(const void* pred, int pred_dtype, const float* t
   StdArgs a;
   a.pred = pred; a.targ = targ; a.alpha = rgba + 3 * hw; a.alpha_stride = rgba_c * hw;
   a.n_img = static_cast<int>(n_img); a.hw = static_cast<unsigned>(hw);
-  a.d0 = (C == 10) ? 8 : 16; a.d1 = (C == 10) ? 10 : 20;       // base_module.py:137
   a.flags = flags; a.depth_w = depth_w; a.fbdiv_w = fbdiv_w; a.lambda = variance_focus; a.grad_scale = grad_scale;
   a.ws = ws; a.out = out8; a.grad = grad;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

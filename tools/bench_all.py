@@ -15,6 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import torch  # noqa: E402
 
@@ -228,26 +229,9 @@ def main():
     report("C4 WCEL", "bins_to_depth backward", px, us, 4.0 * Cc + 8.0, g)
     del logits, gl, sm
 
-    # ---------------- MiDaS alignment (evaluation side): 64 x 384 x 384 ----------------------------
-    Bm, Hm, Wm = 64, 384, 384
-    tgt = torch.rand((Bm, Hm, Wm), device=dev) * 9.5 + 0.5
-    tgt[torch.rand((Bm, Hm, Wm), device=dev) < 0.2] = 0.0
-    prd = 0.7 / tgt.clamp_min(0.3) + 0.2
-    sc = torch.empty(Bm, device=dev); sh = torch.empty(Bm, device=dev); al = torch.empty_like(prd)
-    ws = _lib.workspace(dev, Bm)
-    pxm = Bm * Hm * Wm
-    fns = [lambda: _lib.check(lib.mde_scale_and_shift(_lib.ptr(prd), 0, _lib.ptr(tgt), None, Bm, Hm * Wm, _lib.ptr(ws), _lib.ptr(sc), _lib.ptr(sh), sp()))]
-    us, g = timed(fns, reps)
-    report("MiDaS 64x384x384", "compute_scale_and_shift (5 masked sums + 2x2 solve per image)", pxm, us, 8.0, g)
-    fns = [lambda: _lib.check(lib.mde_apply_scale_shift(_lib.ptr(prd), 0, _lib.ptr(sc), _lib.ptr(sh), Bm, Hm * Wm, _lib.ptr(al), sp()))]
-    us, g = timed(fns, reps)
-    report("MiDaS 64x384x384", "apply scale/shift", pxm, us, 8.0, g)
-    lg = torch.empty_like(prd)
-    tg3 = tgt
-    fns = [lambda: _lib.check(lib.mde_midas_loss(_lib.ptr(prd), 0, _lib.ptr(tg3), Bm, Hm, Wm, 0, 0.5, 4, 1.0, _lib.ptr(ws), _lib.ptr(loss_t), _lib.ptr(lg), sp()))]
-    us, g = timed(fns, reps)
-    report("MiDaS 64x384x384", "MidasLoss('mse', alpha 0.5, 4 scales) fwd+bwd", pxm, us, 12.0, g)
-    del tgt, prd, al, lg
+    # ---------------- the 'next' rows: MiDaS family, TrimmedProcrustes, layered-depth criterion -----------
+    import bench_next
+    bench_next.run(report, timed, reps)
 
     # ---------------- C5: NYU-test-shaped eval, 654 x 480 x 640, 10 metrics ------------------------------------
     B = 654 if not QUICK else 64
