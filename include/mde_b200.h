@@ -304,8 +304,10 @@ int mde_midas_ssi_backward(const float* pred, const float* target, const float* 
  * valid pixel. stats_* [n_img][8] fp32 = {m, s, n_valid, k (bit pattern of the uint32 index that holds the median),
  * mask_k, Z = sum mask sign(x - m), s_was_clamped, 0}. pred/target/outputs fp32 [n_img, hw].
  */
-int mde_robust_normalize(const float* pred, const float* target, int64_t n_img, int64_t hw, float* stats_pred,
-                         float* stats_target, float* pred_out, float* target_out, void* stream);
+size_t mde_robust_scratch_bytes(int64_t n_img);
+int mde_robust_normalize(const float* pred, const float* target, int64_t n_img, int64_t hw,
+                         void* scratch /* device, mde_robust_scratch_bytes(n_img), 8-byte aligned, any content */,
+                         float* stats_pred, float* stats_target, float* pred_out, float* target_out, void* stream);
 /* mde_midas_loss on tensors whose validity is NOT target > 0: valid_src > 0 decides (criteria.py:351 takes the mask
  * from the original target, the loss is evaluated on the normalised one). No scale/shift. Otherwise as mde_midas_loss. */
 int mde_midas_loss_masked(const void* pred, int pred_dtype, const float* target, const float* valid_src,

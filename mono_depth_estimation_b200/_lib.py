@@ -71,7 +71,8 @@ SIGNATURES = {
     "mde_midas_loss": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "mde_midas_ssi_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mde_stdepth_loss": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
-    "mde_robust_normalize": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "mde_robust_scratch_bytes": (C.c_size_t, [_i64]),
+    "mde_robust_normalize": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mde_midas_loss_masked": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "mde_robust_backward": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mde_point_cloud": (_i32, [_vp, _i64, _i64, _i64, _f32, _f32, _f32, C.POINTER(C.c_float), _i32, _vp, _vp]),

@@ -504,7 +504,8 @@ def normalize_prediction_robust(target, mask=None):
         st_a = torch.empty((n_img, 8), dtype=torch.float32, device=dev)
         st_b = torch.empty((n_img, 8), dtype=torch.float32, device=dev)
         out_a, out_b = torch.empty_like(x), torch.empty_like(x)
-        _lib.check(lib.mde_robust_normalize(_lib.ptr(x), _lib.ptr(x), n_img, h * w, _lib.ptr(st_a), _lib.ptr(st_b),
+        scratch = torch.empty(int(lib.mde_robust_scratch_bytes(n_img)) // 8, dtype=torch.float64, device=dev)
+        _lib.check(lib.mde_robust_normalize(_lib.ptr(x), _lib.ptr(x), n_img, h * w, _lib.ptr(scratch), _lib.ptr(st_a), _lib.ptr(st_b),
                                             _lib.ptr(out_a), _lib.ptr(out_b), _lib.stream_ptr(dev)))
     return out_b.view(target.shape)
 
@@ -551,7 +552,8 @@ class TrimmedProcrustesLoss(nn.Module):
                 st_t = torch.empty((B, 8), dtype=torch.float32, device=dev)
                 pn, tn = torch.empty_like(pc), torch.empty_like(t)
                 grad = torch.empty_like(pc) if need_grad else None
-                _lib.check(lib.mde_robust_normalize(_lib.ptr(pc), _lib.ptr(t), B, H * W, _lib.ptr(st_p), _lib.ptr(st_t),
+                scratch = torch.empty(int(lib.mde_robust_scratch_bytes(B)) // 8, dtype=torch.float64, device=dev)
+                _lib.check(lib.mde_robust_normalize(_lib.ptr(pc), _lib.ptr(t), B, H * W, _lib.ptr(scratch), _lib.ptr(st_p), _lib.ptr(st_t),
                                                     _lib.ptr(pn), _lib.ptr(tn), sp))
                 _lib.check(lib.mde_midas_loss_masked(_lib.ptr(pn), _lib.dtype_code(pn), _lib.ptr(tn), _lib.ptr(t), B, H, W, 1,
                                                      alpha, scales, 1.0, _lib.ptr(ws), _lib.ptr(loss), _lib.ptr(grad), sp))

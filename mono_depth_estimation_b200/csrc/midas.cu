@@ -220,7 +220,7 @@ __device__ __forceinline__ void pos_advance(PixPos& q, const MidasArgs& a) {
   q.img += a.dimg + carry;
 }
 
-template <typename PT, bool VS, int MAXS>
+template <typename PT, bool VS>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm_d[2 * kWarps];
@@ -237,11 +237,20 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
   const float* __restrict__ vs = a.vsrc;
   // prediction as the loss sees it: aligned with two separately rounded ops, as `scale * prediction + shift` is
   auto align = [&](float p, float sc, float sh) -> float { return ssi ? __fadd_rn(__fmul_rn(sc, p), sh) : p; };
-  // residual of one pixel, 0 and invalid where the mask is off (criteria.py:322: mask = target > 0 on the ORIGINAL target)
+  // residual of one pixel and its validity (criteria.py:322: mask = target > 0 on the ORIGINAL target)
   auto residual = [&](unsigned idx, float sc, float sh, bool& v) -> float {
     const float t = __ldg(gt + idx);
+    const float p = Elem<PT>::ld1(pred + idx);
     v = VS ? (__ldg(vs + idx) > 0.f) : (t > 0.f);
-    return align(Elem<PT>::ld1(pred + idx), sc, sh) - t;
+    return align(p, sc, sh) - t;
+  };
+  // grid point g of scale s (the [::2^s, ::2^s] slicing of criteria.py:298-300) -> image, row, column
+  auto grid_point = [&](unsigned g, int s, unsigned Ws, unsigned HWs, PixPos& q) {
+    q.img = g / HWs;
+    const unsigned rem = g - q.img * HWs;
+    const unsigned is = rem / Ws;
+    q.i = is << s;
+    q.j = (rem - is * Ws) << s;
   };
 
   Ws ws = ws_view(a.ws);
@@ -258,72 +267,72 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
     q0.j = rem - q0.i * W;
   }
 
-  // ---------------- phase A ---------------------------------------------------------------------------
+  // ---------------- phase A: data term and scale 0 over every pixel ---------------------------------------------
   {
     // fp32 within a thread for at most 64 pixels, then fp64; counts are exact integers
-    float f_data = 0.f, f_s[MAXS];
-    unsigned c_data = 0u, c_s[MAXS];
-    double d_data = 0.0, d_s[MAXS];
-#pragma unroll
-    for (int s = 0; s < MAXS; ++s) { f_s[s] = 0.f; c_s[s] = 0u; d_s[s] = 0.0; }
+    float f_data = 0.f, f_s0 = 0.f;
+    unsigned c_data = 0u;
+    double d_data = 0.0, d_s0 = 0.0;
     PixPos q = q0;
     unsigned it = 0u;
     for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
       const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
-      // scale 0 touches every pixel: centre, right and lower neighbour are requested together
       const bool has_r = q.j + 1u < W, has_d = q.i + 1u < H;
-      bool v, v_r, v_d;
+      bool v, v_r, v_d;                                        // centre, right and lower neighbour requested together
       const float res_c = residual(idx, sc, sh, v);
       const float res_r = residual(has_r ? idx + 1u : idx, sc, sh, v_r);
       const float res_d = residual(has_d ? idx + W : idx, sc, sh, v_d);
       const float res = v ? res_c : 0.f;
       f_data += (a.kind == 0) ? res * res : fabsf(res);
       c_data += v ? 1u : 0u;
-      if (S > 0) {
-        c_s[0] += v ? 1u : 0u;
-        float e = 0.f;
-        if (v && has_r && v_r) e += fabsf(res_r - res);
-        if (v && has_d && v_d) e += fabsf(res_d - res);
-        f_s[0] += e;
-      }
-#pragma unroll
-      for (int s = 1; s < MAXS; ++s) {
-        if (s >= S) break;
-        const unsigned step = 1u << s;
-        if (((q.i | q.j) & (step - 1u)) != 0u) break;          // off this grid: off every coarser grid too
-        c_s[s] += v ? 1u : 0u;
-        if (!v) continue;
-        float e = 0.f;
-        bool vn;
-        if (q.j + step < W) {
-          const float rn = residual(idx + step, sc, sh, vn);
-          if (vn) e += fabsf(rn - res);
-        }
-        if (q.i + step < H) {
-          const float rn = residual(idx + step * W, sc, sh, vn);
-          if (vn) e += fabsf(rn - res);
-        }
-        f_s[s] += e;
-      }
+      float e = 0.f;
+      if (v && has_r && v_r) e += fabsf(res_r - res);
+      if (v && has_d && v_d) e += fabsf(res_d - res);
+      f_s0 += e;
       if ((++it & 63u) == 0u) {
         d_data += static_cast<double>(f_data); f_data = 0.f;
-#pragma unroll
-        for (int s = 0; s < MAXS; ++s) { d_s[s] += static_cast<double>(f_s[s]); f_s[s] = 0.f; }
+        d_s0 += static_cast<double>(f_s0); f_s0 = 0.f;
       }
     }
-    d_data += static_cast<double>(f_data);
     {
-      const double pair[2] = {d_data, static_cast<double>(c_data)};
+      const double pair[2] = {d_data + static_cast<double>(f_data), static_cast<double>(c_data)};
       const double tot = block_sum<2>(pair, sm_d);
       if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[threadIdx.x], tot);
     }
-#pragma unroll
-    for (int s = 0; s < MAXS; ++s) {
-      if (s < S) {                                               // uniform over the grid
-        const double pair[2] = {d_s[s] + static_cast<double>(f_s[s]), static_cast<double>(c_s[s])};
-        const double tot = block_sum<2>(pair, sm_d);
-        if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + 2 * s + threadIdx.x], tot);
+    if (S > 0) {
+      const double pair[2] = {d_s0 + static_cast<double>(f_s0), static_cast<double>(c_data)};
+      const double tot = block_sum<2>(pair, sm_d);
+      if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + threadIdx.x], tot);
+    }
+    // coarser scales: a dense loop over the grid points of each scale (every lane has work)
+#pragma unroll 1
+    for (int s = 1; s < S; ++s) {
+      const unsigned step = 1u << s;
+      const unsigned Hs = (H + step - 1u) >> s, Ws = (W + step - 1u) >> s, HWs = Hs * Ws;
+      const unsigned count = static_cast<unsigned>(a.n_img) * HWs;
+      float f = 0.f;
+      unsigned c = 0u;
+      double d = 0.0;
+      it = 0u;
+      for (unsigned g = tid; g < count; g += nthr) {
+        grid_point(g, s, Ws, HWs, q);
+        const unsigned idx = q.img * HW + q.i * W + q.j;
+        const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
+        const bool has_r = q.j + step < W, has_d = q.i + step < H;
+        bool v, v_r, v_d;
+        const float res = residual(idx, sc, sh, v);
+        const float res_r = residual(has_r ? idx + step : idx, sc, sh, v_r);
+        const float res_d = residual(has_d ? idx + step * W : idx, sc, sh, v_d);
+        c += v ? 1u : 0u;
+        float e = 0.f;
+        if (v && has_r && v_r) e += fabsf(res_r - res);
+        if (v && has_d && v_d) e += fabsf(res_d - res);
+        f += e;
+        if ((++it & 63u) == 0u) { d += static_cast<double>(f); f = 0.f; }
       }
+      const double pair[2] = {d + static_cast<double>(f), static_cast<double>(c)};
+      const double tot = block_sum<2>(pair, sm_d);
+      if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + 2 * s + threadIdx.x], tot);
     }
   }
   grid.sync();
@@ -349,68 +358,78 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
   __syncthreads();
   if (grad == nullptr) return;
 
-  // ---------------- phase B: gradient -----------------------------------------------------------------------
+  // ---------------- phase B: gradient of the data term and of scale 0, every pixel --------------------------------
   const float cd = sm_c[0], c0 = sm_c[1];
-  PixPos q = q0;
-  for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
-    const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
-    // the five points of the scale-0 stencil are requested together
-    const bool has_r = q.j + 1u < W, has_l = q.j >= 1u, has_d = q.i + 1u < H, has_u = q.i >= 1u;
-    bool v, v_r, v_l, v_d, v_u;
-    const float res = residual(idx, sc, sh, v);
-    const float res_r = residual(has_r ? idx + 1u : idx, sc, sh, v_r);
-    const float res_l = residual(has_l ? idx - 1u : idx, sc, sh, v_l);
-    const float res_d = residual(has_d ? idx + W : idx, sc, sh, v_d);
-    const float res_u = residual(has_u ? idx - W : idx, sc, sh, v_u);
-    float g = 0.f;
-    if (v) {
-      g = cd * (a.kind == 0 ? res : sgnf(res));
-      if (S > 0) {
+  {
+    PixPos q = q0;
+    for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
+      const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
+      const bool on = S > 0;
+      const bool has_r = on && (q.j + 1u < W), has_l = on && (q.j >= 1u), has_d = on && (q.i + 1u < H), has_u = on && (q.i >= 1u);
+      bool v, v_r, v_l, v_d, v_u;                              // the five points of the stencil requested together
+      const float res = residual(idx, sc, sh, v);
+      const float res_r = residual(has_r ? idx + 1u : idx, sc, sh, v_r);
+      const float res_l = residual(has_l ? idx - 1u : idx, sc, sh, v_l);
+      const float res_d = residual(has_d ? idx + W : idx, sc, sh, v_d);
+      const float res_u = residual(has_u ? idx - W : idx, sc, sh, v_u);
+      float g = 0.f;
+      if (v) {
         float sg = 0.f;   // sum over the four pairs of d|.|/d(res of this pixel)
         if (has_r && v_r) sg -= sgnf(res_r - res);
         if (has_l && v_l) sg += sgnf(res - res_l);
         if (has_d && v_d) sg -= sgnf(res_d - res);
         if (has_u && v_u) sg += sgnf(res - res_u);
-        g = fmaf(c0, sg, g);
+        g = fmaf(c0, sg, cd * (a.kind == 0 ? res : sgnf(res)));
       }
-#pragma unroll
-      for (int s = 1; s < MAXS; ++s) {
-        if (s >= S) break;
+      Elem<PT>::st1(grad + idx, g);
+    }
+  }
+  if (S <= 1) return;
+  // coarser scales: every pixel of the stride-2 grid adds its share for all the scales it is on (one thread per pixel,
+  // hence no race), after every CTA has written the pass above
+  __threadfence();
+  grid.sync();
+  {
+    const unsigned Hs = (H + 1u) >> 1, Ws = (W + 1u) >> 1, HWs = Hs * Ws;
+    const unsigned count = static_cast<unsigned>(a.n_img) * HWs;
+    PixPos q;
+    for (unsigned gp = tid; gp < count; gp += nthr) {
+      grid_point(gp, 1, Ws, HWs, q);
+      const unsigned idx = q.img * HW + q.i * W + q.j;
+      const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
+      bool v;
+      const float res = residual(idx, sc, sh, v);
+      if (!v) continue;
+      float add = 0.f;
+#pragma unroll 1
+      for (int s = 1; s < S; ++s) {
         const unsigned step = 1u << s;
-        if (((q.i | q.j) & (step - 1u)) != 0u) break;
-        const float cs = sm_c[1 + s];
+        if (((q.i | q.j) & (step - 1u)) != 0u) break;          // off this grid: off every coarser grid too
+        const bool has_r = q.j + step < W, has_l = q.j >= step, has_d = q.i + step < H, has_u = q.i >= step;
+        bool v_r, v_l, v_d, v_u;
+        const float res_r = residual(has_r ? idx + step : idx, sc, sh, v_r);
+        const float res_l = residual(has_l ? idx - step : idx, sc, sh, v_l);
+        const float res_d = residual(has_d ? idx + step * W : idx, sc, sh, v_d);
+        const float res_u = residual(has_u ? idx - step * W : idx, sc, sh, v_u);
         float sg = 0.f;
-        bool vn;
-        if (q.j + step < W) {
-          const float rn = residual(idx + step, sc, sh, vn);
-          if (vn) sg -= sgnf(rn - res);
-        }
-        if (q.j >= step) {
-          const float rn = residual(idx - step, sc, sh, vn);
-          if (vn) sg += sgnf(res - rn);
-        }
-        if (q.i + step < H) {
-          const float rn = residual(idx + step * W, sc, sh, vn);
-          if (vn) sg -= sgnf(rn - res);
-        }
-        if (q.i >= step) {
-          const float rn = residual(idx - step * W, sc, sh, vn);
-          if (vn) sg += sgnf(res - rn);
-        }
-        g = fmaf(cs, sg, g);
+        if (has_r && v_r) sg -= sgnf(res_r - res);
+        if (has_l && v_l) sg += sgnf(res - res_l);
+        if (has_d && v_d) sg -= sgnf(res_d - res);
+        if (has_u && v_u) sg += sgnf(res - res_u);
+        add = fmaf(sm_c[1 + s], sg, add);
+      }
+      if (add != 0.f) {
+        const float g0 = static_cast<float>(__ldcg(grad + idx));
+        Elem<PT>::st1(grad + idx, g0 + add);
       }
     }
-    Elem<PT>::st1(grad + idx, g);
   }
 }
 
 template <typename PT>
 int launch_midas(MidasArgs& a, cudaStream_t st) {
-  const void* fn;
-  if (a.scales <= 4) fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true, 4>)
-                                 : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, 4>);
-  else fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true, kMaxScales>)
-                   : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, kMaxScales>);
+  const void* fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true>)
+                          : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false>);
   const int64_t n = static_cast<int64_t>(a.n_img) * a.h * a.w;
   int64_t grid = (n + kBlock - 1) / kBlock;
   const int cap = coop_grid(fn, kBlock, 0);
@@ -589,9 +608,9 @@ extern "C" int mde_midas_ssi_backward(const float* pred, const float* target, co
 //     '--loss ssitrim', modules/midas.py:36-37): trimmed_mae (= l1 as written, :208-217) + alpha * GradientLoss on
 //     the two normalised tensors, the mask still being `target > 0` of the ORIGINAL target (:351).
 //
-// Statistics: one CTA per (image, tensor) finds the median EXACTLY with a 3-round radix select on the
-// order-preserving key of the fp32 bit pattern (11 + 11 + 10 bits, shared-memory histogram), then one more pass
-// finds the first index that holds it (the element the median's gradient goes to), the deviation sum and
+// Statistics: the median is found EXACTLY with a 3-round radix select on the order-preserving key of the fp32 bit
+// pattern (11 + 11 + 10 bits; shared-memory histograms per unit, one global histogram per (image, tensor)), then one
+// more sweep finds the first index that holds it (the element the median's gradient goes to), the deviation sum and
 // Z = sum mask sign(x - m). stats row (8 floats): {m, s, n, k as int bits, mask_k, Z, clamped, 0}.
 namespace mde {
 namespace {
@@ -608,96 +627,193 @@ __device__ __forceinline__ float okey_inv(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-__global__ void __launch_bounds__(kRBlock) robust_stats_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
-                                                              int64_t hw, float* __restrict__ stats_pred,
-                                                              float* __restrict__ stats_gt) {
-  __shared__ unsigned hist[2048];
-  __shared__ unsigned sm_u[3];
-  __shared__ double sm_d[3 * kRWarps];
-  const int64_t img = blockIdx.x >> 1;
-  const bool is_gt = (blockIdx.x & 1) != 0;
-  const float* x = (is_gt ? gt : pred) + img * hw;
-  const float* t = gt + img * hw;
-  float* out = (is_gt ? stats_gt : stats_pred) + img * kStatW;
-  const unsigned n = static_cast<unsigned>(hw);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // mask * x as the reference forms it (0 * x keeps the sign of x at masked-out pixels; -0 == +0 as a median value)
-  auto masked = [&](unsigned i) -> float { const float xv = __ldg(x + i); return (__ldg(t + i) > 0.f) ? xv : 0.f * xv; };
+// scratch (caller-owned, any content on entry): per pair (image, tensor) 4 doubles {n, deviation, Z, -}, then per pair
+// 2048 + 4 words {histogram, prefix, rank, first index, -}
+constexpr int kRBins = 2048;
+constexpr int kRWords = kRBins + 4;
 
-  unsigned prefix = 0u, rank = (n - 1u) >> 1;   // lower median: sorted[(n - 1) / 2]
-  unsigned fixed = 0u;                           // key bits already decided
+struct RobustArgs {
+  const float* pred;
+  const float* gt;
+  unsigned hw, chunk;     // pixels per image, pixels per unit (multiple of 4)
+  int pairs, parts;       // pairs = 2 * n_img; every pair is split into `parts` units
+  double* facc;           // [pairs][4]
+  unsigned* words;        // [pairs][kRWords]
+  float* stats_pred;
+  float* stats_gt;
+};
+
+// One cooperative launch: every (image, tensor) pair is cut into `parts` units so that all SMs work even for a small
+// batch. Round r: each unit histograms digit r of the keys that match the prefix found so far (shared memory, lanes
+// atomics), flushes the non-empty bins to the pair's global histogram; after a grid
+// sync one CTA per pair picks the bin that holds the rank. Then one more sweep for the index, deviation and sign sum.
+__global__ void __launch_bounds__(kRBlock, 1) robust_stats_kernel(RobustArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ unsigned hist[kRBins];
+  __shared__ unsigned sm_u[4];
+  __shared__ double sm_d[3 * kRWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned n = a.hw;
+  const int units = a.pairs * a.parts;
+
+  // ---- phase 0: scratch to its initial state ----
+  {
+    const size_t nw = static_cast<size_t>(a.pairs) * kRWords;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * kRBlock + threadIdx.x; i < nw; i += static_cast<size_t>(gridDim.x) * kRBlock) {
+      const unsigned w = static_cast<unsigned>(i % kRWords);
+      a.words[i] = (w == kRBins + 1) ? ((n - 1u) >> 1) : ((w == kRBins + 2) ? 0xffffffffu : 0u);   // rank of the lower median
+    }
+    for (int i = blockIdx.x * kRBlock + threadIdx.x; i < a.pairs * 4; i += gridDim.x * kRBlock) a.facc[i] = 0.0;
+  }
+  __threadfence();
+  grid.sync();
+
+  // ---- three radix rounds: 11 + 11 + 10 bits of the order-preserving key ----
+  unsigned fixed = 0u;
 #pragma unroll 1
   for (int r = 0; r < 3; ++r) {
     const int shift = (r == 0) ? 21 : ((r == 1) ? 10 : 0);
     const unsigned bins = (r == 2) ? 1024u : 2048u;
-    for (unsigned i = threadIdx.x; i < 2048u; i += kRBlock) hist[i] = 0u;
-    __syncthreads();
-    for (unsigned i = threadIdx.x; i < n; i += kRBlock) {
-      const unsigned k = okey(masked(i));
-      if ((k & fixed) == prefix) atomicAdd(&hist[(k >> shift) & (bins - 1u)], 1u);
-    }
-    __syncthreads();
-    if (warp == 0) {   // the bin holding the rank: warp-wide scan over `bins` counters, 64 (or 32) per lane
-      const unsigned per = bins / 32u;
-      unsigned mine = 0u;
-      for (unsigned b = 0; b < per; ++b) mine += hist[lane * per + b];
-      unsigned incl = mine;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int pair = u / a.parts, part = u - pair * a.parts;
+      const int64_t img = pair >> 1;
+      const float* x = ((pair & 1) ? a.gt : a.pred) + img * n;
+      const float* t = a.gt + img * n;
+      unsigned* w = a.words + static_cast<size_t>(pair) * kRWords;
+      const unsigned prefix = __ldcg(w + kRBins);
+      const unsigned lo = static_cast<unsigned>(part) * a.chunk;
+      unsigned hi = lo + a.chunk;
+      if (hi > n) hi = n;
+      for (unsigned i = threadIdx.x; i < kRBins; i += kRBlock) hist[i] = 0u;
+      __syncthreads();
+      for (unsigned i0 = lo; i0 < hi; i0 += 8u * kRBlock) {
+        float xv[8], tv[8];                                      // eight elements requested before the first use
+        bool ok[8];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      const unsigned excl = incl - mine;
-      if (excl <= rank && rank < incl) {         // exactly one lane
-        unsigned acc = excl, b = lane * per;
-        for (;; ++b) {
-          const unsigned h = hist[b];
-          if (acc + h > rank) break;
-          acc += h;
+        for (int k = 0; k < 8; ++k) {
+          const unsigned i = i0 + static_cast<unsigned>(k) * kRBlock + threadIdx.x;
+          ok[k] = i < hi;
+          xv[k] = ok[k] ? __ldg(x + i) : 0.f;
+          tv[k] = ok[k] ? __ldg(t + i) : 0.f;
         }
-        sm_u[0] = b;
-        sm_u[1] = rank - acc;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const unsigned key = okey((tv[k] > 0.f) ? xv[k] : 0.f * xv[k]);     // mask * x as the reference forms it
+          const bool take = ok[k] && ((key & fixed) == prefix);
+          const unsigned bin = (key >> shift) & (bins - 1u);
+          if (take) atomicAdd(&hist[bin], 1u);
+        }
       }
+      __syncthreads();
+      for (unsigned b = threadIdx.x; b < bins; b += kRBlock) {
+        const unsigned c = hist[b];
+        if (c) atomicAdd(w + b, c);
+      }
+      __syncthreads();
+    }
+    __threadfence();
+    grid.sync();
+    for (int pair = blockIdx.x; pair < a.pairs; pair += gridDim.x) {
+      unsigned* w = a.words + static_cast<size_t>(pair) * kRWords;
+      const unsigned rank = __ldcg(w + kRBins + 1);
+      {   // the bin holding the rank: CTA-wide scan, two counters per thread
+        const unsigned b0 = 2u * threadIdx.x;
+        const unsigned c0 = (b0 < bins) ? __ldcg(w + b0) : 0u, c1 = (b0 + 1u < bins) ? __ldcg(w + b0 + 1u) : 0u;
+        const unsigned mine = c0 + c1;
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += y;
+        }
+        if (lane == 31) hist[warp] = incl;                   // hist is free between the rounds
+        __syncthreads();
+        if (warp == 0) {
+          const unsigned tot = hist[lane];
+          unsigned wi = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+          }
+          hist[32 + lane] = wi - tot;                        // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const unsigned excl = hist[32 + warp] + incl - mine;
+        if (excl <= rank && rank < excl + mine) {            // exactly one thread
+          const bool second = rank >= excl + c0;
+          sm_u[0] = b0 + (second ? 1u : 0u);
+          sm_u[1] = rank - excl - (second ? c0 : 0u);
+        }
+      }
+      __syncthreads();
+      for (unsigned b = threadIdx.x; b < bins; b += kRBlock) w[b] = 0u;
+      if (threadIdx.x == 0) {
+        w[kRBins] = __ldcg(w + kRBins) | (sm_u[0] << shift);
+        w[kRBins + 1] = sm_u[1];
+      }
+      __syncthreads();
+    }
+    fixed |= (bins - 1u) << shift;
+    __threadfence();
+    grid.sync();
+  }
+
+  // ---- final sweep: first index holding the median, valid count, deviation sum, sign sum ----
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int pair = u / a.parts, part = u - pair * a.parts;
+    const int64_t img = pair >> 1;
+    const float* x = ((pair & 1) ? a.gt : a.pred) + img * n;
+    const float* t = a.gt + img * n;
+    unsigned* w = a.words + static_cast<size_t>(pair) * kRWords;
+    const unsigned prefix = __ldcg(w + kRBins);
+    const float med = okey_inv(prefix);
+    const unsigned lo = static_cast<unsigned>(part) * a.chunk;
+    unsigned hi = lo + a.chunk;
+    if (hi > n) hi = n;
+    unsigned kmin = 0xffffffffu;
+    float cnt = 0.f, zs = 0.f;                     // exact small integers in fp32 (< 2^24 per thread)
+    double dev = 0.0;
+    for (unsigned i = lo + threadIdx.x; i < hi; i += kRBlock) {
+      const bool v = __ldg(t + i) > 0.f;
+      const float xv = __ldg(x + i);
+      if (i < kmin && okey(v ? xv : 0.f * xv) == prefix) kmin = i;
+      if (v) {
+        const float d = xv - med;
+        cnt += 1.f;
+        dev += static_cast<double>(fabsf(d));
+        zs += (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+      }
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    const double c2 = warp_sum(static_cast<double>(cnt)), d2 = warp_sum(dev), z2 = warp_sum(static_cast<double>(zs));
+    if (lane == 0) {
+      if (kmin != 0xffffffffu) atomicMin(w + kRBins + 2, kmin);
+      sm_d[warp] = c2; sm_d[kRWarps + warp] = d2; sm_d[2 * kRWarps + warp] = z2;
     }
     __syncthreads();
-    prefix |= sm_u[0] << shift;
-    rank = sm_u[1];
-    fixed |= (bins - 1u) << shift;
-  }
-  const float med = okey_inv(prefix);
-  if (threadIdx.x == 0) sm_u[2] = 0xffffffffu;
-  __syncthreads();
-  unsigned kmin = 0xffffffffu;
-  double cnt = 0.0, dev = 0.0, zs = 0.0;
-  for (unsigned i = threadIdx.x; i < n; i += kRBlock) {
-    const bool v = __ldg(t + i) > 0.f;
-    const float xv = __ldg(x + i);
-    if (i < kmin && okey(v ? xv : 0.f * xv) == prefix) kmin = i;
-    if (v) {
-      const float d = xv - med;
-      cnt += 1.0;
-      dev += static_cast<double>(fabsf(d));
-      zs += (d > 0.f) ? 1.0 : ((d < 0.f) ? -1.0 : 0.0);
+    if (threadIdx.x < 3) {
+      double tot = 0.0;
+      for (int q = 0; q < kRWarps; ++q) tot += sm_d[threadIdx.x * kRWarps + q];
+      if (tot != 0.0) atomicAdd(a.facc + pair * 4 + threadIdx.x, tot);
     }
+    __syncthreads();
   }
-  kmin = __reduce_min_sync(0xffffffffu, kmin);
-  cnt = warp_sum(cnt); dev = warp_sum(dev); zs = warp_sum(zs);
-  if (lane == 0) {
-    atomicMin(&sm_u[2], kmin);
-    sm_d[warp] = cnt; sm_d[kRWarps + warp] = dev; sm_d[2 * kRWarps + warp] = zs;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double nn = 0.0, dv = 0.0, z = 0.0;
-    for (int w = 0; w < kRWarps; ++w) { nn += sm_d[w]; dv += sm_d[kRWarps + w]; z += sm_d[2 * kRWarps + w]; }
-    const unsigned k = sm_u[2];
+  __threadfence();
+  grid.sync();
+  for (int pair = blockIdx.x * kRBlock + threadIdx.x; pair < a.pairs; pair += gridDim.x * kRBlock) {
+    const int64_t img = pair >> 1;
+    const unsigned* w = a.words + static_cast<size_t>(pair) * kRWords;
+    float* out = ((pair & 1) ? a.stats_gt : a.stats_pred) + img * kStatW;
+    const double nn = __ldcg(a.facc + pair * 4), dv = __ldcg(a.facc + pair * 4 + 1), z = __ldcg(a.facc + pair * 4 + 2);
+    const unsigned k = __ldcg(w + kRBins + 2);
     float m = 0.f, s = 1.f, clamped = 1.f, mk = 0.f;
     if (nn > 0.0) {                                         // criteria.py:139, :144-150
-      m = med;
+      m = okey_inv(__ldcg(w + kRBins));
       const float raw = static_cast<float>(dv / nn);
       clamped = (raw < 1e-6f) ? 1.f : 0.f;
       s = (raw < 1e-6f) ? 1e-6f : raw;
-      mk = (k < n && __ldg(t + k) > 0.f) ? 1.f : 0.f;
+      mk = (k < n && __ldg(a.gt + img * n + k) > 0.f) ? 1.f : 0.f;
     }
     out[0] = m; out[1] = s; out[2] = static_cast<float>(nn); out[3] = __uint_as_float(k);
     out[4] = mk; out[5] = static_cast<float>(z); out[6] = clamped; out[7] = 0.f;
@@ -794,16 +910,40 @@ __global__ void __launch_bounds__(kMBlock) robust_update_kernel(const float* __r
 }  // namespace
 }  // namespace mde
 
-extern "C" int mde_robust_normalize(const float* pred, const float* target, int64_t n_img, int64_t hw, float* stats_pred,
-                                    float* stats_target, float* pred_out, float* target_out, void* stream) {
+extern "C" size_t mde_robust_scratch_bytes(int64_t n_img) {
+  if (n_img < 1) n_img = 1;
+  return static_cast<size_t>(2 * n_img) * (4 * sizeof(double) + mde::kRWords * sizeof(unsigned));
+}
+
+extern "C" int mde_robust_normalize(const float* pred, const float* target, int64_t n_img, int64_t hw, void* scratch,
+                                    float* stats_pred, float* stats_target, float* pred_out, float* target_out, void* stream) {
   using namespace mde;
-  MDE_REQUIRE(pred && target && stats_pred && stats_target && pred_out && target_out, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(pred && target && scratch && stats_pred && stats_target && pred_out && target_out, MDE_EINVAL, "null pointer");
   MDE_REQUIRE(n_img > 0 && hw > 0, MDE_EINVAL, "empty input");
-  MDE_REQUIRE(hw < (int64_t(1) << 31) && n_img < (int64_t(1) << 30), MDE_ETOOBIG, "image too large");
+  MDE_REQUIRE(hw < (int64_t(1) << 31) && n_img < (int64_t(1) << 20), MDE_ETOOBIG, "image or batch too large");
+  MDE_REQUIRE(aligned_to(scratch, 8), MDE_EALIGN, "scratch must be 8-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  robust_stats_kernel<<<static_cast<unsigned>(2 * n_img), kRBlock, 0, st>>>(pred, target, hw, stats_pred, stats_target);
-  count_launch();
-  MDE_CUDA_TRY(cudaGetLastError());
+  {
+    const void* fn = reinterpret_cast<const void*>(&robust_stats_kernel);
+    const int cap = coop_grid(fn, kRBlock, 0);
+    if (cap <= 0) return MDE_ECUDA;
+    RobustArgs a;
+    a.pred = pred; a.gt = target; a.hw = static_cast<unsigned>(hw); a.pairs = static_cast<int>(2 * n_img);
+    int64_t parts = cap / a.pairs;                       // fill the GPU, but keep >= 8192 pixels per unit
+    const int64_t max_parts = (hw + 8191) / 8192;
+    if (parts > max_parts) parts = max_parts;
+    if (parts < 1) parts = 1;
+    a.parts = static_cast<int>(parts);
+    a.chunk = static_cast<unsigned>(((hw + parts - 1) / parts + 3) / 4 * 4);
+    a.facc = static_cast<double*>(scratch);
+    a.words = reinterpret_cast<unsigned*>(static_cast<char*>(scratch) + static_cast<size_t>(a.pairs) * 4 * sizeof(double));
+    a.stats_pred = stats_pred; a.stats_gt = stats_target;
+    int64_t grid = static_cast<int64_t>(a.pairs) * a.parts;
+    if (grid > cap) grid = cap;
+    void* args[] = {&a};
+    MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kRBlock), args, 0, st));
+    count_launch();
+  }
   int64_t grid = (n_img * hw + kMBlock - 1) / kMBlock;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   if (grid > cap) grid = cap;

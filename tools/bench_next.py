@@ -50,9 +50,21 @@ def run(report, timed, reps):
         us, g = timed([f], reps)
         report(cfg, name, pxm, us, 12.0, g)
     stp = torch.empty((Bm, 8), device=dev); stt = torch.empty((Bm, 8), device=dev); tn = torch.empty_like(tgt)
-    fns = [lambda: _lib.check(lib.mde_robust_normalize(_lib.ptr(prd), _lib.ptr(tgt), Bm, Hm * Wm, _lib.ptr(stp), _lib.ptr(stt), _lib.ptr(al), _lib.ptr(tn), sp()))]
+    scr = torch.empty(int(lib.mde_robust_scratch_bytes(Bm)) // 8, dtype=torch.float64, device=dev)
+    fns = [lambda: _lib.check(lib.mde_robust_normalize(_lib.ptr(prd), _lib.ptr(tgt), Bm, Hm * Wm, _lib.ptr(scr), _lib.ptr(stp), _lib.ptr(stt), _lib.ptr(al), _lib.ptr(tn), sp()))]
     us, g = timed(fns, reps)
     report(cfg, "normalize_prediction_robust of pred and target (exact medians + normalisation, 2 launches)", pxm, us, 16.0, g)
+    # the same at the training batch of the `midas` method (8 images): every pair is cut into units that fill the GPU
+    B8 = 8
+    fns = [lambda: _lib.check(lib.mde_robust_normalize(_lib.ptr(prd), _lib.ptr(tgt), B8, Hm * Wm, _lib.ptr(scr), _lib.ptr(stp), _lib.ptr(stt), _lib.ptr(al), _lib.ptr(tn), sp()))]
+    us, g = timed(fns, reps)
+    report("MiDaS 8x384x384", "normalize_prediction_robust of pred and target (2 launches)", B8 * Hm * Wm, us, 16.0, g)
+    mod = criteria.TrimmedProcrustesLoss(alpha=0.5)
+    p8, t8 = prd[:B8].contiguous(), tgt[:B8].contiguous()
+    def f8():
+        mod(p8.detach().requires_grad_(True), t8).backward()
+    us, g = timed([f8], reps)
+    report("MiDaS 8x384x384", "TrimmedProcrustesLoss fwd+bwd via module (5 launches)", B8 * Hm * Wm, us, 12.0, g)
     del tgt, prd, al, lg, tn
 
     # ---------------- layered-depth base criterion (bts default 'silma'): 8 x 10 x 512 x 512 ---------------------------

@@ -57,6 +57,25 @@ elif name == "wcel":
     ws = _lib.workspace(dev, B)
     f = lambda: _lib.check(lib.mde_wcel_loss(_lib.ptr(logits), 0, _lib.ptr(bins), _lib.ptr(gt), _lib.ptr(w32), _lib.ptr(rowsum), B, Cc, H * W,
                                              1.0, _lib.ptr(ws), _lib.ptr(loss_t), _lib.ptr(gl), sp()))
+elif name in ("midas_mse", "robust"):
+    Bm, Hm, Wm = 64, 384, 384
+    tgt = torch.rand((Bm, Hm, Wm), device=dev) * 9.5 + 0.5
+    tgt[torch.rand((Bm, Hm, Wm), device=dev) < 0.2] = 0.0
+    prd = 0.7 / tgt.clamp_min(0.3) + 0.2 + torch.rand((Bm, Hm, Wm), device=dev) * 1e-3
+    ws = _lib.workspace(dev, Bm); lg = torch.empty_like(prd)
+    if name == "midas_mse":
+        f = lambda: _lib.check(lib.mde_midas_loss(_lib.ptr(prd), 0, _lib.ptr(tgt), None, None, Bm, Hm, Wm, 0, 0.5, 4, 1.0, _lib.ptr(ws), _lib.ptr(loss_t), _lib.ptr(lg), sp()))
+    else:
+        stp = torch.empty((Bm, 8), device=dev); stt = torch.empty((Bm, 8), device=dev); tn = torch.empty_like(tgt)
+        scr = torch.empty(int(lib.mde_robust_scratch_bytes(Bm)) // 8, dtype=torch.float64, device=dev)
+        f = lambda: _lib.check(lib.mde_robust_normalize(_lib.ptr(prd), _lib.ptr(tgt), Bm, Hm * Wm, _lib.ptr(scr), _lib.ptr(stp), _lib.ptr(stt), _lib.ptr(lg), _lib.ptr(tn), sp()))
+elif name == "stdepth":
+    from mono_depth_estimation_b200 import stdepth
+    from oracle.gen_golden_inputs import stdepth_inputs
+    B, Cc, H, W = 8, 10, 512, 512
+    pred, targ, rgba = (v.to(dev) for v in stdepth_inputs(900, B, Cc, H, W))
+    ws = _lib.workspace(dev, B); out8 = torch.empty(8, device=dev); gr = torch.empty_like(pred)
+    f = lambda: _lib.check(lib.mde_stdepth_loss(_lib.ptr(pred), 0, _lib.ptr(targ), _lib.ptr(rgba), 4, B, Cc, H * W, 3, 1.0, 1.0, 0.85, 1.0, _lib.ptr(ws), _lib.ptr(out8), _lib.ptr(gr), sp()))
 elif name == "pointcloud":
     d = torch.rand((64, 480, 640), device=dev) * 12; out = torch.empty((64, 480, 640, 3), device=dev)
     f = lambda: _lib.check(lib.mde_point_cloud(_lib.ptr(d), 64, 480, 640, 0.8575, 0.1, 100.0, None, 0, _lib.ptr(out), sp()))
@@ -65,4 +84,4 @@ else:
 for _ in range(reps):
     f()
 torch.cuda.synchronize()
-print("ok", name, float(loss_t) if name not in ("c5_metrics", "c2_metrics", "dorn_decode", "pointcloud") else "")
+print("ok", name, float(loss_t) if name not in ("c5_metrics", "c2_metrics", "dorn_decode", "pointcloud", "robust", "stdepth") else "")
