@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
   const unsigned tid = blockIdx.x * kBlock + threadIdx.x, nthr = gridDim.x * kBlock;
   const int flags = a.flags;
   constexpr int d0 = (C == 10) ? 8 : 16, d1 = C;                // depth channels (base_module.py:137)
+  constexpr unsigned PX = (C == 10) ? 2u : 1u;                  // pixels in flight per thread
 
   Ws ws = ws_view(a.ws);
   unsigned epoch;
@@ -78,18 +79,31 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
     double acc[A_COUNT];
 #pragma unroll
     for (int q = 0; q < A_COUNT; ++q) acc[q] = 0.0;
-    for (unsigned px = tid; px < npx; px += nthr) {
-      const unsigned b = px / HW, pix = px - b * HW;
-      const size_t base = static_cast<size_t>(b) * C * HW + pix;
-      const bool m1 = __ldg(a.alpha + static_cast<size_t>(b) * a.alpha_stride + pix) > 0.f;
+    for (unsigned px0 = tid; px0 < npx; px0 += PX * nthr) {
+      float pva[PX][C], tva[PX][C];                              // all 2C loads of PX pixels are requested before any use
+      bool m1a[PX], ona[PX];
+#pragma unroll
+      for (int u = 0; u < PX; ++u) {
+        const unsigned px = px0 + static_cast<unsigned>(u) * nthr;
+        ona[u] = px < npx;
+        const unsigned pxc = ona[u] ? px : px0;
+        const unsigned b = pxc / HW, pix = pxc - b * HW;
+        const size_t base = static_cast<size_t>(b) * C * HW + pix;
+        m1a[u] = __ldg(a.alpha + static_cast<size_t>(b) * a.alpha_stride + pix) > 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          pva[u][c] = Elem<PT>::ld1(pred + base + static_cast<size_t>(c) * HW);
+          tva[u][c] = __ldg(targ + base + static_cast<size_t>(c) * HW);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PX; ++u) {
+      if (!ona[u]) continue;
+      const bool m1 = m1a[u];
+      const float (&pv)[C] = pva[u];
+      const float (&tv)[C] = tva[u];
       float cabs = 0.f, csq = 0.f, aabs = 0.f, asq = 0.f, dabs = 0.f, dsq = 0.f, sd = 0.f, sdd = 0.f, nd = 0.f, ns = 0.f;
       float pf[3], pb[3], tf[3], tb[3];
-      float pv[C], tv[C];                                        // all 2C loads of the pixel are requested before any use
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        pv[c] = Elem<PT>::ld1(pred + base + static_cast<size_t>(c) * HW);
-        tv[c] = __ldg(targ + base + static_cast<size_t>(c) * HW);
-      }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float p = pv[c], t = tv[c];
@@ -116,6 +130,7 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
       }
       acc[A_ND] += static_cast<double>(nd); acc[A_DABS] += static_cast<double>(dabs); acc[A_DSQ] += static_cast<double>(dsq);
       acc[A_NS] += static_cast<double>(ns); acc[A_SD] += static_cast<double>(sd); acc[A_SDD] += static_cast<double>(sdd);
+      }
     }
 #pragma unroll
     for (int q = 0; q < A_COUNT; q += 2) {
@@ -170,18 +185,33 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
 
   // ---------------- phase B: gradient of every term --------------------------------------------------------
   const float k_sil = sm_c[0], k_mean = sm_c[1], k_col = sm_c[2], k_all = sm_c[3], k_dep = sm_c[4], k_fb = sm_c[5];
-  for (unsigned px = tid; px < npx; px += nthr) {
-    const unsigned b = px / HW, pix = px - b * HW;
-    const size_t base = static_cast<size_t>(b) * C * HW + pix;
-    const bool m1 = __ldg(a.alpha + static_cast<size_t>(b) * a.alpha_stride + pix) > 0.f;
+  for (unsigned px0 = tid; px0 < npx; px0 += PX * nthr) {
+    float pva[PX][C], tva[PX][C];
+    bool m1a[PX], ona[PX];
+    size_t basea[PX];
+#pragma unroll
+    for (int u = 0; u < PX; ++u) {
+      const unsigned px = px0 + static_cast<unsigned>(u) * nthr;
+      ona[u] = px < npx;
+      const unsigned pxc = ona[u] ? px : px0;
+      const unsigned b = pxc / HW, pix = pxc - b * HW;
+      basea[u] = static_cast<size_t>(b) * C * HW + pix;
+      m1a[u] = __ldg(a.alpha + static_cast<size_t>(b) * a.alpha_stride + pix) > 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        pva[u][c] = Elem<PT>::ld1(pred + basea[u] + static_cast<size_t>(c) * HW);
+        tva[u][c] = __ldg(targ + basea[u] + static_cast<size_t>(c) * HW);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PX; ++u) {
+    if (!ona[u]) continue;
+    const bool m1 = m1a[u];
+    const size_t base = basea[u];
+    const float (&pv)[C] = pva[u];
+    const float (&tv)[C] = tva[u];
     float g[C];
     float pf[3], pb[3], tf[3], tb[3];
-    float pv[C], tv[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      pv[c] = Elem<PT>::ld1(pred + base + static_cast<size_t>(c) * HW);
-      tv[c] = __ldg(targ + base + static_cast<size_t>(c) * HW);
-    }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float p = pv[c], t = tv[c];
@@ -216,6 +246,7 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) Elem<PT>::st1(grad + base + static_cast<size_t>(c) * HW, g[c]);
+    }
   }
 }
 

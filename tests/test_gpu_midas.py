@@ -174,3 +174,42 @@ def test_trimmed_procrustes_vs_oracle(Cr, shape):
     close(ssi.prediction_ssi.cpu().reshape(shape), (pred - med.view(-1, 1, 1, 1)) / s.view(-1, 1, 1, 1), 1e-5, 1e-6)
     with pytest.raises(NotImplementedError):
         Cr.TrimmedProcrustesLoss(reduction="image-based")
+
+
+def test_trimmed_procrustes_many_small_images(Cr):
+    """More (image, tensor) pairs than CTAs of the cooperative statistics launch (2 x 80 > 148), tiny images."""
+    from tests.gpu_util import run_loss
+    shape = (80, 1, 24, 32)
+    g = torch.Generator().manual_seed(99)
+    target = torch.rand(shape, generator=g) * 9.5 + 0.5
+    target[torch.rand(shape, generator=g) < 0.2] = 0.0
+    pred = 0.7 / (target.clamp_min(0.4) + torch.randn(shape, generator=g) * 0.3).clamp_min(0.3) + 0.2
+    pred = pred + torch.rand(shape, generator=g) * 1e-3
+    p64 = pred.double().requires_grad_(True)
+    l64, ssi64 = om.trimmed_procrustes_loss(p64, target.double(), alpha=0.5)
+    (g64,) = torch.autograd.grad(l64, p64)
+    mod = Cr.TrimmedProcrustesLoss(alpha=0.5)
+    loss, grad = run_loss(mod, pred.cuda(), target.cuda())
+    close(loss, l64.detach(), 2e-5)
+    close(mod.prediction_ssi, ssi64.detach(), 2e-5, 2e-6)
+    _tp_compare(grad, g64, pred, target)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_midas_loss_half_prediction(Cr, dtype):
+    """AMP: a half-precision prediction is read as is, the gradient comes back in the same dtype (the coarse scales
+    add their share to the stored gradient in a second pass)."""
+    from tests.gpu_util import run_loss
+    shape = (3, 1, 66, 90)
+    g = torch.Generator().manual_seed(41)
+    target = torch.rand(shape, generator=g) * 9.5 + 0.5
+    target[torch.rand(shape, generator=g) < 0.2] = 0.0
+    pred = (target.clamp_min(0.4) + torch.randn(shape, generator=g) * 0.3).to(dtype)
+    p64 = pred.double().requires_grad_(True)
+    l64 = om.midas_loss(p64, target.double(), alpha=0.5, loss="l1")
+    (g64,) = torch.autograd.grad(l64, p64)
+    loss, grad = run_loss(Cr.MidasLoss(alpha=0.5, loss="l1"), pred.cuda(), target.cuda())
+    assert grad.dtype == dtype
+    close(loss, l64.detach(), 1e-5)
+    tol = 2e-3 if dtype == torch.float16 else 1.6e-2
+    close(grad, g64, tol, tol * float(g64.abs().max()))
