@@ -9,6 +9,8 @@
 // products and 5 reductions; here one pass over pred/target (8 B/px) accumulates all five in fp64, and the last
 // CTA solves every image in fp64 and re-zeroes the per-image
 // accumulators (workspace region 0, shared with the metrics kernel: zero on entry, zero on exit).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mde {
@@ -193,6 +195,8 @@ struct MidasArgs {
   const float* vsrc;    // nullable: validity comes from vsrc > 0 instead of gt > 0 (TrimmedProcrustesLoss: gt is normalised)
   int n_img, h, w;
   unsigned dj, di, dimg;   // grid stride in (columns, rows, images); filled by launch_midas
+  unsigned djq, diq, dimgq; // the same for a stride counted in quads (4 pixels of a row); vec4 path
+  int vec4;                // w % 4 == 0 and 16-byte aligned tensors: scale 0 runs on quads with 128-bit accesses
   const float* scale;   // nullable: per-image alignment p^ = scale * p + shift (the 'ssi' variants)
   const float* shift;
   int kind;        // 0: mse, 1: l1 (= trim)
@@ -210,14 +214,17 @@ __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 
 struct PixPos {
   unsigned img, i, j;
 };
-__device__ __forceinline__ void pos_advance(PixPos& q, const MidasArgs& a) {
-  q.j += a.dj;
+__device__ __forceinline__ void pos_advance(PixPos& q, unsigned dj, unsigned di, unsigned dimg, unsigned w, unsigned h) {
+  q.j += dj;
   unsigned carry = 0u;
-  if (q.j >= static_cast<unsigned>(a.w)) { q.j -= a.w; carry = 1u; }
-  q.i += a.di + carry;
+  if (q.j >= w) { q.j -= w; carry = 1u; }
+  q.i += di + carry;
   carry = 0u;
-  if (q.i >= static_cast<unsigned>(a.h)) { q.i -= a.h; carry = 1u; }
-  q.img += a.dimg + carry;
+  if (q.i >= h) { q.i -= h; carry = 1u; }
+  q.img += dimg + carry;
+}
+__device__ __forceinline__ void pos_advance(PixPos& q, const MidasArgs& a) {
+  pos_advance(q, a.dj, a.di, a.dimg, static_cast<unsigned>(a.w), static_cast<unsigned>(a.h));
 }
 
 template <typename PT, bool VS>
@@ -243,6 +250,16 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
     const float p = Elem<PT>::ld1(pred + idx);
     v = VS ? (__ldg(vs + idx) > 0.f) : (t > 0.f);
     return align(p, sc, sh) - t;
+  };
+  // the same for the quad of pixels idx .. idx + 3 of one row (128-bit accesses; idx % 4 == 0)
+  auto residual4 = [&](unsigned idx, float sc, float sh, float (&r)[4], bool (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(gt + idx));
+    const float4 p = Elem<PT>::template ld4<true>(pred + idx);
+    float4 m = t;
+    if (VS) m = __ldg(reinterpret_cast<const float4*>(vs + idx));
+    r[0] = align(p.x, sc, sh) - t.x; r[1] = align(p.y, sc, sh) - t.y;
+    r[2] = align(p.z, sc, sh) - t.z; r[3] = align(p.w, sc, sh) - t.w;
+    v[0] = m.x > 0.f; v[1] = m.y > 0.f; v[2] = m.z > 0.f; v[3] = m.w > 0.f;
   };
   // grid point g of scale s (the [::2^s, ::2^s] slicing of criteria.py:298-300) -> image, row, column
   auto grid_point = [&](unsigned g, int s, unsigned Ws, unsigned HWs, PixPos& q) {
@@ -275,6 +292,44 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
     double d_data = 0.0, d_s0 = 0.0;
     PixPos q = q0;
     unsigned it = 0u;
+    if (a.vec4) {
+      // quads: the row below comes as a second 128-bit pair, the pixel right of the quad as one scalar pair
+      const unsigned Wq = W >> 2, nquads = total >> 2;
+      PixPos qq;
+      {
+        const unsigned first = (tid < nquads) ? tid : 0u;
+        qq.img = first / (H * Wq);
+        const unsigned rem = first - qq.img * (H * Wq);
+        qq.i = rem / Wq;
+        qq.j = rem - qq.i * Wq;
+      }
+      for (unsigned qd = tid; qd < nquads; qd += nthr, pos_advance(qq, a.djq, a.diq, a.dimgq, Wq, H)) {
+        const unsigned idx = qd << 2, j0 = qq.j << 2;
+        const float sc = ssi ? __ldg(a.scale + qq.img) : 1.f, sh = ssi ? __ldg(a.shift + qq.img) : 0.f;
+        const bool has_re = j0 + 4u < W, has_d = qq.i + 1u < H;
+        float r[4], rd[4];
+        bool v[4], vd[4], v_re;
+        residual4(idx, sc, sh, r, v);
+        residual4(has_d ? idx + W : idx, sc, sh, rd, vd);
+        const float r_re = residual(has_re ? idx + 4u : idx, sc, sh, v_re);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float res = v[k] ? r[k] : 0.f;
+          f_data += (a.kind == 0) ? res * res : fabsf(res);
+          c_data += v[k] ? 1u : 0u;
+          const bool vr = (k < 3) ? v[(k + 1) & 3] : (has_re && v_re);
+          const float rr = (k < 3) ? r[(k + 1) & 3] : r_re;
+          float e = 0.f;
+          if (v[k] && vr) e += fabsf(rr - res);
+          if (v[k] && has_d && vd[k]) e += fabsf(rd[k] - res);
+          f_s0 += e;
+        }
+        if ((++it & 15u) == 0u) {
+          d_data += static_cast<double>(f_data); f_data = 0.f;
+          d_s0 += static_cast<double>(f_s0); f_s0 = 0.f;
+        }
+      }
+    } else
     for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
       const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
       const bool has_r = q.j + 1u < W, has_d = q.i + 1u < H;
@@ -360,7 +415,46 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
 
   // ---------------- phase B: gradient of the data term and of scale 0, every pixel --------------------------------
   const float cd = sm_c[0], c0 = sm_c[1];
-  {
+  if (a.vec4) {
+    const unsigned Wq = W >> 2, nquads = total >> 2;
+    PixPos qq;
+    {
+      const unsigned first = (tid < nquads) ? tid : 0u;
+      qq.img = first / (H * Wq);
+      const unsigned rem = first - qq.img * (H * Wq);
+      qq.i = rem / Wq;
+      qq.j = rem - qq.i * Wq;
+    }
+    const bool on = S > 0;
+    for (unsigned qd = tid; qd < nquads; qd += nthr, pos_advance(qq, a.djq, a.diq, a.dimgq, Wq, H)) {
+      const unsigned idx = qd << 2, j0 = qq.j << 2;
+      const float sc = ssi ? __ldg(a.scale + qq.img) : 1.f, sh = ssi ? __ldg(a.shift + qq.img) : 0.f;
+      const bool has_re = on && (j0 + 4u < W), has_le = on && (j0 >= 1u), has_d = on && (qq.i + 1u < H), has_u = on && (qq.i >= 1u);
+      float r[4], rd[4], ru[4];
+      bool v[4], vd[4], vu[4], v_re, v_le;
+      residual4(idx, sc, sh, r, v);                            // three rows of the quad, then the two pixels beside it
+      residual4(has_d ? idx + W : idx, sc, sh, rd, vd);
+      residual4(has_u ? idx - W : idx, sc, sh, ru, vu);
+      const float r_re = residual(has_re ? idx + 4u : idx, sc, sh, v_re);
+      const float r_le = residual(has_le ? idx - 1u : idx, sc, sh, v_le);
+      float g[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float res = r[k];
+        const bool vr = (k < 3) ? (on && v[(k + 1) & 3]) : (has_re && v_re);
+        const float rr = (k < 3) ? r[(k + 1) & 3] : r_re;
+        const bool vl = (k > 0) ? (on && v[(k + 3) & 3]) : (has_le && v_le);
+        const float rl = (k > 0) ? r[(k + 3) & 3] : r_le;
+        float sg = 0.f;   // sum over the four pairs of d|.|/d(res of this pixel)
+        if (vr) sg -= sgnf(rr - res);
+        if (vl) sg += sgnf(res - rl);
+        if (has_d && vd[k]) sg -= sgnf(rd[k] - res);
+        if (has_u && vu[k]) sg += sgnf(res - ru[k]);
+        g[k] = v[k] ? fmaf(c0, sg, cd * (a.kind == 0 ? res : sgnf(res))) : 0.f;
+      }
+      Elem<PT>::st4(grad + idx, make_float4(g[0], g[1], g[2], g[3]));
+    }
+  } else {
     PixPos q = q0;
     for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
       const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
@@ -442,6 +536,13 @@ int launch_midas(MidasArgs& a, cudaStream_t st) {
     const int64_t t1 = nthr / a.w;
     a.di = static_cast<unsigned>(t1 % a.h);
     a.dimg = static_cast<unsigned>(t1 / a.h);
+    const int64_t wq = (a.w % 4 == 0) ? a.w / 4 : 1;
+    a.djq = static_cast<unsigned>(nthr % wq);
+    const int64_t t2 = nthr / wq;
+    a.diq = static_cast<unsigned>(t2 % a.h);
+    a.dimgq = static_cast<unsigned>(t2 / a.h);
+    a.vec4 = (a.w % 4 == 0) && aligned_to(a.pred, 16) && aligned_to(a.gt, 16) && (a.vsrc == nullptr || aligned_to(a.vsrc, 16)) &&
+             (a.grad == nullptr || aligned_to(a.grad, 16)) && (getenv("MDE_MIDAS_SCALAR") == nullptr);
   }
   void* args[] = {&a};
   MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, 0, st));

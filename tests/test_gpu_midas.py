@@ -195,12 +195,13 @@ def test_trimmed_procrustes_many_small_images(Cr):
     _tp_compare(grad, g64, pred, target)
 
 
+@pytest.mark.parametrize("width", [90, 88])     # 88: rows of whole quads, the 128-bit path
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-def test_midas_loss_half_prediction(Cr, dtype):
+def test_midas_loss_half_prediction(Cr, dtype, width):
     """AMP: a half-precision prediction is read as is, the gradient comes back in the same dtype (the coarse scales
     add their share to the stored gradient in a second pass)."""
     from tests.gpu_util import run_loss
-    shape = (3, 1, 66, 90)
+    shape = (3, 1, 66, width)
     g = torch.Generator().manual_seed(41)
     target = torch.rand(shape, generator=g) * 9.5 + 0.5
     target[torch.rand(shape, generator=g) < 0.2] = 0.0
@@ -213,3 +214,21 @@ def test_midas_loss_half_prediction(Cr, dtype):
     close(loss, l64.detach(), 1e-5)
     tol = 2e-3 if dtype == torch.float16 else 1.6e-2
     close(grad, g64, tol, tol * float(g64.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 37, 64), (5, 1, 16, 4), (3, 1, 1, 128), (2, 1, 9, 132)])
+def test_midas_loss_quad_path_edges(Cr, shape):
+    """Widths that are multiples of 4 (scale 0 runs on quads): narrow rows, a single row, a width that is not a
+    multiple of the warp's 128 pixels; 'l1' and the aligned 'ssimse'."""
+    from tests.gpu_util import LOSS_RTOL, grad_close, run_loss
+    g = torch.Generator().manual_seed(7 + shape[2])
+    target = torch.rand(shape, generator=g) * 9.5 + 0.5
+    target[torch.rand(shape, generator=g) < 0.25] = 0.0
+    pred = target.clamp_min(0.4) + torch.randn(shape, generator=g) * 0.3
+    for kw in (dict(alpha=0.5, loss="l1"), dict(alpha=0.7, loss="mse", scales=3)):
+        p64 = pred.double().requires_grad_(True)
+        l64 = om.midas_loss(p64, target.double(), **kw)
+        (g64,) = torch.autograd.grad(l64, p64)
+        loss, grad = run_loss(Cr.MidasLoss(**kw), pred.cuda(), target.cuda())
+        close(loss, l64.detach(), LOSS_RTOL, msg=str(kw))
+        grad_close(grad, g64, msg=str(kw))
