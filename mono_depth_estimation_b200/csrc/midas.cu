@@ -227,7 +227,7 @@ __device__ __forceinline__ void pos_advance(PixPos& q, const MidasArgs& a) {
   pos_advance(q, a.dj, a.di, a.dimg, static_cast<unsigned>(a.w), static_cast<unsigned>(a.h));
 }
 
-template <typename PT, bool VS>
+template <typename PT, bool VS, int MAXS>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm_d[2 * kWarps];
@@ -293,8 +293,16 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
     PixPos q = q0;
     unsigned it = 0u;
     if (a.vec4) {
-      // quads: the row below comes as a second 128-bit pair, the pixel right of the quad as one scalar pair
+      // quads: the row below comes as a second 128-bit pair, the pixel right of the quad as one scalar pair. The coarse
+      // scales ride along: on even rows pixels 0 and 2 of the quad are on the stride-2 grid (their neighbours are in
+      // the quad, right of it, or two rows down: one more 128-bit pair), pixel 0 is on the grid of every scale >= 2
+      // whose step divides its row and column (scalar neighbours).
       const unsigned Wq = W >> 2, nquads = total >> 2;
+      float fs[MAXS];
+      unsigned cs[MAXS];
+      double ds[MAXS];
+#pragma unroll
+      for (int s = 0; s < MAXS; ++s) { fs[s] = 0.f; cs[s] = 0u; ds[s] = 0.0; }
       PixPos qq;
       {
         const unsigned first = (tid < nquads) ? tid : 0u;
@@ -322,14 +330,62 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
           float e = 0.f;
           if (v[k] && vr) e += fabsf(rr - res);
           if (v[k] && has_d && vd[k]) e += fabsf(rd[k] - res);
-          f_s0 += e;
+          fs[0] += e;
+        }
+        if (S > 1 && (qq.i & 1u) == 0u) {
+          const bool has_d2 = qq.i + 2u < H;
+          float rd2[4];
+          bool vd2[4];
+          residual4(has_d2 ? idx + 2u * W : idx, sc, sh, rd2, vd2);
+          cs[1] += (v[0] ? 1u : 0u) + (v[2] ? 1u : 0u);
+          float e = 0.f;
+          if (v[0]) {
+            if (v[2]) e += fabsf(r[2] - r[0]);
+            if (has_d2 && vd2[0]) e += fabsf(rd2[0] - r[0]);
+          }
+          if (v[2]) {
+            if (has_re && v_re) e += fabsf(r_re - r[2]);
+            if (has_d2 && vd2[2]) e += fabsf(rd2[2] - r[2]);
+          }
+          fs[1] += e;
+#pragma unroll
+          for (int s = 2; s < MAXS; ++s) {
+            if (s >= S) break;
+            const unsigned step = 1u << s;
+            if (((qq.i | j0) & (step - 1u)) != 0u) break;        // off this grid: off every coarser grid too
+            cs[s] += v[0] ? 1u : 0u;
+            if (!v[0]) continue;
+            const bool has_r = j0 + step < W, has_dn = qq.i + step < H;
+            bool vr, vdn;
+            const float rr = residual(has_r ? idx + step : idx, sc, sh, vr);
+            const float rdn = residual(has_dn ? idx + step * W : idx, sc, sh, vdn);
+            float es = 0.f;
+            if (has_r && vr) es += fabsf(rr - r[0]);
+            if (has_dn && vdn) es += fabsf(rdn - r[0]);
+            fs[s] += es;
+          }
         }
         if ((++it & 15u) == 0u) {
           d_data += static_cast<double>(f_data); f_data = 0.f;
-          d_s0 += static_cast<double>(f_s0); f_s0 = 0.f;
+#pragma unroll
+          for (int s = 0; s < MAXS; ++s) { ds[s] += static_cast<double>(fs[s]); fs[s] = 0.f; }
         }
       }
-    } else
+      cs[0] = c_data;
+      {
+        const double pair[2] = {d_data + static_cast<double>(f_data), static_cast<double>(c_data)};
+        const double tot = block_sum<2>(pair, sm_d);
+        if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[threadIdx.x], tot);
+      }
+#pragma unroll
+      for (int s = 0; s < MAXS; ++s) {
+        if (s < S) {                                             // uniform over the grid
+          const double pair[2] = {ds[s] + static_cast<double>(fs[s]), static_cast<double>(cs[s])};
+          const double tot = block_sum<2>(pair, sm_d);
+          if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + 2 * s + threadIdx.x], tot);
+        }
+      }
+    } else {
     for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
       const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
       const bool has_r = q.j + 1u < W, has_d = q.i + 1u < H;
@@ -389,6 +445,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
       const double tot = block_sum<2>(pair, sm_d);
       if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + 2 * s + threadIdx.x], tot);
     }
+    }   // scalar path
   }
   grid.sync();
 
@@ -452,8 +509,53 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
         if (has_u && vu[k]) sg += sgnf(res - ru[k]);
         g[k] = v[k] ? fmaf(c0, sg, cd * (a.kind == 0 ? res : sgnf(res))) : 0.f;
       }
+      if (S > 1 && (qq.i & 1u) == 0u) {                        // the coarse scales of pixels 0 and 2 (see phase A)
+        const bool has_d2 = qq.i + 2u < H, has_u2 = qq.i >= 2u, has_l2 = j0 >= 2u;
+        float rd2[4], ru2[4];
+        bool vd2[4], vu2[4], v_l2;
+        residual4(has_d2 ? idx + 2u * W : idx, sc, sh, rd2, vd2);
+        residual4(has_u2 ? idx - 2u * W : idx, sc, sh, ru2, vu2);
+        const float r_l2 = residual(has_l2 ? idx - 2u : idx, sc, sh, v_l2);
+        const float c1 = sm_c[2];
+        if (v[0]) {
+          float sg = 0.f;
+          if (v[2]) sg -= sgnf(r[2] - r[0]);
+          if (has_l2 && v_l2) sg += sgnf(r[0] - r_l2);
+          if (has_d2 && vd2[0]) sg -= sgnf(rd2[0] - r[0]);
+          if (has_u2 && vu2[0]) sg += sgnf(r[0] - ru2[0]);
+          g[0] = fmaf(c1, sg, g[0]);
+        }
+        if (v[2]) {
+          float sg = 0.f;
+          if (has_re && v_re) sg -= sgnf(r_re - r[2]);
+          if (v[0]) sg += sgnf(r[2] - r[0]);
+          if (has_d2 && vd2[2]) sg -= sgnf(rd2[2] - r[2]);
+          if (has_u2 && vu2[2]) sg += sgnf(r[2] - ru2[2]);
+          g[2] = fmaf(c1, sg, g[2]);
+        }
+        if (v[0]) {
+#pragma unroll 1
+          for (int s = 2; s < S; ++s) {
+            const unsigned step = 1u << s;
+            if (((qq.i | j0) & (step - 1u)) != 0u) break;
+            const bool has_r = j0 + step < W, has_l = j0 >= step, has_dn = qq.i + step < H, has_up = qq.i >= step;
+            bool vr, vl, vdn, vup;
+            const float rr = residual(has_r ? idx + step : idx, sc, sh, vr);
+            const float rl = residual(has_l ? idx - step : idx, sc, sh, vl);
+            const float rdn = residual(has_dn ? idx + step * W : idx, sc, sh, vdn);
+            const float rup = residual(has_up ? idx - step * W : idx, sc, sh, vup);
+            float sg = 0.f;
+            if (has_r && vr) sg -= sgnf(rr - r[0]);
+            if (has_l && vl) sg += sgnf(r[0] - rl);
+            if (has_dn && vdn) sg -= sgnf(rdn - r[0]);
+            if (has_up && vup) sg += sgnf(r[0] - rup);
+            g[0] = fmaf(sm_c[1 + s], sg, g[0]);
+          }
+        }
+      }
       Elem<PT>::st4(grad + idx, make_float4(g[0], g[1], g[2], g[3]));
     }
+    return;                                                    // every scale is in: no second pass
   } else {
     PixPos q = q0;
     for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
@@ -522,8 +624,11 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
 
 template <typename PT>
 int launch_midas(MidasArgs& a, cudaStream_t st) {
-  const void* fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true>)
-                          : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false>);
+  const void* fn;
+  if (a.scales <= 4) fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true, 4>)
+                                 : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, 4>);
+  else fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true, kMaxScales>)
+                   : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, kMaxScales>);
   const int64_t n = static_cast<int64_t>(a.n_img) * a.h * a.w;
   int64_t grid = (n + kBlock - 1) / kBlock;
   const int cap = coop_grid(fn, kBlock, 0);

@@ -216,7 +216,7 @@ def test_midas_loss_half_prediction(Cr, dtype, width):
     close(grad, g64, tol, tol * float(g64.abs().max()))
 
 
-@pytest.mark.parametrize("shape", [(2, 1, 37, 64), (5, 1, 16, 4), (3, 1, 1, 128), (2, 1, 9, 132)])
+@pytest.mark.parametrize("shape", [(2, 1, 37, 64), (5, 1, 16, 4), (3, 1, 1, 128), (2, 1, 9, 132), (2, 1, 40, 43)])
 def test_midas_loss_quad_path_edges(Cr, shape):
     """Widths that are multiples of 4 (scale 0 runs on quads): narrow rows, a single row, a width that is not a
     multiple of the warp's 128 pixels; 'l1' and the aligned 'ssimse'."""
@@ -225,7 +225,8 @@ def test_midas_loss_quad_path_edges(Cr, shape):
     target = torch.rand(shape, generator=g) * 9.5 + 0.5
     target[torch.rand(shape, generator=g) < 0.25] = 0.0
     pred = target.clamp_min(0.4) + torch.randn(shape, generator=g) * 0.3
-    for kw in (dict(alpha=0.5, loss="l1"), dict(alpha=0.7, loss="mse", scales=3)):
+    for kw in (dict(alpha=0.5, loss="l1"), dict(alpha=0.7, loss="mse", scales=3), dict(alpha=0.3, loss="l1", scales=6),
+               dict(alpha=0.5, loss="mse", scales=1)):
         p64 = pred.double().requires_grad_(True)
         l64 = om.midas_loss(p64, target.double(), **kw)
         (g64,) = torch.autograd.grad(l64, p64)

@@ -84,7 +84,28 @@ def run(report, timed, reps):
         del ring
 
 
+def run_ord(report, timed, reps):
+    """ordLoss(P, y) alone (reference criteria.py:744-787 as modules/dorn.py:160-163 calls it) at C3."""
+    from mono_depth_estimation_b200 import _lib, dorn, synth
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    N, C2, H, W = 8, 136, 257, 353
+    _, gt = synth.dorn_inputs((N, C2, H, W), 103, device=dev)
+    prob = torch.rand((N, C2 // 2, H, W), device=dev)
+    y = dorn.depth_to_label(gt, 0.001, 1.0, C2 // 2)
+    gp = torch.empty_like(prob)
+    ws = _lib.workspace(dev, 1)
+    loss_t = torch.empty((), device=dev)
+    fns = [lambda: _lib.check(lib.mde_ord_loss(_lib.ptr(prob), _lib.ptr(y), N, C2 // 2, H * W, 1.0, _lib.ptr(ws), _lib.ptr(loss_t),
+                                               _lib.ptr(gp), _lib.stream_ptr(dev)))]
+    us, g = timed(fns, reps)
+    report("C3", "ordLoss(P, y) fwd+bwd", N * H * W, us, 4.0 * (C2 // 2) * 2 + 4.0, g)
+
+
 if __name__ == "__main__":
     import bench_all
     bench_all.dev  # noqa: B018
-    run(bench_all.report, bench_all.timed, 5 if "--quick" in sys.argv else 30)
+    if "--ord" in sys.argv:
+        run_ord(bench_all.report, bench_all.timed, 30)
+    else:
+        run(bench_all.report, bench_all.timed, 5 if "--quick" in sys.argv else 30)
