@@ -239,6 +239,7 @@ def main():
 
     side = torch.cuda.Stream(device=dev)
     graphs = None
+    mega = None          # one graph holding a whole pass over the ring (args.ring steps): no graph boundary between steps
     launches_per_step = None
     with torch.cuda.stream(side):
         for i in range(3):
@@ -256,25 +257,41 @@ def main():
                     with torch.cuda.graph(g, stream=side):
                         o = step(*ring[i])
                     graphs.append((g, o))
+                mega = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(mega, stream=side):
+                    mega_out = [step(*ring[i]) for i in range(args.ring)]
             except Exception as e:  # capture unsupported (e.g. a collective that cannot be captured) -> eager steps
                 sys.stderr.write("graph capture failed (%s); timing eager steps\n" % (str(e).splitlines()[0],))
                 graphs = None
+                mega = None
                 torch.cuda.synchronize()
         if world > 1:  # every rank must take the same path
             flag = torch.tensor([1 if graphs is not None else 0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag) == 0:
                 graphs = None
+                mega = None
 
     def run_steps(n, first=0):
-        for i in range(n):
+        """Exactly n steps. Whole passes over the ring are replayed as one graph, the rest step by step."""
+        i = 0
+        since = 0
+        while i < n:
             j = (first + i) % args.ring
-            if graphs is not None:
+            if mega is not None and j == 0 and n - i >= args.ring:
+                mega.replay()
+                done = args.ring
+            elif graphs is not None:
                 graphs[j][0].replay()
+                done = 1
             else:
                 step(*ring[j])
-            if (i + 1) % args.sync_every == 0:
+                done = 1
+            i += done
+            since += done
+            if since >= args.sync_every:
                 exchange()
+                since = 0
         exchange()
 
     def barrier():
@@ -426,7 +443,7 @@ def main():
                            "metrics": TRAIN_METRICS, "variance_focus": 0.85,
                            "l2_policy": "ring of %d distinct batches (%.0f MB) larger than the 126 MB L2" %
                                         (args.ring, args.ring * 2 * 4 * npx / 1e6),
-                           "cuda_graph": graphs is not None, "parallelism": "image-sharded x%d" % world,
+                           "cuda_graph": graphs is not None, "steps_per_graph": (args.ring if mega is not None else 1), "parallelism": "image-sharded x%d" % world,
                            "collective": None if world == 1 else "all-reduce of 12 doubles every %d steps (NCCL)" % args.sync_every},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step) * K,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}

@@ -300,3 +300,23 @@ def test_silog_shared_memory_variant_is_bit_reproducible(Cr):
                     close(vals, ref_vals, 1e-12)
             if it % 3 == 0:
                 run_loss(Cr.silog_loss(0.85), other_p, other_g)
+
+
+@pytest.mark.parametrize("shape,dtype", [((2, 1, 37, 41), torch.float32), ((16, 1, 480, 640), torch.float32),
+                                         ((3, 1, 64, 80), torch.float16), ((1, 1, 5, 7), torch.bfloat16)])
+def test_upstream_gradient_scales_the_stashed_gradient(shape, dtype):
+    """loss.backward() stashes dL/dpred at forward time; an upstream gradient other than 1 (a GradScaler, a weighted
+    sum of losses) multiplies it in place (mde_scale_inplace: 128-bit path and the scalar tail)."""
+    from mono_depth_estimation_b200 import criteria
+    g = torch.Generator().manual_seed(3)
+    gt = torch.rand(shape, generator=g) * 9.5 + 0.5
+    gt[torch.rand(shape, generator=g) < 0.2] = 0.0
+    pred = (gt.clamp_min(0.5) + torch.randn(shape, generator=g) * 0.3).clamp_min(1e-3).to(dtype).cuda()
+    gt = gt.cuda()
+    p1 = pred.clone().requires_grad_(True)
+    criteria.MaskedL1Loss()(p1, gt).backward()
+    p2 = pred.clone().requires_grad_(True)
+    (criteria.MaskedL1Loss()(p2, gt) * 2.5).backward()
+    assert p2.grad.dtype == dtype
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    torch.testing.assert_close(p2.grad.float(), p1.grad.float() * 2.5, rtol=tol, atol=0.0)
