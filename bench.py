@@ -219,14 +219,15 @@ def main():
     crit = criteria.silog_loss(0.85).fuse_metrics(None if args.unfused else mcomp)
     raw_acc = torch.zeros(_lib.METRIC_NQ, dtype=torch.float64, device=dev)
 
-    def step(pred, gt):
+    def step(pred, gt, pool=True):
         p = pred.detach().requires_grad_(True)
         loss = crit(p, gt)                       # reference modules/bts.py:106
         loss.backward()
         vals = mcomp.compute(p.detach(), gt)     # reference metrics.py:16-17 (log_train)
-        if world > 1:  # pooled raw sums of this rank, accumulated on the device between exchanges
-            raw_acc.add_(mcomp.last_f64[2 * _lib.METRIC_NM:2 * _lib.METRIC_NM + _lib.METRIC_NQ])
-        return loss, vals, p.grad
+        raw = mcomp.last_f64[2 * _lib.METRIC_NM:2 * _lib.METRIC_NM + _lib.METRIC_NQ]
+        if world > 1 and pool:  # pooled raw sums of this rank, accumulated on the device between exchanges
+            raw_acc.add_(raw)
+        return loss, vals, p.grad, raw
 
     def exchange():
         # The ONLY inter-GPU traffic of the path: 12 doubles (pooled metric sums and exact counts) summed
@@ -259,7 +260,9 @@ def main():
                     graphs.append((g, o))
                 mega = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(mega, stream=side):
-                    mega_out = [step(*ring[i]) for i in range(args.ring)]
+                    mega_out = [step(*ring[i], pool=False) for i in range(args.ring)]
+                    if world > 1:   # the pass's pooled sums in one go (3 small launches per pass instead of one per step)
+                        raw_acc.add_(torch.stack([o[3] for o in mega_out]).sum(0))
             except Exception as e:  # capture unsupported (e.g. a collective that cannot be captured) -> eager steps
                 sys.stderr.write("graph capture failed (%s); timing eager steps\n" % (str(e).splitlines()[0],))
                 graphs = None
