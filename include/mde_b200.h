@@ -320,6 +320,16 @@ int mde_midas_loss_masked(const void* pred, int pred_dtype, const float* target,
 int mde_robust_backward(const float* pred_norm, const float* target, const float* stats_pred, int64_t n_img,
                         int64_t hw, void* ws, float* coef_scratch, float* grad_inout, void* stream);
 
+/* ---- depth map -> colours ------------------------------------------------ */
+/*
+ * colored_depthmap(depth, d_min, d_max, do_mapping) (reference visualize.py:8-17): rel = (depth - d_min) / (d_max -
+ * d_min) * 255 in float32, cast to uint8 as numpy does, then OpenCV's COLORMAP_INFERNO (BGR). auto_range != 0: d_min /
+ * d_max are the minimum / maximum of the map (NaN when it holds a NaN, as np.min / np.max), found on the device in
+ * scratch4 (4 words, any content). out: uint8 [n, 3] (do_mapping) or [n], 4-byte aligned.
+ */
+int mde_colored_depthmap(const float* depth, int64_t n, float d_min, float d_max, int auto_range, int do_mapping,
+                         unsigned* scratch4, uint8_t* out, void* stream);
+
 /* ---- layered-depth ("stdepth") base criterion -------------------------- */
 /*
  * The closure BaseModule.setup_criterion returns (reference modules/base_module.py:124-208; the criterion of the

@@ -9,6 +9,6 @@ from . import synth  # noqa: F401  (pure torch, no CUDA needed)
 
 def __getattr__(name):
     import importlib
-    if name in ("criteria", "metrics", "dorn", "pointcloud", "distributed", "wcel", "stdepth", "_lib", "build"):
+    if name in ("criteria", "metrics", "dorn", "pointcloud", "distributed", "wcel", "stdepth", "visualize", "_lib", "build"):
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -70,6 +70,7 @@ SIGNATURES = {
     "mde_apply_scale_shift": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp]),
     "mde_midas_loss": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "mde_midas_ssi_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "mde_colored_depthmap": (_i32, [_vp, _i64, _f32, _f32, _i32, _i32, _vp, _vp, _vp]),
     "mde_stdepth_loss": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "mde_robust_scratch_bytes": (C.c_size_t, [_i64]),
     "mde_robust_normalize": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

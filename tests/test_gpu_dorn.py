@@ -164,3 +164,32 @@ def test_sid_tables(D):
     assert a.dtype == torch.int32 and int((a - b).abs().max()) <= 1 and float((a != b).float().mean()) < 0.02
     close(D.label_to_depth(lab.cuda().float(), 0.5, 10.0, 68, "UD"), odorn.label_to_depth(lab.float(), 0.5, 10.0, 68, "UD"), 1e-6)
     close(D.depth_to_label(d.cuda(), 0.5, 10.0, 68, "UD"), odorn.depth_to_label(d, 0.5, 10.0, 68, "UD"), 1e-5, 1e-5)
+
+
+def test_config_c3_full_size_consistency(D, Cr):
+    """C3 at full size (8 x 136 x 257 x 353 logits, 395 MB), size-independent properties: the fused step equals the
+    layer followed by ordLoss (decode bit-exact, loss and gradient to fp32 rounding); the batch loss is the mean of the
+    per-image losses; decode never exceeds K and counts exactly the pairs with b' - a' above the tie margin."""
+    shape = synth.SHAPES["C3"]
+    N, C2, H, W = shape
+    K = C2 // 2
+    x, gt = synth.dorn_inputs(shape, 103, device="cuda")
+    xr = x.clone().requires_grad_(True)
+    loss, decode, depth, _ = D.dorn_fused(xr, gt, K, 0.001, 1.0)
+    loss.backward()
+    dec2, P = D.OrdinalRegressionLayer()(x)
+    assert torch.equal(dec2, decode) and decode.dtype == torch.int64
+    assert int(decode.min()) >= 0 and int(decode.max()) <= K
+    a, b = x[:, 0::2].clamp(1e-8, 1e4), x[:, 1::2].clamp(1e-8, 1e4)
+    assert torch.equal(decode, ((b - a) > 1.5 * 2.0 ** -24).sum(1, keepdim=True))
+    del a, b
+    Pl = P.detach().requires_grad_(True)
+    l2 = Cr.ordLoss()(Pl, D.depth_to_label(gt, 0.001, 1.0, K))
+    close(l2, loss.detach(), 2e-6)
+    per_image = [float(D.dorn_fused(x[i:i + 1], gt[i:i + 1], K, 0.001, 1.0)[0]) for i in range(N)]
+    close(loss.detach(), sum(per_image) / N, 2e-6)
+    assert bool(torch.isfinite(xr.grad).all())
+    # channels of a pair receive opposite gradients wherever both logits are inside the clamp
+    ga, gb = xr.grad[:, 0::2], xr.grad[:, 1::2]
+    inside = (x[:, 0::2] > 1e-8) & (x[:, 0::2] < 1e4) & (x[:, 1::2] > 1e-8) & (x[:, 1::2] < 1e4)
+    assert torch.equal(ga[inside], -gb[inside])

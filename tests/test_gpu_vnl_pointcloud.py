@@ -108,3 +108,18 @@ def test_point_cloud_tiled_path(Cr, shape):
     np.testing.assert_array_equal(np.nan_to_num(out32), np.nan_to_num(ref0.astype(np.float32)))
     outw = PC.point_cloud_world(depth[0], cam)
     np.testing.assert_allclose(np.nan_to_num(outw), np.nan_to_num(opc.to_world(ref0, cam.matrix_world)), rtol=1e-6, atol=1e-6)
+
+
+def test_vnl_config_c4_full_size_properties(Cr):
+    """C4 at full size (8 x 385 x 385, 100 000 triplets), size-independent properties: the loss does not depend on
+    the order of the triplets nor on the order of the three points' columns being permuted together; the valid-set
+    size and the trim count are integers that survive the permutation exactly; gradients agree to fp32 atomics noise."""
+    gt, pred, trip = synth.vnl_inputs(synth.SHAPES["C4"], 104)
+    loss, grad, stats = _vnl(Cr, gt, pred, trip)
+    perm = torch.randperm(trip.shape[1], generator=torch.Generator().manual_seed(1))
+    loss_p, grad_p, stats_p = _vnl(Cr, gt, pred, trip[:, perm].contiguous())
+    assert int(stats[0]) == int(stats_p[0]) and int(stats[1]) == int(stats_p[1])
+    assert int(stats[1]) == int(int(stats[0]) * 0.25)
+    close(loss_p, loss, 2e-6)
+    close(grad_p, grad, 1e-4, 2e-6 * float(grad.abs().max()))
+    assert 0.2 < int(stats[0]) / (8 * trip.shape[1]) < 0.4        # the survey's probe: 25-32 % of the triplets are valid
