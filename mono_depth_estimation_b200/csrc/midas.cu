@@ -20,6 +20,32 @@ constexpr int kMBlock = 256;
 constexpr int kMWarps = kMBlock / 32;
 constexpr int kMChunk = kMBlock * 16;   // pixels per CTA step
 
+// Elementwise pass over [n_img, hw] with per-image coefficients: a CTA takes tiles of 8 * kMBlock pixels of ONE image
+// (one division per tile instead of one 64-bit division per pixel), eight independent elements per thread.
+// f(img, global index).
+template <typename F>
+__device__ __forceinline__ void for_each_pixel_by_image(int64_t n_img, int64_t hw, F f) {
+  constexpr int64_t kTile = 8 * kMBlock;
+  const int64_t tiles_per_img = (hw + kTile - 1) / kTile;
+  const int64_t n_tiles = n_img * tiles_per_img;
+  for (int64_t w = blockIdx.x; w < n_tiles; w += gridDim.x) {
+    const int64_t img = w / tiles_per_img;
+    const int64_t c0 = (w - img * tiles_per_img) * kTile + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t i = c0 + k * kMBlock;
+      if (i < hw) f(img, img * hw + i);
+    }
+  }
+}
+inline unsigned by_image_grid(int64_t n_img, int64_t hw, int per_sm) {
+  int64_t g = n_img * ((hw + 8 * kMBlock - 1) / (8 * kMBlock));
+  const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
 template <typename PT>
 __global__ void __launch_bounds__(kMBlock) scale_shift_kernel(const PT* __restrict__ pred, const float* __restrict__ gt,
                                                              const uint8_t* __restrict__ mask, int64_t n_img, int64_t hw,
@@ -99,12 +125,9 @@ template <typename PT>
 __global__ void __launch_bounds__(kMBlock) apply_scale_shift_kernel(const PT* __restrict__ pred, const float* __restrict__ scale,
                                                                    const float* __restrict__ shift, int64_t n_img, int64_t hw,
                                                                    float* __restrict__ out) {
-  const int64_t total = n_img * hw;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kMBlock + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * kMBlock) {
-    const int64_t b = i / hw;
+  for_each_pixel_by_image(n_img, hw, [&](int64_t b, int64_t i) {
     __stcs(out + i, __fadd_rn(__fmul_rn(__ldg(scale + b), Elem<PT>::ld1(pred + i)), __ldg(shift + b)));
-  }
+  });
 }
 
 template <typename PT>
@@ -127,11 +150,8 @@ int launch_scale_shift(const void* pred, const float* gt, const uint8_t* mask, i
 template <typename PT>
 int launch_apply(const void* pred, const float* scale, const float* shift, int64_t n_img, int64_t hw, float* out,
                  cudaStream_t st) {
-  int64_t grid = (n_img * hw + kMBlock - 1) / kMBlock;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
-  if (grid > cap) grid = cap;
-  apply_scale_shift_kernel<PT><<<static_cast<unsigned>(grid), kMBlock, 0, st>>>(static_cast<const PT*>(pred), scale, shift, n_img,
-                                                                               hw, out);
+  apply_scale_shift_kernel<PT><<<by_image_grid(n_img, hw, 8), kMBlock, 0, st>>>(static_cast<const PT*>(pred), scale, shift, n_img,
+                                                                                 hw, out);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
@@ -760,16 +780,13 @@ __global__ void __launch_bounds__(kMBlock) ssi_reduce_kernel(const float* __rest
 __global__ void __launch_bounds__(kMBlock) ssi_update_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                             const float* __restrict__ coef, int64_t n_img, int64_t hw,
                                                             float* __restrict__ g) {
-  const int64_t total = n_img * hw;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kMBlock + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * kMBlock) {
-    const int64_t b = i / hw;
+  for_each_pixel_by_image(n_img, hw, [&](int64_t b, int64_t i) {
     const float4 c = __ldg(reinterpret_cast<const float4*>(coef) + b);
     const float y = __ldg(gt + i);
     float out = c.x * g[i];
     if (y > 0.f) out += fmaf(c.y, y, fmaf(c.z, __ldg(pred + i), c.w));
     g[i] = out;
-  }
+  });
 }
 
 }  // namespace
@@ -794,10 +811,7 @@ extern "C" int mde_midas_ssi_backward(const float* pred, const float* target, co
                                                                     shift, sums, coef_scratch);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
-  int64_t g2 = (n_img * hw + kMBlock - 1) / kMBlock;
-  const int64_t cap2 = static_cast<int64_t>(sm_count()) * 8;
-  if (g2 > cap2) g2 = cap2;
-  ssi_update_kernel<<<static_cast<unsigned>(g2), kMBlock, 0, st>>>(pred, target, coef_scratch, n_img, hw, grad_inout);
+  ssi_update_kernel<<<by_image_grid(n_img, hw, 8), kMBlock, 0, st>>>(pred, target, coef_scratch, n_img, hw, grad_inout);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
@@ -1031,15 +1045,12 @@ __global__ void __launch_bounds__(kMBlock) robust_apply_kernel(const float* __re
                                                               const float* __restrict__ stats_pred,
                                                               const float* __restrict__ stats_gt, int64_t n_img, int64_t hw,
                                                               float* __restrict__ pred_out, float* __restrict__ gt_out) {
-  const int64_t total = n_img * hw;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kMBlock + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * kMBlock) {
-    const int64_t b = i / hw;
+  for_each_pixel_by_image(n_img, hw, [&](int64_t b, int64_t i) {
     const float mp = __ldg(stats_pred + b * kStatW), sp = __ldg(stats_pred + b * kStatW + 1);
     const float mt = __ldg(stats_gt + b * kStatW), st = __ldg(stats_gt + b * kStatW + 1);
     pred_out[i] = __fdiv_rn(__fsub_rn(__ldg(pred + i), mp), sp);
     gt_out[i] = __fdiv_rn(__fsub_rn(__ldg(gt + i), mt), st);
-  }
+  });
 }
 
 // Backward through the normalisation of the prediction, x' = (x - m) / s with m = x_k mask_k (median element k) and
@@ -1101,16 +1112,13 @@ __global__ void __launch_bounds__(kMBlock) robust_reduce_kernel(const float* __r
 __global__ void __launch_bounds__(kMBlock) robust_update_kernel(const float* __restrict__ xn, const float* __restrict__ gt,
                                                                const float* __restrict__ coef, int64_t n_img, int64_t hw,
                                                                float* __restrict__ g) {
-  const int64_t total = n_img * hw;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kMBlock + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * kMBlock) {
-    const int64_t b = i / hw;
+  for_each_pixel_by_image(n_img, hw, [&](int64_t b, int64_t i) {
     const float4 c = __ldg(reinterpret_cast<const float4*>(coef) + b);
     float out = c.x * g[i];
     if (__ldg(gt + i) > 0.f) out = fmaf(c.y, sgnf(__ldg(xn + i)), out);     // sign(x - m) = sign(x')
     if (static_cast<unsigned>(i - b * hw) == __float_as_uint(c.w)) out += c.z;
     g[i] = out;
-  }
+  });
 }
 
 }  // namespace
@@ -1150,11 +1158,8 @@ extern "C" int mde_robust_normalize(const float* pred, const float* target, int6
     MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kRBlock), args, 0, st));
     count_launch();
   }
-  int64_t grid = (n_img * hw + kMBlock - 1) / kMBlock;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
-  if (grid > cap) grid = cap;
-  robust_apply_kernel<<<static_cast<unsigned>(grid), kMBlock, 0, st>>>(pred, target, stats_pred, stats_target, n_img, hw, pred_out,
-                                                                      target_out);
+  robust_apply_kernel<<<by_image_grid(n_img, hw, 8), kMBlock, 0, st>>>(pred, target, stats_pred, stats_target, n_img, hw, pred_out,
+                                                                        target_out);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
@@ -1187,10 +1192,7 @@ extern "C" int mde_robust_backward(const float* pred_norm, const float* target, 
                                                                        stats_pred, coef_scratch);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
-  int64_t g2 = (n_img * hw + kMBlock - 1) / kMBlock;
-  const int64_t cap2 = static_cast<int64_t>(sm_count()) * 8;
-  if (g2 > cap2) g2 = cap2;
-  robust_update_kernel<<<static_cast<unsigned>(g2), kMBlock, 0, st>>>(pred_norm, target, coef_scratch, n_img, hw, grad_inout);
+  robust_update_kernel<<<by_image_grid(n_img, hw, 8), kMBlock, 0, st>>>(pred_norm, target, coef_scratch, n_img, hw, grad_inout);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
