@@ -864,9 +864,10 @@ struct RobustArgs {
 };
 
 // One cooperative launch: every (image, tensor) pair is cut into `parts` units so that all SMs work even for a small
-// batch. Round r: each unit histograms digit r of the keys that match the prefix found so far (shared memory, lanes
-// atomics), flushes the non-empty bins to the pair's global histogram; after a grid
-// sync one CTA per pair picks the bin that holds the rank. Then one more sweep for the index, deviation and sign sum.
+// batch. Round r: each unit histograms digit r of the keys that match the prefix found so far (shared-memory
+// atomics) and flushes the non-empty bins to the pair's global histogram;
+// the last unit of a pair to arrive picks the bin that holds the rank (per-pair ticket), one grid sync per round hands
+// the prefix to the next digit. Then one more sweep for the index, deviation and sign sum.
 __global__ void __launch_bounds__(kRBlock, 1) robust_stats_kernel(RobustArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ unsigned hist[kRBins];
@@ -929,14 +930,15 @@ __global__ void __launch_bounds__(kRBlock, 1) robust_stats_kernel(RobustArgs a) 
         const unsigned c = hist[b];
         if (c) atomicAdd(w + b, c);
       }
+      // the last unit of this pair to get here (per-pair ticket) picks the bin that holds the rank
+      __threadfence();
       __syncthreads();
-    }
-    __threadfence();
-    grid.sync();
-    for (int pair = blockIdx.x; pair < a.pairs; pair += gridDim.x) {
-      unsigned* w = a.words + static_cast<size_t>(pair) * kRWords;
+      if (threadIdx.x == 0) sm_u[3] = (atomicAdd(w + kRBins + 3, 1u) == static_cast<unsigned>(a.parts - 1)) ? 1u : 0u;
+      __syncthreads();
+      if (sm_u[3] == 0u) continue;                             // uniform over the CTA
+      __threadfence();
       const unsigned rank = __ldcg(w + kRBins + 1);
-      {   // the bin holding the rank: CTA-wide scan, two counters per thread
+      {   // CTA-wide scan, two counters per thread
         const unsigned b0 = 2u * threadIdx.x;
         const unsigned c0 = (b0 < bins) ? __ldcg(w + b0) : 0u, c1 = (b0 + 1u < bins) ? __ldcg(w + b0 + 1u) : 0u;
         const unsigned mine = c0 + c1;
@@ -969,14 +971,15 @@ __global__ void __launch_bounds__(kRBlock, 1) robust_stats_kernel(RobustArgs a) 
       __syncthreads();
       for (unsigned b = threadIdx.x; b < bins; b += kRBlock) w[b] = 0u;
       if (threadIdx.x == 0) {
-        w[kRBins] = __ldcg(w + kRBins) | (sm_u[0] << shift);
+        w[kRBins] = prefix | (sm_u[0] << shift);
         w[kRBins + 1] = sm_u[1];
+        w[kRBins + 3] = 0u;                                      // ticket for the next round
       }
       __syncthreads();
     }
     fixed |= (bins - 1u) << shift;
     __threadfence();
-    grid.sync();
+    grid.sync();                                                 // one per round: the next digit needs every pair's prefix
   }
 
   // ---- final sweep: first index holding the median, valid count, deviation sum, sign sum ----
@@ -1017,26 +1020,26 @@ __global__ void __launch_bounds__(kRBlock, 1) robust_stats_kernel(RobustArgs a) 
       for (int q = 0; q < kRWarps; ++q) tot += sm_d[threadIdx.x * kRWarps + q];
       if (tot != 0.0) atomicAdd(a.facc + pair * 4 + threadIdx.x, tot);
     }
+    // the last unit of the pair writes its statistics row
+    __threadfence();
     __syncthreads();
-  }
-  __threadfence();
-  grid.sync();
-  for (int pair = blockIdx.x * kRBlock + threadIdx.x; pair < a.pairs; pair += gridDim.x * kRBlock) {
-    const int64_t img = pair >> 1;
-    const unsigned* w = a.words + static_cast<size_t>(pair) * kRWords;
-    float* out = ((pair & 1) ? a.stats_gt : a.stats_pred) + img * kStatW;
-    const double nn = __ldcg(a.facc + pair * 4), dv = __ldcg(a.facc + pair * 4 + 1), z = __ldcg(a.facc + pair * 4 + 2);
-    const unsigned k = __ldcg(w + kRBins + 2);
-    float m = 0.f, s = 1.f, clamped = 1.f, mk = 0.f;
-    if (nn > 0.0) {                                         // criteria.py:139, :144-150
-      m = okey_inv(__ldcg(w + kRBins));
-      const float raw = static_cast<float>(dv / nn);
-      clamped = (raw < 1e-6f) ? 1.f : 0.f;
-      s = (raw < 1e-6f) ? 1e-6f : raw;
-      mk = (k < n && __ldg(a.gt + img * n + k) > 0.f) ? 1.f : 0.f;
+    if (threadIdx.x == 0 && atomicAdd(w + kRBins + 3, 1u) == static_cast<unsigned>(a.parts - 1)) {
+      __threadfence();
+      float* out = ((pair & 1) ? a.stats_gt : a.stats_pred) + img * kStatW;
+      const double nn = __ldcg(a.facc + pair * 4), dv = __ldcg(a.facc + pair * 4 + 1), z = __ldcg(a.facc + pair * 4 + 2);
+      const unsigned k = __ldcg(w + kRBins + 2);
+      float m = 0.f, s = 1.f, clamped = 1.f, mk = 0.f;
+      if (nn > 0.0) {                                         // criteria.py:139, :144-150
+        m = med;
+        const float raw = static_cast<float>(dv / nn);
+        clamped = (raw < 1e-6f) ? 1.f : 0.f;
+        s = (raw < 1e-6f) ? 1e-6f : raw;
+        mk = (k < n && __ldg(t + k) > 0.f) ? 1.f : 0.f;
+      }
+      out[0] = m; out[1] = s; out[2] = static_cast<float>(nn); out[3] = __uint_as_float(k);
+      out[4] = mk; out[5] = static_cast<float>(z); out[6] = clamped; out[7] = 0.f;
     }
-    out[0] = m; out[1] = s; out[2] = static_cast<float>(nn); out[3] = __uint_as_float(k);
-    out[4] = mk; out[5] = static_cast<float>(z); out[6] = clamped; out[7] = 0.f;
+    __syncthreads();
   }
 }
 
