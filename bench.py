@@ -189,6 +189,9 @@ def main():
     ap.add_argument("--unfused", action="store_true", help="separate loss and metrics launches (20 B/px)")
     ap.add_argument("--sync-every", type=int, default=50, help="N>1: all-reduce the metric sums every this many steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager-gpu", action="store_true",
+                    help="also time the reference's op chain (the oracle port: the same ATen sequence) run EAGERLY on this GPU; "
+                         "informative second baseline of SURVEY 8(d), off by default")
     args = ap.parse_args()
     shape = (args.batch, 1, 480, 640)
     if args.impl == "reference":
@@ -438,6 +441,28 @@ def main():
         cb = time_cpu(shape, 12, 2)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    eager_gpu = None
+    if rank == 0 and world == 1 and args.eager_gpu:
+        # the reference's own way of running this step on a GPU: ~40 ATen launches with boolean-mask gathers (each a
+        # device->host sync for the output size). Baseline only: nothing of the product path is involved.
+        from oracle import losses as olosses, metrics as ometrics
+        def eager_step(i):
+            pr, g = ring[i % args.ring]
+            loss, grad = olosses.loss_and_grad(olosses.silog, pr, g, 0.85)
+            vals = ometrics.compute(pr, g, TRAIN_METRICS)
+            return float(loss) + float(vals[0])
+        for i in range(3):
+            eager_step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ne = 20
+        for i in range(ne):
+            eager_step(i)
+        torch.cuda.synchronize()
+        eg_ms = 1e3 * (time.perf_counter() - t0) / ne
+        eager_gpu = {"value": npx / (eg_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": eg_ms, "steps": ne,
+                     "kind": "oracle port of the reference's ATen chain, eager on cuda:0, inputs resident"}
+
     if rank == 0:
         line = {"metric": "Mpix/s, depth supervision+eval step (silog fwd+bwd + metrics)", "value": value, "unit": "Mpix/s",
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -450,6 +475,8 @@ def main():
                            "collective": None if world == 1 else "all-reduce of 12 doubles every %d steps (NCCL)" % args.sync_every},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step) * K,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
+        if eager_gpu is not None:
+            line["eager_gpu_baseline"] = eager_gpu
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -436,7 +436,7 @@ def _base_module_criterion(method, single_layer):
     return ns["setup_criterion"](types.SimpleNamespace(method=method, single_layer=single_layer))
 
 
-from oracle.gen_golden_inputs import stdepth_inputs  # noqa: E402
+from mono_depth_estimation_b200.synth import stdepth_inputs  # noqa: E402
 
 
 def gen_stdepth():

@@ -92,7 +92,7 @@ def test_robust_normalize_stays_inside_its_buffers(shape):
 def test_stdepth_stays_inside_its_buffers(shape):
     from mono_depth_estimation_b200 import _lib
     from oracle import stdepth as ost
-    from oracle.gen_golden_inputs import stdepth_inputs
+    from mono_depth_estimation_b200.synth import stdepth_inputs
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     B, C, H, W = shape

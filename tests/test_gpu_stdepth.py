@@ -80,7 +80,7 @@ def test_empty_depth_mask_and_errors(S, golden):
                                                    ((3, 10, 64, 80), "silma", torch.float16)])
 def test_vs_oracle(S, shape, loss_name, dtype):
     """BTS's default 'silma' at a training-like size, odd sizes, three layers, AMP (fp16 prediction)."""
-    from oracle.gen_golden_inputs import stdepth_inputs
+    from mono_depth_estimation_b200.synth import stdepth_inputs
     B, C, H, W = shape
     pred, targ, rgba = stdepth_inputs(31 + B + C, B, C, H, W)
     pred = pred.to(dtype)

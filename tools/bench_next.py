@@ -18,7 +18,7 @@ import torch  # noqa: E402
 
 def run(report, timed, reps):
     from mono_depth_estimation_b200 import _lib, criteria, stdepth
-    from oracle.gen_golden_inputs import stdepth_inputs
+    from mono_depth_estimation_b200.synth import stdepth_inputs
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     sp = lambda: _lib.stream_ptr(dev)  # noqa: E731

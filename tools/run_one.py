@@ -71,7 +71,7 @@ elif name in ("midas_mse", "robust"):
         f = lambda: _lib.check(lib.mde_robust_normalize(_lib.ptr(prd), _lib.ptr(tgt), Bm, Hm * Wm, _lib.ptr(scr), _lib.ptr(stp), _lib.ptr(stt), _lib.ptr(lg), _lib.ptr(tn), sp()))
 elif name == "stdepth":
     from mono_depth_estimation_b200 import stdepth
-    from oracle.gen_golden_inputs import stdepth_inputs
+    from mono_depth_estimation_b200.synth import stdepth_inputs
     B, Cc, H, W = 8, 10, 512, 512
     pred, targ, rgba = (v.to(dev) for v in stdepth_inputs(900, B, Cc, H, W))
     ws = _lib.workspace(dev, B); out8 = torch.empty(8, device=dev); gr = torch.empty_like(pred)
