@@ -152,3 +152,39 @@ def test_decode_rule_matches_softmax_on_cpu():
     rule = (bc - ac) > 8.940696716308594e-08
     assert torch.equal(rule.view(-1), (P > 0.5).view(-1))
     assert int(decode.sum()) == int(rule.sum())
+
+
+def test_layered_depth_term_selection_on_host():
+    """The substring tests of BaseModule.setup_criterion (reference modules/base_module.py:156-194) and what is out of
+    scope (SSIM / compositing terms), decided on the host before any launch."""
+    import types
+    from mono_depth_estimation_b200 import stdepth
+    F = stdepth.TERM_FLAGS
+    assert stdepth._flags_of("silma") == F["depth_silog"] | F["color_mae"]              # bts default (modules/bts.py:237)
+    assert stdepth._flags_of("silms") == F["depth_silog"] | F["color_mse"]
+    assert stdepth._flags_of("mse") == F["all_mse"] and stdepth._flags_of("mae") == F["all_mae"]
+    assert stdepth._flags_of("mae+mse+fbdivergence") == F["all_mae"] | F["all_mse"] | F["fb_divergence"]
+    assert stdepth._flags_of("silma+fbdivergence") == F["depth_silog"] | F["color_mae"] | F["fb_divergence"]
+    for name in ("mae+composite", "silma+colorssim", "allssim", "composite+ssim"):      # laina's default is the first
+        with pytest.raises(NotImplementedError):
+            stdepth._flags_of(name)
+    with pytest.raises(RuntimeError):
+        stdepth._flags_of("dorn")                                                        # selects no term
+    m = types.SimpleNamespace(loss="silma", variance_focus=0.85, depth_loss_weight=1.0, comp_loss_weight=1.0,
+                              fbdiv_loss_weight=1.0, ssim_loss_weight=1.0)
+    crit = stdepth.setup_criterion(m, single_layer=True)
+    with pytest.raises(RuntimeError):                                                    # CPU tensors: no fallback
+        crit(torch.zeros(1, 10, 4, 4), torch.zeros(1, 10, 4, 4), torch.zeros(1, 4, 4, 4))
+
+
+def test_midas_family_host_contract():
+    from mono_depth_estimation_b200 import criteria
+    for cls in (criteria.MidasLoss, criteria.TrimmedProcrustesLoss):
+        with pytest.raises(NotImplementedError):
+            cls(reduction="image-based")
+        assert len(cls().state_dict()) == 0                                              # checkpoints load strictly
+    with pytest.raises(ValueError):
+        criteria.MidasLoss(loss="huber")                                                 # criteria.py:316-317
+    assert criteria.TrimmedProcrustesLoss().prediction_ssi is None                       # criteria.py:343
+    with pytest.raises(RuntimeError):
+        criteria.TrimmedProcrustesLoss()(torch.ones(1, 1, 4, 4), torch.ones(1, 1, 4, 4))
