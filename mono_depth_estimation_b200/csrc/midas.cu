@@ -247,7 +247,7 @@ __device__ __forceinline__ void pos_advance(PixPos& q, const MidasArgs& a) {
   pos_advance(q, a.dj, a.di, a.dimg, static_cast<unsigned>(a.w), static_cast<unsigned>(a.h));
 }
 
-template <typename PT, bool VS, int MAXS>
+template <typename PT, bool VS, int MAXS, bool SSI>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm_d[2 * kWarps];
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
   const unsigned HW = H * W;
   const unsigned total = static_cast<unsigned>(a.n_img) * HW;
   const unsigned tid = blockIdx.x * kBlock + threadIdx.x, nthr = gridDim.x * kBlock;
-  const bool ssi = a.scale != nullptr;
+  constexpr bool ssi = SSI;                 // a.scale != nullptr: per-image alignment on load
   const float* __restrict__ vs = a.vsrc;
   // prediction as the loss sees it: aligned with two separately rounded ops, as `scale * prediction + shift` is
   auto align = [&](float p, float sc, float sh) -> float { return ssi ? __fadd_rn(__fmul_rn(sc, p), sh) : p; };
@@ -644,11 +644,17 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
 
 template <typename PT>
 int launch_midas(MidasArgs& a, cudaStream_t st) {
+  // validity source (TrimmedProcrustes) and alignment (the 'ssi' variants) never come together
   const void* fn;
-  if (a.scales <= 4) fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true, 4>)
-                                 : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, 4>);
-  else fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true, kMaxScales>)
-                   : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, kMaxScales>);
+  if (a.scales <= 4) {
+    fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true, 4, false>)
+                : (a.scale ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, 4, true>)
+                           : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, 4, false>));
+  } else {
+    fn = a.vsrc ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, true, kMaxScales, false>)
+                : (a.scale ? reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, kMaxScales, true>)
+                           : reinterpret_cast<const void*>(&midas_loss_kernel<PT, false, kMaxScales, false>));
+  }
   const int64_t n = static_cast<int64_t>(a.n_img) * a.h * a.w;
   int64_t grid = (n + kBlock - 1) / kBlock;
   const int cap = coop_grid(fn, kBlock, 0);
