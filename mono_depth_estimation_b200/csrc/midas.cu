@@ -201,9 +201,17 @@ extern "C" int mde_apply_scale_shift(const void* pred, int pred_dtype, const flo
 //   loss = data + alpha * reg (alpha > 0). This is the criterion of the registered method `my`
 //   (modules/my.py:39: MidasLoss(alpha=0.5, loss='mse', reduction='batch-based')).
 //
-// One cooperative launch: phase A reduces {S_data, N, S_s, N_s (s < scales)} with a 3-point stencil per scale
-// (neighbours come from L1/L2), a grid sync publishes them, phase B writes the gradient with the 5-point stencil
-// per scale. The reference runs ~15 masked full-tensor ops per scale plus 4 strided slicing copies.
+// One cooperative launch: phase A reduces {S_data, N, S_s, N_s (s < scales)} with a 3-point stencil per scale, a grid
+// sync publishes them, phase B writes the gradient with the 5-point stencil per scale. The reference runs ~15 masked
+// full-tensor ops per scale plus 4 strided slicing copies.
+//   Rows of whole quads (W % 4 == 0, 16-byte aligned tensors): a thread owns 4 consecutive pixels of a row; the rows
+//   above / below arrive as 128-bit pairs, the pixels beside the quad as scalars, and the coarse scales ride along
+//   (pixels 0 and 2 of a quad on even rows are the stride-2 grid, pixel 0 is on every coarser grid whose step divides
+//   its row and column): one sweep per phase.
+//   Other widths: scalar sweep for scale 0, dense loops over the grid points of every coarser scale, and for the
+//   gradient a second pass (after one more grid sync) in which the thread owning a stride-2 pixel adds the share of
+//   all the coarse scales.
+//   Positions (image, row, column) advance by a host-computed stride: no division per pixel.
 namespace mde {
 namespace {
 
@@ -405,67 +413,67 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) midas_loss_kernel(MidasArg
           if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + 2 * s + threadIdx.x], tot);
         }
       }
-    } else {
-    for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
-      const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
-      const bool has_r = q.j + 1u < W, has_d = q.i + 1u < H;
-      bool v, v_r, v_d;                                        // centre, right and lower neighbour requested together
-      const float res_c = residual(idx, sc, sh, v);
-      const float res_r = residual(has_r ? idx + 1u : idx, sc, sh, v_r);
-      const float res_d = residual(has_d ? idx + W : idx, sc, sh, v_d);
-      const float res = v ? res_c : 0.f;
-      f_data += (a.kind == 0) ? res * res : fabsf(res);
-      c_data += v ? 1u : 0u;
-      float e = 0.f;
-      if (v && has_r && v_r) e += fabsf(res_r - res);
-      if (v && has_d && v_d) e += fabsf(res_d - res);
-      f_s0 += e;
-      if ((++it & 63u) == 0u) {
-        d_data += static_cast<double>(f_data); f_data = 0.f;
-        d_s0 += static_cast<double>(f_s0); f_s0 = 0.f;
-      }
-    }
-    {
-      const double pair[2] = {d_data + static_cast<double>(f_data), static_cast<double>(c_data)};
-      const double tot = block_sum<2>(pair, sm_d);
-      if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[threadIdx.x], tot);
-    }
-    if (S > 0) {
-      const double pair[2] = {d_s0 + static_cast<double>(f_s0), static_cast<double>(c_data)};
-      const double tot = block_sum<2>(pair, sm_d);
-      if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + threadIdx.x], tot);
-    }
-    // coarser scales: a dense loop over the grid points of each scale (every lane has work)
-#pragma unroll 1
-    for (int s = 1; s < S; ++s) {
-      const unsigned step = 1u << s;
-      const unsigned Hs = (H + step - 1u) >> s, Ws = (W + step - 1u) >> s, HWs = Hs * Ws;
-      const unsigned count = static_cast<unsigned>(a.n_img) * HWs;
-      float f = 0.f;
-      unsigned c = 0u;
-      double d = 0.0;
-      it = 0u;
-      for (unsigned g = tid; g < count; g += nthr) {
-        grid_point(g, s, Ws, HWs, q);
-        const unsigned idx = q.img * HW + q.i * W + q.j;
+    } else {   // rows that are not whole quads: scalar sweep, then dense loops over the coarse grids
+      for (unsigned idx = tid; idx < total; idx += nthr, pos_advance(q, a)) {
         const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
-        const bool has_r = q.j + step < W, has_d = q.i + step < H;
-        bool v, v_r, v_d;
-        const float res = residual(idx, sc, sh, v);
-        const float res_r = residual(has_r ? idx + step : idx, sc, sh, v_r);
-        const float res_d = residual(has_d ? idx + step * W : idx, sc, sh, v_d);
-        c += v ? 1u : 0u;
+        const bool has_r = q.j + 1u < W, has_d = q.i + 1u < H;
+        bool v, v_r, v_d;                                        // centre, right and lower neighbour requested together
+        const float res_c = residual(idx, sc, sh, v);
+        const float res_r = residual(has_r ? idx + 1u : idx, sc, sh, v_r);
+        const float res_d = residual(has_d ? idx + W : idx, sc, sh, v_d);
+        const float res = v ? res_c : 0.f;
+        f_data += (a.kind == 0) ? res * res : fabsf(res);
+        c_data += v ? 1u : 0u;
         float e = 0.f;
         if (v && has_r && v_r) e += fabsf(res_r - res);
         if (v && has_d && v_d) e += fabsf(res_d - res);
-        f += e;
-        if ((++it & 63u) == 0u) { d += static_cast<double>(f); f = 0.f; }
+        f_s0 += e;
+        if ((++it & 63u) == 0u) {
+          d_data += static_cast<double>(f_data); f_data = 0.f;
+          d_s0 += static_cast<double>(f_s0); f_s0 = 0.f;
+        }
       }
-      const double pair[2] = {d + static_cast<double>(f), static_cast<double>(c)};
-      const double tot = block_sum<2>(pair, sm_d);
-      if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + 2 * s + threadIdx.x], tot);
+      {
+        const double pair[2] = {d_data + static_cast<double>(f_data), static_cast<double>(c_data)};
+        const double tot = block_sum<2>(pair, sm_d);
+        if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[threadIdx.x], tot);
+      }
+      if (S > 0) {
+        const double pair[2] = {d_s0 + static_cast<double>(f_s0), static_cast<double>(c_data)};
+        const double tot = block_sum<2>(pair, sm_d);
+        if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + threadIdx.x], tot);
+      }
+      // coarser scales: a dense loop over the grid points of each scale (every lane has work)
+#pragma unroll 1
+      for (int s = 1; s < S; ++s) {
+        const unsigned step = 1u << s;
+        const unsigned Hs = (H + step - 1u) >> s, Ws = (W + step - 1u) >> s, HWs = Hs * Ws;
+        const unsigned count = static_cast<unsigned>(a.n_img) * HWs;
+        float f = 0.f;
+        unsigned c = 0u;
+        double d = 0.0;
+        it = 0u;
+        for (unsigned g = tid; g < count; g += nthr) {
+          grid_point(g, s, Ws, HWs, q);
+          const unsigned idx = q.img * HW + q.i * W + q.j;
+          const float sc = ssi ? __ldg(a.scale + q.img) : 1.f, sh = ssi ? __ldg(a.shift + q.img) : 0.f;
+          const bool has_r = q.j + step < W, has_d = q.i + step < H;
+          bool v, v_r, v_d;
+          const float res = residual(idx, sc, sh, v);
+          const float res_r = residual(has_r ? idx + step : idx, sc, sh, v_r);
+          const float res_d = residual(has_d ? idx + step * W : idx, sc, sh, v_d);
+          c += v ? 1u : 0u;
+          float e = 0.f;
+          if (v && has_r && v_r) e += fabsf(res_r - res);
+          if (v && has_d && v_d) e += fabsf(res_d - res);
+          f += e;
+          if ((++it & 63u) == 0u) { d += static_cast<double>(f); f = 0.f; }
+        }
+        const double pair[2] = {d + static_cast<double>(f), static_cast<double>(c)};
+        const double tot = block_sum<2>(pair, sm_d);
+        if (threadIdx.x < 2 && tot != 0.0) atomicAdd(&gacc[2 + 2 * s + threadIdx.x], tot);
+      }
     }
-    }   // scalar path
   }
   grid.sync();
 

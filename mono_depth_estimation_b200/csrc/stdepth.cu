@@ -98,38 +98,38 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
       }
 #pragma unroll
       for (int u = 0; u < PX; ++u) {
-      if (!ona[u]) continue;
-      const bool m1 = m1a[u];
-      const float (&pv)[C] = pva[u];
-      const float (&tv)[C] = tva[u];
-      float cabs = 0.f, csq = 0.f, aabs = 0.f, asq = 0.f, dabs = 0.f, dsq = 0.f, sd = 0.f, sdd = 0.f, nd = 0.f, ns = 0.f;
-      float pf[3], pb[3], tf[3], tb[3];
+        if (!ona[u]) continue;
+        const bool m1 = m1a[u];
+        const float (&pv)[C] = pva[u];
+        const float (&tv)[C] = tva[u];
+        float cabs = 0.f, csq = 0.f, aabs = 0.f, asq = 0.f, dabs = 0.f, dsq = 0.f, sd = 0.f, sdd = 0.f, nd = 0.f, ns = 0.f;
+        float pf[3], pb[3], tf[3], tb[3];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float p = pv[c], t = tv[c];
-        const float diff = p - t;
-        if (c < 3) { pf[c] = p; tf[c] = t; }
-        if (c >= 4 && c < 7) { pb[c - 4] = p; tb[c - 4] = t; }
-        if (m1) {
-          aabs += fabsf(diff); asq = fmaf(diff, diff, asq);
-          if (c < 8) { cabs += fabsf(diff); csq = fmaf(diff, diff, csq); }
-        }
-        if (c >= d0 && c < d1 && t > 0.f) {                      // maskD                      base_module.py:138
-          nd += 1.f; dabs += fabsf(diff); dsq = fmaf(diff, diff, dsq);
-          if ((flags & ST_SILOG) && t > 1e-2f) {                 // silog's own mask           criteria.py:729
-            const float dl = logf(p) - logf(t);
-            ns += 1.f; sd += dl; sdd = fmaf(dl, dl, sdd);
+        for (int c = 0; c < C; ++c) {
+          const float p = pv[c], t = tv[c];
+          const float diff = p - t;
+          if (c < 3) { pf[c] = p; tf[c] = t; }
+          if (c >= 4 && c < 7) { pb[c - 4] = p; tb[c - 4] = t; }
+          if (m1) {
+            aabs += fabsf(diff); asq = fmaf(diff, diff, asq);
+            if (c < 8) { cabs += fabsf(diff); csq = fmaf(diff, diff, csq); }
+          }
+          if (c >= d0 && c < d1 && t > 0.f) {                      // maskD                      base_module.py:138
+            nd += 1.f; dabs += fabsf(diff); dsq = fmaf(diff, diff, dsq);
+            if ((flags & ST_SILOG) && t > 1e-2f) {                 // silog's own mask           criteria.py:729
+              const float dl = logf(p) - logf(t);
+              ns += 1.f; sd += dl; sdd = fmaf(dl, dl, sdd);
+            }
           }
         }
-      }
-      if (m1) {
-        acc[A_N1] += 1.0;
-        acc[A_CABS] += static_cast<double>(cabs); acc[A_CSQ] += static_cast<double>(csq);
-        acc[A_AABS] += static_cast<double>(aabs); acc[A_ASQ] += static_cast<double>(asq);
-        if (flags & ST_FBDIV) acc[A_FB] += static_cast<double>(fb_term(pf, tb).f + fb_term(pb, tf).f);
-      }
-      acc[A_ND] += static_cast<double>(nd); acc[A_DABS] += static_cast<double>(dabs); acc[A_DSQ] += static_cast<double>(dsq);
-      acc[A_NS] += static_cast<double>(ns); acc[A_SD] += static_cast<double>(sd); acc[A_SDD] += static_cast<double>(sdd);
+        if (m1) {
+          acc[A_N1] += 1.0;
+          acc[A_CABS] += static_cast<double>(cabs); acc[A_CSQ] += static_cast<double>(csq);
+          acc[A_AABS] += static_cast<double>(aabs); acc[A_ASQ] += static_cast<double>(asq);
+          if (flags & ST_FBDIV) acc[A_FB] += static_cast<double>(fb_term(pf, tb).f + fb_term(pb, tf).f);
+        }
+        acc[A_ND] += static_cast<double>(nd); acc[A_DABS] += static_cast<double>(dabs); acc[A_DSQ] += static_cast<double>(dsq);
+        acc[A_NS] += static_cast<double>(ns); acc[A_SD] += static_cast<double>(sd); acc[A_SDD] += static_cast<double>(sdd);
       }
     }
 #pragma unroll
@@ -205,47 +205,47 @@ __global__ void __launch_bounds__(kBlock, 1) stdepth_loss_kernel(StdArgs a) {
     }
 #pragma unroll
     for (int u = 0; u < PX; ++u) {
-    if (!ona[u]) continue;
-    const bool m1 = m1a[u];
-    const size_t base = basea[u];
-    const float (&pv)[C] = pva[u];
-    const float (&tv)[C] = tva[u];
-    float g[C];
-    float pf[3], pb[3], tf[3], tb[3];
+      if (!ona[u]) continue;
+      const bool m1 = m1a[u];
+      const size_t base = basea[u];
+      const float (&pv)[C] = pva[u];
+      const float (&tv)[C] = tva[u];
+      float g[C];
+      float pf[3], pb[3], tf[3], tb[3];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float p = pv[c], t = tv[c];
-      const float diff = p - t;
-      if (c < 3) { pf[c] = p; tf[c] = t; }
-      if (c >= 4 && c < 7) { pb[c - 4] = p; tb[c - 4] = t; }
-      float gc = 0.f;
-      if (m1) {
-        if (c < 8) {
-          if (flags & ST_CMAE) gc = fmaf(k_col, sgn0(diff), gc);
-          if (flags & ST_CMSE) gc = fmaf(2.f * k_col, diff, gc);
+      for (int c = 0; c < C; ++c) {
+        const float p = pv[c], t = tv[c];
+        const float diff = p - t;
+        if (c < 3) { pf[c] = p; tf[c] = t; }
+        if (c >= 4 && c < 7) { pb[c - 4] = p; tb[c - 4] = t; }
+        float gc = 0.f;
+        if (m1) {
+          if (c < 8) {
+            if (flags & ST_CMAE) gc = fmaf(k_col, sgn0(diff), gc);
+            if (flags & ST_CMSE) gc = fmaf(2.f * k_col, diff, gc);
+          }
+          if (flags & ST_ALLMSE) gc = fmaf(2.f * k_all, diff, gc);
+          if (flags & ST_ALLMAE) gc = fmaf(k_all, sgn0(diff), gc);
         }
-        if (flags & ST_ALLMSE) gc = fmaf(2.f * k_all, diff, gc);
-        if (flags & ST_ALLMAE) gc = fmaf(k_all, sgn0(diff), gc);
+        if (c >= d0 && c < d1 && t > 0.f) {
+          if (flags & ST_ALLMSE) gc = fmaf(2.f * k_dep, diff, gc);
+          if (flags & ST_ALLMAE) gc = fmaf(k_dep, sgn0(diff), gc);
+          if ((flags & ST_SILOG) && t > 1e-2f) gc += __fdividef(k_sil * ((logf(p) - logf(t)) - k_mean), p);
+        }
+        g[c] = gc;
       }
-      if (c >= d0 && c < d1 && t > 0.f) {
-        if (flags & ST_ALLMSE) gc = fmaf(2.f * k_dep, diff, gc);
-        if (flags & ST_ALLMAE) gc = fmaf(k_dep, sgn0(diff), gc);
-        if ((flags & ST_SILOG) && t > 1e-2f) gc += __fdividef(k_sil * ((logf(p) - logf(t)) - k_mean), p);
-      }
-      g[c] = gc;
-    }
-    if ((flags & ST_FBDIV) && m1) {
-      const FbTerm f1 = fb_term(pf, tb), f2 = fb_term(pb, tf);
-      const float r1 = (f1.np > 0.f) ? f1.dot * f1.nt / (f1.mag * f1.mag * f1.np) : 0.f;
-      const float r2 = (f2.np > 0.f) ? f2.dot * f2.nt / (f2.mag * f2.mag * f2.np) : 0.f;
+      if ((flags & ST_FBDIV) && m1) {
+        const FbTerm f1 = fb_term(pf, tb), f2 = fb_term(pb, tf);
+        const float r1 = (f1.np > 0.f) ? f1.dot * f1.nt / (f1.mag * f1.mag * f1.np) : 0.f;
+        const float r2 = (f2.np > 0.f) ? f2.dot * f2.nt / (f2.mag * f2.mag * f2.np) : 0.f;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        g[c] = fmaf(k_fb, tb[c] / f1.mag - r1 * pf[c], g[c]);
-        g[4 + c] = fmaf(k_fb, tf[c] / f2.mag - r2 * pb[c], g[4 + c]);
+        for (int c = 0; c < 3; ++c) {
+          g[c] = fmaf(k_fb, tb[c] / f1.mag - r1 * pf[c], g[c]);
+          g[4 + c] = fmaf(k_fb, tf[c] / f2.mag - r2 * pb[c], g[4 + c]);
+        }
       }
-    }
 #pragma unroll
-    for (int c = 0; c < C; ++c) Elem<PT>::st1(grad + base + static_cast<size_t>(c) * HW, g[c]);
+      for (int c = 0; c < C; ++c) Elem<PT>::st1(grad + base + static_cast<size_t>(c) * HW, g[c]);
     }
   }
 }
