@@ -232,14 +232,20 @@ def main():
             raw_acc.add_(raw)
         return loss, vals, p.grad, raw
 
+    pending = []
+
     def exchange():
         # The ONLY inter-GPU traffic of the path: 12 doubles (pooled metric sums and exact counts) summed
         # over the ranks, once per logging interval. The loss itself is local, as under the reference's
         # DDP (pl.Trainer(gpus=N), train.py:137) - which never synchronises metrics at all (no sync_dist,
         # metrics.py:19-39). Issued eagerly, outside the CUDA graphs.
+        # Asynchronous: the sums are snapshotted on the step stream and reduced on NCCL's own stream,
+        # the steps go on meanwhile; run_steps waits for every outstanding reduction before it returns (inside the
+        # timed region).
         if world > 1:
-            dist.all_reduce(raw_acc)
+            snap = raw_acc.clone()
             raw_acc.zero_()
+            pending.append((dist.all_reduce(snap, async_op=True), snap))
 
     side = torch.cuda.Stream(device=dev)
     graphs = None
@@ -299,6 +305,9 @@ def main():
                 exchange()
                 since = 0
         exchange()
+        for work, _ in pending:
+            work.wait()
+        pending.clear()
 
     def barrier():
         if world > 1:
