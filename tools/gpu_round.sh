@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 rc=0
-for f in tests/test_gpu_metrics.py tests/test_gpu_losses.py tests/test_gpu_dorn.py tests/test_gpu_vnl_pointcloud.py tests/test_gpu_wcel.py tests/test_gpu_midas.py; do
+for f in tests/test_gpu_*.py; do
   n=$(basename $f .py)
   timeout 900 python -m pytest $f -m gpu -q --timeout 300 -p no:cacheprovider > gpurun_out/$n.log 2>&1 || rc=1
   tail -n 3 gpurun_out/$n.log
