@@ -78,6 +78,8 @@ enum {
 #define MDE_METRICS_NEED_LOG (1u << 8)   /* MDE_Q_LOG10, MDE_Q_LNSQ  -> log10, rmse_log */
 #define MDE_METRICS_NEED_LOG1P (1u << 9) /* MDE_Q_SLE               -> msle */
 #define MDE_METRICS_NEED_REL (1u << 10)  /* MDE_Q_ABSREL/SQREL/RSQ  -> absrel, sqrel, rmse */
+#define MDE_METRICS_NEED_RSQ (1u << 11)  /* MDE_Q_RSQ alone         -> rmse (the reference's default
+                                            train list, train.py:67, needs no absrel / sqrel) */
 
 /*
  * Masked error metrics over a batch of depth maps in ONE pass (8 B/px).

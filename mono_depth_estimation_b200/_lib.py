@@ -12,14 +12,14 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmde_b200.so")
+LIB_PATH = os.environ.get("MDE_B200_LIB") or os.path.join(_HERE, "libmde_b200.so")   # the override is for instrumented builds (tools/)
 
 # enums of include/mde_b200.h
 F32, F16, BF16 = 0, 1, 2
 METRIC_NQ, METRIC_NM = 12, 12
 METRICS_OUT_F64 = 2 * METRIC_NM + METRIC_NQ + 1
 METRICS_REFERENCE_MATH = 1
-METRICS_NEED_LOG, METRICS_NEED_LOG1P, METRICS_NEED_REL = 1 << 8, 1 << 9, 1 << 10
+METRICS_NEED_LOG, METRICS_NEED_LOG1P, METRICS_NEED_REL, METRICS_NEED_RSQ = 1 << 8, 1 << 9, 1 << 10, 1 << 11
 LOSS_L1, LOSS_MSE, LOSS_BERHU, LOSS_LAINA_BERHU, LOSS_SILOG, LOSS_EIGEN = range(6)
 LOSS_NTOTALS = 8
 DISC_SID, DISC_UD = 0, 1
@@ -27,7 +27,7 @@ DISC_SID, DISC_UD = 0, 1
 METRIC_INDEX = {"delta1": 0, "delta2": 1, "delta3": 2, "mae": 3, "mse": 4, "log10": 5, "msle": 6,
                 "absrel": 7, "sqrel": 8, "rmse": 9, "rmse_true": 10, "rmse_log": 11}
 METRIC_GROUP = {"log10": METRICS_NEED_LOG, "rmse_log": METRICS_NEED_LOG, "msle": METRICS_NEED_LOG1P,
-                "absrel": METRICS_NEED_REL, "sqrel": METRICS_NEED_REL, "rmse": METRICS_NEED_REL}
+                "absrel": METRICS_NEED_REL, "sqrel": METRICS_NEED_REL, "rmse": METRICS_NEED_RSQ}
 RAW_INDEX = {"n_valid": 0, "d1": 1, "d2": 2, "d3": 3, "abs": 4, "sq": 5, "log10": 6, "sle": 7,
              "absrel": 8, "sqrel": 9, "rsq": 10, "lnsq": 11}
 

@@ -290,6 +290,87 @@ __device__ __forceinline__ void grid_sum4_bcast(unsigned long long* slots, unsig
 }
 #endif
 
+// Variant with an arrival counter (round 2). In grid_sum4_bcast every thread of every waiting CTA polls the slots:
+// a CTA that finishes early hammers ~150 L2 lines with 74 warp-loads per round for microseconds, the lines are
+// hot-spots for 296 x 16 warps at once, and the last arriver's stores queue behind that traffic (measured: 2.5 to
+// 4.5 us between the last publication and the last CTA leaving). Here a CTA publishes its slot, bumps ONE counter
+// (red.relaxed, no fence: the slot words validate themselves) and ONE thread per CTA polls that counter while the
+// other warps sleep in bar.sync; only then are the slots gathered, normally in a single pass.
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// sm_own: this CTA's totals, [4][NW] doubles (row q = per-warp partials of quantity q), complete before the call;
+// sm_part: [NW][4] doubles of scratch. After the counter fills, ALL threads gather the slots in one go (every load of
+// a thread in flight before the first is looked at: one L2 round trip), a shuffle tree and one shared-memory pass
+// form the four totals in sm_tot. (Measured alternatives: three dependent rounds per thread = 1.9 us after the
+// counter filled; warp 0 alone in five batches of 16 loads = 5 us.)
+template <int NW, typename MidFn>
+__device__ __forceinline__ void grid_sum4_counted(unsigned long long* slots, unsigned* arrivals, unsigned seq, const double* sm_own,
+                                                  double* sm_part, double* sm_tot, MidFn&& mid_fn) {
+  const unsigned long long tag = static_cast<unsigned long long>(seq) << 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NT = NW * 32;
+  if (threadIdx.x < 4) {
+    double mine = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mine += sm_own[threadIdx.x * NW + w];
+    const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine));
+    unsigned long long* w2 = slots + (static_cast<size_t>(blockIdx.x) * 4 + threadIdx.x) * 2;
+    st_relaxed_u64(w2, tag | (b >> 32));
+    st_relaxed_u64(w2 + 1, tag | (b & 0xffffffffull));
+  }
+  if (threadIdx.x < 32) {
+    __syncwarp();
+    if (lane == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(arrivals) : "memory");
+  }
+  mid_fn();
+  if (threadIdx.x == 0) {
+    while (ld_relaxed_u32(arrivals) < gridDim.x) {}
+  }
+  __syncthreads();
+  // slot words of CTA c, quantity q: slots[(c * 4 + q) * 2 + {0, 1}]; thread t handles pairs i = t, t + NT, ...
+  // (i & 3 == t & 3: one quantity per thread)
+  const int n = static_cast<int>(gridDim.x) * 4;
+  constexpr int kIt = (kSlotCtas * 4 + NT - 1) / NT;
+  unsigned long long hi[kIt], lo[kIt];
+#pragma unroll
+  for (int u = 0; u < kIt; ++u) {
+    const int i = static_cast<int>(threadIdx.x) + NT * u;
+    if (i < n) {
+      hi[u] = ld_relaxed_u64(slots + static_cast<size_t>(i) * 2);
+      lo[u] = ld_relaxed_u64(slots + static_cast<size_t>(i) * 2 + 1);
+    }
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int u = 0; u < kIt; ++u) {
+    const int i = static_cast<int>(threadIdx.x) + NT * u;
+    if (i < n) {
+      // the counter can run ahead of a slot's words by a few hundred ns: re-read until both carry this launch's tag
+      while ((hi[u] >> 32) != seq || (lo[u] >> 32) != seq) {
+        hi[u] = ld_relaxed_u64(slots + static_cast<size_t>(i) * 2);
+        lo[u] = ld_relaxed_u64(slots + static_cast<size_t>(i) * 2 + 1);
+      }
+      acc += __longlong_as_double(static_cast<long long>((hi[u] << 32) | (lo[u] & 0xffffffffull)));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 4; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane < 4) sm_part[warp * 4 + lane] = acc;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) x += sm_part[w * 4 + threadIdx.x];
+    sm_tot[threadIdx.x] = x;
+  }
+  // the caller's thread 0 reads sm_tot after a __syncwarp (threads 0..3 are in its warp)
+}
+#endif
+
 // ---- optional per-CTA phase trace (debug / profiling aid) -------------------------------------------
 // mde_debug_set_trace(buf) arms it: slot k of CTA b receives the GPU global timer (ns) when the CTA
 // passes trace point k. One pointer per translation unit (no relocatable device code in this build).

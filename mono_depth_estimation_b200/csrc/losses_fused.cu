@@ -26,8 +26,10 @@ extern "C" int mde_masked_loss_metrics(int kind, const void* pred, int pred_dtyp
   LossArgs a = make_loss_args(pred, target, mask_u8, n_img, h, w, params, grad_scale, ws, loss_out, totals_out, grad);
   a.met_f64 = metrics_f64;
   a.met_f32 = metrics_f32;
-  unsigned g = (metric_flags >> 8) & kGrpAll;
-  // two instantiations: {log, rel} (the reference's default metric list) and everything
+  unsigned g = (metric_flags >> 8) & kGrpMask;
+  // two instantiations: {log, rel} (the reference's default metric list) and everything; the SS SILog kernel has a
+  // third, {log, rsq}, for lists that need only the 'rmse' sum of the REL group
+  a.rsq_only = (g & kGrpRsq) != 0 && (g & kGrpRel) == 0;
   if (g != 0 && (g & kGrpLog1p) == 0) return launch_loss_kind<(kGrpLog | kGrpRel)>(kind, a, pred_dtype, st);
   return launch_loss_kind<kGrpAll>(kind, a, pred_dtype, st);
 }

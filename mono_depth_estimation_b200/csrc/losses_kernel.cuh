@@ -9,7 +9,6 @@
 #include "metric_math.cuh"
 
 namespace mde {
-namespace {
 
 struct LossArgs {
   const void* pred;
@@ -28,8 +27,15 @@ struct LossArgs {
   int sched;        // 0: tiles claimed from an atomic counter; 1: static interleaved tiles (tile = k*grid + cta)
   double* met_f64;  // fused metrics (MG != 0): same layout as mde_metrics' out_f64
   float* met_f32;
+  float* met_accum;  // optional: running sums of the metric values (+= in the finaliser), MDE_METRIC_NM floats
+  int rsq_only;      // the REL group is requested for MDE_Q_RSQ only
   int64_t n_img;
 };
+
+// SS variant of SILog (silog_ss.cu): `taken` = false leaves the call to the generic kernel below
+int launch_silog_ss(LossArgs& a, unsigned mg, cudaStream_t st, bool& taken);
+
+namespace {
 
 constexpr unsigned kStashInvalid = 0xffc0dead;  // quiet-NaN payload marking "pixel outside the mask"
 
@@ -392,137 +398,6 @@ __device__ __forceinline__ void tiles_map(const PT* __restrict__ pred, const flo
   }
 }
 
-// ---- SILog with the residuals parked in SHARED memory between the phases (SS variant) -----------------
-// Per CTA: kSsSlots tile slots of 8 KB + a ring of kSsRing target tiles (2 CTAs x 13 x 8 KB = 208 KB of the
-// SM's shared memory). The reduce phase is fed by the bulk-copy engine (cp.async.bulk + one mbarrier per
-// slot): the prediction tile lands directly in the slot that will hold its residuals (each thread replaces
-// its own quad in place), the target tile in the ring; copies run kSsRing tiles ahead of the arithmetic
-// without costing a register, which is what the 1 us of loaded HBM latency needs at ~0.7 us of issue time
-// per tile. The gradient phase walks the CTA's slots backwards, d_i from shared memory and p_i through L2.
-// Compared with the stash in the gradient buffer this removes 4 B/px of L2 writes from the reduce phase and
-// 4 B/px of L2 reads from the gradient phase, and the gradient phase needs no tile counter. The first
-// kSsRing tiles of a CTA are static (cta + j x grid), the rest are claimed from an atomic counter (HBM/L2
-// bandwidth is not shared fairly between SMs); a CTA stops claiming when its slots are committed and the
-// launch guarantees grid x kSsSlots >= number of tiles.
-constexpr int kSsSlots = 11;
-constexpr int kSsRing = 2;
-constexpr size_t kSsBytes = static_cast<size_t>(kSsSlots + kSsRing) * kBlock * sizeof(float4);
-
-// ss: [kSsSlots + kSsRing][kBlock] float4 (slots, then the target ring); bars: kSsSlots mbarriers, used once each
-template <typename PT, typename Body, typename Pre, typename Fold>
-__device__ __forceinline__ int tiles_forward_ss(const PT* __restrict__ pred, const float* __restrict__ gt, float4* ss,
-                                                int* list, unsigned long long* bars, const LossArgs& a, TileSched ts,
-                                                Body&& body, Pre&& pre, Fold&& fold) {
-  static_assert(sizeof(PT) == 4, "the SS variant is fp32 only");
-  const int64_t nq = a.n >> 2;
-  const int64_t nt = (nq + kBlock - 1) / kBlock;
-  const unsigned G = gridDim.x;
-  float4* ring = ss + kSsSlots * kBlock;
-  // thread 0 is the producer: arm slot k's barrier and start both copies of tile `tile`
-  auto issue = [&](int k, int64_t tile) {
-    const int64_t q0 = tile * kBlock;
-    const unsigned bytes = static_cast<unsigned>(((nq - q0 < kBlock) ? (nq - q0) : kBlock) * sizeof(float4));
-    mbar_expect_tx(&bars[k], 2u * bytes);
-    bulk_g2s(ss + k * kBlock, pred + 4 * q0, bytes, &bars[k]);
-    bulk_g2s(ring + (k % kSsRing) * kBlock, gt + 4 * q0, bytes, &bars[k]);
-  };
-  if (threadIdx.x == 0) {
-    for (int k = 0; k < kSsSlots; ++k) mbar_init(&bars[k], 1u);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int k = 0; k < kSsRing; ++k) {   // static head of the CTA's tile sequence
-      const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(k) * G;
-      list[k] = (tile < nt) ? static_cast<int>(tile) : -1;
-      if (tile < nt) issue(k, tile);
-    }
-    for (int k = kSsRing; k < kSsSlots; ++k) list[k] = -1;
-  }
-  __syncthreads();
-  int k = 0;
-  for (; k < kSsSlots; ++k) {
-    const int tile = list[k];
-    if (tile < 0) break;
-    // claim the tile that will use slot k + kSsRing; its id is only needed after this tile's arithmetic
-    unsigned claim = 0u;
-    const bool want = (threadIdx.x == 0) && (k + kSsRing < kSsSlots);
-    if (want) claim = atomicAdd(ts.ctr, 1u);
-    mbar_wait(&bars[k], 0u);
-    const int64_t q = static_cast<int64_t>(tile) * kBlock + threadIdx.x;
-    if (q < nq) {
-      const float4 p = ss[k * kBlock + threadIdx.x];
-      const float4 t = ring[(k % kSsRing) * kBlock + threadIdx.x];
-      ss[k * kBlock + threadIdx.x] = eval_quad(body, pre, 4 * q, p, t);
-    }
-    fold();
-    __syncthreads();   // every thread is done with ring slot k % kSsRing: it may be refilled
-    if (want) {
-      const int64_t nxt = static_cast<int64_t>(kSsRing) * G + claim;
-      if (nxt < nt) {
-        list[k + kSsRing] = static_cast<int>(nxt);
-        issue(k + kSsRing, nxt);
-      }
-    }
-    // list[k + kSsRing] is read kSsRing - 1 iterations (and barriers) later
-  }
-  if (blockIdx.x == gridDim.x - 1) {  // n % 4 tail: summed here, its gradient is recomputed in the map phase
-    const int64_t i = (nq << 2) + threadIdx.x;
-    if (i < a.n) eval_one(body, pre, i, Elem<PT>::ld1(pred + i), __ldg(gt + i));
-  }
-  __syncthreads();
-  return k;
-}
-
-// Gradient phase of the SS variant, last slot first. The predictions of the kSsPre slots that are consumed
-// first are requested (through L2) BEFORE the grid barrier into registers - the reduce loop's registers
-// are free by then - so their latency is spent inside the barrier wait; the remaining slots are requested
-// right after the barrier and consumed behind those. After the barrier the phase is d_i from shared memory,
-// arithmetic and streaming stores.
-template <typename PT, int kSsPre>
-struct SsPred {
-  float4 p[kSsPre];
-};
-template <typename PT, int kSsPre>
-__device__ __forceinline__ void tiles_prefetch_ss(const PT* __restrict__ pred, const int* list, int ns, const LossArgs& a,
-                                                  SsPred<PT, kSsPre>& r) {
-  const int64_t nq = a.n >> 2;
-#pragma unroll
-  for (int j = 0; j < kSsPre; ++j) {
-    const int sl = ns - 1 - j;
-    if (sl >= 0) {
-      const int64_t q = static_cast<int64_t>(list[sl]) * kBlock + threadIdx.x;
-      if (q < nq) r.p[j] = Elem<PT>::template ld4<false>(pred + 4 * q);
-    }
-  }
-}
-template <typename PT, int kSsPre, typename Body>
-__device__ __forceinline__ void tiles_map_ss(const PT* __restrict__ pred, const SsPred<PT, kSsPre>& r, const float4* ss,
-                                             const int* list, int ns, PT* out, const LossArgs& a, Body&& body) {
-  const int64_t nq = a.n >> 2;
-  float4 late[(kSsSlots - kSsPre) > 0 ? (kSsSlots - kSsPre) : 1];
-#pragma unroll
-  for (int j = kSsPre; j < kSsSlots; ++j) {
-    const int sl = ns - 1 - j;
-    if (sl >= 0) {
-      const int64_t q = static_cast<int64_t>(list[sl]) * kBlock + threadIdx.x;
-      if (q < nq) late[j - kSsPre] = Elem<PT>::template ld4<false>(pred + 4 * q);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < kSsSlots; ++j) {
-    const int sl = ns - 1 - j;
-    if (sl >= 0) {
-      const int64_t q = static_cast<int64_t>(list[sl]) * kBlock + threadIdx.x;
-      if (q < nq) {
-        const float4 d = ss[sl * kBlock + threadIdx.x];
-        const float4 p = (j < kSsPre) ? r.p[j < kSsPre ? j : 0] : late[j < kSsPre ? 0 : j - kSsPre];
-        float4 g;
-        g.x = body(p.x, d.x); g.y = body(p.y, d.y); g.z = body(p.z, d.z); g.w = body(p.w, d.w);
-        Elem<PT>::st4(out + 4 * q, g);
-      }
-    }
-  }
-}
-
 // block-reduce N doubles and add them to gacc[0..N)
 template <int N>
 __device__ __forceinline__ void publish_sums(const double (&v)[N], double* gacc, double* sm) {
@@ -585,23 +460,17 @@ constexpr int kMetBase = 16;  // gacc[kMetBase + q] = pooled raw metric sum q
 
 // LONG = false (a thread sees <= 96 pixels): sums stay in fp32 registers until the end of the chunk and
 // the loads are software-pipelined; LONG = true folds every 8 pixels into fp64 running sums.
-// SS = true: the shared-memory stash variant of SILog (fp32, 128-bit path, short runs, gradient requested)
-template <int KIND, typename PT, bool VEC, unsigned MG, bool LONG, bool SS = false>
+// (SILog / fp32 with a gradient and few enough tiles runs in silog_ss_kernel below instead.)
+template <int KIND, typename PT, bool VEC, unsigned MG, bool LONG>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArgs a) {
   __shared__ double sm_d[(MG ? 12 : 4) * kWarps];
-  __shared__ double sm_own[SS ? 4 * kWarps : 1];
   __shared__ float sm_k[4];
   __shared__ float sm_f[kWarps];
   __shared__ int sm_tile[2];
-  __shared__ int sm_list[SS ? kSsSlots : 1];
-  __shared__ __align__(8) unsigned long long sm_bars[SS ? kSsSlots : 1];
-  extern __shared__ float4 sm_ss[];  // SS: [kSsSlots + kSsRing][kBlock] quads (residual slots, target ring)
-  static_assert(!SS || (KIND == MDE_LOSS_SILOG && std::is_same<PT, float>::value && VEC && !LONG), "SS is a SILog/fp32 variant");
   constexpr bool kCanStash = (KIND == MDE_LOSS_SILOG) && std::is_same<PT, float>::value;
-  // residuals in log2 units: whenever they come from MUFU.LG2 (shared with the metric suite, or the SS variant)
+  // residuals in log2 units: whenever they come from MUFU.LG2 (shared with the metric suite)
   constexpr bool kSilogShare = (KIND == MDE_LOSS_SILOG) && (MG & kGrpLog) != 0;
-  constexpr bool kSilogLog2 = kSilogShare || SS;
-  int ss_n = 0;
+  constexpr bool kSilogLog2 = kSilogShare;
 
   const PT* __restrict__ pred = static_cast<const PT*>(a.pred);
   const float* __restrict__ gt = a.gt;
@@ -644,7 +513,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   }
 
   // ---------------- phase A1: masked sums and counts ------------------------------------------------
-  double ss_mine = 0.0;                 // SS: this CTA's total q in thread q < 4
   float met_run[MG ? 8 : 1];            // per-thread metric sums / counts handed to flush_metrics()
   int met_cnt[MG ? 4 : 1];
   {
@@ -685,7 +553,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     // sum d^2 is the suite's s_lnsq, n its valid count - and the rare path books the differences in s1 / c0.
     auto pre_sum = [&](const float4& p4, const float4& t4) -> bool {
       if constexpr (MG == 0) {
-        if constexpr (SS) return !(fminf(fminf(p4.x, p4.y), fminf(p4.z, p4.w)) >= 1.17549435e-38f);
         return false;
       } else if constexpr (kSilogShare) {
         const float ta = (t4.x > 0.f) ? t4.x : 1.0f, tb = (t4.y > 0.f) ? t4.y : 1.0f;
@@ -732,14 +599,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
             return 0.f;
           } else if constexpr (KIND == MDE_LOSS_SILOG) {
             bool v;
-            float d;
-            if constexpr (SS) {   // MG == 0 here: log2 units, MUFU.LG2 on the common path
-              v = t > 0.01f;
-              if constexpr (kSlow) d = v ? log_ratio_slow(p, t) * 1.4426950408889634f : 0.f;
-              else d = mufu_lg2(v ? p : 1.0f) - mufu_lg2(v ? t : 1.0f);
-            } else {
-              d = silog_resid(p, t, v);
-            }
+            const float d = silog_resid(p, t, v);
             s0 += d;
             s1 = fmaf(d, d, s1);
             c0 += v ? 1 : 0;
@@ -769,39 +629,18 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
         };
     // short runs: dynamically claimed tiles (balance matters, fixed costs dominate); long runs: one static
     // contiguous chunk per CTA with two quads per iteration (more independent work per instruction stream)
-    if constexpr (SS) ss_n = tiles_forward_ss<PT>(pred, gt, sm_ss, sm_list, sm_bars, a, TileSched{ukey + 2, sm_tile, true}, body_sum, pre_sum, fold);
-    else if constexpr (VEC && !LONG) tiles_forward<PT, kCanStash>(pred, gt, stash, a, TileSched{ukey + 2, sm_tile, a.sched == 0}, body_sum, pre_sum, fold);
+    if constexpr (VEC && !LONG) tiles_forward<PT, kCanStash>(pred, gt, stash, a, TileSched{ukey + 2, sm_tile, a.sched == 0}, body_sum, pre_sum, fold);
     else chunk_forward<PT, VEC, kCanStash, false>(pred, gt, stash, a, body_sum, pre_sum, fold);
     trace_point(1);
     fold_now();
     run[2] = static_cast<double>(c0);
     run[3] = static_cast<double>(c1);
-    if constexpr (SS && kSilogShare) {   // the suite's sum of squares / valid count complete the loss totals
-      run[1] += mrun[7];
-      run[2] += static_cast<double>(mc.n);
-    }
     if constexpr (MG != 0) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) met_run[q] = static_cast<float>(mrun[q]);
       met_cnt[0] = mc.n; met_cnt[1] = mc.c1; met_cnt[2] = mc.c2; met_cnt[3] = mc.c3;
     }
-    if constexpr (SS) {
-      // loss totals only (rows 0-3 of sm_own stay valid for the all-reduce below); the metric sums are
-      // flushed while the slots travel
-      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const double sq = warp_sum(run[q]);
-        if (lane == 0) sm_own[q * kWarps + warp] = sq;
-      }
-      __syncthreads();
-      if (threadIdx.x < 4) {
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) ss_mine += sm_own[threadIdx.x * kWarps + w];
-      }
-    } else {
-      publish_sums<4>(run, gacc, sm_d);
-    }
+    publish_sums<4>(run, gacc, sm_d);
   }
   // pooled metric sums of this CTA -> 12 fp64 atomics (4 counts + 8 float sums: 32-lane tree in fp32 /
   // REDUX, widened before crossing warps and CTAs)
@@ -829,11 +668,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       __syncthreads();
     }
   };
-  if constexpr (!SS) flush_metrics();
+  flush_metrics();
   trace_point(2);
-  // slots requested before the barrier: all of them, or what fits beside the fused suite's live registers
-  constexpr int kSsPre = (MG != 0) ? 6 : kSsSlots;
-  SsPred<PT, kSsPre> ss_pred;
   // ---------------- grid barrier; its last arriver turns the totals into loss + coefficients ------------
   struct Totals { double S0, S1, N0, N1, loss; };
   // totals -> loss value and the fp32 gradient coefficients
@@ -842,7 +678,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
       S0 *= 0.69314718055994531;
       S1 *= 0.48045301391820142;
     }
-    if constexpr (kSilogShare && !SS) {  // + the suite's sum of squares / valid count (S1, N0 held the rare-path differences)
+    if constexpr (kSilogShare) {  // + the suite's sum of squares / valid count (S1, N0 held the rare-path differences)
       S1 += __ldcg(&gacc[kMetBase + MDE_Q_LNSQ]);
       N0 += __ldcg(&gacc[kMetBase + MDE_Q_NVALID]);
     }
@@ -891,37 +727,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     }
     ws.hdr->epoch = epoch + 1u;
   };
-  if constexpr (SS) {
-    // ticket-free all-reduce of the four totals (common.cuh); every CTA derives the coefficients itself.
-    // While the slots travel: flush the metric sums (arrival counted on ukey[6] for the finaliser below)
-    // and request this CTA's predictions for the gradient phase.
-    __shared__ double sm_tot[4];
-    __shared__ double sm_gather[kWarps * 4];
-    grid_sum4_bcast(ws.slots, epoch * 4u + 2u, ss_mine, sm_tot, sm_gather, [&](int q) {
-      double tot = 0.0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) tot += sm_own[q * kWarps + w];
-      return tot;
-    }, [&] {
-      flush_metrics();
-      if (grad != nullptr) tiles_prefetch_ss<PT, kSsPre>(pred, sm_list, ss_n, a, ss_pred);
-    });
-    if (threadIdx.x == 0) {
-      float v[4];
-      const Totals t = coefficients(sm_tot[0], sm_tot[1], sm_tot[2], sm_tot[3], v);
-      sm_k[0] = v[0]; sm_k[1] = v[1]; sm_k[2] = v[2]; sm_k[3] = v[3];
-      if (blockIdx.x == 0) write_results(t);
-    }
-    __syncthreads();
-    if constexpr (MG != 0) {
-      // arrival for the metric finaliser (end of the kernel), off everybody's critical path: the CTA's
-      // metric atomics (flush_metrics) were issued before the __syncthreads above, so this fence orders them
-      if (threadIdx.x == kBlock - 32) {
-        __threadfence();
-        atomicAdd(ukey + 6, 1u);
-      }
-    }
-  } else {
+  {
     Totals tt{0.0, 0.0, 0.0, 0.0, 0.0};   // only meaningful in the last arriver
     grid_barrier_bcast(ukey + 6, ws.hdr->bcast, epoch * 4u + 2u, sm_k, [&](float (&v)[4]) {
       tt = coefficients(__ldcg(&gacc[0]), __ldcg(&gacc[1]), __ldcg(&gacc[2]), __ldcg(&gacc[3]), v);
@@ -931,19 +737,11 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   const float k1 = sm_k[0], k2 = sm_k[1], k3 = sm_k[2];
 
   // pooled metric values (one mean over all valid pixels of the call, metrics.py:58-67), formed by the LAST
-  // warp of the LAST CTA: right after the ticket barrier, or (SS) at the very end of the kernel, when every
-  // CTA's arrival has long been counted
+  // warp of the LAST CTA right after the ticket barrier
   auto finalize_metrics = [&] {
   if constexpr (MG != 0) {
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= kBlock - 32) {
       const int lane = threadIdx.x & 31;
-      if constexpr (SS) {   // the all-reduce above is no memory barrier: wait for every CTA's metric atomics
-        if (lane == 0) {
-          while (*reinterpret_cast<volatile unsigned*>(ukey + 6) < gridDim.x) {}
-          __threadfence();
-        }
-        __syncwarp();
-      }
       const bool own = lane < MDE_METRIC_NM;
       const double P = own ? __ldcg(&gacc[kMetBase + lane]) : 0.0;
       const double nn = __shfl_sync(0xffffffffu, P, MDE_Q_NVALID);
@@ -964,33 +762,11 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     }
   }
   };
-  if constexpr (!SS) finalize_metrics();
-  if (grad == nullptr) {
-    if constexpr (SS) finalize_metrics();
-    return;
-  }
+  finalize_metrics();
+  if (grad == nullptr) return;
   trace_point(4);
 
   // ---------------- phase B: gradient, chunk walked backwards ----------------------------------------
-  if constexpr (SS) {
-    const float ks1 = k3, ks2 = sm_k[3];
-    tiles_map_ss<PT, kSsPre>(pred, ss_pred, sm_ss, sm_list, ss_n, grad, a, [&](float p, float d) -> float {
-      const bool v = __float_as_uint(d) != kStashInvalid;
-      return v ? ks1 * (d - ks2) * rcp_nr(p) : 0.f;
-    });
-    if (blockIdx.x == gridDim.x - 1) {   // n % 4 tail, recomputed
-      const int64_t i = ((a.n >> 2) << 2) + threadIdx.x;
-      if (i < a.n) {
-        bool v;
-        const float p = Elem<PT>::ld1(pred + i);
-        const float d = silog_resid(p, __ldg(gt + i), v);
-        Elem<PT>::st1(grad + i, v ? k1 * (d - k2) * rcp_nr(p) : 0.f);
-      }
-    }
-    trace_point(5);
-    finalize_metrics();
-    return;
-  }
   if constexpr (kCanStash) {
     if (a.use_stash) {
       // grad[i] holds d_i (or the off-mask marker): g = k1 (d - k2) / p
@@ -1058,28 +834,6 @@ int launch_loss_l(LossArgs& a, cudaStream_t st) {
   return MDE_OK;
 }
 
-// SILog / fp32 / 128-bit path with a gradient and few enough tiles: residuals parked in shared memory
-template <unsigned MG>
-int launch_loss_ss(LossArgs& a, cudaStream_t st, bool& taken) {
-  taken = false;
-  static const bool off = [] { const char* e = getenv("MDE_NO_SMEM_STASH"); return e && atoi(e) != 0; }();
-  if (off) return MDE_OK;
-  const void* fn = reinterpret_cast<const void*>(&masked_loss_kernel<MDE_LOSS_SILOG, float, true, MG, false, true>);
-  const int cap = coop_grid(fn, kBlock, kSsBytes);
-  if (cap <= 0) return MDE_OK;   // (e.g. the carve-out is not available) -> generic path
-  const int64_t nq = a.n >> 2;
-  const int64_t nt = (nq + kBlock - 1) / kBlock;
-  int64_t grid = nt < cap ? nt : cap;
-  if (grid < 1) grid = 1;
-  if (nt > grid * kSsSlots) return MDE_OK;
-  a.chunk = make_chunking(nq, 8, static_cast<int>(grid));
-  void* args[] = {&a};
-  MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, kSsBytes, st));
-  count_launch();
-  taken = true;
-  return MDE_OK;
-}
-
 template <int KIND, typename PT, bool VEC, unsigned MG>
 int launch_loss(LossArgs& a, cudaStream_t st) {
   const int64_t threads = static_cast<int64_t>(sm_count()) * kCtasPerSm * kBlock;
@@ -1087,7 +841,7 @@ int launch_loss(LossArgs& a, cudaStream_t st) {
   if constexpr (KIND == MDE_LOSS_SILOG && std::is_same<PT, float>::value && VEC) {
     if (!is_long && a.grad != nullptr) {
       bool taken = false;
-      const int rc = launch_loss_ss<MG>(a, st, taken);
+      const int rc = launch_silog_ss(a, MG, st, taken);
       if (rc != MDE_OK || taken) return rc;
     }
   }
@@ -1140,6 +894,8 @@ inline LossArgs make_loss_args(const void* pred, const float* target, const uint
   a.use_stash = (a.n * 12 <= (int64_t(96) << 20)) ? 1 : 0;
   a.met_f64 = nullptr;
   a.met_f32 = nullptr;
+  a.met_accum = nullptr;
+  a.rsq_only = 0;
   a.n_img = n_img;
   return a;
 }

@@ -230,6 +230,96 @@ __device__ __forceinline__ void metric_px(float p, float t, MetricTile& a, Metri
   metric_px_ex<G, Ref>(p, t, a, c, L, d);
 }
 
+// ---- "lean" fast form (round 2) ---------------------------------------------------------------------
+// The fast form above costs ~20 ALU-pipe instructions per pixel (FSETP / FSEL / FMNMX / SEL / IADD issue at
+// half the rate of the FMA pipe on B200) and was issue-bound. The lean form moves everything it can to the
+// FMA pipe and drops what the caller can guarantee:
+//   * |p - t| = hi - lo (the same subtraction, sign dropped): no separate difference, no abs;
+//   * the three threshold counts are FLOAT counters fed by FSET/FADD (exact below 2^24) instead of a packed
+//     byte histogram (3 SEL + SEL + IADD); invalid pixels (replaced by p = t = 1, ratio 1) are counted by all
+//     three; the valid pixels are counted the same way (FMUL.SAT + FADD) and the caller removes the
+//     (pixels seen - valid) surplus once per flush;
+//   * NOCLAMP: the caller's per-quad rare test already sent p < 1e-7 (and NaN) to the exact path, so
+//     clamp_min(pred, 1e-7) is the identity here;
+//   * kGrpRsq: only the 'rmse' quirk sum of the REL group (the reference's default train metrics need no
+//     absrel / sqrel).
+// Per pixel with {log, rsq}: 11 ALU-pipe + 15 FMA-pipe + 3 MUFU instructions.
+constexpr unsigned kGrpRsq = 8u;    // MDE_Q_RSQ only (implied by kGrpRel)
+constexpr unsigned kGrpMask = 15u;
+
+struct MetricAcc {
+  float s_abs, s_sq, s_log10, s_sle, s_absrel, s_sqrel, s_rsq, s_lnsq;   // MetricTile order
+  float c1, c2, c3;   // pixels below each threshold, INCLUDING the invalid ones seen by the lean form
+  float nval;         // valid pixels seen by the lean form (float counter)
+  int n_x, c1_x, c2_x, c3_x;   // exact counts booked by the rare (reference-arithmetic) path
+  __device__ __forceinline__ void zero() {
+    s_abs = s_sq = s_log10 = s_sle = s_absrel = s_sqrel = s_rsq = s_lnsq = 0.f;
+    c1 = c2 = c3 = nval = 0.f;
+    n_x = c1_x = c2_x = c3_x = 0;
+  }
+  // exact counts after `lean_px` pixels went through metric_px_lean
+  __device__ __forceinline__ int n_valid(int) const { return static_cast<int>(nval) + n_x; }
+  __device__ __forceinline__ int count(int k, int lean_px) const {
+    const float c = (k == 1) ? c1 : (k == 2) ? c2 : c3;
+    const int x = (k == 1) ? c1_x : (k == 2) ? c2_x : c3_x;
+    return static_cast<int>(c) - (lean_px - static_cast<int>(nval)) + x;
+  }
+  __device__ __forceinline__ float sum(int q) const {
+    return (q == 0) ? s_abs : (q == 1) ? s_sq : (q == 2) ? s_log10 : (q == 3) ? s_sle
+         : (q == 4) ? s_absrel : (q == 5) ? s_sqrel : (q == 6) ? s_rsq : s_lnsq;
+  }
+};
+
+// One pixel, lean form. Returns log2(p) - log2(t) (0 off the mask) when G has kGrpLog.
+template <unsigned G, bool NOCLAMP>
+__device__ __forceinline__ float metric_px_lean(float p, float t, MetricAcc& a) {
+  const bool v = t > 0.f;                          // metrics.py:60
+  const float tt = v ? t : 1.0f;
+  float pp = v ? p : 1.0f;
+  if (!NOCLAMP) pp = fmax_nan(pp, 1e-7f);          // clamp_min(pred, 1e-7), NaN preserved (metrics.py:59)
+  const float hi = fmax_nan(pp, tt), lo = fminf(pp, tt);
+  const float ad = hi - lo;                        // |p - t|
+  a.s_abs += ad;
+  a.s_sq = fmaf(ad, ad, a.s_sq);
+  const float e = lo * 5.9604644775390625e-08f;
+  a.c1 += (fmaf(lo, 1.25f, -hi) > e) ? 1.0f : 0.0f;      // strict '<' (metrics.py:77,82,87), exact (header)
+  a.c2 += (fmaf(lo, 1.5625f, -hi) > e) ? 1.0f : 0.0f;
+  a.c3 += (fmaf(lo, 1.953125f, -hi) > e) ? 1.0f : 0.0f;
+  // valid count on the FMA pipe: sat(t * 2^126) is exactly 1 for every normal t > 0 and 0 for t <= 0 / NaN (a valid
+  // SUBNORMAL target never reaches the lean form: the caller's rare test sends its quad to the exact path)
+  a.nval += __saturatef(t * 8.507059173023462e37f);
+  float dl = 0.f;
+  if (G & kGrpLog) {
+    dl = mufu_lg2(pp) - mufu_lg2(tt);
+    a.s_log10 += fabsf(dl);                        // x log10(2) at the flush
+    a.s_lnsq = fmaf(dl, dl, a.s_lnsq);             // x ln(2)^2 at the flush
+  }
+  if (G & kGrpLog1p) {
+    const float d1 = mufu_lg2(1.0f + pp) - mufu_lg2(1.0f + tt);
+    a.s_sle = fmaf(d1, d1, a.s_sle);
+  }
+  if (G & kGrpRel) {
+    const float rs = mufu_rsq(tt);
+    const float ar = ad * (rs * rs);
+    a.s_absrel += ar;
+    a.s_sqrel = fmaf(ar, ad, a.s_sqrel);
+    a.s_rsq = fmaf(ad, rs, a.s_rsq);
+  } else if (G & kGrpRsq) {
+    a.s_rsq = fmaf(ad, mufu_rsq(tt), a.s_rsq);     // sqrt((p-t)^2/t) = |p-t| / sqrt(t)
+  }
+  return dl;
+}
+
+// rare path for the lean accumulators: one pixel in reference arithmetic, booked in the lean units
+__device__ __forceinline__ void metric_add_contrib(const MetricContrib& r, MetricAcc& a) {
+  a.s_abs += r.s.s_abs; a.s_sq += r.s.s_sq;
+  a.s_log10 += r.s.s_log10 * (1.0f / tile_scale<false>(2));
+  a.s_sle += r.s.s_sle * (1.0f / tile_scale<false>(3));
+  a.s_absrel += r.s.s_absrel; a.s_sqrel += r.s.s_sqrel; a.s_rsq += r.s.s_rsq;
+  a.s_lnsq += r.s.s_lnsq * (1.0f / tile_scale<false>(7));
+  a.n_x += r.c.n; a.c1_x += r.c.c1; a.c2_x += r.c.c2; a.c3_x += r.c.c3;
+}
+
 // finished values from raw sums (shared by the device finaliser and mde_metrics_finalize_host)
 __host__ __device__ inline void metric_values(const double* raw, double* val) {
   const double n = raw[MDE_Q_NVALID];

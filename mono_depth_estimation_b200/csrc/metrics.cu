@@ -403,7 +403,8 @@ template <typename PT>
 int dispatch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t hw, unsigned flags, void* ws,
                      double* out_f64, float* out_f32, double* piv, double* pir, cudaStream_t st) {
   const bool ref = (flags & MDE_METRICS_REFERENCE_MATH) != 0;
-  unsigned g = (flags >> 8) & kGrpAll;
+  unsigned g = (flags >> 8) & kGrpMask;
+  if (g & kGrpRsq) g = (g & kGrpAll) | kGrpRel;   // 'rmse' alone: served by the REL group here
   if (g == 0) g = kGrpAll;
   const bool vec = (hw % 4 == 0) && aligned_to(pred, 4 * sizeof(PT)) && aligned_to(gt, 16);
 #define MDE_CASE(V, GG, R) return launch_metrics<PT, V, GG, R>(pred, gt, n_img, hw, ws, out_f64, out_f32, piv, pir, st)

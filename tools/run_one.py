@@ -10,7 +10,7 @@ name = sys.argv[1]; reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 sp = lambda: _lib.stream_ptr(dev)
 loss_t = torch.empty((), device=dev)
 lp = _lib.LossParams(0.85, 1e-9, 1, 1)
-mflags = _lib.METRICS_NEED_LOG | _lib.METRICS_NEED_REL
+mflags = _lib.METRICS_NEED_LOG | _lib.METRICS_NEED_RSQ
 if name in ("c5_metrics", "c2_metrics"):
     B = 654 if name == "c5_metrics" else 16
     pr, gt = synth.depth_pair((B, 1, 480, 640), 105, device=dev)

@@ -11,20 +11,33 @@ ws = _lib.workspace(dev, 16)
 loss_t = torch.empty((), device=dev); grad_t = torch.empty(shape, device=dev)
 lp = _lib.LossParams(0.85, 1e-9, 1, 1)
 trace = torch.zeros(296 * 8, dtype=torch.int64, device=dev)
+FUSED = os.environ.get("MDE_TRACE_FUSED", "1") != "0"
+o64 = torch.empty(_lib.METRICS_OUT_F64, dtype=torch.float64, device=dev); o32 = torch.empty(24, device=dev)
+mflags = _lib.METRICS_NEED_LOG | _lib.METRICS_NEED_RSQ
 def run(i):
     pr, g = ring[i % 8]
-    _lib.check(lib.mde_masked_loss(_lib.LOSS_SILOG, _lib.ptr(pr), 0, _lib.ptr(g), None, 16, 480, 640, C.byref(lp), 1.0,
-               _lib.ptr(ws), _lib.ptr(loss_t), None, _lib.ptr(grad_t), _lib.stream_ptr(dev)))
+    if FUSED:
+        _lib.check(lib.mde_masked_loss_metrics(_lib.LOSS_SILOG, _lib.ptr(pr), 0, _lib.ptr(g), None, 16, 480, 640, C.byref(lp), 1.0, mflags,
+                   _lib.ptr(ws), _lib.ptr(loss_t), None, _lib.ptr(grad_t), _lib.ptr(o64), _lib.ptr(o32), _lib.stream_ptr(dev)))
+    else:
+        _lib.check(lib.mde_masked_loss(_lib.LOSS_SILOG, _lib.ptr(pr), 0, _lib.ptr(g), None, 16, 480, 640, C.byref(lp), 1.0,
+                   _lib.ptr(ws), _lib.ptr(loss_t), None, _lib.ptr(grad_t), _lib.stream_ptr(dev)))
 for i in range(5): run(i)
 torch.cuda.synchronize()
 _lib.check(lib.mde_debug_set_trace(_lib.ptr(trace)))
 out = []
 for rep in range(4):
-    trace.zero_(); torch.cuda.synchronize(); run(5 + rep); torch.cuda.synchronize()
+    # 300 back-to-back launches keep the SM clock at its loaded value; every launch overwrites the trace, the last one is read
+    for i in range(300): run(i)
+    torch.cuda.synchronize()
     t = trace.view(296, 8).cpu()
     t0 = int(t[:, 0].min())
     out.append({"smid": t[:, 7].tolist(), "a_done": [round((int(v) - t0) / 1e3, 2) for v in t[:, 1]],
-                "end": [round((int(v) - t0) / 1e3, 2) for v in t[:, 5]], "b_start": [round((int(v) - t0) / 1e3, 2) for v in t[:, 4]]})
+                "end": [round((int(v) - t0) / 1e3, 2) for v in t[:, 5]], "b_start": [round((int(v) - t0) / 1e3, 2) for v in t[:, 4]],
+                "start": [round((int(v) - t0) / 1e3, 2) for v in t[:, 0]], "published": [round((int(v) - t0) / 1e3, 2) for v in t[:, 2]],
+                "bar_exit": [round((int(v) - t0) / 1e3, 2) for v in t[:, 3]],
+                "w0_wait_comp": [((int(v) >> 32) & 0xffffffff, int(v) & 0xffffffff) for v in t[:, 6]],
+                "w15_wait_comp": [((int(v) >> 32) & 0xffffffff, int(v) & 0xffffffff) for v in t[:, 4]]})
 _lib.check(lib.mde_debug_set_trace(None))
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "trace_dump_%s.json" % os.environ.get("MDE_SCHED", "0")), "w"))
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "trace_dump_%s.json" % ("fused" if FUSED else "plain")), "w"))
 print("ok")

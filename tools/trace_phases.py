@@ -10,7 +10,7 @@ ring = [synth.depth_pair(shape, 500 + i, device=dev) for i in range(8)]
 ws = _lib.workspace(dev, 16)
 loss_t = torch.empty((), device=dev); grad_t = torch.empty(shape, device=dev)
 o64 = torch.empty(_lib.METRICS_OUT_F64, dtype=torch.float64, device=dev); o32 = torch.empty(24, device=dev)
-lp = _lib.LossParams(0.85, 1e-9, 1, 1); mflags = _lib.METRICS_NEED_LOG | _lib.METRICS_NEED_REL
+lp = _lib.LossParams(0.85, 1e-9, 1, 1); mflags = _lib.METRICS_NEED_LOG | _lib.METRICS_NEED_RSQ
 trace = torch.zeros(296 * 8, dtype=torch.int64, device=dev)
 def run(i, fused):
     pr, g = ring[i % 8]
