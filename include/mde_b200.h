@@ -94,10 +94,13 @@ enum {
  *                             SURVEY 3.2); images without a valid pixel are skipped and counted
  *     [2NM, 2NM+NQ)           pooled raw sums
  *     [2NM+NQ]                number of images that had >= 1 valid pixel
+ *     [2NM+NQ+1, 3NM+NQ+1)    sum over those images of the per-image values (image-mean x count), so that
+ *                             out_f64[2NM ...] = {pooled raw sums, #images, per-image value sums} is ONE
+ *                             contiguous vector a multi-GPU evaluation can all-reduce in place
  *   out_f32 (nullable): first 2NM entries of out_f64 rounded to fp32 (what callers log)
  *   per_image_values (nullable): [n_img][NM] doubles;  per_image_raw (nullable): [n_img][NQ]
  */
-#define MDE_METRICS_OUT_F64 (2 * MDE_METRIC_NM + MDE_METRIC_NQ + 1)
+#define MDE_METRICS_OUT_F64 (3 * MDE_METRIC_NM + MDE_METRIC_NQ + 1)
 int mde_metrics(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t hw,
                 unsigned flags, void* ws, double* out_f64, float* out_f32,
                 double* per_image_values, double* per_image_raw, void* stream);
@@ -128,6 +131,9 @@ typedef struct {
   float clamp_val;      /* laina: clamp_val (criteria.py:479, 1e-9) */
   int use_logs;         /* laina: use_logs (criteria.py:479) */
   int size_average;     /* laina: size_average (criteria.py:479) */
+  float* metrics_accum; /* mde_masked_loss_metrics only, nullable: MDE_METRIC_NM device floats that receive
+                           `+= pooled value` from the launch's finaliser - MetricComputation's running sums
+                           (reference metrics.py:65-66) without a launch of their own */
 } mde_loss_params;
 
 /*

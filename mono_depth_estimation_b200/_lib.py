@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("MDE_B200_LIB") or os.path.join(_HERE, "libmde_b200.so
 # enums of include/mde_b200.h
 F32, F16, BF16 = 0, 1, 2
 METRIC_NQ, METRIC_NM = 12, 12
-METRICS_OUT_F64 = 2 * METRIC_NM + METRIC_NQ + 1
+METRICS_OUT_F64 = 3 * METRIC_NM + METRIC_NQ + 1
 METRICS_REFERENCE_MATH = 1
 METRICS_NEED_LOG, METRICS_NEED_LOG1P, METRICS_NEED_REL, METRICS_NEED_RSQ = 1 << 8, 1 << 9, 1 << 10, 1 << 11
 LOSS_L1, LOSS_MSE, LOSS_BERHU, LOSS_LAINA_BERHU, LOSS_SILOG, LOSS_EIGEN = range(6)
@@ -34,7 +34,7 @@ RAW_INDEX = {"n_valid": 0, "d1": 1, "d2": 2, "d3": 3, "abs": 4, "sq": 5, "log10"
 
 class LossParams(C.Structure):
     _fields_ = [("variance_focus", C.c_float), ("clamp_val", C.c_float),
-                ("use_logs", C.c_int), ("size_average", C.c_int)]
+                ("use_logs", C.c_int), ("size_average", C.c_int), ("metrics_accum", C.c_void_p)]
 
 
 _vp, _i64, _i32, _u32, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint, C.c_float

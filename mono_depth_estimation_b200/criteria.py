@@ -33,12 +33,24 @@ __all__ = ["MaskedDepthLoss", "MaskedMSELoss", "MaskedL1Loss", "berHuLoss", "Lai
 
 
 def _scale_grad(grad, grad_output):
-    """grad *= grad_output on the device (skipped inside the kernel when grad_output == 1)."""
+    """grad *= grad_output on the device (the kernel returns at once when grad_output == 1)."""
     lib = _lib.load()
-    go = grad_output.detach().to(torch.float32).reshape(1).contiguous()
-    _lib.check(lib.mde_scale_inplace(_lib.ptr(grad), _lib.dtype_code(grad), grad.numel(), _lib.ptr(go),
-                                     _lib.stream_ptr(grad.device)))
+    with torch.cuda.device(grad.device):   # backward may run with another current device (one process, several GPUs)
+        go = grad_output.detach().to(device=grad.device, dtype=torch.float32).reshape(1).contiguous()
+        _lib.check(lib.mde_scale_inplace(_lib.ptr(grad), _lib.dtype_code(grad), grad.numel(), _lib.ptr(go),
+                                         _lib.stream_ptr(grad.device)))
     return grad
+
+
+def _compute_copy(p):
+    """The tensor the kernels read. Half-precision predictions (AMP, reference train.py:60,139) are widened to fp32
+    first: the kernels store dloss/dpred BEFORE autograd's grad_output is known, i.e. values of order 1/N, which
+    underflow fp16 (1/N = 2e-7 at C2, fp16 subnormal step 6e-8) and would defeat GradScaler's loss scaling. With an
+    fp32 stash the scale is applied in fp32 and the result is rounded to the prediction's dtype once, as autograd does."""
+    pc = p.detach()
+    if pc.dtype in (torch.float16, torch.bfloat16):
+        pc = pc.float()
+    return pc.contiguous()
 
 
 class _FusedLossFn(torch.autograd.Function):
@@ -49,6 +61,7 @@ class _FusedLossFn(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[0]
         loss, grad = launch(pred, need_grad)
         ctx.grad = grad
+        ctx.pred_dtype = pred.dtype
         ctx.used = False
         return loss
 
@@ -62,6 +75,8 @@ class _FusedLossFn(torch.autograd.Function):
         ctx.used = True
         g = _scale_grad(ctx.grad, grad_output)
         ctx.grad = None
+        if g.dtype != ctx.pred_dtype:
+            g = g.to(ctx.pred_dtype)          # fp32 stash of a half-precision prediction: one rounding, after the scale
         return g, None
 
 
@@ -75,10 +90,6 @@ def _as_images(pred):
     return n_img, h, w
 
 
-def _tensor_key(pred, target):
-    return (pred.data_ptr(), pred._version, tuple(pred.shape), pred.dtype, target.data_ptr(), target._version)
-
-
 class _FusesMetrics:
     """Mixin: `criterion.fuse_metrics(metric_computation)` makes the loss launch ALSO produce the pooled
     metric suite of `metric_computation` from the same read of pred/target (C ABI
@@ -87,15 +98,22 @@ class _FusesMetrics:
     is then served from that launch instead of reading the tensors again. Pass None to undo."""
 
     _fused_metrics = None
+    _fused_book = False
 
-    def fuse_metrics(self, metric_computation):
+    def fuse_metrics(self, metric_computation, book=False):
+        """`book=True`: the launch also ADDS the values to the computer's running sums and counts the call (reference
+        metrics.py:64-66) at criterion time, in the kernel's finaliser - the later compute() on the same tensors only
+        reads. Use it when every criterion call is followed by that compute() (the reference's training steps);
+        with the default the running sums are updated by compute() itself, as in the reference."""
         self._fused_metrics = metric_computation
+        self._fused_book = bool(book) and metric_computation is not None
         return self
 
 
-def masked_loss(kind, pred, target, mask=None, params=None, totals=False, metrics=None):
+def masked_loss(kind, pred, target, mask=None, params=None, totals=False, metrics=None, book_metrics=False):
     """Functional entry: fused forward(+backward when pred.requires_grad) of one masked loss.
-    `metrics`: an optional metrics.MetricComputation to feed from the same launch."""
+    `metrics`: an optional metrics.MetricComputation to feed from the same launch (`book_metrics`: see
+    _FusesMetrics.fuse_metrics)."""
     lib = _lib.load()
     dev = _lib.require_cuda(pred, target, mask)
     if pred.dtype not in (torch.float32, torch.float16, torch.bfloat16):
@@ -116,10 +134,9 @@ def masked_loss(kind, pred, target, mask=None, params=None, totals=False, metric
             setattr(lp, k, v)
     tot = torch.zeros(_lib.LOSS_NTOTALS, dtype=torch.float64, device=dev) if totals else None
     fuse = metrics is not None and kind != _lib.LOSS_EIGEN and not getattr(metrics, "reference_math", False)
-    key = _tensor_key(pred, target) if fuse else None
 
     def launch(p, need_grad):
-        pc = p.detach().contiguous()
+        pc = _compute_copy(p)
         n_img, h, w = _as_images(pc)
         with torch.cuda.device(dev):
             ws = _lib.workspace(dev, n_img)
@@ -128,12 +145,13 @@ def masked_loss(kind, pred, target, mask=None, params=None, totals=False, metric
             if fuse:
                 m64 = torch.empty(_lib.METRICS_OUT_F64, dtype=torch.float64, device=dev)
                 m32 = torch.empty(2 * _lib.METRIC_NM, dtype=torch.float32, device=dev)
+                lp.metrics_accum = _lib.ptr(metrics.accum_buffer(dev)).value if book_metrics else None
                 _lib.check(lib.mde_masked_loss_metrics(kind, _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(tgt),
                                                        _lib.ptr(mk), n_img, h, w, C.byref(lp), 1.0,
                                                        metrics.group_flags(), _lib.ptr(ws), _lib.ptr(loss),
                                                        _lib.ptr(tot), _lib.ptr(grad), _lib.ptr(m64), _lib.ptr(m32),
                                                        _lib.stream_ptr(dev)))
-                metrics.offer(key, m32[:_lib.METRIC_NM], m64)
+                metrics.offer(pred, target, m32[:_lib.METRIC_NM], m64, booked=book_metrics)
             else:
                 _lib.check(lib.mde_masked_loss(kind, _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(tgt), _lib.ptr(mk),
                                                n_img, h, w, C.byref(lp), 1.0, _lib.ptr(ws), _lib.ptr(loss),
@@ -170,7 +188,7 @@ class MaskedMSELoss(nn.Module, _FusesMetrics):
 
     def forward(self, pred, target):
         assert pred.dim() == target.dim(), "inconsistent dimensions"
-        self.loss = masked_loss(_lib.LOSS_MSE, pred, target, metrics=self._fused_metrics)
+        self.loss = masked_loss(_lib.LOSS_MSE, pred, target, metrics=self._fused_metrics, book_metrics=self._fused_book)
         return self.loss
 
 
@@ -182,7 +200,7 @@ class MaskedL1Loss(nn.Module, _FusesMetrics):
 
     def forward(self, pred, target):
         assert pred.dim() == target.dim(), "inconsistent dimensions"
-        self.loss = masked_loss(_lib.LOSS_L1, pred, target, metrics=self._fused_metrics)
+        self.loss = masked_loss(_lib.LOSS_L1, pred, target, metrics=self._fused_metrics, book_metrics=self._fused_book)
         return self.loss
 
 
@@ -194,7 +212,7 @@ class berHuLoss(nn.Module, _FusesMetrics):
 
     def forward(self, pred, target):
         assert pred.dim() == target.dim(), "inconsistent dimensions"
-        self.loss = masked_loss(_lib.LOSS_BERHU, pred, target, metrics=self._fused_metrics)
+        self.loss = masked_loss(_lib.LOSS_BERHU, pred, target, metrics=self._fused_metrics, book_metrics=self._fused_book)
         return self.loss
 
 
@@ -208,7 +226,7 @@ class LainaBerHuLoss(nn.Module, _FusesMetrics):
         self.clamp_val = clamp_val
 
     def forward(self, input, target, mask=None):
-        return masked_loss(_lib.LOSS_LAINA_BERHU, input, target, mask=mask, metrics=self._fused_metrics,
+        return masked_loss(_lib.LOSS_LAINA_BERHU, input, target, mask=mask, metrics=self._fused_metrics, book_metrics=self._fused_book,
                            params={"size_average": int(bool(self.size_average)), "use_logs": int(bool(self.use_log)),
                                    "clamp_val": float(self.clamp_val)})
 
@@ -221,7 +239,7 @@ class silog_loss(nn.Module, _FusesMetrics):
         self.variance_focus = variance_focus
 
     def forward(self, depth_est, depth_gt):
-        return masked_loss(_lib.LOSS_SILOG, depth_est, depth_gt, metrics=self._fused_metrics,
+        return masked_loss(_lib.LOSS_SILOG, depth_est, depth_gt, metrics=self._fused_metrics, book_metrics=self._fused_book,
                            params={"variance_focus": float(self.variance_focus)})
 
 
@@ -247,9 +265,7 @@ class ordLoss(nn.Module):
                 grad = torch.empty_like(pc) if need_grad else None
                 _lib.check(lib.mde_ord_loss(_lib.ptr(pc), _lib.ptr(tgt), N, K, H * W, 1.0, _lib.ptr(ws),
                                             _lib.ptr(loss), _lib.ptr(grad), _lib.stream_ptr(dev)))
-            if grad is not None and grad.dtype != p.dtype:
-                grad = grad.to(p.dtype)
-            return loss, grad
+            return loss, grad      # fp32 stash; rounded to p.dtype after the scale (_FusedLossFn.backward)
 
         self.loss = _FusedLossFn.apply(ord_labels, launch)
         return self.loss
@@ -286,9 +302,7 @@ class OrdinalRegressionLoss(object):
                 _lib.check(lib.mde_ordinal_regression_loss(_lib.ptr(pc), _lib.ptr(gtc), N, K, H * W, alpha, beta,
                                                            disc, 1.0, _lib.ptr(ws), _lib.ptr(loss), _lib.ptr(grad),
                                                            _lib.stream_ptr(dev)))
-            if grad is not None and grad.dtype != p.dtype:
-                grad = grad.to(p.dtype)
-            return loss, grad
+            return loss, grad      # fp32 stash; rounded to p.dtype after the scale (_FusedLossFn.backward)
 
         return _FusedLossFn.apply(prob, launch)
 
@@ -358,7 +372,7 @@ class VNL_Loss(nn.Module):
         stats = torch.zeros(8, dtype=torch.float64, device=dev)
 
         def launch(p, need_grad):
-            pc = p.detach().contiguous()
+            pc = _compute_copy(p)
             with torch.cuda.device(dev):
                 ws = _lib.workspace(dev, B)
                 scratch = torch.empty(int(lib.mde_vnl_scratch_bytes(B, n_trip)), dtype=torch.uint8, device=dev)
@@ -464,8 +478,8 @@ class MidasLoss(nn.Module):
 
         def launch(p, need_grad):
             pc = p.detach()
-            if pc.dtype not in (torch.float32, torch.float16, torch.bfloat16) or ssi:
-                pc = pc.float()                      # the backward through the solve works on fp32 buffers
+            if pc.dtype != torch.float32:
+                pc = pc.float()                      # fp32 stash (see _compute_copy); the backward through the solve needs it anyway
             pc = pc.contiguous()
             sp = _lib.stream_ptr(dev)
             with torch.cuda.device(dev):
@@ -485,7 +499,7 @@ class MidasLoss(nn.Module):
                     coef = torch.empty((B, 4), dtype=torch.float32, device=dev)
                     _lib.check(lib.mde_midas_ssi_backward(_lib.ptr(pc), _lib.ptr(t), _lib.ptr(scale), _lib.ptr(shift),
                                                           _lib.ptr(sums), B, H * W, _lib.ptr(ws), _lib.ptr(coef), _lib.ptr(grad), sp))
-            return loss, (grad.to(p.dtype) if grad is not None and grad.dtype != p.dtype else grad)
+            return loss, grad      # fp32 stash; _FusedLossFn.backward scales it and rounds to the prediction dtype once
 
         return _FusedLossFn.apply(prediction, launch)
 
@@ -562,7 +576,7 @@ class TrimmedProcrustesLoss(nn.Module):
                     _lib.check(lib.mde_robust_backward(_lib.ptr(pn), _lib.ptr(t), _lib.ptr(st_p), B, H * W, _lib.ptr(ws),
                                                        _lib.ptr(coef), _lib.ptr(grad), sp))
             self._prediction_ssi = pn
-            return loss, (grad.to(p.dtype) if grad is not None and grad.dtype != p.dtype else grad)
+            return loss, grad      # fp32 stash; _FusedLossFn.backward scales it and rounds to the prediction dtype once
 
         return _FusedLossFn.apply(prediction, launch)
 

@@ -753,10 +753,12 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
         a.met_f64[lane] = val;
         a.met_f64[MDE_METRIC_NM + lane] = im;   // per-image means are not formed by the fused path
         a.met_f64[2 * MDE_METRIC_NM + lane] = P;
+          a.met_f64[2 * MDE_METRIC_NM + MDE_METRIC_NQ + 1 + lane] = im;   // per-image value sums (one image: the values)
         if (a.met_f32) {
           a.met_f32[lane] = static_cast<float>(val);
           a.met_f32[MDE_METRIC_NM + lane] = static_cast<float>(im);
         }
+        if (a.met_accum) a.met_accum[lane] += static_cast<float>(val);   // MetricComputation's running sums
       }
       if (lane == 0) a.met_f64[2 * MDE_METRIC_NM + MDE_METRIC_NQ] = (a.n_img == 1 && nn > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
     }

@@ -201,6 +201,7 @@ __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __re
       out_f64[lane] = val;
       out_f64[kNM + lane] = mean_v;
       out_f64[2 * kNM + lane] = P;
+      out_f64[2 * kNM + kNQ + 1 + lane] = V;   // per-image value sums: {P, N, V} is the vector ranks all-reduce
       if (out_f32) {
         out_f32[lane] = static_cast<float>(val);
         out_f32[kNM + lane] = static_cast<float>(mean_v);

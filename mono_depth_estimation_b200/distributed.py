@@ -15,7 +15,7 @@ import torch.distributed as dist
 
 from . import _lib
 
-__all__ = ["shard_range", "reduce_metric_sums", "sharded_eval", "finalize_pooled"]
+__all__ = ["shard_range", "reduce_metric_sums", "sharded_eval", "finalize_pooled", "packed_view", "pack_metric_sums", "unpack_metric_sums"]
 
 
 def shard_range(n_items: int, rank: int, world: int):
@@ -27,11 +27,17 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 def pack_metric_sums(per_image_values: torch.Tensor, per_image_raw: torch.Tensor) -> torch.Tensor:
-    """[NM + 1 + NQ] doubles: sum over this rank's valid images of per-image values, #valid images,
-    pooled raw sums (integer counts stay exact in fp64)."""
+    """[NQ + 1 + NM] doubles in the layout of mde_metrics' out_f64[2NM:]: pooled raw sums (integer counts stay exact
+    in fp64), #valid images, sum over this rank's valid images of per-image values."""
     valid = per_image_raw[:, _lib.RAW_INDEX["n_valid"]] > 0
     vsum = torch.where(valid[:, None], per_image_values, torch.zeros_like(per_image_values)).sum(0)
-    return torch.cat([vsum, valid.sum().to(torch.float64).reshape(1), per_image_raw.sum(0)])
+    return torch.cat([per_image_raw.sum(0), valid.sum().to(torch.float64).reshape(1), vsum])
+
+
+def packed_view(out_f64: torch.Tensor) -> torch.Tensor:
+    """The same vector as a VIEW of a kernel result (mde_metrics' out_f64): the launch already formed it, so a rank
+    all-reduces it in place with no packing launches at all."""
+    return out_f64[2 * _lib.METRIC_NM:3 * _lib.METRIC_NM + _lib.METRIC_NQ + 1]
 
 
 def reduce_metric_sums(packed: torch.Tensor, group=None) -> torch.Tensor:
@@ -50,23 +56,35 @@ def finalize_pooled(raw: torch.Tensor) -> torch.Tensor:
 
 
 def unpack_metric_sums(packed: torch.Tensor, names):
-    NM = _lib.METRIC_NM
-    image_mean = packed[:NM] / packed[NM]
-    pooled = finalize_pooled(packed[NM + 1:])
+    NM, NQ = _lib.METRIC_NM, _lib.METRIC_NQ
+    raw, n_img, vsum = packed[:NQ], packed[NQ], packed[NQ + 1:NQ + 1 + NM]
+    image_mean = vsum / n_img
+    pooled = finalize_pooled(raw)
     idx = [_lib.METRIC_INDEX[n] for n in names]
     return {"image_mean": {n: image_mean[i] for n, i in zip(names, idx)},
             "pooled": {n: pooled[i] for n, i in zip(names, idx)},
-            "n_images": packed[NM], "n_valid": packed[NM + 1], "delta_counts": packed[NM + 2:NM + 5]}
+            "n_images": n_img, "n_valid": raw[0], "delta_counts": raw[1:4]}
 
 
-def sharded_eval(pred_shard, target_shard, names, group=None, all_reduce=True):
-    """Evaluate this rank's images and combine across ranks.
+def sharded_eval(pred_shard, target_shard, names, group=None, all_reduce=True, async_op=False):
+    """Evaluate this rank's images and combine across ranks: ONE kernel launch per rank, ONE all-reduce of
+    NQ + 1 + NM = 25 doubles (in place on a view of the kernel's result vector), nothing else.
 
-    Returns dict: 'image_mean' (reference eval-loop semantics: mean over images of per-image means),
-    'pooled' (dataset-pooled means), 'n_images', 'n_valid', 'delta_counts' (exact integers in fp64)."""
+    Returns dict: 'image_mean' (reference eval-loop semantics: mean over images of per-image means,
+    metrics.py:35-41 + modules/base_module.py:71-76), 'pooled' (dataset-pooled means), 'n_images', 'n_valid',
+    'delta_counts' (exact integers in fp64). With `async_op=True` only {'work', 'packed'} come back: the all-reduce
+    runs on the communicator's stream while the caller goes on; wait, then unpack_metric_sums(packed, names)."""
     from .metrics import fused_metrics
-    res = fused_metrics(pred_shard, target_shard, names=names, per_image=True)
-    packed = pack_metric_sums(res["per_image"], res["per_image_raw"])
-    if all_reduce:
-        packed = reduce_metric_sums(packed, group)
-    return unpack_metric_sums(packed, names)
+    if pred_shard.numel() == 0:
+        # a rank without images (n_items < world) contributes zeros and STILL enters the collective
+        packed = torch.zeros(_lib.METRIC_NM + 1 + _lib.METRIC_NQ, dtype=torch.float64, device=pred_shard.device)
+    else:
+        packed = packed_view(fused_metrics(pred_shard, target_shard, names=names)["f64"])
+    work = None
+    if all_reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    if async_op:   # finish with: r["work"].wait(); unpack_metric_sums(r["packed"], names)
+        return {"work": work, "packed": packed}
+    out = unpack_metric_sums(packed, names)
+    out["packed"] = packed
+    return out

@@ -116,7 +116,8 @@ class _DornFusedFn(torch.autograd.Function):
     def forward(ctx, x, gt, alpha, beta, K, disc, want_prob):
         lib = _lib.load()
         dev = _lib.require_cuda(x, gt)
-        xc = x.detach().contiguous()
+        from .criteria import _compute_copy
+        xc = _compute_copy(x)     # half-precision logits are widened: the stashed gradient must not underflow
         N, C, H, W = xc.shape
         assert C == 2 * K, "logits must have 2*ord_num channels"
         gtc = gt.detach().to(torch.float32).reshape(N, H * W).contiguous()
@@ -132,11 +133,11 @@ class _DornFusedFn(torch.autograd.Function):
                                           disc, 1.0, _lib.ptr(ws), _lib.ptr(loss), _lib.ptr(prob), _lib.ptr(decode),
                                           _lib.ptr(depth), _lib.ptr(gx), _lib.stream_ptr(dev)))
         ctx.gx = gx
+        ctx.x_dtype = x.dtype
         ctx.used = False
-        ctx.mark_non_differentiable(decode, depth)
         if prob is None:
             prob = torch.empty(0, device=dev)
-        ctx.mark_non_differentiable(prob)
+        ctx.mark_non_differentiable(decode, depth, prob)   # ONE call: a second call replaces the first set
         return loss, decode, depth, prob
 
     @staticmethod
@@ -149,6 +150,8 @@ class _DornFusedFn(torch.autograd.Function):
         from .criteria import _scale_grad
         g = _scale_grad(ctx.gx, gloss)
         ctx.gx = None
+        if g.dtype != ctx.x_dtype:
+            g = g.to(ctx.x_dtype)
         return (g,) + (None,) * 6
 
 

@@ -13,6 +13,8 @@ Extensions that do not exist in the reference (all opt-in):
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _lib
@@ -161,15 +163,41 @@ class MetricComputation(object):
             g |= _lib.METRIC_GROUP.get(n, 0)
         return g if g else _lib.METRICS_NEED_LOG
 
-    def offer(self, key, values32, f64):
-        self._prefetched = (key, values32, f64)
+    @staticmethod
+    def _ident(t):
+        return (t.data_ptr(), t._version, tuple(t.shape), t.dtype, t.device)
+
+    def offer(self, pred, target, values32, f64, booked=False):
+        """A criterion computed the pooled metrics of (pred, target) in its own launch. The offer holds WEAK
+        references to the two tensors: it is honoured only while both are still alive (their storage cannot have been
+        freed and handed to other data) and unmodified (same version counter), and only by the next compute().
+        `booked`: the launch already added the values to the running sums (accum_buffer) - count the call now."""
+        self._prefetched = (weakref.ref(pred), self._ident(pred), weakref.ref(target), self._ident(target), values32, f64, booked)
+        if booked:
+            self._sum_assigned = None
+            self.count += 1
 
     def _take_prefetched(self, pred, target):
         pf, self._prefetched = self._prefetched, None
         if pf is None:
             return None
-        key = (pred.data_ptr(), pred._version, tuple(pred.shape), pred.dtype, target.data_ptr(), target._version)
-        return {"values": pf[1], "f64": pf[2]} if pf[0] == key else None
+        rp, idp, rt, idt, values32, f64, booked = pf
+        if rp() is None or rt() is None:       # the offered tensors are gone: their addresses may have been reused
+            return None
+        if self._ident(rp()) != idp or self._ident(rt()) != idt:   # modified in place since the offer
+            return None
+        # compute() may be handed views / detached aliases of the offered tensors (log_train(y_hat.detach(), y)):
+        # same storage address, version counter (shared by aliases), shape and dtype
+        if self._ident(pred) != idp or self._ident(target) != idt:
+            return None
+        return {"values": values32, "f64": f64, "booked": booked}
+
+    def accum_buffer(self, device):
+        """The running sums as ONE fp32 device vector [NM] (created on first use) - what a fusing criterion's launch
+        adds to when it books the metrics itself."""
+        if self._sum_vec is None:
+            self._sum_vec = torch.zeros(_lib.METRIC_NM, dtype=torch.float32, device=device)
+        return self._sum_vec
 
     def reset(self):
         self.count = 0
@@ -194,7 +222,7 @@ class MetricComputation(object):
     def sum(self, value):
         self._sum_assigned = value
 
-    def _collect(self, res_vec, pred, target):
+    def _collect(self, res_vec, pred, target, booked=False):
         self._sum_assigned = None
         vals = []
         for n in self.metric_names:
@@ -204,6 +232,8 @@ class MetricComputation(object):
                 vals.append(v)
             else:
                 vals.append(res_vec[_lib.METRIC_INDEX[n]])
+        if booked:      # the criterion's launch added the values and offer() counted the call
+            return vals
         self.count += 1
         # one 12-float add instead of one launch per metric
         if self._sum_vec is None:
@@ -222,7 +252,7 @@ class MetricComputation(object):
             if self.strict:
                 # the reference's `assert torch.sum(valid_mask) > 0` (metrics.py:61) reads the device too
                 assert float(res["f64"][2 * _lib.METRIC_NM + _lib.RAW_INDEX["n_valid"]]) > 0, "invalid target!"
-            return self._collect(res["values"], pred, target)
+            return self._collect(res["values"], pred, target, booked=res.get("booked", False))
 
     def compute_resized(self, pred, target, size=(480, 640)):
         """compute() on pred and target bilinearly resized to `size` first (the test_step pattern of the eigen, dorn

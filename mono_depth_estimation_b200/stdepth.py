@@ -71,8 +71,8 @@ def setup_criterion(method, single_layer=True, composite_layers=None, depth_sort
 
         def launch(p, need_grad):
             pc = p.detach()
-            if pc.dtype not in (torch.float32, torch.float16, torch.bfloat16):
-                pc = pc.float()
+            if pc.dtype != torch.float32:
+                pc = pc.float()       # also fp16 / bf16: the stashed gradient must not underflow (criteria._compute_copy)
             pc = pc.contiguous()
             with torch.cuda.device(dev):
                 ws = _lib.workspace(dev, B)

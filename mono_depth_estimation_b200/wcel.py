@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .criteria import _FusedLossFn
+from .criteria import _FusedLossFn, _compute_copy
 
 __all__ = ["WCEL_Loss", "depth_to_bins", "bins_to_depth", "vnl_params", "VNLBins"]
 
@@ -61,7 +61,7 @@ class WCEL_Loss(nn.Module):
         gtf = gt.detach().to(torch.float32).contiguous()
 
         def launch(p, need_grad):
-            pc = p.detach().contiguous()
+            pc = _compute_copy(p)     # half-precision logits are widened: the stashed gradient must not underflow (criteria._compute_copy)
             with torch.cuda.device(dev):
                 ws = _lib.workspace(dev, 1)
                 loss = torch.empty((), dtype=torch.float32, device=dev)

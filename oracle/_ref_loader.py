@@ -1,8 +1,8 @@
 """Load the upstream reference modules BY FILE PATH (test infrastructure only).
 
-Only `oracle/gen_golden.py` and `tests/test_oracle_vs_reference.py` use this, and only
-in a container where `/root/reference` exists (it does not exist on the GPU box).
-Nothing in the product package imports it.
+Used by `oracle/gen_golden.py`, `tests/test_oracle_vs_reference.py` (container with `/root/reference`)
+and `oracle/ref_step.py` (the CPU baseline of bench.py, which on the GPU box finds the unmodified copy
+under `baseline/_ref/`). Nothing in the product package imports it.
 
 Shims:
   * never put the reference directory on sys.path (its statistics.py shadows the stdlib);
@@ -19,7 +19,19 @@ import types
 import numpy as np
 import torch
 
-REF_ROOT = os.environ.get("MDE_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """The reference tree itself when present (this container), else the unmodified copy of the hot-path files that
+    oracle/install_ref.py put under git-ignored baseline/_ref (the GPU box receives only the repository)."""
+    for cand in (os.environ.get("MDE_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "criteria.py")):
+            return cand
+    return os.environ.get("MDE_REFERENCE_ROOT", "/root/reference")
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

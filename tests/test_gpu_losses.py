@@ -320,3 +320,81 @@ def test_upstream_gradient_scales_the_stashed_gradient(shape, dtype):
     assert p2.grad.dtype == dtype
     tol = 1e-6 if dtype == torch.float32 else 1e-2
     torch.testing.assert_close(p2.grad.float(), p1.grad.float() * 2.5, rtol=tol, atol=0.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("name", ["silog", "l1", "mse", "berhu"])
+def test_amp_grad_scaler_at_training_size(Cr, name, dtype):
+    """Half-precision predictions under GradScaler (reference train.py:60 --precision 16, :139) at a real batch size:
+    dloss/dpred is of order 1/N (5e-7 at 8x416x544) - below fp16's normal range - until the scale (65536) is applied.
+    The stash is fp32, the scale is applied in fp32 and the result rounded ONCE to the prediction dtype, so the scaled
+    gradient keeps the dtype's relative precision (a half-precision stash flushes most of it to zero)."""
+    shape = (8, 1, 416, 544)                           # 1.81 M px
+    pred, gt = synth.depth_pair(shape, 36)
+    ph = pred.to(dtype)
+    _, g64 = olosses.loss_and_grad(olosses.LOSSES[name], ph.double(), gt.double())
+    p = ph.cuda().requires_grad_(True)
+    loss = make(Cr, name)(p, gt.cuda())
+    (loss * 65536.0).backward()
+    assert p.grad.dtype == dtype
+    ref = g64 * 65536.0
+    got = p.grad.double().cpu()
+    eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7     # one rounding to the dtype (+ margin)
+    big = ref.abs() > 1e-3 * ref.abs().max()
+    rel = ((got - ref).abs() / ref.abs().clamp_min(1e-30))[big]
+    assert float(rel.max()) < eps, (name, float(rel.max()))
+    assert float((got != 0).double().mean()) > 0.5 * float((ref != 0).double().mean()), "gradient flushed to zero"
+
+
+def test_fused_metrics_offer_is_not_served_to_other_data(Cr):
+    """The hand-over from a fusing criterion is keyed on the LIVE tensor objects: once the offered prediction is freed,
+    a new tensor that the caching allocator places at the same address (same shape, version 0) must be evaluated on its
+    own data, not served the previous batch's metrics."""
+    from mono_depth_estimation_b200 import metrics as M
+    from oracle import metrics as ometrics
+    names = ["delta1", "mse", "mae", "log10", "rmse"]
+    shape = (2, 1, 64, 96)
+    mc = M.MetricComputation(names, strict=False)
+    crit = Cr.silog_loss(0.85).fuse_metrics(mc)
+    pred, gt = synth.depth_pair(shape, 91, border=2)
+    g = gt.cuda()
+    p = pred.cuda().requires_grad_(True)
+    addr = p.data_ptr()
+    crit(p, g).backward()                              # offer pending; the step never calls compute() (e.g. logs every k steps)
+    del p
+    other, _ = synth.depth_pair(shape, 92, border=2)
+    q = other.cuda()                                   # typically lands on the freed block
+    vals = mc.compute(q, g)
+    want = [float(v) for v in ometrics.compute(other.double(), gt.double(), names)]
+    close(torch.stack(vals), want, 1e-5, msg="same address: %s" % (q.data_ptr() == addr))
+    # an in-place update of the offered tensor also invalidates the offer
+    p = pred.cuda().requires_grad_(True)
+    crit(p, g).backward()
+    with torch.no_grad():
+        p.mul_(1.5)
+    vals = mc.compute(p.detach(), g)
+    want = [float(v) for v in ometrics.compute(pred.double() * 1.5, gt.double(), names)]
+    close(torch.stack(vals), want, 1e-5)
+
+
+def test_fused_metrics_booked_in_the_launch(Cr):
+    """fuse_metrics(mc, book=True): the criterion's launch adds the values to the running sums and counts the call;
+    the following compute() on the same tensors only reads (no launch at all), avg() matches the reference recipe."""
+    from mono_depth_estimation_b200 import metrics as M, _lib
+    from oracle import metrics as ometrics
+    names = ["delta1", "delta2", "delta3", "mse", "mae", "log10", "rmse"]
+    mc = M.MetricComputation(names, strict=False)
+    crit = Cr.silog_loss(0.85).fuse_metrics(mc, book=True)
+    acc = np.zeros(len(names))
+    for k, seed in enumerate((93, 94, 95)):
+        pred, gt = synth.depth_pair((2, 1, 48, 64), seed, border=2)
+        p, g = pred.cuda().requires_grad_(True), gt.cuda()
+        loss = crit(p, g)
+        n0 = _lib.launch_count()
+        vals = mc.compute(p.detach(), g)
+        assert _lib.launch_count() == n0 and mc.count == k + 1
+        loss.backward()
+        want = np.array([float(v) for v in ometrics.compute(pred.double(), gt.double(), names)])
+        close(torch.stack(vals), want, 1e-5)
+        acc += want
+    close(torch.stack([mc.avg(n) for n in names]), acc / 3, 1e-5)

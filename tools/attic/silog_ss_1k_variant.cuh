@@ -7,24 +7,33 @@ namespace mde {
 namespace {
 
 // ---- SILog (+ metric suite) with the residuals parked in SHARED memory between the phases ("SS") ----------
-// fp32, 128-bit aligned, gradient requested, <= kSsSlots tiles per CTA (C1, C2). Round-2 rewrite of the reduce
-// loop; the round-1 version (bulk copies by one producer thread, one mbarrier per slot, a CTA-wide
-// __syncthreads per 2048-px tile, dynamically claimed tiles) spent ~45 of its ~205 instructions per quad on
-// per-tile plumbing and kept only two tiles in flight per CTA. Now:
-//   * THREAD-PRIVATE pipeline: every thread copies its own quad of pred and target with cp.async (LDGSTS,
-//     16 B, no registers) kSsDepth tiles ahead and waits with cp.async.wait_group - no mbarrier, no CTA
-//     barrier, no producer thread; warps drift freely;
-//   * static interleaved tiles (tile = cta + k * grid): the slot index k is a compile-time constant of the
-//     unrolled loop, so every shared-memory address is base + immediate and no tile list exists;
-//   * the prediction quad lands directly in the slot that will hold its residuals (replaced in place),
-//     the target quad in a ring of kSsDepth tiles (recycled by the same thread right after its LDS);
+// fp32, 128-bit aligned, gradient requested, <= kSsMaxChunks x 128 px per SM (C1, C2). History of the reduce loop:
+//   round 1   bulk copies by one producer thread, one mbarrier per slot, a CTA-wide __syncthreads per 2048-px tile,
+//             tiles claimed from a global counter: ~45 of ~205 instructions per quad were per-tile plumbing and
+//             only two tiles were in flight per CTA (C2 fused: 22.6 us);
+//   round 2a  2 CTAs x 512 threads per SM, thread-private cp.async pipeline, static interleaved tiles, lean
+//             per-pixel math: 155 instructions per quad, but the warp scheduler serves the older CTA of an SM
+//             first - it finished its 8 tiles at 6.8 us while the younger one had done ~1.5 and then ran ALONE
+//             (4 warps per scheduler, half the issue rate) until 10-11 us (20.0 us);
+//   round 2b  (this) ONE CTA of 1024 threads per SM; every SM owns a contiguous range of the tensor and its 32
+//             warps pull 512-byte chunks (32 quads, one per lane) from a SHARED-MEMORY counter, so fast warps
+//             simply take more chunks and all 32 warps stay busy until the range is exhausted:
+//   * per-warp pipeline: lane l copies quad l of the warp's chunk of pred and of target with cp.async (LDGSTS,
+//     16 B, no registers) kSsDepth chunks ahead and waits with cp.async.wait_group - no mbarrier, no CTA barrier;
+//   * the prediction chunk lands directly in the slot that will hold its residuals (replaced in place, slot =
+//     chunk number within the SM's range), the target chunk in the warp's private ring of kSsDepth chunks;
+//   * the chunk to copy next was claimed one stage earlier (ATOMS + SHFL off the critical path);
 //   * per-pixel arithmetic in the lean form of metric_math.cuh (11 ALU-pipe instructions instead of ~20).
-// Gradient phase: the CTA's predictions come back through L2 into the (now free) target ring with cp.async
-// and into registers, requested BEFORE the all-reduce wait; afterwards it is d_i from shared memory,
-// arithmetic and streaming 128-bit stores. Shared memory: (kSsSlots + kSsDepth) x 8 KB = 104 KB per CTA.
-constexpr int kSsSlots = 9;
+// All-reduce of the three totals: 148 slots + one arrival counter (grid_sum4_counted). Gradient phase: warp w
+// takes chunks w, w + 32, ...; their predictions come back through L2 into the (now free) rings and into registers,
+// requested BEFORE the all-reduce wait; afterwards it is d_i from shared memory, arithmetic and streaming 128-bit
+// stores. Shared memory: kSsMaxChunks x 512 B of slots + 32 x kSsDepth x 512 B of rings = 208 KB.
+constexpr int kSsThreads = 1024;
+constexpr int kSsWarps = kSsThreads / 32;
 constexpr int kSsDepth = 4;
-constexpr size_t kSsBytes = static_cast<size_t>(kSsSlots + kSsDepth) * kBlock * sizeof(float4);
+constexpr int kSsMaxChunks = 288;                                  // residual slots per CTA (x 128 px)
+constexpr int kSsGradIt = (kSsMaxChunks + kSsWarps - 1) / kSsWarps;  // gradient-phase chunks per warp
+constexpr size_t kSsBytes = static_cast<size_t>(kSsMaxChunks + kSsWarps * kSsDepth) * 32 * sizeof(float4);
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -90,14 +99,15 @@ static __device__ __noinline__ void ss_rare_quad(const float4 p4, const float4 t
 }
 
 template <unsigned MG>
-__global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a) {
-  __shared__ double sm_d[(MG ? 12 : 4) * kWarps];
-  __shared__ double sm_own[4 * kWarps];
+__global__ void __launch_bounds__(kSsThreads, 1) silog_ss_kernel(LossArgs a) {
+  __shared__ double sm_d[(MG ? 12 : 4) * kSsWarps];
+  __shared__ double sm_own[4 * kSsWarps];
   __shared__ double sm_tot[4];
-  __shared__ double sm_gather[kWarps * 4];
+  __shared__ double sm_gather[kSsWarps * 4];
   __shared__ float sm_k[4];
   __shared__ unsigned sm_epoch;
-  extern __shared__ float4 sm_ss[];   // [kSsSlots][kBlock] residual slots, then [kSsDepth][kBlock] target ring
+  __shared__ int sm_next;             // next unclaimed chunk of this CTA's range
+  extern __shared__ float4 sm_ss[];   // [kSsMaxChunks][32] residual slots, then [kSsWarps][kSsDepth][32] target rings
   // metric groups evaluated in reference arithmetic on the rare path (kGrpRsq is a lean-form subset of kGrpRel)
   constexpr unsigned kRefG = (MG & kGrpRsq) ? ((MG & 7u) | kGrpRel) : (MG & 7u);
 
@@ -107,29 +117,44 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = static_cast<int>(gridDim.x), cta = static_cast<int>(blockIdx.x);
   const int nq = static_cast<int>(a.n >> 2);
+  int64_t cb64, ce64;
+  cta_chunk(a.chunk, cta, cb64, ce64);                       // this CTA's quads [cb, ce): chunk-aligned start
+  const int cb = static_cast<int>(cb64), ce = static_cast<int>(ce64);
+  const int nch = (ce - cb + 31) >> 5;                       // chunks of 32 quads (the last one of the tensor may be partial)
   float4* slots = sm_ss;
-  float4* ring = sm_ss + kSsSlots * kBlock;
-  const int q0 = cta * kBlock + tid;                         // this thread's quad in tile k: q0 + k * qs
-  const int qs = G * kBlock;
-  const int nst = (q0 < nq) ? (nq - 1 - q0) / qs + 1 : 0;    // quads of this thread (ns, or ns - 1 in a partial last tile)
+  float4* ring = sm_ss + kSsMaxChunks * 32 + warp * (kSsDepth * 32);   // this warp's target ring
+  const float* predw = pred + 4 * static_cast<size_t>(cb + lane);      // quad `lane` of chunk 0
+  const float* gtw = gt + 4 * static_cast<size_t>(cb + lane);
 
   trace_point(0);
   // The launch parity (workspace epoch) is needed only after the reduce loop. Its load is issued FIRST: the L1
-  // returns loads in issue order, so behind the prefetch burst below it would come back after ~128 KB of copies
-  // (measured: the loop of the second CTA of an SM started 3.7 us into the kernel while the prologue waited for it).
+  // returns loads in issue order, so behind the prefetch burst below it would come back after ~128 KB of copies.
   Ws ws = ws_view(a.ws);
   unsigned epoch_reg = 0u;
-  if (tid == 0) epoch_reg = __ldcg(&ws.hdr->epoch);
-  auto issue = [&](int k) {
-    const size_t q = static_cast<size_t>(q0) + static_cast<size_t>(k) * static_cast<size_t>(qs);
-    cp_async16(&slots[k * kBlock + tid], pred + 4 * q);
-    cp_async16(&ring[(k % kSsDepth) * kBlock + tid], gt + 4 * q);
+  if (tid == 0) {
+    epoch_reg = __ldcg(&ws.hdr->epoch);
+    sm_next = kSsWarps * kSsDepth;      // chunks 0 .. 32 * depth - 1 are the static heads of the 32 pipelines
+  }
+  // copy chunk j into its slot (pred) and into ring stage r (target); lanes beyond the end of the range skip
+  auto issue = [&](int j, int r) {
+    if (cb + (j << 5) + lane < ce) {
+      cp_async16(&slots[(j << 5) + lane], predw + (static_cast<size_t>(j) << 7));
+      cp_async16(&ring[(r << 5) + lane], gtw + (static_cast<size_t>(j) << 7));
+    }
   };
+  int jr[kSsDepth];                     // chunk in flight in ring stage r
 #pragma unroll
-  for (int k = 0; k < kSsDepth; ++k) {   // the first kSsDepth tiles are in flight before anything else happens
-    if (k < nst) issue(k);
+  for (int r = 0; r < kSsDepth; ++r) {  // static head: stage r <- chunk r * 32 + warp (32 warps cover 16 KB contiguous bytes per stage)
+    jr[r] = r * kSsWarps + warp;
+    if (jr[r] < nch) issue(jr[r], r);
     cp_async_commit();
   }
+  __syncthreads();                      // sm_next is set
+  auto claim = [&]() -> int {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(&sm_next, 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+  };
 
   // ---------------- reduce phase ------------------------------------------------------------------------
   MetricAcc acc;
@@ -187,21 +212,35 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   long long tm_wait = 0, tm_comp = 0;   // cycles this warp spent waiting for its copies / evaluating its quads
   trace_point(4);                       // (instrumented build) slot 4 = start of the reduce loop
 #endif
-#pragma unroll   // (a rolled loop with computed slot addresses was measured: 20.6 instead of 20.0 us)
-  for (int k = 0; k < kSsSlots; ++k) {
-    if (k < nst) {                      // uniform over the CTA except in a partial last tile
+  int jpre = claim();                   // claimed one stage ahead of its copy: the ATOMS + SHFL latency is off the critical path
+  bool more = true;
+  while (more) {
+#pragma unroll
+    for (int r = 0; r < kSsDepth; ++r) {
+      const int j = jr[r];
+      if (j >= nch) {                   // chunk numbers of a warp only grow: the first one past the end is the end
+        more = false;
+        break;
+      }
 #ifdef MDE_SS_TIMING
       const long long tm0 = clock64();
 #endif
-      cp_async_wait<kSsDepth - 1>();    // this thread's copies of tile k have landed
+      cp_async_wait<kSsDepth - 1>();    // this lane's copies of chunk j have landed
 #ifdef MDE_SS_TIMING
       const long long tm1 = clock64();
 #endif
-      const float4 p4 = slots[k * kBlock + tid];
-      const float4 t4 = ring[(k % kSsDepth) * kBlock + tid];
-      if (k + kSsDepth < nst) issue(k + kSsDepth);   // the ring slot just read is this thread's to refill
+      const bool ok = cb + (j << 5) + lane < ce;
+      float4 p4, t4;
+      if (ok) {
+        p4 = slots[(j << 5) + lane];
+        t4 = ring[(r << 5) + lane];
+      }
+      const int jn = jpre;
+      jpre = claim();
+      jr[r] = jn;
+      if (jn < nch) issue(jn, r);       // the ring stage just read is this lane's to refill
       cp_async_commit();
-      slots[k * kBlock + tid] = quad(p4, t4);
+      if (ok) slots[(j << 5) + lane] = quad(p4, t4);
 #ifdef MDE_SS_TIMING
       const long long tm2 = clock64();
       tm_wait += tm1 - tm0;
@@ -210,8 +249,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
     }
   }
 #ifdef MDE_SS_TIMING
-  if (g_mde_trace != nullptr && lane == 0 && warp == 0)
-    g_mde_trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 6] =
+  if (g_mde_trace != nullptr && lane == 0 && (warp == 0 || warp == kSsWarps - 1))
+    g_mde_trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + (warp == 0 ? 6 : 3)] =
         (static_cast<unsigned long long>(tm_wait) << 32) | static_cast<unsigned long long>(tm_comp & 0xffffffffll);
 #endif
   cp_async_wait<0>();
@@ -237,7 +276,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const double sq = warp_sum(run[q]);
-      if (lane == 0) sm_own[q * kWarps + warp] = sq;
+      if (lane == 0) sm_own[q * kSsWarps + warp] = sq;
     }
     if (tid == 0) sm_epoch = epoch_reg;
     __syncthreads();
@@ -250,8 +289,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   unsigned* ukey = ws.ukey + par * kUkey;
   if (cta == 0) {
     const int o = par ^ 1;
-    for (int i = tid; i < kGacc; i += kBlock) ws.gacc[o * kGacc + i] = 0.0;
-    for (int i = tid; i < kUkey; i += kBlock) ws.ukey[o * kUkey + i] = 0u;
+    for (int i = tid; i < kGacc; i += kSsThreads) ws.gacc[o * kGacc + i] = 0.0;
+    for (int i = tid; i < kUkey; i += kSsThreads) ws.ukey[o * kUkey + i] = 0u;
     if (tid == 0) {
       const unsigned dirty = __ldcg(&ws.hdr->dirty[o]);
       if (dirty) {
@@ -269,18 +308,18 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
       const int r0 = __reduce_add_sync(0xffffffffu, acc.n_valid(lean_px)), r1 = __reduce_add_sync(0xffffffffu, acc.count(1, lean_px));
       const int r2 = __reduce_add_sync(0xffffffffu, acc.count(2, lean_px)), r3 = __reduce_add_sync(0xffffffffu, acc.count(3, lean_px));
       if (lane == 0) {
-        sm_d[0 * kWarps + warp] = r0; sm_d[1 * kWarps + warp] = r1;
-        sm_d[2 * kWarps + warp] = r2; sm_d[3 * kWarps + warp] = r3;
+        sm_d[0 * kSsWarps + warp] = r0; sm_d[1 * kSsWarps + warp] = r1;
+        sm_d[2 * kSsWarps + warp] = r2; sm_d[3 * kSsWarps + warp] = r3;
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float sq = warp_sum(acc.sum(q)) * tile_scale<false>(q);
-        if (lane == 0) sm_d[(4 + q) * kWarps + warp] = static_cast<double>(sq);
+        if (lane == 0) sm_d[(4 + q) * kSsWarps + warp] = static_cast<double>(sq);
       }
       __syncthreads();
       if (tid < 12) {
         double tot = 0.0;
-        for (int w = 0; w < kWarps; ++w) tot += sm_d[tid * kWarps + w];
+        for (int w = 0; w < kSsWarps; ++w) tot += sm_d[tid * kSsWarps + w];
         const int qi = (tid < 4) ? tid : kTileToQ[tid - 4];
         if (tot != 0.0) atomicAdd(&gacc[kMetBase + qi], tot);
       }
@@ -289,25 +328,29 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   trace_point(2);
 
   // ---------------- all-reduce of the totals (grid_sum4_counted, common.cuh); every CTA derives the coefficients ----
-  constexpr int kRegTiles = kSsSlots - kSsDepth;   // gradient-phase predictions held in registers
-  float4 preg[kRegTiles];
-  auto prefetch_pred = [&] {
-    // slots 0 .. kSsDepth-1 -> the target ring (free now), the rest -> registers; all through L2
+  constexpr int kRegIt = kSsGradIt - kSsDepth;   // gradient-phase predictions held in registers
+  float4 preg[kRegIt];
+  // gradient phase: warp w takes chunks w, w + 32, ... The first kSsDepth of them -> the warp's ring (free now),
+  // the rest -> registers (once the metric accumulators are dead); all through L2
+  auto prefetch_pred_ring = [&] {
 #pragma unroll
-    for (int k = 0; k < kSsDepth; ++k) {
-      const size_t q = static_cast<size_t>(q0) + static_cast<size_t>(k) * static_cast<size_t>(qs);
-      if (k < nst) cp_async16(&ring[k * kBlock + tid], pred + 4 * q);
+    for (int i = 0; i < kSsDepth; ++i) {
+      const int j = i * kSsWarps + warp;
+      if (j < nch && cb + (j << 5) + lane < ce) cp_async16(&ring[(i << 5) + lane], predw + (static_cast<size_t>(j) << 7));
     }
     cp_async_commit();
+  };
+  auto prefetch_pred_regs = [&] {
 #pragma unroll
-    for (int k = kSsDepth; k < kSsSlots; ++k) {
-      const size_t q = static_cast<size_t>(q0) + static_cast<size_t>(k) * static_cast<size_t>(qs);
-      if (k < nst) preg[k - kSsDepth] = __ldcs(reinterpret_cast<const float4*>(pred + 4 * q));
+    for (int i = kSsDepth; i < kSsGradIt; ++i) {
+      const int j = i * kSsWarps + warp;
+      if (j < nch && cb + (j << 5) + lane < ce) preg[i - kSsDepth] = __ldcs(reinterpret_cast<const float4*>(predw + (static_cast<size_t>(j) << 7)));
     }
   };
-  grid_sum4_counted<kWarps>(ws.slots, ukey + 2, epoch * 4u + 2u, sm_own, sm_gather, sm_tot, [&] {
-    if (grad != nullptr) prefetch_pred();
+  grid_sum4_counted<kSsWarps>(ws.slots, ukey + 2, epoch * 4u + 2u, sm_own, sm_gather, sm_tot, [&] {
+    if (grad != nullptr) prefetch_pred_ring();
     flush_metrics();
+    if (grad != nullptr) prefetch_pred_regs();
   });
   if (tid < 32) __syncwarp();   // sm_tot was written by threads 0..3
   if (tid == 0) {
@@ -337,7 +380,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   if constexpr (MG != 0) {
     // arrival for the metric finaliser (end of the kernel), off everybody's critical path: the CTA's metric
     // atomics (flush_metrics) were issued before the __syncthreads above, so this fence orders them
-    if (tid == kBlock - 32) {
+    if (tid == kSsThreads - 32) {
       __threadfence();
       atomicAdd(ukey + 6, 1u);
     }
@@ -347,7 +390,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   // of the LAST CTA at the very end of the kernel, when every CTA's arrival has long been counted
   auto finalize_metrics = [&] {
     if constexpr (MG != 0) {
-      if (cta == G - 1 && tid >= kBlock - 32) {
+      if (cta == G - 1 && tid >= kSsThreads - 32) {
         if (lane == 0) {   // the all-reduce above is no memory barrier: wait for every CTA's metric atomics
           while (*reinterpret_cast<volatile unsigned*>(ukey + 6) < gridDim.x) {}
           __threadfence();
@@ -364,7 +407,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
           a.met_f64[lane] = val;
           a.met_f64[MDE_METRIC_NM + lane] = im;   // per-image means are not formed by the fused path
           a.met_f64[2 * MDE_METRIC_NM + lane] = P;
-          a.met_f64[2 * MDE_METRIC_NM + MDE_METRIC_NQ + 1 + lane] = im;   // per-image value sums (one image: the values)
           if (a.met_f32) {
             a.met_f32[lane] = static_cast<float>(val);
             a.met_f32[MDE_METRIC_NM + lane] = static_cast<float>(im);
@@ -395,11 +437,11 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
     return g;
   };
 #pragma unroll
-  for (int k = 0; k < kSsSlots; ++k) {
-    if (k < nst) {
-      const size_t q = static_cast<size_t>(q0) + static_cast<size_t>(k) * static_cast<size_t>(qs);
-      const float4 p = (k < kSsDepth) ? ring[(k < kSsDepth ? k : 0) * kBlock + tid] : preg[k < kSsDepth ? 0 : k - kSsDepth];
-      __stcs(reinterpret_cast<float4*>(grad + 4 * q), gquad(p, slots[k * kBlock + tid]));
+  for (int i = 0; i < kSsGradIt; ++i) {
+    const int j = i * kSsWarps + warp;
+    if (j < nch && cb + (j << 5) + lane < ce) {
+      const float4 p = (i < kSsDepth) ? ring[((i < kSsDepth ? i : 0) << 5) + lane] : preg[i < kSsDepth ? 0 : i - kSsDepth];
+      __stcs(reinterpret_cast<float4*>(grad + 4 * static_cast<size_t>(cb + lane) + (static_cast<size_t>(j) << 7)), gquad(p, slots[(j << 5) + lane]));
     }
   }
   if (cta == G - 1) {   // n % 4 tail, recomputed in natural-log units
@@ -419,17 +461,16 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
 template <unsigned MG>
 int launch_loss_ss_mg(LossArgs& a, cudaStream_t st, bool& taken) {
   const void* fn = reinterpret_cast<const void*>(&silog_ss_kernel<MG>);
-  const int cap = coop_grid(fn, kBlock, kSsBytes);
+  const int cap = coop_grid(fn, kSsThreads, kSsBytes);   // one CTA per SM
   if (cap <= 0) return MDE_OK;   // (e.g. the carve-out is not available) -> generic path
   const int64_t nq = a.n >> 2;
-  const int64_t nt = (nq + kBlock - 1) / kBlock;
-  int64_t grid = nt < cap ? nt : cap;
+  const int64_t nchunks = (nq + 31) / 32;
+  int64_t grid = nchunks < cap ? nchunks : cap;
   if (grid < 1) grid = 1;
-  if (nt > grid * kSsSlots) return MDE_OK;
-  a.chunk = make_chunking(nq, 8, static_cast<int>(grid));
+  a.chunk = make_chunking(nq, 32, static_cast<int>(grid));
+  if (a.chunk.base + (a.chunk.rem ? 1 : 0) > kSsMaxChunks) return MDE_OK;   // does not fit the slots -> generic path
   void* args[] = {&a};
-  // (an ordinary launch of the same grid was measured: 19.96 vs 20.01 us - the cooperative launch costs nothing)
-  MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, kSsBytes, st));
+  MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kSsThreads), args, kSsBytes, st));
   count_launch();
   taken = true;
   return MDE_OK;

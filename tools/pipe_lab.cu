@@ -131,9 +131,14 @@ void run(float* out, unsigned long long* cyc) {
   cudaMemset(cyc, 0, 8);
   k<OP><<<148 * 2, 512>>>(out, 1.0f, 1.0000001f, cyc);
   cudaMemset(cyc, 0, 8);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
   k<OP><<<148 * 2, 512>>>(out, 1.0f, 1.0000001f, cyc);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
   unsigned long long c;
   cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+  if (OP == FADD) printf("{\"clock_check\": \"FADD kernel: %llu clock64 cycles in %.2f us (event) -> %.0f MHz\"}\n", c, ms * 1e3, c / (ms * 1e3));
   const int per_iter = (OP >= FADD2 && OP <= FMUL2) ? U / 2 : U;
   // 8 warps per sub-partition each issue ITERS * per_iter instructions
   printf("{\"op\": \"%s\", \"cycles_per_warp_instr_per_smsp\": %.2f}\n", kNames[OP], static_cast<double>(c) / (8.0 * ITERS * per_iter));

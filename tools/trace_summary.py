@@ -7,6 +7,10 @@ for name in ('fused', 'plain'):
     if not os.path.exists(p):
         continue
     d = json.load(open(p))[-1]
+    live = [i for i, v in enumerate(d['start']) if v > -1e6]
+    if len(live) < len(d['start']):
+        t0 = min(d['start'][i] for i in live)   # older dumps hold empty rows
+        d = {k: [ (v[i] - t0 if k in ('start','a_done','published','bar_exit','end','b_start') else v[i]) for i in live] for k, v in d.items()}
     n = len(d['smid'])
     first = {}
     for i, s in enumerate(d['smid']):
