@@ -354,7 +354,8 @@ def main():
     # the criterion's launch also produces the metric suite (one read of pred/gt for the whole step) and books it
     # into the computer's running sums, as the log_train() that follows every criterion call would (metrics.py:16-17)
     crit = criteria.silog_loss(0.85).fuse_metrics(None if args.unfused else mcomp, book=True)
-    raw_acc = torch.zeros(_lib.METRIC_NQ, dtype=torch.float64, device=dev)
+    # N > 1: the pooled raw sums of this rank between two exchanges are accumulated by the same launch (no launch of their own)
+    raw_acc = mcomp.raw_accum_buffer(dev) if (world > 1 and not args.unfused) else torch.zeros(_lib.METRIC_NQ, dtype=torch.float64, device=dev)
 
     def step(pred, gt, pool=True):
         p = pred.detach().requires_grad_(True)
@@ -362,7 +363,7 @@ def main():
         loss.backward()
         vals = mcomp.compute(p.detach(), gt)     # reference metrics.py:16-17 (log_train)
         raw = mcomp.last_f64[2 * _lib.METRIC_NM:2 * _lib.METRIC_NM + _lib.METRIC_NQ]
-        if world > 1 and pool:  # pooled raw sums of this rank, accumulated on the device between exchanges
+        if world > 1 and args.unfused and pool:
             raw_acc.add_(raw)
         return loss, vals, p.grad, raw
 
@@ -402,7 +403,7 @@ def main():
                 mega = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(mega, stream=side):
                     mega_out = [step(*ring[i], pool=False) for i in range(args.ring)]
-                    if world > 1:   # the pass's pooled sums in one go (3 small launches per pass instead of one per step)
+                    if world > 1 and args.unfused:   # the pass's pooled sums in one go
                         raw_acc.add_(torch.stack([o[3] for o in mega_out]).sum(0))
             except Exception as e:  # capture unsupported -> eager steps
                 sys.stderr.write("graph capture failed (%s); timing eager steps\n" % (str(e).splitlines()[0],))

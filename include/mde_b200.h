@@ -134,6 +134,8 @@ typedef struct {
   float* metrics_accum; /* mde_masked_loss_metrics only, nullable: MDE_METRIC_NM device floats that receive
                            `+= pooled value` from the launch's finaliser - MetricComputation's running sums
                            (reference metrics.py:65-66) without a launch of their own */
+  double* metrics_raw_accum; /* same, nullable: MDE_METRIC_NQ device doubles that receive `+= pooled raw sum`
+                           (what a rank pools between two all-reduces of the metric sums) */
 } mde_loss_params;
 
 /*

@@ -34,7 +34,8 @@ RAW_INDEX = {"n_valid": 0, "d1": 1, "d2": 2, "d3": 3, "abs": 4, "sq": 5, "log10"
 
 class LossParams(C.Structure):
     _fields_ = [("variance_focus", C.c_float), ("clamp_val", C.c_float),
-                ("use_logs", C.c_int), ("size_average", C.c_int), ("metrics_accum", C.c_void_p)]
+                ("use_logs", C.c_int), ("size_average", C.c_int), ("metrics_accum", C.c_void_p),
+                ("metrics_raw_accum", C.c_void_p)]
 
 
 _vp, _i64, _i32, _u32, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint, C.c_float

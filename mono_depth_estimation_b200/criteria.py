@@ -146,6 +146,7 @@ def masked_loss(kind, pred, target, mask=None, params=None, totals=False, metric
                 m64 = torch.empty(_lib.METRICS_OUT_F64, dtype=torch.float64, device=dev)
                 m32 = torch.empty(2 * _lib.METRIC_NM, dtype=torch.float32, device=dev)
                 lp.metrics_accum = _lib.ptr(metrics.accum_buffer(dev)).value if book_metrics else None
+                lp.metrics_raw_accum = _lib.ptr(metrics._raw_vec).value if (book_metrics and getattr(metrics, "_raw_vec", None) is not None) else None
                 _lib.check(lib.mde_masked_loss_metrics(kind, _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(tgt),
                                                        _lib.ptr(mk), n_img, h, w, C.byref(lp), 1.0,
                                                        metrics.group_flags(), _lib.ptr(ws), _lib.ptr(loss),

@@ -27,6 +27,7 @@ extern "C" int mde_masked_loss_metrics(int kind, const void* pred, int pred_dtyp
   a.met_f64 = metrics_f64;
   a.met_f32 = metrics_f32;
   a.met_accum = params ? params->metrics_accum : nullptr;
+  a.met_raw_accum = params ? params->metrics_raw_accum : nullptr;
   unsigned g = (metric_flags >> 8) & kGrpMask;
   // two instantiations: {log, rel} (the reference's default metric list) and everything; the SS SILog kernel has a
   // third, {log, rsq}, for lists that need only the 'rmse' sum of the REL group

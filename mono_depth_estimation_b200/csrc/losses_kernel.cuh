@@ -28,6 +28,7 @@ struct LossArgs {
   double* met_f64;  // fused metrics (MG != 0): same layout as mde_metrics' out_f64
   float* met_f32;
   float* met_accum;  // optional: running sums of the metric values (+= in the finaliser), MDE_METRIC_NM floats
+  double* met_raw_accum;  // optional: running pooled raw sums (+= in the finaliser), MDE_METRIC_NQ doubles
   int rsq_only;      // the REL group is requested for MDE_Q_RSQ only
   int64_t n_img;
 };
@@ -759,6 +760,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
           a.met_f32[MDE_METRIC_NM + lane] = static_cast<float>(im);
         }
         if (a.met_accum) a.met_accum[lane] += static_cast<float>(val);   // MetricComputation's running sums
+        if (a.met_raw_accum) a.met_raw_accum[lane] += P;
       }
       if (lane == 0) a.met_f64[2 * MDE_METRIC_NM + MDE_METRIC_NQ] = (a.n_img == 1 && nn > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
     }
@@ -897,6 +899,7 @@ inline LossArgs make_loss_args(const void* pred, const float* target, const uint
   a.met_f64 = nullptr;
   a.met_f32 = nullptr;
   a.met_accum = nullptr;
+  a.met_raw_accum = nullptr;
   a.rsq_only = 0;
   a.n_img = n_img;
   return a;

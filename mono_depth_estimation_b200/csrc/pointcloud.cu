@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) point_cloud_kernel(const float* __restric
     const int r = static_cast<int>(rem / w), c = static_cast<int>(rem - static_cast<int64_t>(r) * w);
     const float d = __ldcs(depth + i);
     const bool valid = (d > clip_start) && (d < clip_end);
-    double x = 0.0, y = 0.0, z = __longlong_as_double(0x7ff8000000000000LL);
+    double x = 0.0, y = 0.0, z = __longlong_as_double(0xfff8000000000000LL);   // -np.where(valid, depth, nan): the NaN carries the minus sign
     if (valid) {
       const float zf = -d;
       const float fz = factor * zf;  // fp32 product, as numpy evaluates `factor * z`
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kPcBlock) point_cloud_tile_kernel(const float*
   const int64_t n_tiles = (total + kPcTilePx - 1) / kPcTilePx;
   const double half_c = static_cast<double>(w) / 2.0, half_r = static_cast<double>(h) / 2.0;
   const double ratio = static_cast<double>(h > w ? h : w), inv_ratio = 1.0 / ratio;
-  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  const double qnan = __longlong_as_double(0xfff8000000000000LL);   // -np.where(valid, depth, nan): the NaN carries the minus sign
   constexpr int kVec = 16 / sizeof(OT);                 // output elements per 128-bit store
   constexpr int kStores = 3 * kPcTilePx / kVec / kPcBlock;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {

@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
             a.met_f32[MDE_METRIC_NM + lane] = static_cast<float>(im);
           }
           if (a.met_accum) a.met_accum[lane] += static_cast<float>(val);   // MetricComputation's running sums
+          if (a.met_raw_accum) a.met_raw_accum[lane] += P;
         }
         if (lane == 0) a.met_f64[2 * MDE_METRIC_NM + MDE_METRIC_NQ] = (a.n_img == 1 && nn > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
       }

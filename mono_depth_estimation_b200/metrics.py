@@ -192,6 +192,14 @@ class MetricComputation(object):
             return None
         return {"values": values32, "f64": f64, "booked": booked}
 
+    def raw_accum_buffer(self, device):
+        """fp64 device vector [NQ] of pooled RAW sums (valid count, exact delta counts, float sums) that a booking
+        criterion's launches add to: what a rank pools between two all-reduces of the metric sums (distributed.py).
+        Created (zeroed) on first use; the caller zeroes it after each exchange."""
+        if getattr(self, "_raw_vec", None) is None:
+            self._raw_vec = torch.zeros(_lib.METRIC_NQ, dtype=torch.float64, device=device)
+        return self._raw_vec
+
     def accum_buffer(self, device):
         """The running sums as ONE fp32 device vector [NM] (created on first use) - what a fusing criterion's launch
         adds to when it books the metrics itself."""

@@ -477,6 +477,42 @@ def gen_stdepth():
     np.savez_compressed(os.path.join(OUT, "stdepth_small.npz"), **out)
 
 
+def _reference_point_cloud():
+    """`point_cloud` of reference depth2pointcloud.py:12-31 compiled from the reference source itself: the file is a
+    Blender script (imports bpy / mathutils at the top, U+200B characters on its blank lines) and cannot be imported,
+    but the function body only needs `np` and `tan`."""
+    import ast
+    from math import tan
+    src = open(os.path.join(R.REF_ROOT, "depth2pointcloud.py"), encoding="utf-8").read().replace("\u200b", "")
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.FunctionDef) and node.name == "point_cloud":
+            ns = {"np": np, "tan": tan}
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "depth2pointcloud.py", "exec"), ns)
+            return ns["point_cloud"]
+    raise RuntimeError("point_cloud not found in depth2pointcloud.py")
+
+
+def gen_pointcloud():
+    """Golden vectors of depth -> point cloud produced by the REFERENCE's function (pins oracle/pointcloud.py, the GPU
+    kernel is compared with both). The camera is the stub the function reads: cam.data.{angle_x, clip_start, clip_end}."""
+    from types import SimpleNamespace
+    fn = _reference_point_cloud()
+    out = {}
+    for tag, shape, seed in (("a", (37, 53), 3), ("b", (48, 64), 11), ("c", (8, 1028), 12)):
+        rs = np.random.RandomState(seed)
+        depth = (rs.rand(*shape) * 12).astype(np.float32)
+        depth[0, :5] = 0.05                      # below clip_start
+        depth[3, 3] = 200.0                      # beyond clip_end
+        depth[5, 7] = 0.1                        # exactly clip_start: strict '>' -> invalid
+        cam = SimpleNamespace(data=SimpleNamespace(angle_x=0.8575560450553894, clip_start=0.1, clip_end=100.0))
+        pts = fn(depth, cam)
+        assert pts.dtype == np.float64 and pts.shape == shape + (3,)
+        out["depth_" + tag] = depth
+        out["points_" + tag] = pts
+    out["camera"] = np.array([0.8575560450553894, 0.1, 100.0])
+    np.savez_compressed(os.path.join(OUT, "pointcloud.npz"), **out)
+
+
 def main():
     assert R.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
@@ -487,6 +523,9 @@ def main():
     if sys.argv[1:] == ["stdepth"]:
         gen_stdepth()
         return
+    if sys.argv[1:] == ["pointcloud"]:
+        gen_pointcloud()
+        return
     gen_losses()
     gen_metrics()
     gen_dorn()
@@ -495,6 +534,7 @@ def main():
     gen_wcel()
     gen_midas()
     gen_stdepth()
+    gen_pointcloud()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

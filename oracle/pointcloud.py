@@ -2,9 +2,11 @@
 
 Follows reference depth2pointcloud.py:12-31 (point_cloud) and :103-108 (camera -> world with
 cam.matrix_world). The reference file is a Blender script (imports bpy/mathutils and carries
-U+200B characters on blank lines) and cannot be imported here, and the reference holds no test
-for it: PARITY UNPINNED by the reference for this function - it is pinned to this restatement
-of lines 12-31, evaluated in the same numpy dtypes (x, y float64 by promotion, z float32).
+U+200B characters on blank lines) and cannot be imported, but its `point_cloud` function only needs
+numpy and `tan`: oracle/gen_golden.py compiles that function from the reference source and stores its
+outputs in tests/golden/pointcloud.npz, and this restatement reproduces them BIT FOR BIT
+(tests/test_oracle_vs_golden.py, tests/test_oracle_vs_reference.py) - PINNED. Only `to_world`
+(:103-108, a per-point mathutils product inside Blender) remains a restatement without a reference run.
 """
 from __future__ import annotations
 

@@ -197,3 +197,31 @@ def test_metrics_of_bilinearly_resized_inputs(M, pshape, tshape):
         close(res["f64"][:12], plain["f64"][:12], 1e-6)
     vals = M.MetricComputation(["delta1", "absrel", "rmse"], strict=False).compute_resized(pred.cuda(), target.cuda(), size)
     close(torch.stack(vals), [v64[ALL.index(n)] for n in ("delta1", "absrel", "rmse")], 2e-5)
+
+
+@pytest.mark.parametrize("pshape,tshape", [((2, 1, 240, 320), (2, 1, 427, 561)), ((1, 1, 257, 353), (1, 1, 480, 640)),
+                                           ((2, 1, 109, 147), (2, 1, 55, 74)), ((2, 1, 228, 304), (2, 1, 480, 640))])
+def test_resized_metrics_counts_exact_vs_cuda_interpolate(M, pshape, tshape):
+    """Integer outputs of the resize-fused metric pass against what the reference executes on a GPU: the two
+    F.interpolate(mode='bilinear') calls ON CUDA (modules/eigen.py:49-51, modules/dorn.py:181-183) followed by the metric
+    oracle's op chain on those CUDA tensors. The kernel samples with ATen's CUDA rule and op order, so the interpolated
+    values agree bit for bit and the valid / delta counts must be EQUAL, pooled and per image (no slack)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(7 * pshape[2] + tshape[3])
+    target = torch.rand(tshape, generator=g) * 9.5 + 0.5
+    target[torch.rand(tshape, generator=g) < 0.2] = 0.0
+    target[:, :, :7, :] = 0.0
+    pred = torch.rand(pshape, generator=g) * 9.0 + 0.6
+    # ratios parked on the thresholds in the SOURCE images survive the blend only where the taps agree; the random ones matter
+    size = (480, 640)
+    pc, tc = pred.cuda(), target.cuda()
+    y_hat = F.interpolate(pc, size, mode="bilinear")
+    y = F.interpolate(tc, size, mode="bilinear")
+    ref_counts = list(ometrics.delta_counts(y_hat, y))                       # torch ops on CUDA tensors
+    res = M.fused_metrics_resized(pc, tc, size, per_image=True)
+    assert _counts(res) == ref_counts
+    for b in range(pshape[0]):
+        rb = ometrics.delta_counts(y_hat[b:b + 1], y[b:b + 1])
+        assert [int(round(v)) for v in res["per_image_raw"][b, :4].tolist()] == list(rb)
+    v64 = [float(v) for v in ometrics.compute(y_hat.double().cpu(), y.double().cpu(), ALL)]
+    close(res["f64"][:12], v64, 1e-5)

@@ -123,3 +123,24 @@ def test_vnl_config_c4_full_size_properties(Cr):
     close(loss_p, loss, 2e-6)
     close(grad_p, grad, 1e-4, 2e-6 * float(grad.abs().max()))
     assert 0.2 < int(stats[0]) / (8 * trip.shape[1]) < 0.4        # the survey's probe: 25-32 % of the triplets are valid
+
+
+def test_point_cloud_reference_golden(Cr, golden):
+    """The kernel against outputs of the REFERENCE's own point_cloud (depth2pointcloud.py:12-31, golden vectors made by
+    oracle/gen_golden.py from the reference source): same NaN pattern, same sign of zero, fp64 values to the last bit
+    on the tiled path (w % 4 == 0) and to 1e-15 relative on the scalar path; fp32 output = the rounded fp64 values."""
+    from mono_depth_estimation_b200 import pointcloud as PC
+    g = golden("pointcloud.npz")
+    angle_x, clip_start, clip_end = (float(v) for v in g["camera"])
+    cam = PC.Camera(angle_x=angle_x, clip_start=clip_start, clip_end=clip_end)
+    for tag in "abc":
+        depth, ref = g["depth_" + tag], g["points_" + tag]
+        out = PC.point_cloud(torch.from_numpy(depth).cuda(), cam).cpu().numpy()
+        assert out.dtype == np.float64 and out.shape == ref.shape
+        assert np.array_equal(np.isnan(out), np.isnan(ref)), tag
+        assert np.array_equal(np.signbit(out), np.signbit(ref)), tag
+        np.testing.assert_allclose(np.nan_to_num(out), np.nan_to_num(ref), rtol=1e-15, atol=0, err_msg=tag)
+        if depth.shape[1] % 4 == 0:
+            assert np.array_equal(np.nan_to_num(out), np.nan_to_num(ref)), tag
+        out32 = PC.point_cloud(torch.from_numpy(depth).cuda(), cam, dtype=torch.float32).cpu().numpy()
+        np.testing.assert_allclose(np.nan_to_num(out32), np.nan_to_num(ref.astype(np.float32)), rtol=2e-7, atol=0, err_msg=tag)

@@ -309,3 +309,19 @@ def test_stdepth_empty_depth_mask(golden):
     l, d = ost.stdepth_loss(T(g["e_pred"]), T(g["e_targ"]), T(g["e_rgba"]), "silma", depth_w=0.7)
     assert float(d["depth_silog"]) == 0.0 and float(g["e_depth_silog32"]) == 0.0       # NaN -> nan_to_num -> 0
     close(l, g["e_loss32"], 2e-6)
+
+
+def test_pointcloud_oracle_vs_reference_golden(golden):
+    """depth -> point cloud: the golden vectors were produced by the REFERENCE's own point_cloud (depth2pointcloud.py:12-31,
+    compiled from the reference source by oracle/gen_golden.py); the numpy restatement must reproduce them bit for bit,
+    including the NaN pattern (clip planes, strict comparisons) and the sign of zero at invalid pixels."""
+    from oracle import pointcloud as opc
+    g = golden("pointcloud.npz")
+    angle_x, clip_start, clip_end = (float(v) for v in g["camera"])
+    for tag in "abc":
+        ref = g["points_" + tag]
+        out = opc.point_cloud(g["depth_" + tag], angle_x, clip_start, clip_end)
+        assert out.dtype == ref.dtype == np.float64 and out.shape == ref.shape
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        assert np.array_equal(np.nan_to_num(out), np.nan_to_num(ref))
+        assert np.array_equal(np.signbit(out), np.signbit(ref))

@@ -82,3 +82,20 @@ def test_vnl_random():
     (go,) = torch.autograd.grad(lo, po)
     np.testing.assert_allclose(lo.detach().numpy(), lr.detach().numpy(), rtol=1e-12)
     np.testing.assert_allclose(go.numpy(), gr.numpy(), rtol=1e-9, atol=1e-14)
+
+
+def test_point_cloud_random_vs_reference_function():
+    """Live check (container with /root/reference): the reference's point_cloud, compiled from depth2pointcloud.py by
+    oracle/gen_golden.py, against oracle/pointcloud.py on fresh random depth maps - bit for bit."""
+    from types import SimpleNamespace
+    from oracle import gen_golden, pointcloud as opc
+    fn = gen_golden._reference_point_cloud()
+    rs = np.random.RandomState(77)
+    for shape in ((19, 23), (64, 48), (5, 260)):
+        depth = (rs.rand(*shape) * 150).astype(np.float32)
+        depth[rs.rand(*shape) < 0.1] = 0.0
+        cam = SimpleNamespace(data=SimpleNamespace(angle_x=1.0471975511965976, clip_start=0.5, clip_end=120.0))
+        ref = fn(depth, cam)
+        out = opc.point_cloud(depth, cam.data.angle_x, cam.data.clip_start, cam.data.clip_end)
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        assert np.array_equal(np.nan_to_num(out), np.nan_to_num(ref)) and np.array_equal(np.signbit(out), np.signbit(ref))
