@@ -343,7 +343,7 @@ def main():
         import datetime
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=60))
     W = max(args.warmup, 3)
     K = args.steps
     npx = shape[0] * shape[2] * shape[3]
@@ -445,11 +445,11 @@ def main():
         torch.cuda.synchronize()
 
     with torch.cuda.stream(side):
-        # clocks: ~150 ms of the same steps before anything is timed (a B200 idles at 120 MHz)
-        t_warm = time.perf_counter()
-        while time.perf_counter() - t_warm < 0.15:
+        # clocks: ~150 ms of the same steps before anything is timed (a B200 idles at 120 MHz). A FIXED number of passes:
+        # every rank must issue the same sequence of collectives (run_steps exchanges every --sync-every steps)
+        for _ in range(750):
             run_steps(args.ring)
-            side.synchronize()
+        side.synchronize()
         run_steps(W)
         barrier()
         # R repetitions of exactly K steps; a repetition that is short in wall time is launch-jitter territory, so R grows

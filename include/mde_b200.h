@@ -165,6 +165,28 @@ int mde_masked_loss_metrics(int kind, const void* pred, int pred_dtype, const fl
                             void* ws, float* loss_out, double* totals_out, void* grad,
                             double* metrics_f64, float* metrics_f32, void* stream);
 
+/*
+ * Split-phase form of the same losses (L1, MSE, BERHU, LAINA_BERHU, SILOG) for GLOBAL-BATCH training over several
+ * GPUs (the batch shards by image, the ranks exchange only the scalar totals, every rank ends with the
+ * loss and the gradient of the single-GPU full-batch call - criteria.py:111-133 needs a max and then sums,
+ * :724-732 the sums of d, d^2 and the count). Plain streaming launches; nothing waits on another rank:
+ *
+ *   partials = {0, 0, 0, 0, -inf, 0, 0, 0}                                       (device, 8 doubles, caller-owned)
+ *   berHu / Laina:  mde_masked_loss_partials(kind, 0, ...)   partials[4] = max over the shard  -> all-reduce(MAX)
+ *   all kinds:      mde_masked_loss_partials(kind, 1, ..., gmax_in = &partials[4], ...)
+ *                                                            partials[0..3] += {S0, S1, N0, N1} -> all-reduce(SUM)
+ *   mde_masked_loss_from_totals(kind, ..., totals = partials, grad_scale, loss_out, grad)
+ *                                                            loss (same on every rank) + dloss/dpred of the shard
+ * The totals are the ones mde_masked_loss reports through totals_out (same order).
+ */
+int mde_masked_loss_partials(int kind, int stage, const void* pred, int pred_dtype, const float* target,
+                             const uint8_t* mask_u8, int64_t n, const mde_loss_params* params,
+                             const double* gmax_in, double* partials, void* stream);
+int mde_masked_loss_from_totals(int kind, const void* pred, int pred_dtype, const float* target,
+                                const uint8_t* mask_u8, int64_t n, const mde_loss_params* params,
+                                const double* totals, float grad_scale, float* loss_out, void* grad,
+                                void* stream);
+
 /* x[i] *= *scale_dev (device scalar) - applies a late-arriving grad_output to a stashed gradient */
 int mde_scale_inplace(void* x, int dtype, int64_t n, const float* scale_dev, void* stream);
 

@@ -49,6 +49,8 @@ SIGNATURES = {
                                _vp, _vp, _vp, _vp, _vp]),
     "mde_masked_loss_metrics": (_i32, [_i32, _vp, _i32, _vp, _vp, _i64, _i64, _i64, C.POINTER(LossParams), _f32,
                                        _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mde_masked_loss_partials": (_i32, [_i32, _i32, _vp, _i32, _vp, _vp, _i64, C.POINTER(LossParams), _vp, _vp, _vp]),
+    "mde_masked_loss_from_totals": (_i32, [_i32, _vp, _i32, _vp, _vp, _i64, C.POINTER(LossParams), _vp, _f32, _vp, _vp, _vp]),
     "mde_scale_inplace": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "mde_ordinal_layer_fwd": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
     "mde_ordinal_layer_bwd": (_i32, [_vp, _i32, _vp, _i64, _i64, _i64, _vp, _vp]),

@@ -35,6 +35,8 @@ __all__ = ["MaskedDepthLoss", "MaskedMSELoss", "MaskedL1Loss", "berHuLoss", "Lai
 def _scale_grad(grad, grad_output):
     """grad *= grad_output on the device (the kernel returns at once when grad_output == 1)."""
     lib = _lib.load()
+    if grad.numel() == 0:
+        return grad
     with torch.cuda.device(grad.device):   # backward may run with another current device (one process, several GPUs)
         go = grad_output.detach().to(device=grad.device, dtype=torch.float32).reshape(1).contiguous()
         _lib.check(lib.mde_scale_inplace(_lib.ptr(grad), _lib.dtype_code(grad), grad.numel(), _lib.ptr(go),

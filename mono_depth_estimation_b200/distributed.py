@@ -15,7 +15,8 @@ import torch.distributed as dist
 
 from . import _lib
 
-__all__ = ["shard_range", "reduce_metric_sums", "sharded_eval", "finalize_pooled", "packed_view", "pack_metric_sums", "unpack_metric_sums"]
+__all__ = ["shard_range", "reduce_metric_sums", "sharded_eval", "finalize_pooled", "packed_view", "pack_metric_sums", "unpack_metric_sums",
+           "SplitLoss", "global_batch_loss", "combine_partials", "loss_from_totals"]
 
 
 def shard_range(n_items: int, rank: int, world: int):
@@ -88,3 +89,161 @@ def sharded_eval(pred_shard, target_shard, names, group=None, all_reduce=True, a
     out = unpack_metric_sums(packed, names)
     out["packed"] = packed
     return out
+
+
+# ---- global-batch loss ----------------------------------------------------------------------------
+# Reference-faithful DDP evaluates every loss on the rank's LOCAL sub-batch (pl.Trainer(gpus=N), train.py:137); the
+# normalisations of berHu (a max over all pixels, then a mean), SILog (a variance) and the masked means then differ from
+# the single-GPU full-batch call. In global-batch mode the ranks exchange the scalar totals between two launches and
+# every rank ends with the loss and the gradient of the full batch.
+_GB_KINDS = {"l1": _lib.LOSS_L1, "mse": _lib.LOSS_MSE, "berhu": _lib.LOSS_BERHU, "laina_berhu": _lib.LOSS_LAINA_BERHU,
+             "silog": _lib.LOSS_SILOG}
+_GB_NEEDS_MAX = (_lib.LOSS_BERHU, _lib.LOSS_LAINA_BERHU)
+
+
+def _kind_of(criterion):
+    """(kind, LossParams) of a criterion module of criteria.py, or of a name in _GB_KINDS."""
+    from . import criteria as Cr
+    lp = _lib.LossParams(0.85, 1e-9, 1, 1)
+    if isinstance(criterion, str):
+        return _GB_KINDS[criterion], lp
+    if isinstance(criterion, Cr.silog_loss):
+        lp.variance_focus = float(criterion.variance_focus)
+        return _lib.LOSS_SILOG, lp
+    if isinstance(criterion, Cr.LainaBerHuLoss):
+        lp.size_average = int(bool(criterion.size_average)); lp.use_logs = int(bool(criterion.use_log)); lp.clamp_val = float(criterion.clamp_val)
+        return _lib.LOSS_LAINA_BERHU, lp
+    for cls, kind in ((Cr.MaskedL1Loss, _lib.LOSS_L1), (Cr.MaskedMSELoss, _lib.LOSS_MSE), (Cr.berHuLoss, _lib.LOSS_BERHU)):
+        if isinstance(criterion, cls):
+            return kind, lp
+    raise TypeError("global_batch_loss supports MaskedL1Loss, MaskedMSELoss, berHuLoss, LainaBerHuLoss and silog_loss")
+
+
+class SplitLoss:
+    """The three stages of a split-phase loss on ONE shard (C ABI mde_masked_loss_partials / _from_totals). The
+    caller combines `partials` across the shards between the stages: MAX of element 4 after stage_max, SUM of
+    elements 0..3 after stage_sums. global_batch_loss() below does that with torch.distributed; tests drive the
+    stages by hand to emulate several ranks on one GPU."""
+
+    def __init__(self, criterion, pred, target, mask=None):
+        import ctypes as C
+        self._C = C
+        self.lib = _lib.load()
+        self.kind, self.lp = _kind_of(criterion)
+        self.dev = _lib.require_cuda(pred, target, mask)
+        self.pred = pred
+        pc = pred.detach()
+        if pc.dtype != torch.float32:
+            pc = pc.float()                     # fp32 stash (criteria._compute_copy): the gradient is scaled before it is rounded
+        self.pc = pc.contiguous()
+        t = target.detach()
+        if t.shape != pred.shape:
+            t = t.expand_as(pred)
+        self.t = t.to(torch.float32).contiguous()
+        self.mk = None
+        if mask is not None:
+            mk = mask.detach()
+            if mk.shape != pred.shape:
+                mk = mk.expand_as(pred)
+            self.mk = (mk != 0).to(torch.uint8).contiguous()
+        self.partials = torch.tensor([0.0, 0.0, 0.0, 0.0, float("-inf"), 0.0, 0.0, 0.0], dtype=torch.float64, device=self.dev)
+
+    @property
+    def needs_max(self):
+        return self.kind in _GB_NEEDS_MAX
+
+    def _stage(self, stage):
+        if self.pc.numel() == 0:
+            return self.partials                # a rank without images contributes the identity and still joins the collectives
+        with torch.cuda.device(self.dev):
+            gmax = _lib.ptr(self.partials[4:5]) if (stage == 1 and self.needs_max) else None
+            _lib.check(self.lib.mde_masked_loss_partials(self.kind, stage, _lib.ptr(self.pc), _lib.dtype_code(self.pc), _lib.ptr(self.t),
+                                                         _lib.ptr(self.mk), self.pc.numel(), self._C.byref(self.lp), gmax,
+                                                         _lib.ptr(self.partials), _lib.stream_ptr(self.dev)))
+        return self.partials
+
+    def stage_max(self):
+        """partials[4] = max over this shard (berHu: max(pred - target) over ALL pixels; Laina: max n_i). No-op otherwise."""
+        return self._stage(0) if self.needs_max else self.partials
+
+    def stage_sums(self):
+        """partials[0..3] += {S0, S1, N0, N1} of this shard, given the GLOBAL max in partials[4]."""
+        return self._stage(1)
+
+    def finish(self):
+        """Loss of the global batch (0-dim fp32, the same value on every rank, attached to autograd) given the GLOBAL
+        totals in `partials`; backward yields dloss/dpred of THIS shard."""
+        from .criteria import _FusedLossFn
+        totals, kind, lp, pc, t, mk, dev, lib, C = self.partials, self.kind, self.lp, self.pc, self.t, self.mk, self.dev, self.lib, self._C
+
+        def launch(p, need_grad):
+            with torch.cuda.device(dev):
+                loss = torch.empty((), dtype=torch.float32, device=dev)
+                grad = torch.empty_like(pc) if (need_grad and pc.numel() > 0) else None
+                if pc.numel() == 0:
+                    # the loss value still comes from the totals: one-pixel dummy launch would need data; use the host formula on device
+                    loss = loss_from_totals(kind, totals, lp, like_kernel=True).to(torch.float32)
+                    return loss, (torch.zeros_like(pc) if need_grad else None)
+                _lib.check(lib.mde_masked_loss_from_totals(kind, _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(t), _lib.ptr(mk), pc.numel(),
+                                                           C.byref(lp), _lib.ptr(totals), 1.0, _lib.ptr(loss), _lib.ptr(grad),
+                                                           _lib.stream_ptr(dev)))
+            if grad is not None and grad.shape != p.shape:
+                grad = grad.view(p.shape)
+            return loss, grad
+
+        return _FusedLossFn.apply(self.pred, launch)
+
+
+def loss_from_totals(kind, totals, lp=None, like_kernel=False):
+    """Host-side restatement of the coefficient step: the loss value from the global totals {S0, S1, N0, N1, max}
+    (torch ops, any device; used for empty shards and by the CPU tests of the exchange logic). `like_kernel` rounds
+    where mde_masked_loss_from_totals rounds (reciprocal first, fp32 square root), so that a rank without images reports
+    bit for bit the value the other ranks' launches wrote."""
+    S0, S1, N0, N1 = totals[0], totals[1], totals[2], totals[3]
+    if like_kernel:
+        if kind in (_lib.LOSS_L1, _lib.LOSS_MSE):
+            return S0 * (1.0 / N0)
+        if kind == _lib.LOSS_SILOG:
+            vf = float(torch.tensor(0.85 if lp is None else float(lp.variance_focus), dtype=torch.float32))
+            inv = 1.0 / N0
+            dm, q = S0 * inv, S1 * inv
+            return 10.0 * torch.sqrt((q - vf * dm * dm).to(torch.float32)).to(torch.float64)
+        if kind == _lib.LOSS_BERHU:
+            return (S0 + S1) * (1.0 / (N0 + N1))
+        size_average = True if lp is None else bool(lp.size_average)
+        return S0 * (1.0 / N0) if size_average else S0
+    if kind in (_lib.LOSS_L1, _lib.LOSS_MSE):
+        return S0 / N0
+    if kind == _lib.LOSS_SILOG:
+        vf = 0.85 if lp is None else float(lp.variance_focus)
+        dm, q = S0 / N0, S1 / N0
+        return 10.0 * torch.sqrt(q - vf * dm * dm)
+    if kind == _lib.LOSS_BERHU:
+        return (S0 + S1) / (N0 + N1)
+    size_average = True if lp is None else bool(lp.size_average)
+    return S0 / N0 if size_average else S0
+
+
+def combine_partials(partials, stage, group=None):
+    """The exchange between two stages, in place: stage 0 -> all-reduce(MAX) of partials[4]; stage 1 -> all-reduce(SUM) of
+    partials[0:4]. No-op without an initialised process group."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return partials
+    if stage == 0:
+        dist.all_reduce(partials[4:5], op=dist.ReduceOp.MAX, group=group)
+    else:
+        dist.all_reduce(partials[0:4], op=dist.ReduceOp.SUM, group=group)
+    return partials
+
+
+def global_batch_loss(criterion, pred_shard, target_shard, mask=None, group=None):
+    """criterion(pred, target) of the GLOBAL batch whose images are sharded over the ranks of `group`: two (berHu /
+    Laina: three) streaming launches per rank and one (two) all-reduce(s) of at most 4 doubles between them. The returned
+    loss is identical on every rank; its backward gives the gradient of the global loss with respect to this rank's
+    predictions - together the ranks hold exactly the gradient of the single-GPU full-batch call.
+    (Under DDP, which AVERAGES parameter gradients over the ranks, scale the loss by the world size.)"""
+    sl = SplitLoss(criterion, pred_shard, target_shard, mask)
+    if sl.needs_max:
+        combine_partials(sl.stage_max(), 0, group)
+    combine_partials(sl.stage_sums(), 1, group)
+    return sl.finish()
