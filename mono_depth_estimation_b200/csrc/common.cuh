@@ -232,6 +232,36 @@ __device__ __forceinline__ void mbar_fence_init() {
 }
 #endif
 
+#ifdef __CUDACC__
+// Warp sum of N values per lane with N - 1 + log2(32 / N) shuffles instead of 5 N (the shuffle unit, not the issue
+// slots, is what 32 warps reducing a dozen sums each run into): at every halving step a lane keeps one half of its
+// values and sends the other half to the lane `mask` away; after log2(N) steps it holds ONE value summed over N lanes,
+// the remaining bits are a plain butterfly. Every lane returns the total of quantity (lane >> log2(32 / N)) & (N - 1).
+// N must be a power of two <= 32; v is clobbered.
+template <int N, typename T>
+__device__ __forceinline__ T warp_multi_sum(T (&v)[N]) {
+  static_assert(N >= 1 && N <= 32 && (N & (N - 1)) == 0, "N must be a power of two");
+  const int lane = threadIdx.x & 31;
+  int mask = 16;
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1) {
+    const bool up = (lane & mask) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const T send = up ? v[j] : v[j + half];
+      const T keep = up ? v[j + half] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+    mask >>= 1;
+  }
+  T r = v[0];
+#pragma unroll
+  for (int m = 16 / N; m >= 1; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+  return r;
+}
+
+#endif
+
 // ---- grid-wide sum of four doubles without a ticket ---------------------------------------------------
 // The ticket barrier above costs four dependent L2 round trips after the last CTA is ready (its atomics,
 // the fence, the ticket, the totals read, the broadcast). Here every CTA stores its four partial totals
@@ -313,27 +343,38 @@ __device__ __forceinline__ void grid_sum4_counted(unsigned long long* slots, uns
   const unsigned long long tag = static_cast<unsigned long long>(seq) << 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NT = NW * 32;
-  if (threadIdx.x < 4) {
-    double mine = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) mine += sm_own[threadIdx.x * NW + w];
-    const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine));
-    unsigned long long* w2 = slots + (static_cast<size_t>(blockIdx.x) * 4 + threadIdx.x) * 2;
-    st_relaxed_u64(w2, tag | (b >> 32));
-    st_relaxed_u64(w2 + 1, tag | (b & 0xffffffffull));
-  }
   if (threadIdx.x < 32) {
+    // this CTA's four totals from the per-warp partials: lane l takes warps l, l + 32, ...; one multi-sum over the warp
+    double v4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double x = 0.0;
+#pragma unroll
+      for (int w = lane; w < NW; w += 32) x += sm_own[q * NW + w];
+      v4[q] = x;
+    }
+    const double mine = warp_multi_sum<4>(v4);          // quantity (lane >> 3) & 3
+    if ((lane & 7) == 0) {
+      const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine));
+      unsigned long long* w2 = slots + (static_cast<size_t>(blockIdx.x) * 4 + (lane >> 3)) * 2;
+      st_relaxed_u64(w2, tag | (b >> 32));
+      st_relaxed_u64(w2 + 1, tag | (b & 0xffffffffull));
+    }
     __syncwarp();
     if (lane == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(arrivals) : "memory");
   }
   mid_fn();
-  if (threadIdx.x == 0) {
-    while (ld_relaxed_u32(arrivals) < gridDim.x) {}
+  const int n = static_cast<int>(gridDim.x) * 4;
+  if (n > NT) {   // more slots than threads (two CTAs per SM): wait for the counter, then gather in one pass
+    if (threadIdx.x == 0) {
+      while (ld_relaxed_u32(arrivals) < gridDim.x) {}
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  // (one CTA per SM: every thread owns at most one slot pair and simply spins on it below - the CTAs arrive within
+  // ~1 us of each other, so the polling is short, and leaving the barrier costs one L2 round trip less)
   // slot words of CTA c, quantity q: slots[(c * 4 + q) * 2 + {0, 1}]; thread t handles pairs i = t, t + NT, ...
   // (i & 3 == t & 3: one quantity per thread)
-  const int n = static_cast<int>(gridDim.x) * 4;
   constexpr int kIt = (kSlotCtas * 4 + NT - 1) / NT;
   unsigned long long hi[kIt], lo[kIt];
 #pragma unroll
@@ -361,13 +402,19 @@ __device__ __forceinline__ void grid_sum4_counted(unsigned long long* slots, uns
   for (int o = 16; o >= 4; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane < 4) sm_part[warp * 4 + lane] = acc;
   __syncthreads();
-  if (threadIdx.x < 4) {
-    double x = 0.0;
+  if (threadIdx.x < 32) {
+    double v4[4];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) x += sm_part[w * 4 + threadIdx.x];
-    sm_tot[threadIdx.x] = x;
+    for (int q = 0; q < 4; ++q) {
+      double x = 0.0;
+#pragma unroll
+      for (int w = lane; w < NW; w += 32) x += sm_part[w * 4 + q];
+      v4[q] = x;
+    }
+    const double tot = warp_multi_sum<4>(v4);
+    if ((lane & 7) == 0) sm_tot[lane >> 3] = tot;
   }
-  // the caller's thread 0 reads sm_tot after a __syncwarp (threads 0..3 are in its warp)
+  // the caller's thread 0 reads sm_tot after a __syncwarp (the writers are in its warp)
 }
 #endif
 

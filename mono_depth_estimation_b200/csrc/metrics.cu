@@ -23,45 +23,97 @@ constexpr int kNM = MDE_METRIC_NM;
 // until the flush (error <= ~4e-7 relative). LONG = true: every 16 iterations (128 pixels) the fp32
 // tile sums are folded into fp64 running sums that live in SHARED memory (one column per thread), so
 // the hot loop carries no fp64 registers and the software-pipelined loads fit without spilling.
+// Fast mode (Ref = false) uses the LEAN per-pixel form of metric_math.cuh (round 2): float threshold / valid
+// counters fed by FSET / FMUL.SAT + FADD, |p - t| = hi - lo, 11 ALU-pipe instructions per pixel instead of ~20.
+// G may carry kGrpRsq (only the 'rmse' sum of the REL group); the reference-arithmetic paths widen it to kGrpRel.
 template <unsigned G, bool Ref, bool LONG>
 struct MetricThread {
-  MetricTile tile;
-  MetricCounts cnt;
-  double* srun;   // LONG: &sm_run[0][threadIdx.x], element q at srun[q * kBlock]
+  static constexpr unsigned kRefG = (G & kGrpRsq) ? ((G & 7u) | kGrpRel) : (G & 7u);
+  MetricTile tile;     // Ref mode
+  MetricCounts cnt;    // Ref mode; in fast mode: the folded integer counts (n, c1, c2, c3)
+  MetricAcc acc;       // fast mode
+  int lean_px;         // pixels that went through the lean form since the last fold
+  double* srun;        // LONG: &sm_run[0][threadIdx.x], element q at srun[q * kBlock]
   int it;
 
   __device__ __forceinline__ void reset() {
     tile.zero();
     cnt.zero();
+    acc.zero();
+    lean_px = 0;
     it = 0;
     if constexpr (LONG) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) srun[q * kBlock] = 0.0;
     }
   }
+  // fast mode: float counters -> exact integer counts (callers keep < 2^24 pixels between two calls)
+  __device__ __forceinline__ void settle_counts() {
+    if constexpr (!Ref) {
+      const int nv = static_cast<int>(acc.nval), inv = lean_px - nv;   // invalid pixels are counted by all three float counters
+      cnt.n += nv;
+      cnt.c1 += static_cast<int>(acc.c1) - inv;
+      cnt.c2 += static_cast<int>(acc.c2) - inv;
+      cnt.c3 += static_cast<int>(acc.c3) - inv;
+      acc.c1 = acc.c2 = acc.c3 = acc.nval = 0.f;
+      lean_px = 0;
+    }
+  }
+  // rare path (fast mode): one pixel in reference arithmetic; sums in the lean units, exact counts straight into cnt
+  __device__ __forceinline__ void rare_px(float p, float t) {
+    const MetricContrib r = metric_px_ref_contrib<kRefG>(p, t);
+    acc.s_abs += r.s.s_abs; acc.s_sq += r.s.s_sq;
+    acc.s_log10 += r.s.s_log10 * (1.0f / tile_scale<false>(2));
+    acc.s_sle += r.s.s_sle * (1.0f / tile_scale<false>(3));
+    acc.s_absrel += r.s.s_absrel; acc.s_sqrel += r.s.s_sqrel; acc.s_rsq += r.s.s_rsq;
+    acc.s_lnsq += r.s.s_lnsq * (1.0f / tile_scale<false>(7));
+    cnt.n += r.c.n; cnt.c1 += r.c.c1; cnt.c2 += r.c.c2; cnt.c3 += r.c.c3;
+  }
   // scalar path: the rare-case test (valid subnormal target, see metric_quad_needs_ref) per pixel
   __device__ __forceinline__ void px(float p, float t) {
-    if (!Ref && t > 0.f && t < 1.17549435e-38f) metric_px_ref_into_fast<G>(p, t, tile, cnt);
-    else metric_px<G, Ref>(p, t, tile, cnt);
+    if constexpr (Ref) {
+      metric_px<kRefG, true>(p, t, tile, cnt);
+    } else {
+      if (t > 0.f && t < 1.17549435e-38f) {
+        rare_px(p, t);
+      } else {
+        metric_px_lean<G, false>(p, t, acc);
+        ++lean_px;
+      }
+    }
   }
   __device__ __forceinline__ void quad(const float4& p, const float4& t) {
-    if (!Ref && metric_quad_needs_ref(t)) {
-      metric_px_ref_into_fast<G>(p.x, t.x, tile, cnt);
-      metric_px_ref_into_fast<G>(p.y, t.y, tile, cnt);
-      metric_px_ref_into_fast<G>(p.z, t.z, tile, cnt);
-      metric_px_ref_into_fast<G>(p.w, t.w, tile, cnt);
+    if constexpr (Ref) {
+      metric_px<kRefG, true>(p.x, t.x, tile, cnt);
+      metric_px<kRefG, true>(p.y, t.y, tile, cnt);
+      metric_px<kRefG, true>(p.z, t.z, tile, cnt);
+      metric_px<kRefG, true>(p.w, t.w, tile, cnt);
+    } else if (metric_quad_needs_ref(t)) {
+      rare_px(p.x, t.x);
+      rare_px(p.y, t.y);
+      rare_px(p.z, t.z);
+      rare_px(p.w, t.w);
     } else {
-      metric_px<G, Ref>(p.x, t.x, tile, cnt);
-      metric_px<G, Ref>(p.y, t.y, tile, cnt);
-      metric_px<G, Ref>(p.z, t.z, tile, cnt);
-      metric_px<G, Ref>(p.w, t.w, tile, cnt);
+      metric_px_lean<G, false>(p.x, t.x, acc);
+      metric_px_lean<G, false>(p.y, t.y, acc);
+      metric_px_lean<G, false>(p.z, t.z, acc);
+      metric_px_lean<G, false>(p.w, t.w, acc);
+      lean_px += 4;
     }
+  }
+  static __device__ __forceinline__ bool used(int q) {
+    return (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
+           ((G & kGrpRel) && (q >= 4 && q <= 6)) || ((G & kGrpRsq) && q == 6);
   }
   // tile sum q in the unit of its raw quantity (the fast forms carry logarithms in log2 units)
   __device__ __forceinline__ float tile_q(int q) const {
-    const float s = (q == 0) ? tile.s_abs : (q == 1) ? tile.s_sq : (q == 2) ? tile.s_log10 : (q == 3) ? tile.s_sle
-                  : (q == 4) ? tile.s_absrel : (q == 5) ? tile.s_sqrel : (q == 6) ? tile.s_rsq : tile.s_lnsq;
-    return s * tile_scale<Ref>(q);
+    if constexpr (Ref) {
+      const float s = (q == 0) ? tile.s_abs : (q == 1) ? tile.s_sq : (q == 2) ? tile.s_log10 : (q == 3) ? tile.s_sle
+                    : (q == 4) ? tile.s_absrel : (q == 5) ? tile.s_sqrel : (q == 6) ? tile.s_rsq : tile.s_lnsq;
+      return s;
+    } else {
+      return acc.sum(q) * tile_scale<false>(q);
+    }
   }
   // value of running sum q at flush time
   __device__ __forceinline__ float total(int q) const {
@@ -79,12 +131,15 @@ struct MetricThread {
     if constexpr (!LONG) return;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
-                        ((G & kGrpRel) && (q >= 4 && q <= 6));
-      if (used) srun[q * kBlock] += static_cast<double>(tile_q(q));
+      if (used(q)) srun[q * kBlock] += static_cast<double>(tile_q(q));
     }
-    tile.zero();
-    cnt.unpack();
+    if constexpr (Ref) {
+      tile.zero();
+      cnt.unpack();
+    } else {
+      acc.s_abs = acc.s_sq = acc.s_log10 = acc.s_sle = acc.s_absrel = acc.s_sqrel = acc.s_rsq = acc.s_lnsq = 0.f;
+      settle_counts();
+    }
   }
 };
 
@@ -97,7 +152,8 @@ __constant__ int kRunToQ[8] = {MDE_Q_ABS, MDE_Q_SQ, MDE_Q_LOG10, MDE_Q_SLE,
 template <unsigned G, bool Ref, bool LONG>
 __device__ __forceinline__ void flush_image(MetricThread<G, Ref, LONG>& th, int64_t img, double* iacc, double* sm_d, int* sm_i) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  th.cnt.unpack();
+  if constexpr (Ref) th.cnt.unpack();
+  else th.settle_counts();
   const int c0 = __reduce_add_sync(0xffffffffu, th.cnt.n);
   const int c1 = __reduce_add_sync(0xffffffffu, th.cnt.c1);
   const int c2 = __reduce_add_sync(0xffffffffu, th.cnt.c2);
@@ -112,9 +168,7 @@ __device__ __forceinline__ void flush_image(MetricThread<G, Ref, LONG>& th, int6
   // widened again before the cross-warp and cross-CTA accumulation
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
-                      ((G & kGrpRel) && (q >= 4 && q <= 6));
-    if (!used) continue;
+    if (!(MetricThread<G, Ref, LONG>::used(q))) continue;
     const float s = warp_sum(th.total(q));
     if (lane == 0) sm_d[q * kWarps + warp] = static_cast<double>(s);
   }
@@ -129,9 +183,7 @@ __device__ __forceinline__ void flush_image(MetricThread<G, Ref, LONG>& th, int6
       qidx = threadIdx.x;  // MDE_Q_NVALID, D1, D2, D3
     } else {
       const int q = threadIdx.x - 4;
-      const bool used = (q < 2) || ((G & kGrpLog) && (q == 2 || q == 7)) || ((G & kGrpLog1p) && q == 3) ||
-                        ((G & kGrpRel) && (q >= 4 && q <= 6));
-      if (used)
+      if (MetricThread<G, Ref, LONG>::used(q))
         for (int w = 0; w < kWarps; ++w) tot += sm_d[q * kWarps + w];
       qidx = kRunToQ[q];
     }
@@ -353,11 +405,9 @@ metrics_resized_kernel(const float* __restrict__ pred, int ph, int pw, const flo
     const float* pimg = pred + img * static_cast<int64_t>(ph) * pw;
     const float* gimg = gt + img * static_cast<int64_t>(gh) * gw;
     th.reset();
-    int it = 0;
     for (int i = c0 + threadIdx.x; i < c1; i += kBlock) {
       const int oy = i / ow, ox = i - oy * ow;
       th.px(bilinear_tap(pimg, ph, pw, spy, spx, oy, ox), bilinear_tap(gimg, gh, gw, sgy, sgx, oy, ox));
-      if ((++it & 63) == 0) th.cnt.unpack();   // the packed level histogram holds 255 pixels
     }
     flush_image<G, false, false>(th, img, ws.iacc, sm_d, sm_i);
   }
@@ -405,7 +455,8 @@ int dispatch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t h
                      double* out_f64, float* out_f32, double* piv, double* pir, cudaStream_t st) {
   const bool ref = (flags & MDE_METRICS_REFERENCE_MATH) != 0;
   unsigned g = (flags >> 8) & kGrpMask;
-  if (g & kGrpRsq) g = (g & kGrpAll) | kGrpRel;   // 'rmse' alone: served by the REL group here
+  if ((g & kGrpRsq) && (g & kGrpRel)) g &= kGrpAll;                      // REL already covers the 'rmse' sum
+  if ((g & kGrpRsq) && g != (kGrpLog | kGrpRsq)) g = (g & kGrpAll) | kGrpRel;   // one lean instantiation: {log, rsq}
   if (g == 0) g = kGrpAll;
   const bool vec = (hw % 4 == 0) && aligned_to(pred, 4 * sizeof(PT)) && aligned_to(gt, 16);
 #define MDE_CASE(V, GG, R) return launch_metrics<PT, V, GG, R>(pred, gt, n_img, hw, ws, out_f64, out_f32, piv, pir, st)
@@ -421,6 +472,7 @@ int dispatch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t h
     case 4: MDE_CASE(4, 4u, false);
     case 5: MDE_CASE(4, 5u, false);
     case 6: MDE_CASE(4, 6u, false);
+    case 9: MDE_CASE(4, 9u, false);   // the reference's default train list: log10 + rmse (+ deltas, mse, mae)
     default: MDE_CASE(4, 7u, false);
   }
 #undef MDE_CASE

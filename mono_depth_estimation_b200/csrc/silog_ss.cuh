@@ -7,10 +7,22 @@ namespace mde {
 namespace {
 
 // ---- SILog (+ metric suite) with the residuals parked in SHARED memory between the phases ("SS") ----------
-// fp32, 128-bit aligned, gradient requested, <= kSsSlots tiles per CTA (C1, C2). Round-2 rewrite of the reduce
-// loop; the round-1 version (bulk copies by one producer thread, one mbarrier per slot, a CTA-wide
-// __syncthreads per 2048-px tile, dynamically claimed tiles) spent ~45 of its ~205 instructions per quad on
-// per-tile plumbing and kept only two tiles in flight per CTA. Now:
+// fp32, 128-bit aligned, gradient requested, <= kSsSlots tiles per CTA (C1, C2). What the reduce loop went through
+// (C2 fused SILog + 7 metrics, CUDA-event time per launch, measured on B200):
+//   round 1   22.6 us  bulk copies by one producer thread, one mbarrier per slot, a CTA-wide __syncthreads per 2048-px
+//                      tile, tiles claimed from a global counter: ~45 of ~205 instructions per quad were per-tile
+//                      plumbing and only two tiles were in flight per CTA;
+//   round 2a  20.0 us  thread-private cp.async pipeline, static interleaved tiles, lean per-pixel math (155 instructions
+//                      per quad), all-reduce with an arrival counter - still 2 CTAs x 512 threads per SM: the warp
+//                      scheduler serves the older CTA of an SM first, it finished its 8 tiles at 6.8 us while the
+//                      younger one had done ~1.5 and then ran alone until 10-11 us;
+//   round 2b  19.1 us  (this) ONE CTA of 1024 threads per SM: all 32 warps start together, 148 instead of 296 slots in
+//                      the all-reduce (every thread spins on at most one), ordered first requests, p and d of the last
+//                      kSsDepth tiles kept on chip for the gradient phase, shuffle-light warp reductions.
+//   (Measured and dropped: per-warp chunks claimed from a shared-memory counter - the claims and spills cost 30 % more
+//   instructions, 25.6 us; a rolled tile loop, 20.6 us; ring depth 2 / 3 / 5 instead of 4, within 0.5 us; an ordinary
+//   instead of a cooperative launch, same time; default instead of streaming stores, +0.4 us.)
+// Structure:
 //   * THREAD-PRIVATE pipeline: every thread copies its own quad of pred and target with cp.async (LDGSTS,
 //     16 B, no registers) kSsDepth tiles ahead and waits with cp.async.wait_group - no mbarrier, no CTA
 //     barrier, no producer thread; warps drift freely;
@@ -19,12 +31,19 @@ namespace {
 //   * the prediction quad lands directly in the slot that will hold its residuals (replaced in place),
 //     the target quad in a ring of kSsDepth tiles (recycled by the same thread right after its LDS);
 //   * per-pixel arithmetic in the lean form of metric_math.cuh (11 ALU-pipe instructions instead of ~20).
-// Gradient phase: the CTA's predictions come back through L2 into the (now free) target ring with cp.async
-// and into registers, requested BEFORE the all-reduce wait; afterwards it is d_i from shared memory,
-// arithmetic and streaming 128-bit stores. Shared memory: (kSsSlots + kSsDepth) x 8 KB = 104 KB per CTA.
+// Gradient phase: the residuals of a thread's LAST kSsDepth tiles went into the (by then free) ring slots instead of
+// over the predictions, so p and d of those tiles are both still in shared memory; the predictions of the earlier
+// tiles (<= 5 per thread) come back through L2 into registers, requested while the totals travel.
+// Shared memory: (kSsSlots + kSsDepth) x 16 KB = 208 KB for the one CTA of an SM.
+#ifndef MDE_SS_THREADS
+#define MDE_SS_THREADS 1024
+#endif
+constexpr int kSsThreads = MDE_SS_THREADS;           // 1024: ONE CTA per SM (512: two)
+constexpr int kSsWarps = kSsThreads / 32;
+constexpr int kSsCtasPerSm = 1024 / kSsThreads;
 constexpr int kSsSlots = 9;
 constexpr int kSsDepth = 4;
-constexpr size_t kSsBytes = static_cast<size_t>(kSsSlots + kSsDepth) * kBlock * sizeof(float4);
+constexpr size_t kSsBytes = static_cast<size_t>(kSsSlots + kSsDepth) * kSsThreads * sizeof(float4);
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -90,14 +109,14 @@ static __device__ __noinline__ void ss_rare_quad(const float4 p4, const float4 t
 }
 
 template <unsigned MG>
-__global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a) {
-  __shared__ double sm_d[(MG ? 12 : 4) * kWarps];
-  __shared__ double sm_own[4 * kWarps];
+__global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(LossArgs a) {
+  __shared__ double sm_d[(MG ? 12 : 4) * kSsWarps];
+  __shared__ double sm_own[4 * kSsWarps];
   __shared__ double sm_tot[4];
-  __shared__ double sm_gather[kWarps * 4];
+  __shared__ double sm_gather[kSsWarps * 4];
   __shared__ float sm_k[4];
   __shared__ unsigned sm_epoch;
-  extern __shared__ float4 sm_ss[];   // [kSsSlots][kBlock] residual slots, then [kSsDepth][kBlock] target ring
+  extern __shared__ float4 sm_ss[];   // [kSsSlots][kSsThreads] residual slots, then [kSsDepth][kSsThreads] target ring
   // metric groups evaluated in reference arithmetic on the rare path (kGrpRsq is a lean-form subset of kGrpRel)
   constexpr unsigned kRefG = (MG & kGrpRsq) ? ((MG & 7u) | kGrpRel) : (MG & 7u);
 
@@ -108,9 +127,9 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   const int G = static_cast<int>(gridDim.x), cta = static_cast<int>(blockIdx.x);
   const int nq = static_cast<int>(a.n >> 2);
   float4* slots = sm_ss;
-  float4* ring = sm_ss + kSsSlots * kBlock;
-  const int q0 = cta * kBlock + tid;                         // this thread's quad in tile k: q0 + k * qs
-  const int qs = G * kBlock;
+  float4* ring = sm_ss + kSsSlots * kSsThreads;
+  const int q0 = cta * kSsThreads + tid;                         // this thread's quad in tile k: q0 + k * qs
+  const int qs = G * kSsThreads;
   const int nst = (q0 < nq) ? (nq - 1 - q0) / qs + 1 : 0;    // quads of this thread (ns, or ns - 1 in a partial last tile)
 
   trace_point(0);
@@ -122,13 +141,17 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   if (tid == 0) epoch_reg = __ldcg(&ws.hdr->epoch);
   auto issue = [&](int k) {
     const size_t q = static_cast<size_t>(q0) + static_cast<size_t>(k) * static_cast<size_t>(qs);
-    cp_async16(&slots[k * kBlock + tid], pred + 4 * q);
-    cp_async16(&ring[(k % kSsDepth) * kBlock + tid], gt + 4 * q);
+    cp_async16(&slots[k * kSsThreads + tid], pred + 4 * q);
+    cp_async16(&ring[(k % kSsDepth) * kSsThreads + tid], gt + 4 * q);
   };
+  // The warp scheduler serves the warps in a fixed priority order, so without the two barriers the favoured warp would
+  // queue ALL its kSsDepth tiles before the last one has asked for its first: tile 0 of the whole CTA goes out first
+  // (its data is back ~1 us earlier for the late warps), then tile 1, then the rest.
 #pragma unroll
-  for (int k = 0; k < kSsDepth; ++k) {   // the first kSsDepth tiles are in flight before anything else happens
+  for (int k = 0; k < kSsDepth; ++k) {
     if (k < nst) issue(k);
     cp_async_commit();
+    if (k < 2) __syncthreads();
   }
 
   // ---------------- reduce phase ------------------------------------------------------------------------
@@ -185,7 +208,6 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   };
 #ifdef MDE_SS_TIMING
   long long tm_wait = 0, tm_comp = 0;   // cycles this warp spent waiting for its copies / evaluating its quads
-  trace_point(4);                       // (instrumented build) slot 4 = start of the reduce loop
 #endif
 #pragma unroll   // (a rolled loop with computed slot addresses was measured: 20.6 instead of 20.0 us)
   for (int k = 0; k < kSsSlots; ++k) {
@@ -197,11 +219,15 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
 #ifdef MDE_SS_TIMING
       const long long tm1 = clock64();
 #endif
-      const float4 p4 = slots[k * kBlock + tid];
-      const float4 t4 = ring[(k % kSsDepth) * kBlock + tid];
-      if (k + kSsDepth < nst) issue(k + kSsDepth);   // the ring slot just read is this thread's to refill
+      const float4 p4 = slots[k * kSsThreads + tid];
+      const float4 t4 = ring[(k % kSsDepth) * kSsThreads + tid];
+      const bool refill = k + kSsDepth < nst;
+      if (refill) issue(k + kSsDepth);   // the ring slot just read is this thread's to refill
       cp_async_commit();
-      slots[k * kBlock + tid] = quad(p4, t4);
+      // residuals: over the prediction while the ring slot is needed again; for the LAST kSsDepth tiles into the ring
+      // slot (free from here on), so that both p and d of those tiles are still in shared memory in the gradient phase
+      float4* dst = refill ? &slots[k * kSsThreads + tid] : &ring[(k % kSsDepth) * kSsThreads + tid];
+      *dst = quad(p4, t4);
 #ifdef MDE_SS_TIMING
       const long long tm2 = clock64();
       tm_wait += tm1 - tm0;
@@ -210,9 +236,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
     }
   }
 #ifdef MDE_SS_TIMING
-  if (g_mde_trace != nullptr && lane == 0 && warp == 0)
-    g_mde_trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 6] =
-        (static_cast<unsigned long long>(tm_wait) << 32) | static_cast<unsigned long long>(tm_comp & 0xffffffffll);
+  (void)tm_wait; (void)tm_comp;
 #endif
   cp_async_wait<0>();
   if (cta == G - 1) {   // n % 4 tail: summed here, its gradient is recomputed below
@@ -229,16 +253,15 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   trace_point(1);
   const int lean_px = 4 * lean_q;
   {
-    double run[4];
-    run[0] = static_cast<double>(s0);
-    run[1] = static_cast<double>(s1) + ((MG != 0) ? static_cast<double>(acc.s_lnsq) : 0.0);
-    run[2] = static_cast<double>(nx) + ((MG != 0) ? static_cast<double>(acc.n_valid(lean_px)) : 0.0);
-    run[3] = 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const double sq = warp_sum(run[q]);
-      if (lane == 0) sm_own[q * kWarps + warp] = sq;
-    }
+    // per-warp loss totals: one shuffle-light multi-sum in fp32 (a thread saw <= 36 pixels; the warp total of sum d and
+    // sum d^2 carries ~1e-7 relative rounding, the count is exact), widened to fp64 across warps and CTAs
+    float run[4];
+    run[0] = s0;
+    run[1] = s1 + ((MG != 0) ? acc.s_lnsq : 0.f);
+    run[2] = nx + ((MG != 0) ? static_cast<float>(acc.n_valid(lean_px)) : 0.f);
+    run[3] = 0.f;
+    const float tot = warp_multi_sum<4>(run);              // quantity (lane >> 3) & 3
+    if ((lane & 7) == 0) sm_own[(lane >> 3) * kSsWarps + warp] = static_cast<double>(tot);
     if (tid == 0) sm_epoch = epoch_reg;
     __syncthreads();
   }
@@ -250,8 +273,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   unsigned* ukey = ws.ukey + par * kUkey;
   if (cta == 0) {
     const int o = par ^ 1;
-    for (int i = tid; i < kGacc; i += kBlock) ws.gacc[o * kGacc + i] = 0.0;
-    for (int i = tid; i < kUkey; i += kBlock) ws.ukey[o * kUkey + i] = 0u;
+    for (int i = tid; i < kGacc; i += kSsThreads) ws.gacc[o * kGacc + i] = 0.0;
+    for (int i = tid; i < kUkey; i += kSsThreads) ws.ukey[o * kUkey + i] = 0u;
     if (tid == 0) {
       const unsigned dirty = __ldcg(&ws.hdr->dirty[o]);
       if (dirty) {
@@ -269,18 +292,22 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
       const int r0 = __reduce_add_sync(0xffffffffu, acc.n_valid(lean_px)), r1 = __reduce_add_sync(0xffffffffu, acc.count(1, lean_px));
       const int r2 = __reduce_add_sync(0xffffffffu, acc.count(2, lean_px)), r3 = __reduce_add_sync(0xffffffffu, acc.count(3, lean_px));
       if (lane == 0) {
-        sm_d[0 * kWarps + warp] = r0; sm_d[1 * kWarps + warp] = r1;
-        sm_d[2 * kWarps + warp] = r2; sm_d[3 * kWarps + warp] = r3;
+        sm_d[0 * kSsWarps + warp] = r0; sm_d[1 * kSsWarps + warp] = r1;
+        sm_d[2 * kSsWarps + warp] = r2; sm_d[3 * kSsWarps + warp] = r3;
       }
+      float v8[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float sq = warp_sum(acc.sum(q)) * tile_scale<false>(q);
-        if (lane == 0) sm_d[(4 + q) * kWarps + warp] = static_cast<double>(sq);
+      for (int q = 0; q < 8; ++q) v8[q] = acc.sum(q);
+      const float sq = warp_multi_sum<8>(v8);               // quantity (lane >> 2) & 7: 9 shuffles instead of 40
+      if ((lane & 3) == 0) {
+        const int q = lane >> 2;
+        const float sc = (q == 2) ? tile_scale<false>(2) : ((q == 3 || q == 7) ? tile_scale<false>(3) : 1.0f);
+        sm_d[(4 + q) * kSsWarps + warp] = static_cast<double>(sq * sc);
       }
       __syncthreads();
       if (tid < 12) {
         double tot = 0.0;
-        for (int w = 0; w < kWarps; ++w) tot += sm_d[tid * kWarps + w];
+        for (int w = 0; w < kSsWarps; ++w) tot += sm_d[tid * kSsWarps + w];
         const int qi = (tid < 4) ? tid : kTileToQ[tid - 4];
         if (tot != 0.0) atomicAdd(&gacc[kMetBase + qi], tot);
       }
@@ -289,26 +316,27 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   trace_point(2);
 
   // ---------------- all-reduce of the totals (grid_sum4_counted, common.cuh); every CTA derives the coefficients ----
-  constexpr int kRegTiles = kSsSlots - kSsDepth;   // gradient-phase predictions held in registers
+  constexpr int kRegTiles = kSsSlots - kSsDepth;   // gradient-phase predictions that are read again (through L2)
+  // The early tiles' predictions were overwritten by their residuals: request them again (L2 hits) while the totals
+  // travel - the gradient phase is bound by L2 bandwidth (20 MB of stores), so these reads are better out of its way.
   float4 preg[kRegTiles];
   auto prefetch_pred = [&] {
-    // slots 0 .. kSsDepth-1 -> the target ring (free now), the rest -> registers; all through L2
 #pragma unroll
-    for (int k = 0; k < kSsDepth; ++k) {
+    for (int k = 0; k < kRegTiles; ++k) {
       const size_t q = static_cast<size_t>(q0) + static_cast<size_t>(k) * static_cast<size_t>(qs);
-      if (k < nst) cp_async16(&ring[k * kBlock + tid], pred + 4 * q);
-    }
-    cp_async_commit();
-#pragma unroll
-    for (int k = kSsDepth; k < kSsSlots; ++k) {
-      const size_t q = static_cast<size_t>(q0) + static_cast<size_t>(k) * static_cast<size_t>(qs);
-      if (k < nst) preg[k - kSsDepth] = __ldcs(reinterpret_cast<const float4*>(pred + 4 * q));
+      if (k + kSsDepth < nst) preg[k] = __ldcs(reinterpret_cast<const float4*>(pred + 4 * q));
     }
   };
-  grid_sum4_counted<kWarps>(ws.slots, ukey + 2, epoch * 4u + 2u, sm_own, sm_gather, sm_tot, [&] {
+  grid_sum4_counted<kSsWarps>(ws.slots, ukey + 2, epoch * 4u + 2u, sm_own, sm_gather, sm_tot, [&] {
     if (grad != nullptr) prefetch_pred();
     flush_metrics();
+#ifdef MDE_SS_TIMING
+    trace_point(4);   // (instrumented build) slot 4 = this CTA starts waiting for the other CTAs' totals
+#endif
   });
+#ifdef MDE_SS_TIMING
+  trace_point(6);     // (instrumented build) slot 6 = totals gathered and reduced
+#endif
   if (tid < 32) __syncwarp();   // sm_tot was written by threads 0..3
   if (tid == 0) {
     // totals (log2 units) -> loss value and gradient coefficients
@@ -337,7 +365,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   if constexpr (MG != 0) {
     // arrival for the metric finaliser (end of the kernel), off everybody's critical path: the CTA's metric
     // atomics (flush_metrics) were issued before the __syncthreads above, so this fence orders them
-    if (tid == kBlock - 32) {
+    if (tid == kSsThreads - 32) {
       __threadfence();
       atomicAdd(ukey + 6, 1u);
     }
@@ -347,7 +375,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
   // of the LAST CTA at the very end of the kernel, when every CTA's arrival has long been counted
   auto finalize_metrics = [&] {
     if constexpr (MG != 0) {
-      if (cta == G - 1 && tid >= kBlock - 32) {
+      if (cta == G - 1 && tid >= kSsThreads - 32) {
         if (lane == 0) {   // the all-reduce above is no memory barrier: wait for every CTA's metric atomics
           while (*reinterpret_cast<volatile unsigned*>(ukey + 6) < gridDim.x) {}
           __threadfence();
@@ -385,22 +413,29 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
 #endif
 
   // ---------------- gradient phase: g_i = k (d_i - c) / p_i on the mask, 0 elsewhere -------------------------
-  const float ks1 = sm_k[2], ks2 = sm_k[3];
-  cp_async_wait<0>();
+  const float ks1 = sm_k[2], ks12 = -sm_k[2] * sm_k[3];   // g = (ks1 d - ks1 ks2) / p; MUFU.RCP alone: ~1 ulp, tolerance 1e-5
   auto gquad = [&](const float4& p, const float4& d) -> float4 {
     float4 g;
-    g.x = (__float_as_uint(d.x) != kStashInvalid) ? ks1 * (d.x - ks2) * rcp_nr(p.x) : 0.f;
-    g.y = (__float_as_uint(d.y) != kStashInvalid) ? ks1 * (d.y - ks2) * rcp_nr(p.y) : 0.f;
-    g.z = (__float_as_uint(d.z) != kStashInvalid) ? ks1 * (d.z - ks2) * rcp_nr(p.z) : 0.f;
-    g.w = (__float_as_uint(d.w) != kStashInvalid) ? ks1 * (d.w - ks2) * rcp_nr(p.w) : 0.f;
+    g.x = (__float_as_uint(d.x) != kStashInvalid) ? fmaf(d.x, ks1, ks12) * mufu_rcp(p.x) : 0.f;
+    g.y = (__float_as_uint(d.y) != kStashInvalid) ? fmaf(d.y, ks1, ks12) * mufu_rcp(p.y) : 0.f;
+    g.z = (__float_as_uint(d.z) != kStashInvalid) ? fmaf(d.z, ks1, ks12) * mufu_rcp(p.z) : 0.f;
+    g.w = (__float_as_uint(d.w) != kStashInvalid) ? fmaf(d.w, ks1, ks12) * mufu_rcp(p.w) : 0.f;
     return g;
   };
+  // the last kSsDepth tiles: p (slot) and d (ring) are both in shared memory
 #pragma unroll
   for (int k = 0; k < kSsSlots; ++k) {
-    if (k < nst) {
+    if (k < nst && k + kSsDepth >= nst) {
       const size_t q = static_cast<size_t>(q0) + static_cast<size_t>(k) * static_cast<size_t>(qs);
-      const float4 p = (k < kSsDepth) ? ring[(k < kSsDepth ? k : 0) * kBlock + tid] : preg[k < kSsDepth ? 0 : k - kSsDepth];
-      __stcs(reinterpret_cast<float4*>(grad + 4 * q), gquad(p, slots[k * kBlock + tid]));
+      __stcs(reinterpret_cast<float4*>(grad + 4 * q), gquad(slots[k * kSsThreads + tid], ring[(k % kSsDepth) * kSsThreads + tid]));
+    }
+  }
+  // the early tiles: d from the slot, p from the registers requested before the wait
+#pragma unroll
+  for (int k = 0; k < kRegTiles; ++k) {
+    if (k + kSsDepth < nst) {
+      const size_t q = static_cast<size_t>(q0) + static_cast<size_t>(k) * static_cast<size_t>(qs);
+      __stcs(reinterpret_cast<float4*>(grad + 4 * q), gquad(preg[k], slots[k * kSsThreads + tid]));
     }
   }
   if (cta == G - 1) {   // n % 4 tail, recomputed in natural-log units
@@ -420,17 +455,17 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) silog_ss_kernel(LossArgs a
 template <unsigned MG>
 int launch_loss_ss_mg(LossArgs& a, cudaStream_t st, bool& taken) {
   const void* fn = reinterpret_cast<const void*>(&silog_ss_kernel<MG>);
-  const int cap = coop_grid(fn, kBlock, kSsBytes);
+  const int cap = coop_grid(fn, kSsThreads, kSsBytes);
   if (cap <= 0) return MDE_OK;   // (e.g. the carve-out is not available) -> generic path
   const int64_t nq = a.n >> 2;
-  const int64_t nt = (nq + kBlock - 1) / kBlock;
+  const int64_t nt = (nq + kSsThreads - 1) / kSsThreads;
   int64_t grid = nt < cap ? nt : cap;
   if (grid < 1) grid = 1;
   if (nt > grid * kSsSlots) return MDE_OK;
   a.chunk = make_chunking(nq, 8, static_cast<int>(grid));
   void* args[] = {&a};
   // (an ordinary launch of the same grid was measured: 19.96 vs 20.01 us - the cooperative launch costs nothing)
-  MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, kSsBytes, st));
+  MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kSsThreads), args, kSsBytes, st));
   count_launch();
   taken = true;
   return MDE_OK;

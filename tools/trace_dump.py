@@ -37,7 +37,8 @@ for rep in range(4):
                 "end": [round((int(v) - t0) / 1e3, 2) for v in t[:, 5]], "b_start": [round((int(v) - t0) / 1e3, 2) for v in t[:, 4]],
                 "start": [round((int(v) - t0) / 1e3, 2) for v in t[:, 0]], "published": [round((int(v) - t0) / 1e3, 2) for v in t[:, 2]],
                 "bar_exit": [round((int(v) - t0) / 1e3, 2) for v in t[:, 3]],
-                "w0_wait_comp": [((int(v) >> 32) & 0xffffffff, int(v) & 0xffffffff) for v in t[:, 6]],
+                "gathered": [round((int(v) - t0) / 1e3, 2) for v in t[:, 6]],
+                "w0_wait_comp": [(0, 0) for v in t[:, 6]],
                 "w15_wait_comp": [((int(v) >> 32) & 0xffffffff, int(v) & 0xffffffff) for v in t[:, 4]]})
 _lib.check(lib.mde_debug_set_trace(None))
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "trace_dump_%s.json" % ("fused" if FUSED else "plain")), "w"))

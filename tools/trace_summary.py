@@ -21,7 +21,11 @@ for name in ('fused', 'plain'):
     print('%s: %d CTAs on %d SMs | start max %.2f | loop done A med %.2f B med %.2f max %.2f | published max %.2f | bar_exit min %.2f max %.2f | end min %.2f max %.2f'
           % (name, n, len(first), max(d['start']), med('a_done', A), med('a_done', B) if B else -1, max(d['a_done']), max(d['published']),
              min(d['bar_exit']), max(d['bar_exit']), min(d['end']), max(d['end'])))
-    if any(w for w, c in d['w0_wait_comp']):
+    if any(v > 0 for v in d['b_start']):
+        # instrumented build: slot 4 (b_start) = the CTA starts waiting for the totals, slot 6 = totals gathered and reduced
+        g6 = [((w << 32) | c) for w, c in d['w0_wait_comp']]
+        print('   wait starts: min %.2f max %.2f | gathered: min %.2f max %.2f' % (min(d['b_start']), max(d['b_start']), min(d.get('gathered', [0])), max(d.get('gathered', [0]))))
+    if False:
         for lab, idx in (('A', A), ('B', B)):
             if idx:
                 w = st.median([d['w0_wait_comp'][i][0] for i in idx]); c = st.median([d['w0_wait_comp'][i][1] for i in idx])
