@@ -33,6 +33,11 @@ void count_launch(int n = 1);
 int sm_count();
 // max co-resident CTAs for a cooperative launch of `func` (cached per function)
 int coop_grid(const void* func, int block, size_t smem);
+// Launch with programmatic dependent launch allowed (on unless MDE_PDL=0): the grid may be scheduled while the previous
+// kernel of the stream drains, so a kernel launched this way must execute griddepcontrol.wait (pdl_wait()) before its
+// first global-memory access; ~1 us of launch latency per call hides behind the predecessor. `cooperative` adds the
+// cooperative attribute. Falls back to the ordinary (cooperative) launch if the driver refuses the combination.
+cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t st, bool cooperative);
 
 #define MDE_CUDA_TRY(expr)                                                              \
   do {                                                                                  \
@@ -131,6 +136,13 @@ __device__ __forceinline__ int coop_prologue(const Ws& ws, unsigned& epoch_out) 
   }
   return par;
 }
+#endif
+
+#ifdef __CUDACC__
+// programmatic dependent launch: nothing a predecessor in the stream wrote may be read before pdl_wait(); pdl_trigger()
+// lets a dependent grid start filling the SMs this grid leaves (both are no-ops for ordinary launches)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 
 // ---- grid barrier that also broadcasts what everybody needs next -------------------------------------

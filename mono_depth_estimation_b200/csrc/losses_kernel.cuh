@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
   const uint8_t* __restrict__ mask = a.mask;
   PT* grad = static_cast<PT*>(a.grad);
 
+  pdl_wait();   // launched with launch_pdl: nothing a predecessor wrote may be read before this point
   trace_point(0);
   Ws ws = ws_view(a.ws);
   unsigned epoch;
@@ -735,6 +736,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) masked_loss_kernel(LossArg
     }, [&] { write_results(tt); });
   }
   trace_point(3);
+  pdl_trigger();
   const float k1 = sm_k[0], k2 = sm_k[1], k3 = sm_k[2];
 
   // pooled metric values (one mean over all valid pixels of the call, metrics.py:58-67), formed by the LAST
@@ -833,7 +835,7 @@ int launch_loss_l(LossArgs& a, cudaStream_t st) {
   if (grid < 1) grid = 1;
   a.chunk = make_chunking(units, VEC ? 8 : 32, static_cast<int>(grid));
   void* args[] = {&a};
-  MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, 0, st));
+  MDE_CUDA_TRY(launch_pdl(fn, dim3(static_cast<unsigned>(grid)), dim3(kBlock), args, 0, st, true));
   count_launch();
   return MDE_OK;
 }

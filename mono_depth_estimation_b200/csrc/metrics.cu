@@ -275,6 +275,7 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
   __shared__ int sm_i[4 * kWarps];
   __shared__ bool sm_last;
 
+  pdl_wait();   // launched with launch_pdl: nothing a predecessor wrote may be read before this point
   Ws ws = ws_view(ws_raw);
   double* iacc = ws.iacc;  // parity set 0: [n_img][kIacc]
 
@@ -432,10 +433,12 @@ int launch_metrics_l(const void* pred, const float* gt, int64_t n_img, int64_t h
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   const Chunking chunk = make_chunking(units, 32 / VEC, static_cast<int>(grid));
-  metrics_kernel<PT, VEC, G, Ref, LONG><<<static_cast<unsigned>(grid), kBlock, 0, st>>>(
-      static_cast<const PT*>(pred), gt, n_img, hw, chunk, ws, out_f64, out_f32, piv, pir);
+  const PT* pred_t = static_cast<const PT*>(pred);
+  Chunking chunk_v = chunk;
+  void* args[] = {&pred_t, &gt, &n_img, &hw, &chunk_v, &ws, &out_f64, &out_f32, &piv, &pir};
+  MDE_CUDA_TRY(launch_pdl(reinterpret_cast<const void*>(&metrics_kernel<PT, VEC, G, Ref, LONG>), dim3(static_cast<unsigned>(grid)),
+                          dim3(kBlock), args, 0, st, false));
   count_launch();
-  MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;
 }
 

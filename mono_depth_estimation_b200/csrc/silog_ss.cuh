@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(Loss
   const int qs = G * kSsThreads;
   const int nst = (q0 < nq) ? (nq - 1 - q0) / qs + 1 : 0;    // quads of this thread (ns, or ns - 1 in a partial last tile)
 
+  pdl_wait();   // launched with launch_pdl: nothing a predecessor wrote may be read before this point
   trace_point(0);
   // The launch parity (workspace epoch) is needed only after the reduce loop. Its load is issued FIRST: the L1
   // returns loads in issue order, so behind the prefetch burst below it would come back after ~128 KB of copies
@@ -371,6 +372,7 @@ __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(Loss
     }
   }
   trace_point(3);
+  pdl_trigger();   // a dependent launch may start filling the SMs this grid leaves
   // pooled metric values (one mean over all valid pixels of the call, metrics.py:58-67), formed by the LAST warp
   // of the LAST CTA at the very end of the kernel, when every CTA's arrival has long been counted
   auto finalize_metrics = [&] {
@@ -465,7 +467,7 @@ int launch_loss_ss_mg(LossArgs& a, cudaStream_t st, bool& taken) {
   a.chunk = make_chunking(nq, 8, static_cast<int>(grid));
   void* args[] = {&a};
   // (an ordinary launch of the same grid was measured: 19.96 vs 20.01 us - the cooperative launch costs nothing)
-  MDE_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(static_cast<unsigned>(grid)), dim3(kSsThreads), args, kSsBytes, st));
+  MDE_CUDA_TRY(launch_pdl(fn, dim3(static_cast<unsigned>(grid)), dim3(kSsThreads), args, kSsBytes, st, true));
   count_launch();
   taken = true;
   return MDE_OK;
