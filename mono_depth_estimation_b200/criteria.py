@@ -512,19 +512,24 @@ def normalize_prediction_robust(target, mask=None):
     default mask `target > 0` (the only one TrimmedProcrustesLoss uses). Evaluation-side function, detached result.
     [B,H,W] fp32 -> [B,H,W] fp32 (C ABI mde_robust_normalize with the tensor as its own mask source)."""
     lib = _lib.load()
-    dev = _lib.require_cuda(target)
-    if mask is not None:
-        raise NotImplementedError("normalize_prediction_robust: only the default mask (target > 0) is built")
+    dev = _lib.require_cuda(target, mask)
     n_img, h, w = _as_images(target)
     x = target.detach().to(torch.float32).contiguous()
+    # the kernel normalises its first tensor over the pixels where its SECOND tensor is > 0 (and the second over
+    # itself): the default mask is the tensor itself, an explicit 0/1 mask takes the second seat
+    if mask is None:
+        src = x
+    else:
+        assert mask.shape == target.shape, "inconsistent dimensions"
+        src = (mask.detach() != 0).to(torch.float32).contiguous()
     with torch.cuda.device(dev):
         st_a = torch.empty((n_img, 8), dtype=torch.float32, device=dev)
         st_b = torch.empty((n_img, 8), dtype=torch.float32, device=dev)
         out_a, out_b = torch.empty_like(x), torch.empty_like(x)
         scratch = torch.empty(int(lib.mde_robust_scratch_bytes(n_img)) // 8, dtype=torch.float64, device=dev)
-        _lib.check(lib.mde_robust_normalize(_lib.ptr(x), _lib.ptr(x), n_img, h * w, _lib.ptr(scratch), _lib.ptr(st_a), _lib.ptr(st_b),
+        _lib.check(lib.mde_robust_normalize(_lib.ptr(x), _lib.ptr(src), n_img, h * w, _lib.ptr(scratch), _lib.ptr(st_a), _lib.ptr(st_b),
                                             _lib.ptr(out_a), _lib.ptr(out_b), _lib.stream_ptr(dev)))
-    return out_b.view(target.shape)
+    return (out_b if mask is None else out_a).view(target.shape)
 
 
 class TrimmedProcrustesLoss(nn.Module):

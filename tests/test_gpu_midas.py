@@ -233,3 +233,22 @@ def test_midas_loss_quad_path_edges(Cr, shape):
         loss, grad = run_loss(Cr.MidasLoss(**kw), pred.cuda(), target.cuda())
         close(loss, l64.detach(), LOSS_RTOL, msg=str(kw))
         grad_close(grad, g64, msg=str(kw))
+
+
+def test_normalize_prediction_robust_explicit_mask(Cr):
+    """normalize_prediction_robust(target, mask) with an explicit 0/1 mask (reference criteria.py:135-152): per image
+    (x - median(mask * x)) / clamp(sum mask |x - median| / sum mask, 1e-6), the masked zeros taking part in the median."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand((3, 40, 56), generator=g) * 8 + 0.3
+    mask = (torch.rand((3, 40, 56), generator=g) < 0.6).float()
+    mask[2] = 0                                               # an image without a valid pixel: m = 0, s = 1
+    if True:
+        ssum = mask.sum((1, 2)); valid = ssum > 0
+        m = torch.zeros_like(ssum); s = torch.ones_like(ssum)
+        m[valid] = torch.median((mask[valid] * x[valid]).view(int(valid.sum()), -1), dim=1).values
+        t = x - m.view(-1, 1, 1)
+        sq = (mask * t.abs()).sum((1, 2))
+        s[valid] = torch.clamp(sq[valid] / ssum[valid], min=1e-6)
+        ref = t / s.view(-1, 1, 1)
+    out = Cr.normalize_prediction_robust(x.cuda(), mask.cuda())
+    close(out, ref, 1e-5, 1e-6)
