@@ -105,6 +105,44 @@ int mde_metrics(const void* pred, int pred_dtype, const float* target, int64_t n
                 unsigned flags, void* ws, double* out_f64, float* out_f32,
                 double* per_image_values, double* per_image_raw, void* stream);
 
+/*
+ * Multi-GPU evaluation in ONE launch per rank (BASELINE configs[4]: 654 images sharded over the GPUs of a
+ * box). The reference itself never combines metrics across ranks (metrics.py:19-39 logs without sync_dist; each rank of
+ * pl.Trainer(gpus=N), train.py:137, averages its own shard); the evaluation result over the whole set - mean over images
+ * of per-image means, metrics.py:35-41 + modules/base_module.py:71-76 - needs the ranks' {pooled raw sums, #valid
+ * images, per-image value sums} added up: 25 doubles per rank. mde_metrics_sharded is mde_metrics whose finaliser does
+ * that exchange itself over NVLink peer memory: it stores its 25 doubles into every peer's mailbox and adds the
+ * world's rows of its own mailbox in rank order (bit-identical totals on every rank), so out_f64 / out_f32 come back
+ * holding the values of the WHOLE sharded set; per_image_* stay local. No collective launch, no host involvement.
+ *
+ *   comm       nullptr: exactly mde_metrics. Otherwise a communicator of mde_peer_comm_create (a small DEVICE-resident
+ *              descriptor: the world's mailboxes as mapped into this process, rank, world, timeout).
+ *   mailboxes  MDE_PEER_MAILBOX_BYTES of device memory per rank, zeroed once (mde_peer_alloc), the own one included.
+ *              Rows are tagged with `seq` and double-buffered by its parity.
+ *   seq        the same on every rank for the same call, never 0, different from the previous call's (count up).
+ *   n_img == 0 is legal here (a rank without images still owes the world its row); pred / target may then be null.
+ *   A peer whose row does not arrive within the timeout (default 2000 ms) is given up on: NaN results and error flag 1
+ *   in the workspace header instead of a hung GPU.
+ * Every rank must make the matching call (same seq), as with any collective.
+ */
+#define MDE_MAX_PEERS 8
+#define MDE_PEER_MAILBOX_BYTES 8192
+#define MDE_PEER_HANDLE_BYTES 64
+int mde_metrics_sharded(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t hw,
+                        unsigned flags, void* ws, double* out_f64, float* out_f32,
+                        double* per_image_values, double* per_image_raw, const void* comm, unsigned seq, void* stream);
+int mde_peer_comm_create(void* const* mailboxes /* [world] */, int rank, int world, unsigned timeout_ms /* 0: 2000 */,
+                         void** comm_out);
+int mde_peer_comm_destroy(void* comm);
+/* Mailbox plumbing (one process per GPU): allocate + zero a block on the current device (synchronous), export its
+ * CUDA IPC handle (MDE_PEER_HANDLE_BYTES, to be handed to the other ranks by any means - torch.distributed's
+ * all_gather_object in distributed.PeerComm), map a peer's block into this process (enables peer access lazily). */
+int mde_peer_alloc(size_t bytes, void** ptr_out);
+int mde_peer_free(void* ptr);
+int mde_peer_export(void* ptr, unsigned char* handle_out);
+int mde_peer_open(const unsigned char* handle, void** ptr_out);
+int mde_peer_close(void* ptr);
+
 /* Finish metric values from raw sums on the HOST (used after an all-reduce of raw sums across
  * ranks): values[NM] from raw[NQ]. Pure arithmetic, no CUDA. */
 void mde_metrics_finalize_host(const double* raw, double* values);

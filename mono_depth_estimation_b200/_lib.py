@@ -28,6 +28,7 @@ METRIC_INDEX = {"delta1": 0, "delta2": 1, "delta3": 2, "mae": 3, "mse": 4, "log1
                 "absrel": 7, "sqrel": 8, "rmse": 9, "rmse_true": 10, "rmse_log": 11}
 METRIC_GROUP = {"log10": METRICS_NEED_LOG, "rmse_log": METRICS_NEED_LOG, "msle": METRICS_NEED_LOG1P,
                 "absrel": METRICS_NEED_REL, "sqrel": METRICS_NEED_REL, "rmse": METRICS_NEED_RSQ}
+MAX_PEERS, PEER_MAILBOX_BYTES, PEER_HANDLE_BYTES = 8, 8192, 64
 RAW_INDEX = {"n_valid": 0, "d1": 1, "d2": 2, "d3": 3, "abs": 4, "sq": 5, "log10": 6, "sle": 7,
              "absrel": 8, "sqrel": 9, "rsq": 10, "lnsq": 11}
 
@@ -43,6 +44,14 @@ _vp, _i64, _i32, _u32, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint, C.c_floa
 # name -> (restype, argtypes); every symbol include/mde_b200.h declares
 SIGNATURES = {
     "mde_metrics": (_i32, [_vp, _i32, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mde_metrics_sharded": (_i32, [_vp, _i32, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
+    "mde_peer_comm_create": (_i32, [C.POINTER(_vp), _i32, _i32, _u32, C.POINTER(_vp)]),
+    "mde_peer_comm_destroy": (_i32, [_vp]),
+    "mde_peer_alloc": (_i32, [C.c_size_t, C.POINTER(_vp)]),
+    "mde_peer_free": (_i32, [_vp]),
+    "mde_peer_export": (_i32, [_vp, C.c_char_p]),
+    "mde_peer_open": (_i32, [C.c_char_p, C.POINTER(_vp)]),
+    "mde_peer_close": (_i32, [_vp]),
     "mde_metrics_resized": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mde_metrics_finalize_host": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mde_masked_loss": (_i32, [_i32, _vp, _i32, _vp, _vp, _i64, _i64, _i64, C.POINTER(LossParams), _f32,

@@ -59,27 +59,93 @@ class _FusedLossFn(torch.autograd.Function):
     """Generic wrapper: `launch(pred, need_grad)` returns (loss 0-dim fp32, grad or None)."""
 
     @staticmethod
-    def forward(ctx, pred, launch):
+    def forward(ctx, pred, launch, flag=None):
         need_grad = ctx.needs_input_grad[0]
         loss, grad = launch(pred, need_grad)
         ctx.grad = grad
         ctx.pred_dtype = pred.dtype
         ctx.used = False
+        ctx.flag = flag
         return loss
 
     @staticmethod
     def backward(ctx, grad_output):
         if ctx.grad is None:
-            return None, None
+            return None, None, None
         if ctx.used:
             raise RuntimeError("the fused loss gradient was already consumed; run the forward again "
                                "(retain_graph is not supported by the fused forward+backward kernel)")
         ctx.used = True
-        g = _scale_grad(ctx.grad, grad_output)
+        # `loss.backward()` on the criterion's own result: the root gradient is autograd's implicit ones, known on the
+        # host (see _fused_apply) - the stashed gradient IS the answer, no launch
+        unit = ctx.flag is not None and ctx.flag.unit
+        g = ctx.grad if unit else _scale_grad(ctx.grad, grad_output)
         ctx.grad = None
         if g.dtype != ctx.pred_dtype:
             g = g.to(ctx.pred_dtype)          # fp32 stash of a half-precision prediction: one rounding, after the scale
-        return g, None
+        return g, None, None
+
+
+class _UnitFlag:
+    """Set while `loss.backward()` (no explicit gradient) runs on the tensor a fused criterion returned."""
+    __slots__ = ("unit",)
+
+    def __init__(self):
+        self.unit = False
+
+
+class FusedLoss(torch.Tensor):
+    """The 0-dim loss a fused criterion returns: a torch.Tensor whose `.backward()` tells the criterion's autograd node
+    that the root gradient is the implicit `ones_like(loss)`. Every operation on it returns a plain Tensor."""
+
+    __torch_function__ = torch._C._disabled_torch_function_impl
+
+    def backward(self, gradient=None, retain_graph=None, create_graph=False, inputs=None):
+        flag = self.__dict__.get("_mde_flag")
+        if flag is None:
+            return super().backward(gradient, retain_graph, create_graph, inputs=inputs)
+        flag.unit = gradient is None and not create_graph
+        if flag.unit:
+            # autograd would materialise `ones_like(loss)` with a fill launch per call; a persistent scalar 1 per device
+            # serves as the explicit root gradient instead (the value is never read: the flag says what it is)
+            gradient = _unit_gradient(self)
+        try:
+            return super().backward(gradient, retain_graph, create_graph, inputs=inputs)
+        finally:
+            flag.unit = False
+
+
+_UNIT_ONES = {}
+
+
+def _unit_gradient(loss):
+    key = (loss.device, loss.dtype)
+    one = _UNIT_ONES.get(key)
+    if one is None:
+        if loss.is_cuda and torch.cuda.is_current_stream_capturing():
+            return None                      # never allocate the shared scalar from a graph's private pool
+        one = torch.ones((), device=loss.device, dtype=loss.dtype)
+        _UNIT_ONES[key] = one
+    return one
+
+
+def _fused_apply(pred, launch):
+    """_FusedLossFn.apply + the host-side knowledge that saves the backward's launch in the common case.
+
+    The fused kernels store dloss/dpred in the forward launch; autograd's grad_output is a DEVICE scalar, so its value
+    is not known on the host and `mde_scale_inplace` has to be launched to apply it - even when it is the implicit
+    `ones_like(loss)` of a plain `loss.backward()` (reference modules/*.py training_step -> Lightning's backward).
+    That one case is recognisable without a device read: `.backward()` is called on the very tensor object returned
+    here, with `gradient=None`. The object is a FusedLoss (class swapped in place: same tensor, same autograd node) whose
+    `backward` raises a flag for the duration of the call; any other route (`(2 * loss).backward()`,
+    `torch.autograd.backward`, GradScaler's scaled copy, an explicit gradient) never touches the flag and takes the
+    scaling launch as before."""
+    flag = _UnitFlag()
+    loss = _FusedLossFn.apply(pred, launch, flag)
+    if loss.requires_grad and type(loss) is torch.Tensor:
+        loss.__class__ = FusedLoss
+        loss._mde_flag = flag
+    return loss
 
 
 def _as_images(pred):
@@ -165,7 +231,7 @@ def masked_loss(kind, pred, target, mask=None, params=None, totals=False, metric
 
     if pred.numel() == 0:
         return torch.full((), float("nan"), device=dev) + 0 * pred.sum()
-    loss = _FusedLossFn.apply(pred, launch)
+    loss = _fused_apply(pred, launch)
     return (loss, tot) if totals else loss
 
 
@@ -270,7 +336,7 @@ class ordLoss(nn.Module):
                                             _lib.ptr(loss), _lib.ptr(grad), _lib.stream_ptr(dev)))
             return loss, grad      # fp32 stash; rounded to p.dtype after the scale (_FusedLossFn.backward)
 
-        self.loss = _FusedLossFn.apply(ord_labels, launch)
+        self.loss = _fused_apply(ord_labels, launch)
         return self.loss
 
 
@@ -307,7 +373,7 @@ class OrdinalRegressionLoss(object):
                                                            _lib.stream_ptr(dev)))
             return loss, grad      # fp32 stash; rounded to p.dtype after the scale (_FusedLossFn.backward)
 
-        return _FusedLossFn.apply(prob, launch)
+        return _fused_apply(prob, launch)
 
 
 # ---- VNL ---------------------------------------------------------------------------------------------------
@@ -386,7 +452,7 @@ class VNL_Loss(nn.Module):
                                             _lib.ptr(loss), _lib.ptr(stats), _lib.ptr(grad), _lib.stream_ptr(dev)))
             return loss, grad
 
-        loss = _FusedLossFn.apply(pred_depth, launch)
+        loss = _fused_apply(pred_depth, launch)
         self.last_stats = stats
         return loss
 
@@ -504,7 +570,7 @@ class MidasLoss(nn.Module):
                                                           _lib.ptr(sums), B, H * W, _lib.ptr(ws), _lib.ptr(coef), _lib.ptr(grad), sp))
             return loss, grad      # fp32 stash; _FusedLossFn.backward scales it and rounds to the prediction dtype once
 
-        return _FusedLossFn.apply(prediction, launch)
+        return _fused_apply(prediction, launch)
 
 
 def normalize_prediction_robust(target, mask=None):
@@ -586,7 +652,7 @@ class TrimmedProcrustesLoss(nn.Module):
             self._prediction_ssi = pn
             return loss, grad      # fp32 stash; _FusedLossFn.backward scales it and rounds to the prediction dtype once
 
-        return _FusedLossFn.apply(prediction, launch)
+        return _fused_apply(prediction, launch)
 
 
 class ModelLoss(nn.Module):

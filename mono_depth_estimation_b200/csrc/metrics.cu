@@ -10,6 +10,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include <cstring>
 #include "metric_math.cuh"
 
 namespace mde {
@@ -200,9 +201,71 @@ __constant__ int kValNum[kNM] = {MDE_Q_D1, MDE_Q_D2, MDE_Q_D3, MDE_Q_ABS, MDE_Q_
 // so an image costs one coalesced L2 read, two shuffles and one fp64 divide per lane; warps stride
 // over the images, then one shared-memory pass combines the warps. Also re-zeroes the per-image
 // accumulators so the workspace is clean for the next call.
+// ---- in-kernel exchange of the evaluation sums over NVLink peer memory -------------------------------
+// A multi-GPU evaluation shards the images over the ranks and needs ONE sum of 25 doubles per rank (pooled raw sums,
+// number of valid images, sum of per-image values). Instead of a collective launched behind the kernel, the finaliser
+// of every rank's launch WRITES its 25 doubles straight into every peer's mailbox (peer-mapped device memory, stores
+// over NVLink) and sums the world's rows of its own mailbox in rank order - the same order on every rank, so all ranks
+// end with bit-identical totals. Every double travels as two self-validating words {seq:32 | half:32}: no flag, no
+// fence, no ordering requirement between the stores. Rows are double-buffered by the parity of seq (a rank can be at
+// most one call ahead of a peer that has not yet read its previous row). A peer that never shows up is given up on
+// after timeout_ms (NaN results + the workspace error flag) instead of hanging the GPU.
+struct PeerDesc {                                 // lives in DEVICE memory (mde_peer_comm_create): the kernels take a pointer
+  unsigned long long* mailbox[MDE_MAX_PEERS];   // [r] = rank r's mailbox as mapped into THIS process
+  int rank, world;
+  unsigned timeout_ms, pad;
+};
+struct PeerXchg {                                 // what the finaliser works with (registers / constant bank)
+  const PeerDesc* d;
+  int rank, world;
+  unsigned seq;
+};
+constexpr int kPeerRowWords = 64;                 // 25 doubles x 2 words, padded
+constexpr int kPeerVals = 2 * kNM + 1;
+static_assert(2 * kPeerVals <= kPeerRowWords, "mailbox row too small");
+static_assert(static_cast<size_t>(2) * MDE_MAX_PEERS * kPeerRowWords * 8 == MDE_PEER_MAILBOX_BYTES, "mailbox size");
+
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_put(const PeerXchg& px, int idx, double v) {
+  const unsigned long long tag = static_cast<unsigned long long>(px.seq) << 32;
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+  const size_t off = (static_cast<size_t>(px.seq & 1u) * MDE_MAX_PEERS + px.rank) * kPeerRowWords + 2 * idx;
+  for (int r = 0; r < px.world; ++r) {
+    unsigned long long* box = px.d->mailbox[r];
+    st_relaxed_sys_u64(box + off, tag | (b >> 32));
+    st_relaxed_sys_u64(box + off + 1, tag | (b & 0xffffffffull));
+  }
+}
+// sum over the ranks (in rank order) of value `idx`; false when a peer's row did not arrive in time
+__device__ __forceinline__ bool peer_get(const PeerXchg& px, int idx, unsigned long long t_give_up, double& out) {
+  const unsigned long long* mine = px.d->mailbox[px.rank] + static_cast<size_t>(px.seq & 1u) * MDE_MAX_PEERS * kPeerRowWords + 2 * idx;
+  double acc = 0.0;
+  for (int s = 0; s < px.world; ++s) {
+    const unsigned long long* w = mine + static_cast<size_t>(s) * kPeerRowWords;
+    unsigned long long hi = ld_relaxed_sys_u64(w), lo = ld_relaxed_sys_u64(w + 1);
+    while ((hi >> 32) != px.seq || (lo >> 32) != px.seq) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now > t_give_up) return false;
+      hi = ld_relaxed_sys_u64(w);
+      lo = ld_relaxed_sys_u64(w + 1);
+    }
+    acc += __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffull)));
+  }
+  out = acc;
+  return true;
+}
+
 __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __restrict__ out_f64,
                                               float* __restrict__ out_f32, double* __restrict__ per_image_values,
-                                              double* __restrict__ per_image_raw, double* sm_d) {
+                                              double* __restrict__ per_image_raw, double* sm_d, const PeerDesc* pd, unsigned seq) {
   double* iacc = ws.iacc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool own = lane < kNM;  // kNM == kNQ == 12
@@ -244,6 +307,28 @@ __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __re
       }
     }
     for (int w = 0; w < kWarps; ++w) N += sm_d[2 * kWarps * kNM + w];
+    if (pd != nullptr) {   // this rank's {P, N, V} -> every peer's mailbox; the world's rows of the own mailbox -> {P, N, V}
+      PeerXchg px;
+      px.d = pd; px.rank = pd->rank; px.world = pd->world; px.seq = seq;
+      if (own) {
+        peer_put(px, lane, P);
+        peer_put(px, kNM + 1 + lane, V);
+      }
+      if (lane == 0) peer_put(px, kNM, N);
+      unsigned long long t_give_up;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_give_up));
+      t_give_up += static_cast<unsigned long long>(pd->timeout_ms) * 1000000ull;
+      bool ok = true;
+      if (own) ok = peer_get(px, lane, t_give_up, P) && peer_get(px, kNM + 1 + lane, t_give_up, V);
+      double n_all = N;
+      if (lane == 0) ok = peer_get(px, kNM, t_give_up, n_all) && ok;
+      N = __shfl_sync(0xffffffffu, n_all, 0);
+      if (!__all_sync(0xffffffffu, ok)) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        P = V = N = nan;
+        if (lane == 0) ws.hdr->error = 1u;
+      }
+    }
     const double n = __shfl_sync(0xffffffffu, P, MDE_Q_NVALID);
     const double num = __shfl_sync(0xffffffffu, P, num_idx);
     double val = num / n;
@@ -270,7 +355,8 @@ template <typename PT, int VEC, unsigned G, bool Ref, bool LONG>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm)
 metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_t n_img, int64_t hw, Chunking chunk,
                void* ws_raw, double* __restrict__ out_f64, float* __restrict__ out_f32,
-               double* __restrict__ per_image_values, double* __restrict__ per_image_raw) {
+               double* __restrict__ per_image_values, double* __restrict__ per_image_raw, const PeerDesc* __restrict__ pd,
+               unsigned seq) {
   __shared__ double sm_d[2 * kNM * kWarps + kWarps];
   __shared__ int sm_i[4 * kWarps];
   __shared__ bool sm_last;
@@ -361,7 +447,15 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
   if (!sm_last) return;
   __threadfence();
 
-  metrics_finalize(ws, n_img, out_f64, out_f32, per_image_values, per_image_raw, sm_d);
+  metrics_finalize(ws, n_img, out_f64, out_f32, per_image_values, per_image_raw, sm_d, pd, seq);
+}
+
+// a rank without images (fewer images than ranks) still owes the world its (all-zero) row
+__global__ void __launch_bounds__(kBlock) metrics_empty_shard_kernel(void* ws_raw, double* __restrict__ out_f64, float* __restrict__ out_f32,
+                                                                      const PeerDesc* __restrict__ pd, unsigned seq) {
+  __shared__ double sm_d[2 * kNM * kWarps + kWarps];
+  pdl_wait();
+  metrics_finalize(ws_view(ws_raw), 0, out_f64, out_f32, nullptr, nullptr, sm_d, pd, seq);
 }
 
 // ---- metrics on bilinearly resized inputs -----------------------------------------------
@@ -420,12 +514,12 @@ metrics_resized_kernel(const float* __restrict__ pred, int ph, int pw, const flo
   __syncthreads();
   if (!sm_last) return;
   __threadfence();
-  metrics_finalize(ws, n_img, out_f64, out_f32, per_image_values, per_image_raw, sm_d);
+  metrics_finalize(ws, n_img, out_f64, out_f32, per_image_values, per_image_raw, sm_d, nullptr, 0u);
 }
 
 template <typename PT, int VEC, unsigned G, bool Ref, bool LONG>
 int launch_metrics_l(const void* pred, const float* gt, int64_t n_img, int64_t hw, void* ws, double* out_f64,
-                   float* out_f32, double* piv, double* pir, cudaStream_t st) {
+                   float* out_f32, double* piv, double* pir, cudaStream_t st, const PeerDesc* pd, unsigned seq) {
   const int64_t units = n_img * (hw / VEC);
   const int64_t per_cta_min = static_cast<int64_t>(kBlock);  // at least one unit per thread
   int64_t grid = (units + per_cta_min - 1) / per_cta_min;
@@ -435,7 +529,7 @@ int launch_metrics_l(const void* pred, const float* gt, int64_t n_img, int64_t h
   const Chunking chunk = make_chunking(units, 32 / VEC, static_cast<int>(grid));
   const PT* pred_t = static_cast<const PT*>(pred);
   Chunking chunk_v = chunk;
-  void* args[] = {&pred_t, &gt, &n_img, &hw, &chunk_v, &ws, &out_f64, &out_f32, &piv, &pir};
+  void* args[] = {&pred_t, &gt, &n_img, &hw, &chunk_v, &ws, &out_f64, &out_f32, &piv, &pir, &pd, &seq};
   MDE_CUDA_TRY(launch_pdl(reinterpret_cast<const void*>(&metrics_kernel<PT, VEC, G, Ref, LONG>), dim3(static_cast<unsigned>(grid)),
                           dim3(kBlock), args, 0, st, false));
   count_launch();
@@ -444,25 +538,25 @@ int launch_metrics_l(const void* pred, const float* gt, int64_t n_img, int64_t h
 
 template <typename PT, int VEC, unsigned G, bool Ref>
 int launch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t hw, void* ws, double* out_f64,
-                   float* out_f32, double* piv, double* pir, cudaStream_t st) {
+                   float* out_f32, double* piv, double* pir, cudaStream_t st, const PeerDesc* pd, unsigned seq) {
   // pixels one thread sees of one image: the whole batch is spread over <= 2 CTAs per SM
-  const int64_t px = n_img * hw;
+  const int64_t npx = n_img * hw;
   const int64_t threads = static_cast<int64_t>(sm_count()) * kCtasPerSm * kBlock;
-  const bool is_long = (px + threads - 1) / threads > 96;
-  if (is_long) return launch_metrics_l<PT, VEC, G, Ref, true>(pred, gt, n_img, hw, ws, out_f64, out_f32, piv, pir, st);
-  return launch_metrics_l<PT, VEC, G, Ref, false>(pred, gt, n_img, hw, ws, out_f64, out_f32, piv, pir, st);
+  const bool is_long = (npx + threads - 1) / threads > 96;
+  if (is_long) return launch_metrics_l<PT, VEC, G, Ref, true>(pred, gt, n_img, hw, ws, out_f64, out_f32, piv, pir, st, pd, seq);
+  return launch_metrics_l<PT, VEC, G, Ref, false>(pred, gt, n_img, hw, ws, out_f64, out_f32, piv, pir, st, pd, seq);
 }
 
 template <typename PT>
 int dispatch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t hw, unsigned flags, void* ws,
-                     double* out_f64, float* out_f32, double* piv, double* pir, cudaStream_t st) {
+                     double* out_f64, float* out_f32, double* piv, double* pir, cudaStream_t st, const PeerDesc* pd, unsigned seq) {
   const bool ref = (flags & MDE_METRICS_REFERENCE_MATH) != 0;
   unsigned g = (flags >> 8) & kGrpMask;
   if ((g & kGrpRsq) && (g & kGrpRel)) g &= kGrpAll;                      // REL already covers the 'rmse' sum
   if ((g & kGrpRsq) && g != (kGrpLog | kGrpRsq)) g = (g & kGrpAll) | kGrpRel;   // one lean instantiation: {log, rsq}
   if (g == 0) g = kGrpAll;
   const bool vec = (hw % 4 == 0) && aligned_to(pred, 4 * sizeof(PT)) && aligned_to(gt, 16);
-#define MDE_CASE(V, GG, R) return launch_metrics<PT, V, GG, R>(pred, gt, n_img, hw, ws, out_f64, out_f32, piv, pir, st)
+#define MDE_CASE(V, GG, R) return launch_metrics<PT, V, GG, R>(pred, gt, n_img, hw, ws, out_f64, out_f32, piv, pir, st, pd, seq)
   if (!vec) {  // odd image sizes: scalar (still coalesced) path, all groups
     if (ref) MDE_CASE(1, kGrpAll, true);
     MDE_CASE(1, kGrpAll, false);
@@ -484,28 +578,110 @@ int dispatch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t h
 }  // namespace
 }  // namespace mde
 
-extern "C" int mde_metrics(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t hw,
-                           unsigned flags, void* ws, double* out_f64, float* out_f32, double* per_image_values,
-                           double* per_image_raw, void* stream) {
+extern "C" int mde_metrics_sharded(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t hw,
+                                   unsigned flags, void* ws, double* out_f64, float* out_f32, double* per_image_values,
+                                   double* per_image_raw, const void* comm, unsigned seq, void* stream) {
   using namespace mde;
-  MDE_REQUIRE(pred && target && ws && out_f64, MDE_EINVAL, "null pointer");
-  MDE_REQUIRE(n_img > 0 && hw > 0, MDE_EINVAL, "empty input");
-  MDE_REQUIRE(aligned_to(target, 4) && aligned_to(out_f64, 8), MDE_EALIGN, "misaligned pointer");
+  MDE_REQUIRE(ws && out_f64, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(aligned_to(out_f64, 8), MDE_EALIGN, "misaligned pointer");
+  const PeerDesc* pd = static_cast<const PeerDesc*>(comm);
+  if (pd != nullptr) MDE_REQUIRE(seq != 0u, MDE_EINVAL, "peer sequence numbers start at 1 (0 is the mailbox's initial tag)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_img == 0) {   // an empty shard: legal only as a member of an exchange
+    MDE_REQUIRE(pd != nullptr, MDE_EINVAL, "empty input");
+    void* args[] = {&ws, &out_f64, &out_f32, &pd, &seq};
+    MDE_CUDA_TRY(launch_pdl(reinterpret_cast<const void*>(&metrics_empty_shard_kernel), dim3(1), dim3(kBlock), args, 0, st, false));
+    count_launch();
+    return MDE_OK;
+  }
+  MDE_REQUIRE(pred && target, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(n_img > 0 && hw > 0, MDE_EINVAL, "empty input");
+  MDE_REQUIRE(aligned_to(target, 4), MDE_EALIGN, "misaligned pointer");
   switch (pred_dtype) {
     case MDE_F32:
       return dispatch_metrics<float>(pred, target, n_img, hw, flags, ws, out_f64, out_f32, per_image_values,
-                                     per_image_raw, st);
+                                     per_image_raw, st, pd, seq);
     case MDE_F16:
       return dispatch_metrics<__half>(pred, target, n_img, hw, flags, ws, out_f64, out_f32, per_image_values,
-                                      per_image_raw, st);
+                                      per_image_raw, st, pd, seq);
     case MDE_BF16:
       return dispatch_metrics<__nv_bfloat16>(pred, target, n_img, hw, flags, ws, out_f64, out_f32,
-                                             per_image_values, per_image_raw, st);
+                                             per_image_values, per_image_raw, st, pd, seq);
     default:
       set_error("mde_metrics: unknown pred_dtype %d", pred_dtype);
       return MDE_EINVAL;
   }
+}
+
+extern "C" int mde_metrics(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t hw,
+                           unsigned flags, void* ws, double* out_f64, float* out_f32, double* per_image_values,
+                           double* per_image_raw, void* stream) {
+  using namespace mde;
+  MDE_REQUIRE(n_img > 0 && hw > 0, MDE_EINVAL, "empty input");
+  return mde_metrics_sharded(pred, pred_dtype, target, n_img, hw, flags, ws, out_f64, out_f32, per_image_values,
+                             per_image_raw, nullptr, 0u, stream);
+}
+
+// ---- peer-mapped mailboxes (one per rank; cudaMalloc'ed here so that the IPC handle covers exactly this block) ---------
+extern "C" int mde_peer_alloc(size_t bytes, void** ptr_out) {
+  using namespace mde;
+  MDE_REQUIRE(ptr_out && bytes > 0, MDE_EINVAL, "null pointer");
+  void* p = nullptr;
+  MDE_CUDA_TRY(cudaMalloc(&p, bytes));
+  MDE_CUDA_TRY(cudaMemset(p, 0, bytes));
+  MDE_CUDA_TRY(cudaDeviceSynchronize());
+  *ptr_out = p;
+  return MDE_OK;
+}
+extern "C" int mde_peer_free(void* ptr) {
+  using namespace mde;
+  MDE_CUDA_TRY(cudaFree(ptr));
+  return MDE_OK;
+}
+extern "C" int mde_peer_export(void* ptr, unsigned char* handle_out) {
+  using namespace mde;
+  static_assert(sizeof(cudaIpcMemHandle_t) == MDE_PEER_HANDLE_BYTES, "IPC handle size");
+  MDE_REQUIRE(ptr && handle_out, MDE_EINVAL, "null pointer");
+  cudaIpcMemHandle_t h;
+  MDE_CUDA_TRY(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle_out, &h, sizeof(h));
+  return MDE_OK;
+}
+extern "C" int mde_peer_open(const unsigned char* handle, void** ptr_out) {
+  using namespace mde;
+  MDE_REQUIRE(handle && ptr_out, MDE_EINVAL, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  MDE_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_out = p;
+  return MDE_OK;
+}
+extern "C" int mde_peer_comm_create(void* const* mailboxes, int rank, int world, unsigned timeout_ms, void** comm_out) {
+  using namespace mde;
+  MDE_REQUIRE(mailboxes && comm_out, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(world >= 1 && world <= MDE_MAX_PEERS && rank >= 0 && rank < world, MDE_EINVAL, "bad rank / world (one box: <= 8 peers)");
+  PeerDesc h{};
+  for (int r = 0; r < world; ++r) {
+    MDE_REQUIRE(mailboxes[r] != nullptr && aligned_to(mailboxes[r], 8), MDE_EINVAL, "null / misaligned peer mailbox");
+    h.mailbox[r] = static_cast<unsigned long long*>(mailboxes[r]);
+  }
+  h.rank = rank; h.world = world; h.timeout_ms = timeout_ms ? timeout_ms : 2000u;
+  void* d = nullptr;
+  MDE_CUDA_TRY(cudaMalloc(&d, sizeof(PeerDesc)));
+  MDE_CUDA_TRY(cudaMemcpy(d, &h, sizeof(PeerDesc), cudaMemcpyHostToDevice));
+  *comm_out = d;
+  return MDE_OK;
+}
+extern "C" int mde_peer_comm_destroy(void* comm) {
+  using namespace mde;
+  MDE_CUDA_TRY(cudaFree(comm));
+  return MDE_OK;
+}
+extern "C" int mde_peer_close(void* ptr) {
+  using namespace mde;
+  MDE_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return MDE_OK;
 }
 
 extern "C" void mde_metrics_finalize_host(const double* raw, double* values) { mde::metric_values(raw, values); }

@@ -108,6 +108,24 @@ static __device__ __noinline__ void ss_rare_quad(const float4 p4, const float4 t
   d_out = make_float4(dv[0], dv[1], dv[2], dv[3]);
 }
 
+// Phase trace. Product build: common.cuh's trace_point (thread 0 stamps global memory when the trace is armed).
+// Instrumented twin (-DMDE_SS_TIMING, tools/libmde_dbg.so): the stamps are parked in shared memory and written out by
+// the LAST warp of the CTA to leave, slot 5 being the latest exit over ALL warps, into the half of the buffer selected by
+// the launch parity - two consecutive launches are read back together, which shows the launch-to-launch period and the
+// gap between one grid's last exit and the next grid's first CTA (buffer: 2 x 296 x kTraceSlots words).
+#ifdef MDE_SS_TIMING
+#define SS_TP(k)                                                              \
+  do {                                                                        \
+    if ((k) != 5 && threadIdx.x == 0) {                                       \
+      unsigned long long ns_;                                                 \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_));                 \
+      sm_trace[k] = ns_;                                                      \
+    }                                                                         \
+  } while (0)
+#else
+#define SS_TP(k) trace_point(k)
+#endif
+
 template <unsigned MG>
 __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(LossArgs a) {
   __shared__ double sm_d[(MG ? 12 : 4) * kSsWarps];
@@ -116,6 +134,17 @@ __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(Loss
   __shared__ double sm_gather[kSsWarps * 4];
   __shared__ float sm_k[4];
   __shared__ unsigned sm_epoch;
+#ifdef MDE_SS_TIMING
+  __shared__ unsigned long long sm_trace[kTraceSlots];
+  __shared__ unsigned sm_tcnt;
+  if (threadIdx.x == 0) {
+    sm_tcnt = 0u;
+    sm_trace[5] = 0ull;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    sm_trace[7] = smid;
+  }
+#endif
   extern __shared__ float4 sm_ss[];   // [kSsSlots][kSsThreads] residual slots, then [kSsDepth][kSsThreads] target ring
   // metric groups evaluated in reference arithmetic on the rare path (kGrpRsq is a lean-form subset of kGrpRel)
   constexpr unsigned kRefG = (MG & kGrpRsq) ? ((MG & 7u) | kGrpRel) : (MG & 7u);
@@ -133,7 +162,7 @@ __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(Loss
   const int nst = (q0 < nq) ? (nq - 1 - q0) / qs + 1 : 0;    // quads of this thread (ns, or ns - 1 in a partial last tile)
 
   pdl_wait();   // launched with launch_pdl: nothing a predecessor wrote may be read before this point
-  trace_point(0);
+  SS_TP(0);
   // The launch parity (workspace epoch) is needed only after the reduce loop. Its load is issued FIRST: the L1
   // returns loads in issue order, so behind the prefetch burst below it would come back after ~128 KB of copies
   // (measured: the loop of the second CTA of an SM started 3.7 us into the kernel while the prologue waited for it).
@@ -251,7 +280,7 @@ __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(Loss
       nx += r.w;
     }
   }
-  trace_point(1);
+  SS_TP(1);
   const int lean_px = 4 * lean_q;
   {
     // per-warp loss totals: one shuffle-light multi-sum in fp32 (a thread saw <= 36 pixels; the warp total of sum d and
@@ -314,7 +343,7 @@ __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(Loss
       }
     }
   };
-  trace_point(2);
+  SS_TP(2);
 
   // ---------------- all-reduce of the totals (grid_sum4_counted, common.cuh); every CTA derives the coefficients ----
   constexpr int kRegTiles = kSsSlots - kSsDepth;   // gradient-phase predictions that are read again (through L2)
@@ -332,28 +361,40 @@ __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(Loss
     if (grad != nullptr) prefetch_pred();
     flush_metrics();
 #ifdef MDE_SS_TIMING
-    trace_point(4);   // (instrumented build) slot 4 = this CTA starts waiting for the other CTAs' totals
+    SS_TP(4);   // (instrumented build) slot 4 = this CTA starts waiting for the other CTAs' totals
 #endif
   });
 #ifdef MDE_SS_TIMING
-  trace_point(6);     // (instrumented build) slot 6 = totals gathered and reduced
+  SS_TP(6);     // (instrumented build) slot 6 = totals gathered and reduced
 #endif
   if (tid < 32) __syncwarp();   // sm_tot was written by threads 0..3
   if (tid == 0) {
-    // totals (log2 units) -> loss value and gradient coefficients
+    // totals (log2 units) -> loss value and gradient coefficients. Every CTA waits for this chain, so the coefficients
+    // come from the SFU (reciprocal and reciprocal square root, one Newton step each: ~1e-7 relative, the gradient
+    // tolerance is 1e-5) instead of two IEEE divisions and a square root (-0.14 us); degenerate totals (no valid pixel,
+    // zero or negative variance) take the exact operations, so that NaN / inf come out as they always did.
     const double S0 = sm_tot[0] * 0.69314718055994531, S1 = sm_tot[1] * 0.48045301391820142, N0 = sm_tot[2];
-    double inv = static_cast<double>(1.0f / static_cast<float>(N0));   // fp32 reciprocal + one Newton step in fp64
+    double inv = static_cast<double>(mufu_rcp(static_cast<float>(N0)));   // + one Newton step in fp64
     inv = inv * (2.0 - N0 * inv);                                        // (relative error ~1e-14; N0 == 0 gives NaN as 1.0 / 0 * 0 does downstream)
     const double dm = S0 * inv, qm = S1 * inv;
     const double var = qm - static_cast<double>(a.vf) * dm * dm;   // the cancellation stays in fp64
-    const float s = sqrtf(static_cast<float>(var));
-    const double loss = 10.0 * static_cast<double>(s);
-    const float k1 = 10.0f * a.grad_scale * static_cast<float>(inv) / s;   // dL/dd_i = k1 * (d_i - k2), natural log
+    const float varf = static_cast<float>(var);
+    float k1;                                                        // dL/dd_i = k1 * (d_i - k2), natural log
+    if (varf > 1e-30f && varf < 1e30f) {
+      float rs = mufu_rsq(varf);
+      rs = rs * fmaf(-0.5f * varf, rs * rs, 1.5f);
+      k1 = 10.0f * a.grad_scale * static_cast<float>(inv) * rs;
+    } else {
+      k1 = 10.0f * a.grad_scale * static_cast<float>(inv) / sqrtf(varf);
+    }
     sm_k[0] = k1;
     sm_k[1] = a.vf * static_cast<float>(dm);
     sm_k[2] = k1 * 0.69314718055994531f;                             // same, for residuals held in log2 units
     sm_k[3] = a.vf * static_cast<float>(dm * 1.4426950408889634);
     if (cta == 0) {
+      // (forming the loss value at the END of the kernel instead was measured: +0.75 us - a serial chain and a store
+      // right before the exit delay the grid's completion)
+      const double loss = 10.0 * static_cast<double>(sqrtf(varf));
       *a.loss_out = static_cast<float>(loss);
       if (a.totals_out) {
         a.totals_out[0] = S0; a.totals_out[1] = S1; a.totals_out[2] = N0; a.totals_out[3] = 0.0;
@@ -371,7 +412,7 @@ __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(Loss
       atomicAdd(ukey + 6, 1u);
     }
   }
-  trace_point(3);
+  SS_TP(3);
   pdl_trigger();   // a dependent launch may start filling the SMs this grid leaves
   // pooled metric values (one mean over all valid pixels of the call, metrics.py:58-67), formed by the LAST warp
   // of the LAST CTA at the very end of the kernel, when every CTA's arrival has long been counted
@@ -406,12 +447,28 @@ __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(Loss
       }
     }
   };
+  auto trace_exit = [&] {
+#ifdef MDE_SS_TIMING
+    unsigned long long* t = g_mde_trace;
+    if (lane == 0 && t != nullptr) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      atomicMax(&sm_trace[5], ns);
+      __threadfence_block();
+      if (atomicAdd(&sm_tcnt, 1u) == static_cast<unsigned>(kSsWarps - 1)) {
+        unsigned long long* row = t + (static_cast<size_t>(epoch & 1u) * 296 + static_cast<size_t>(cta)) * kTraceSlots;
+        for (int k = 0; k < kTraceSlots; ++k) row[k] = *reinterpret_cast<volatile unsigned long long*>(&sm_trace[k]);
+      }
+    }
+#endif
+  };
   if (grad == nullptr) {
     finalize_metrics();
+    trace_exit();
     return;
   }
 #ifndef MDE_SS_TIMING
-  trace_point(4);
+  SS_TP(4);
 #endif
 
   // ---------------- gradient phase: g_i = k (d_i - c) / p_i on the mask, 0 elsewhere -------------------------
@@ -449,8 +506,9 @@ __global__ void __launch_bounds__(kSsThreads, kSsCtasPerSm) silog_ss_kernel(Loss
       grad[i] = v ? sm_k[0] * (d - sm_k[1]) * rcp_nr(p) : 0.f;
     }
   }
-  trace_point(5);
+  SS_TP(5);
   finalize_metrics();
+  trace_exit();
 }
 
 // SILog / fp32 / 128-bit path with a gradient and few enough tiles: residuals parked in shared memory

@@ -15,8 +15,73 @@ import torch.distributed as dist
 
 from . import _lib
 
-__all__ = ["shard_range", "reduce_metric_sums", "sharded_eval", "finalize_pooled", "packed_view", "pack_metric_sums", "unpack_metric_sums",
+__all__ = ["PeerComm", "shard_range", "reduce_metric_sums", "sharded_eval", "finalize_pooled", "packed_view", "pack_metric_sums", "unpack_metric_sums",
            "SplitLoss", "global_batch_loss", "combine_partials", "loss_from_totals"]
+
+
+class PeerComm:
+    """The ranks' mailboxes for the in-kernel exchange of mde_metrics_sharded (one process per GPU, one box, <= 8 ranks).
+
+    Every rank allocates 8 KB of device memory through the library (cudaMalloc, zeroed), the CUDA IPC handles travel
+    once over the process group (`all_gather_object`), every rank maps the others' blocks into its address space
+    (NVLink peer access) and hands the pointer table to the library, which keeps it in a small device-resident
+    descriptor. From then on an evaluation is ONE launch per rank and nothing else: the launch's finaliser stores the
+    rank's 25 doubles into every peer's mailbox and sums the world's rows of its own. `next_seq()` numbers the calls; all
+    ranks must make the same calls in the same order (as with any collective). Not for CUDA graphs: the sequence number
+    is a launch argument. Collective constructor; `close()` (collective) releases the mappings."""
+
+    def __init__(self, group=None, timeout_ms=2000):
+        import ctypes as C
+        self._C = C
+        self.lib = _lib.load()
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if on else 0
+        self.world = dist.get_world_size(group) if on else 1
+        self.seq = 0
+        self.handle = None
+        self._own = None
+        self._peers = []
+        if self.world == 1:
+            return
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError("PeerComm serves the GPUs of one box (<= %d ranks)" % _lib.MAX_PEERS)
+        own = C.c_void_p()
+        _lib.check(self.lib.mde_peer_alloc(_lib.PEER_MAILBOX_BYTES, C.byref(own)))
+        self._own = own
+        hbuf = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        _lib.check(self.lib.mde_peer_export(own, hbuf))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(hbuf.raw), group=group)
+        table = (C.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                table[r] = own.value
+            else:
+                p = C.c_void_p()
+                _lib.check(self.lib.mde_peer_open(C.create_string_buffer(handles[r], _lib.PEER_HANDLE_BYTES), C.byref(p)))
+                self._peers.append(p)
+                table[r] = p.value
+        comm = C.c_void_p()
+        _lib.check(self.lib.mde_peer_comm_create(table, self.rank, self.world, int(timeout_ms), C.byref(comm)))
+        self.handle = comm
+        dist.barrier(group)          # nobody launches before every mapping exists
+
+    def next_seq(self):
+        self.seq = self.seq % 0xFFFFFFFF + 1     # never 0 (the mailboxes' initial tag)
+        return self.seq
+
+    def close(self):
+        if self.handle is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(self.group)     # no launch of any rank may still be writing
+        for p in self._peers:
+            self.lib.mde_peer_close(p)
+        self.lib.mde_peer_comm_destroy(self.handle)
+        dist.barrier(self.group)     # every mapping is gone before the blocks are freed
+        self.lib.mde_peer_free(self._own)
+        self.handle, self._own, self._peers = None, None, []
 
 
 def shard_range(n_items: int, rank: int, world: int):
@@ -67,15 +132,36 @@ def unpack_metric_sums(packed: torch.Tensor, names):
             "n_images": n_img, "n_valid": raw[0], "delta_counts": raw[1:4]}
 
 
-def sharded_eval(pred_shard, target_shard, names, group=None, all_reduce=True, async_op=False):
-    """Evaluate this rank's images and combine across ranks: ONE kernel launch per rank, ONE all-reduce of
-    NQ + 1 + NM = 25 doubles (in place on a view of the kernel's result vector), nothing else.
+def _views_of_result(out_f64: torch.Tensor, names):
+    """The evaluation dict as VIEWS of a kernel result vector whose sums already cover the whole set (no launches)."""
+    NM, NQ = _lib.METRIC_NM, _lib.METRIC_NQ
+    idx = [_lib.METRIC_INDEX[n] for n in names]
+    return {"image_mean": {n: out_f64[NM + i] for n, i in zip(names, idx)},
+            "pooled": {n: out_f64[i] for n, i in zip(names, idx)},
+            "n_images": out_f64[2 * NM + NQ], "n_valid": out_f64[2 * NM], "delta_counts": out_f64[2 * NM + 1:2 * NM + 4],
+            "packed": packed_view(out_f64), "work": None}
+
+
+def sharded_eval(pred_shard, target_shard, names, group=None, all_reduce=True, async_op=False, comm=None):
+    """Evaluate this rank's images and combine across ranks.
+
+    With `comm` (a PeerComm): ONE kernel launch per rank and nothing else - the launch's finaliser exchanges the 25 doubles
+    {pooled raw sums, #valid images, per-image value sums} with the other ranks' launches over NVLink peer memory and
+    finishes the values of the whole set itself (C ABI mde_metrics_sharded); the result dict holds views of its output.
+    Without: one launch + ONE all-reduce of the same 25 doubles over the process group (NCCL; gloo in the CPU tests of
+    the host logic), in place on a view of the kernel's result vector.
 
     Returns dict: 'image_mean' (reference eval-loop semantics: mean over images of per-image means,
     metrics.py:35-41 + modules/base_module.py:71-76), 'pooled' (dataset-pooled means), 'n_images', 'n_valid',
-    'delta_counts' (exact integers in fp64). With `async_op=True` only {'work', 'packed'} come back: the all-reduce
-    runs on the communicator's stream while the caller goes on; wait, then unpack_metric_sums(packed, names)."""
+    'delta_counts' (exact integers in fp64). With `async_op=True` (process-group path) only {'work', 'packed'} come back:
+    the all-reduce runs on the communicator's stream while the caller goes on; wait, then unpack_metric_sums(packed, names)."""
     from .metrics import fused_metrics
+    if comm is not None and comm.world > 1 and all_reduce:
+        return _views_of_result(fused_metrics(pred_shard, target_shard, names=names, comm=comm)["f64"], names)
+    multi = all_reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not multi and pred_shard.numel() > 0 and not async_op:
+        # one rank (or no exchange asked for): the launch's own result vector is final
+        return _views_of_result(fused_metrics(pred_shard, target_shard, names=names)["f64"], names)
     if pred_shard.numel() == 0:
         # a rank without images (n_items < world) contributes zeros and STILL enters the collective
         packed = torch.zeros(_lib.METRIC_NM + 1 + _lib.METRIC_NQ, dtype=torch.float64, device=pred_shard.device)
@@ -173,7 +259,7 @@ class SplitLoss:
     def finish(self):
         """Loss of the global batch (0-dim fp32, the same value on every rank, attached to autograd) given the GLOBAL
         totals in `partials`; backward yields dloss/dpred of THIS shard."""
-        from .criteria import _FusedLossFn
+        from .criteria import _fused_apply
         totals, kind, lp, pc, t, mk, dev, lib, C = self.partials, self.kind, self.lp, self.pc, self.t, self.mk, self.dev, self.lib, self._C
 
         def launch(p, need_grad):
@@ -191,7 +277,7 @@ class SplitLoss:
                 grad = grad.view(p.shape)
             return loss, grad
 
-        return _FusedLossFn.apply(self.pred, launch)
+        return _fused_apply(self.pred, launch)
 
 
 def loss_from_totals(kind, totals, lp=None, like_kernel=False):

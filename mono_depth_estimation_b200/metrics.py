@@ -36,8 +36,12 @@ def _prep(pred, target):
     return dev, pred, target
 
 
-def fused_metrics(pred, target, names=None, per_image=False, reference_math=False, image_dims=2):
+def fused_metrics(pred, target, names=None, per_image=False, reference_math=False, image_dims=2, comm=None):
     """Launch the fused kernel once.
+
+    `comm` (distributed.PeerComm, world > 1): the launch's finaliser exchanges this rank's sums with the other ranks'
+    launches over NVLink peer memory (C ABI mde_metrics_sharded), so 'values' / 'image_mean' / 'f64' describe the WHOLE
+    sharded set, identically on every rank; 'per_image*' stay local. An empty shard is legal then. Every rank must call.
 
     Returns a dict with
       'values'      fp32 [NM] pooled over all valid pixels of the call (reference compute() semantics)
@@ -55,7 +59,8 @@ def fused_metrics(pred, target, names=None, per_image=False, reference_math=Fals
     for s in pred.shape[pred.dim() - image_dims:]:
         hw *= int(s)
     n_img = pred.numel() // max(hw, 1)
-    if pred.numel() == 0:
+    exchange = comm is not None and comm.world > 1
+    if pred.numel() == 0 and not exchange:
         raise AssertionError("invalid target!")
     flags = _lib.METRICS_REFERENCE_MATH if reference_math else 0
     if names is not None:
@@ -73,9 +78,14 @@ def fused_metrics(pred, target, names=None, per_image=False, reference_math=Fals
         if per_image:
             piv = torch.empty((n_img, _lib.METRIC_NM), dtype=torch.float64, device=dev)
             pir = torch.empty((n_img, _lib.METRIC_NQ), dtype=torch.float64, device=dev)
-        _lib.check(lib.mde_metrics(_lib.ptr(pred), _lib.dtype_code(pred), _lib.ptr(target), n_img, hw, flags,
-                                   _lib.ptr(ws), _lib.ptr(out64), _lib.ptr(out32), _lib.ptr(piv), _lib.ptr(pir),
-                                   _lib.stream_ptr(dev)))
+        if exchange:
+            _lib.check(lib.mde_metrics_sharded(_lib.ptr(pred) if n_img else None, _lib.dtype_code(pred), _lib.ptr(target) if n_img else None,
+                                               n_img, max(hw, 1), flags, _lib.ptr(ws), _lib.ptr(out64), _lib.ptr(out32), _lib.ptr(piv),
+                                               _lib.ptr(pir), comm.handle, comm.next_seq(), _lib.stream_ptr(dev)))
+        else:
+            _lib.check(lib.mde_metrics(_lib.ptr(pred), _lib.dtype_code(pred), _lib.ptr(target), n_img, hw, flags,
+                                       _lib.ptr(ws), _lib.ptr(out64), _lib.ptr(out32), _lib.ptr(piv), _lib.ptr(pir),
+                                       _lib.stream_ptr(dev)))
     res = {"values": out32[:_lib.METRIC_NM], "image_mean": out32[_lib.METRIC_NM:], "f64": out64}
     if per_image:
         res["per_image"] = piv

@@ -17,7 +17,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .criteria import _FusedLossFn
+from .criteria import _fused_apply
 
 __all__ = ["setup_criterion", "TERM_FLAGS"]
 
@@ -84,7 +84,7 @@ def setup_criterion(method, single_layer=True, composite_layers=None, depth_sort
             box["out8"] = out8
             return out8[0], grad
 
-        loss = _FusedLossFn.apply(pred, launch)
+        loss = _fused_apply(pred, launch)
         ret = [loss]
         if return_composited:                                         # base_module.py:142-155
             if composite_layers is None or (not single_layer and depth_sort is None):

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .criteria import _FusedLossFn, _compute_copy
+from .criteria import _fused_apply, _compute_copy
 
 __all__ = ["WCEL_Loss", "depth_to_bins", "bins_to_depth", "vnl_params", "VNLBins"]
 
@@ -71,7 +71,7 @@ class WCEL_Loss(nn.Module):
                                              _lib.ptr(loss), _lib.ptr(grad), _lib.stream_ptr(dev)))
             return loss, grad
 
-        return _FusedLossFn.apply(pred_logit, launch)
+        return _fused_apply(pred_logit, launch)
 
 
 def depth_to_bins(depth, depth_min=0.01, depth_max=1.1, dec_out_c=150, depth_min_log=None, depth_bin_interval=None):

@@ -202,7 +202,7 @@ def test_loss_with_fused_metrics(Cr, name, names):
         assert mc.count == 1
         # a different tensor is NOT served from the cache
         vals2 = mc.compute((p.detach() * 1.0), g)
-        assert _lib.launch_count() - n0 >= 3
+        assert _lib.launch_count() - n0 >= 2           # the loss launch (no scaling launch for a plain backward) + this one
         close(torch.stack(vals2), v64, 1e-5)
 
 
@@ -398,3 +398,23 @@ def test_fused_metrics_booked_in_the_launch(Cr):
         close(torch.stack(vals), want, 1e-5)
         acc += want
     close(torch.stack([mc.avg(n) for n in names]), acc / 3, 1e-5)
+
+
+def test_plain_backward_needs_no_scaling_launch(Cr):
+    """`loss.backward()` on the criterion's result takes the stashed gradient as it is (the root gradient is autograd's
+    implicit ones, known on the host); a scaled loss goes through mde_scale_inplace and gives the scaled gradient."""
+    from mono_depth_estimation_b200 import _lib
+    pred, gt = synth.depth_pair((2, 1, 48, 64), 11, border=2)
+    l64, g64 = olosses.loss_and_grad(olosses.silog, pred.double(), gt.double())
+    crit = Cr.silog_loss(0.85)
+    p = pred.cuda().requires_grad_(True)
+    _lib.workspace(p.device, 2)
+    n0 = _lib.launch_count()
+    crit(p, gt.cuda()).backward()
+    assert _lib.launch_count() - n0 == 1
+    grad_close(p.grad, g64)
+    q = pred.cuda().requires_grad_(True)
+    n0 = _lib.launch_count()
+    (crit(q, gt.cuda()) * 4.0).backward()
+    assert _lib.launch_count() - n0 == 2
+    grad_close(q.grad, 4.0 * g64)

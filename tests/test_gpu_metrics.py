@@ -225,3 +225,93 @@ def test_resized_metrics_counts_exact_vs_cuda_interpolate(M, pshape, tshape):
         assert [int(round(v)) for v in res["per_image_raw"][b, :4].tolist()] == list(rb)
     v64 = [float(v) for v in ometrics.compute(y_hat.double().cpu(), y.double().cpu(), ALL)]
     close(res["f64"][:12], v64, 1e-5)
+
+
+class _EmulatedRank:
+    """Stand-in for distributed.PeerComm: rank `rank` of an emulated world whose mailboxes all live on THIS GPU."""
+
+    def __init__(self, handle, world):
+        self.handle, self.world, self.seq = handle, world, 0
+
+    def next_seq(self):
+        self.seq += 1
+        return self.seq
+
+
+def test_in_kernel_exchange_emulated_on_one_gpu(M):
+    """mde_metrics_sharded with three 'ranks' emulated on one GPU: three mailboxes and three communicators built straight
+    from the C ABI, one launch per rank on its own stream - the finalisers wait for one another exactly as they do across
+    NVLink. All ranks end with bit-identical result vectors; image count, valid count and delta counts equal the single
+    launch over all images bit for bit (and the CPU oracle's per-image means to 1e-5); an empty shard takes part; the
+    rows are double-buffered, so back-to-back calls do not disturb one another."""
+    import ctypes as C
+    from mono_depth_estimation_b200 import _lib
+    lib = _lib.load()
+    world = 3
+    boxes = []
+    for _ in range(world):
+        p = C.c_void_p()
+        _lib.check(lib.mde_peer_alloc(_lib.PEER_MAILBOX_BYTES, C.byref(p)))
+        boxes.append(p)
+    table = (C.c_void_p * world)(*[b.value for b in boxes])
+    comms = []
+    for r in range(world):
+        h = C.c_void_p()
+        _lib.check(lib.mde_peer_comm_create(table, r, world, 3000, C.byref(h)))
+        comms.append(_EmulatedRank(h, world))
+    names = ["delta1", "delta2", "delta3", "mse", "mae", "log10", "rmse", "absrel", "sqrel", "msle"]
+    pred, gt = synth.depth_pair((7, 1, 120, 160), 321, border=3)
+    gt[2] = 0                                                   # an image without a valid pixel
+    pred, gt = pred.cuda(), gt.cuda()
+    single = M.fused_metrics(pred, gt, names=names)["f64"].cpu().numpy()
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    for st in streams:      # per-stream workspaces and allocator blocks exist BEFORE the first exchange: a cudaMalloc between
+        with torch.cuda.stream(st):   # the launches would wait for the first rank's kernel, which waits for the others
+            M.fused_metrics(pred, gt, names=names)
+    # ... and so is the empty-shard kernel's code (CUDA loads a kernel lazily at its first launch, which waits for the device):
+    # one launch through a communicator of a world of one, which is also a legal (if pointless) configuration
+    solo_tab = (C.c_void_p * 1)(boxes[0].value)
+    solo_h = C.c_void_p()
+    _lib.check(lib.mde_peer_comm_create(solo_tab, 0, 1, 3000, C.byref(solo_h)))
+    solo = _EmulatedRank(solo_h, 2)     # (world > 1 on the Python side selects the sharded entry point)
+    alone = M.fused_metrics(pred[:0], gt[:0], names=names, comm=solo)["f64"]
+    torch.cuda.synchronize()
+    assert float(alone[2 * 12 + 12]) == 0.0 and float(alone[2 * 12]) == 0.0      # no image, no valid pixel
+    lib.mde_peer_comm_destroy(solo_h)
+    lib.mde_peer_free(boxes[0])
+    _lib.check(lib.mde_peer_alloc(_lib.PEER_MAILBOX_BYTES, C.byref(boxes[0])))   # a fresh (zeroed) mailbox for rank 0
+    table = (C.c_void_p * world)(*[b.value for b in boxes])
+    for c in comms:
+        lib.mde_peer_comm_destroy(c.handle)
+    comms = []
+    for r in range(world):
+        h = C.c_void_p()
+        _lib.check(lib.mde_peer_comm_create(table, r, world, 3000, C.byref(h)))
+        comms.append(_EmulatedRank(h, world))
+    torch.cuda.synchronize()
+    try:
+        for shards in ([(0, 3), (3, 5), (5, 7)], [(0, 7), (7, 7), (7, 7)], [(0, 1), (1, 6), (6, 7)]):   # the middle one: two empty shards
+            outs = []
+            for r, (a, b) in enumerate(shards):
+                streams[r].wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(streams[r]):
+                    outs.append(M.fused_metrics(pred[a:b], gt[a:b], names=names, comm=comms[r])["f64"])
+            torch.cuda.synchronize()
+            outs = [o.cpu().numpy() for o in outs]
+            for o in outs[1:]:
+                assert np.array_equal(o, outs[0])               # same summation order on every rank
+            NM, NQ = 12, 12
+            packed, ref = outs[0][2 * NM:], single[2 * NM:]
+            assert packed[NQ] == ref[NQ] == 6.0                 # images with a valid pixel
+            assert np.array_equal(packed[:4], ref[:4])          # valid count and the three delta counts
+            np.testing.assert_allclose(outs[0], single, rtol=2e-6, atol=0)   # fp32 tile sums grouped by other CTA partitions
+        keep = [0, 1, 3, 4, 5, 6]                             # the reference's eval loop never sees an image without a valid pixel
+        want = ometrics.compute_per_image_mean(pred.cpu()[keep].double(), gt.cpu()[keep].double(), names)
+        idx = [ALL.index(n) for n in names]
+        close(outs[0][12:24][idx], [float(v) for v in want], METRIC_RTOL)
+    finally:
+        torch.cuda.synchronize()
+        for c in comms:
+            lib.mde_peer_comm_destroy(c.handle)
+        for b in boxes:
+            lib.mde_peer_free(b)

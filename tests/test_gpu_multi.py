@@ -45,6 +45,25 @@ def _worker(rank, world, port, q):
         idx = [_lib.METRIC_INDEX[n] for n in EVAL]
         out["eval_single"] = {"image_mean": [float(f64[NM + i]) for i in idx], "pooled": [float(f64[i]) for i in idx],
                               "n_images": float(f64[2 * NM + NQ]), "n_valid": float(f64[2 * NM]), "delta_counts": [float(f64[2 * NM + k]) for k in (1, 2, 3)]}
+    # ---- the same evaluation with the exchange INSIDE the launch (NVLink peer mailboxes, no collective), three calls in a
+    # row (the rows are double-buffered by call parity), then a 1-image set (rank 1's shard is empty)
+    comm = D.PeerComm()
+    n0 = _lib.launch_count()
+    for rep in range(3):
+        res = D.sharded_eval(pred[a:b].to(dev), gt[a:b].to(dev), EVAL, comm=comm)
+        torch.cuda.synchronize()
+    out["peer_launches"] = (_lib.launch_count() - n0) / 3.0
+    out["peer_eval"] = {"image_mean": [float(res["image_mean"][n]) for n in EVAL], "pooled": [float(res["pooled"][n]) for n in EVAL],
+                        "n_images": float(res["n_images"]), "n_valid": float(res["n_valid"]), "delta_counts": [float(c) for c in res["delta_counts"]],
+                        "packed": res["packed"].cpu().numpy()}
+    a1, b1 = D.shard_range(1, rank, world)
+    res1 = D.sharded_eval(pred[a1:b1].to(dev), gt[a1:b1].to(dev), EVAL, comm=comm)
+    out["peer_one_image"] = {"n_images": float(res1["n_images"]), "delta1": float(res1["image_mean"]["delta1"]), "n_valid": float(res1["n_valid"])}
+    if rank == 0:
+        one = M.fused_metrics(pred[:1].to(dev), gt[:1].to(dev), names=EVAL)["f64"].cpu()
+        out["one_image_single"] = {"n_images": float(one[2 * _lib.METRIC_NM + _lib.METRIC_NQ]), "delta1": float(one[_lib.METRIC_NM + _lib.METRIC_INDEX["delta1"]]),
+                                   "n_valid": float(one[2 * _lib.METRIC_NM])}
+    comm.close()
     # ---- global-batch losses: C1 batch (8 images) sharded 4 + 4
     pred, gt = synth.config_inputs("C1")
     pred[6, 0, 50, 60] = gt[6, 0, 50, 60] + 25.0        # the berHu / Laina maximum lives on rank 1
@@ -90,6 +109,23 @@ def test_sharded_eval_equals_single_gpu(two_rank_results):
         assert ev["n_valid"] == single["n_valid"] and ev["delta_counts"] == single["delta_counts"]
         np.testing.assert_allclose(ev["image_mean"], single["image_mean"], rtol=1e-6)   # fp32 tile sums grouped by another CTA partition
         np.testing.assert_allclose(ev["pooled"], single["pooled"], rtol=2e-6)   # different CTA partitions of the fp32 tile sums
+
+
+def test_in_kernel_peer_exchange_equals_collective_and_single_gpu(two_rank_results):
+    """sharded_eval(comm=PeerComm): ONE launch per rank, the 25 doubles exchanged by the launches' finalisers over NVLink
+    peer memory. Both ranks end with bit-identical vectors (same summation order), the counts equal the single-GPU launch
+    bit for bit, the float values equal the NCCL path's; an empty shard still takes part."""
+    r0, r1 = two_rank_results[0], two_rank_results[1]
+    assert r0["peer_launches"] == 1.0 and r1["peer_launches"] == 1.0
+    assert np.array_equal(r0["peer_eval"]["packed"], r1["peer_eval"]["packed"])
+    single = r0["eval_single"]
+    for r in (r0, r1):
+        ev = r["peer_eval"]
+        assert ev["n_images"] == single["n_images"] == 12.0
+        assert ev["n_valid"] == single["n_valid"] and ev["delta_counts"] == single["delta_counts"]
+        np.testing.assert_allclose(ev["image_mean"], r["eval"]["image_mean"], rtol=1e-12)
+        np.testing.assert_allclose(ev["pooled"], r["eval"]["pooled"], rtol=1e-12)
+        assert r["peer_one_image"] == r0["one_image_single"]
 
 
 @pytest.mark.parametrize("name", ["silog", "berhu", "laina_berhu", "l1"])
