@@ -289,8 +289,15 @@ __device__ __forceinline__ float metric_px_lean(float p, float t, MetricAcc& a) 
   // SUBNORMAL target never reaches the lean form: the caller's rare test sends its quad to the exact path)
   a.nval += __saturatef(t * 8.507059173023462e37f);
   float dl = 0.f;
+  // 1/sqrt(t) serves the REL / RSQ sums AND the logarithm: log2 p - log2 t = log2((p rs) rs) is ONE MUFU.LG2 instead of
+  // two (MUFU issues at 1/8 of the FMA rate: the SFU ops are most of this pixel's issue cycles). The SFU reciprocal
+  // square root is good to 1.2e-7 relative (profiles/r01_mathlab_sfu_accuracy.jsonl), so the ratio carries 2.5e-7 and
+  // the logarithm ~7e-7 absolute in log2 units against ~5e-7 for the difference of two MUFU.LG2 - the sums move by
+  // ~3e-7 relative (measured for the same form with MUFU.RCP: aggregate 2.8e-7), tolerance 1e-5.
+  float rs = 0.f;
+  if (G & (kGrpRel | kGrpRsq)) rs = mufu_rsq(tt);
   if (G & kGrpLog) {
-    dl = mufu_lg2(pp) - mufu_lg2(tt);
+    dl = (G & (kGrpRel | kGrpRsq)) ? mufu_lg2((pp * rs) * rs) : mufu_lg2(pp) - mufu_lg2(tt);
     a.s_log10 += fabsf(dl);                        // x log10(2) at the flush
     a.s_lnsq = fmaf(dl, dl, a.s_lnsq);             // x ln(2)^2 at the flush
   }
@@ -299,13 +306,12 @@ __device__ __forceinline__ float metric_px_lean(float p, float t, MetricAcc& a) 
     a.s_sle = fmaf(d1, d1, a.s_sle);
   }
   if (G & kGrpRel) {
-    const float rs = mufu_rsq(tt);
     const float ar = ad * (rs * rs);
     a.s_absrel += ar;
     a.s_sqrel = fmaf(ar, ad, a.s_sqrel);
     a.s_rsq = fmaf(ad, rs, a.s_rsq);
   } else if (G & kGrpRsq) {
-    a.s_rsq = fmaf(ad, mufu_rsq(tt), a.s_rsq);     // sqrt((p-t)^2/t) = |p-t| / sqrt(t)
+    a.s_rsq = fmaf(ad, rs, a.s_rsq);               // sqrt((p-t)^2/t) = |p-t| / sqrt(t)
   }
   return dl;
 }
