@@ -77,7 +77,11 @@ def test_empty_depth_mask_and_errors(S, golden):
 @pytest.mark.parametrize("shape,loss_name,dtype", [((4, 10, 256, 256), "silma", torch.float32),
                                                    ((2, 10, 97, 131), "silms+fbdivergence", torch.float32),
                                                    ((2, 20, 128, 160), "mae+mse+fbdivergence", torch.float32),
-                                                   ((3, 10, 64, 80), "silma", torch.float16)])
+                                                   ((3, 10, 64, 80), "silma", torch.float16),
+                                                   ((2, 20, 64, 96), "silma", torch.float32),       # quad kernel, three layers
+                                                   ((2, 10, 64, 96), "mae+mse", torch.float32),     # quad kernel, all-channel terms
+                                                   ((2, 20, 40, 52), "silms", torch.float32),
+                                                   ((2, 10, 64, 96), "silms+fbdivergence", torch.float32)])   # quad kernel with the front/back term
 def test_vs_oracle(S, shape, loss_name, dtype):
     """BTS's default 'silma' at a training-like size, odd sizes, three layers, AMP (fp16 prediction)."""
     from mono_depth_estimation_b200.synth import stdepth_inputs

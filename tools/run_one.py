@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run ONE hot-path call a few times (for ncu / compute-sanitizer).  python tools/run_one.py <name> [reps]
-names: c5_metrics, c2_metrics, c2_fused, dorn_fused, dorn_decode, ord_loss, vnl, c1_berhu, pointcloud, wcel"""
+names: c5_metrics, c5_metrics10, c2_metrics, c2_fused, dorn_fused, dorn_decode, ord_loss, vnl, c1_berhu, pointcloud, wcel"""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
@@ -11,8 +11,10 @@ sp = lambda: _lib.stream_ptr(dev)
 loss_t = torch.empty((), device=dev)
 lp = _lib.LossParams(0.85, 1e-9, 1, 1)
 mflags = _lib.METRICS_NEED_LOG | _lib.METRICS_NEED_RSQ
-if name in ("c5_metrics", "c2_metrics"):
-    B = 654 if name == "c5_metrics" else 16
+if name in ("c5_metrics", "c5_metrics10", "c2_metrics"):
+    B = 16 if name == "c2_metrics" else 654
+    if name == "c5_metrics10":
+        mflags = 0     # all groups: the 10 keys of the evaluation list
     pr, gt = synth.depth_pair((B, 1, 480, 640), 105, device=dev)
     ws = _lib.workspace(dev, B)
     o64 = torch.empty(_lib.METRICS_OUT_F64, dtype=torch.float64, device=dev); o32 = torch.empty(24, device=dev)
@@ -84,4 +86,4 @@ else:
 for _ in range(reps):
     f()
 torch.cuda.synchronize()
-print("ok", name, float(loss_t) if name not in ("c5_metrics", "c2_metrics", "dorn_decode", "pointcloud", "robust", "stdepth") else "")
+print("ok", name, float(loss_t) if name not in ("c5_metrics", "c5_metrics10", "c2_metrics", "dorn_decode", "pointcloud", "robust", "stdepth") else "")
