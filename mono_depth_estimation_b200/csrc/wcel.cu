@@ -89,6 +89,13 @@ struct WcelArgs {
 // 4.8 TB/s). Three variants were tried and were SLOWER, so they are not kept: L2 evict_last / evict_first cache
 // hints (430 us), one CTA per SM with 32 channels in flight (45 MB in flight, 464 us), and a shared-memory
 // staged kernel (cp.async tile of 32 px x C per warp, 7 warps per SM beside the 91 KB table: 576 us).
+// Round 2 tried the obvious way to read the logits ONCE: a pixel's 150 logits held in registers between the passes
+// (75 per thread, exponentials written over the logits, one MUFU.EX2 per element instead of three), the channels split
+// over two lanes of a warp (64 contiguous bytes of two planes per access: 440 us) or over two warps behind a named
+// barrier (128 bytes of one plane per access: 428 us). Both move 8C + 8 B/px and both are SLOWER than this kernel's
+// 12C at 410 us: 170 registers per thread leave 12 warps per SM, each of them alternating between a burst of 75 loads,
+// the arithmetic and a burst of 75 stores, so about half of the ~115 KB the register file can hold is in flight on
+// average - less than the latency x bandwidth product of an SM (~66 KB at 1.5 us) needs with any margin.
 template <typename XT, bool HAS_GRAD, bool SMEM_TABLE, int U, int PER_SM>
 __global__ void __launch_bounds__(kWBlock, PER_SM) wcel_kernel(WcelArgs a) {
   extern __shared__ float sm_w[];   // SMEM_TABLE: [C][stride] weights, then [C] row sums
