@@ -634,20 +634,42 @@ def main():
     Kc = max(3, min(K, 20))            # evaluations per repetition
     Rc = 30
     c5_ms = []
+    c5_graph = None
     with torch.cuda.stream(side):
         for _ in range(3):
             c5_eval(False)
+        side.synchronize()
+        # one launch per evaluation and rank, the exchange inside it: the Kc evaluations of a repetition replay as ONE CUDA
+        # graph (at N = 8 an evaluation takes ~55 us on the GPU, less than the Python call that launches it). The
+        # process-group path (a collective per evaluation) is timed eagerly.
+        if (comm is not None or world == 1) and not args.no_graph:
+            try:
+                c5_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(c5_graph, stream=side):
+                    c5_keep = [c5_eval(False) for _ in range(Kc)]
+            except Exception as e:
+                sys.stderr.write("C5 graph capture failed (%s); timing eager launches\n" % (str(e).splitlines()[0],))
+                c5_graph = None
+                torch.cuda.synchronize()
+        if world > 1:
+            flag = torch.tensor([1 if c5_graph is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag) == 0:
+                c5_graph = None
         barrier()
         for r in range(Rc):
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(side)
-            works = []
-            for _ in range(Kc):
-                works.append(c5_eval(world > 1))      # (NCCL path: the all-reduce of evaluation i overlaps the launch of evaluation i+1)
-            for wk in works:
-                if wk.get("work") is not None:
-                    wk["work"].wait()                # the step stream waits for every reduction before the region closes
+            if c5_graph is not None:
+                c5_graph.replay()
+            else:
+                works = []
+                for _ in range(Kc):
+                    works.append(c5_eval(world > 1))      # (NCCL path: the all-reduce of evaluation i overlaps the launch of evaluation i+1)
+                for wk in works:
+                    if wk.get("work") is not None:
+                        wk["work"].wait()                # the step stream waits for every reduction before the region closes
             e1.record(side)
             barrier()
             c5_ms.append(e0.elapsed_time(e1) / Kc)
@@ -661,7 +683,7 @@ def main():
                       (len(EVAL_METRICS), "/".join(str(mdist.shard_range(n_img_total, r, world)[1] - mdist.shard_range(n_img_total, r, world)[0])
                                                    for r in range(world))),
           "value": c5_px / (c5_med * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_eval": c5_med, "scaling": "strong",
-          "evals_per_repetition": Kc, "repetitions": Rc, "hbm_frac_per_gpu": 8.0 * c5_px / world / (c5_med * 1e-3) / 1e9 / peak,
+          "evals_per_repetition": Kc, "repetitions": Rc, "cuda_graph": c5_graph is not None, "hbm_frac_per_gpu": 8.0 * c5_px / world / (c5_med * 1e-3) / 1e9 / peak,
           "collective": None if world == 1 else ("none: 25 doubles per rank exchanged inside the launch (finaliser stores into the peers' mailboxes over NVLink, tagged words)"
                                                   if comm is not None else "one all-reduce of 25 doubles per evaluation (NCCL, in place on the kernel's result vector)"),
           "collective_note": comm_note,

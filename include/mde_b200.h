@@ -119,7 +119,9 @@ int mde_metrics(const void* pred, int pred_dtype, const float* target, int64_t n
  *              descriptor: the world's mailboxes as mapped into this process, rank, world, timeout).
  *   mailboxes  MDE_PEER_MAILBOX_BYTES of device memory per rank, zeroed once (mde_peer_alloc), the own one included.
  *              Rows are tagged with `seq` and double-buffered by its parity.
- *   seq        the same on every rank for the same call, never 0, different from the previous call's (count up).
+ *   seq        0: the communicator numbers its calls itself (a counter in its device-resident descriptor, advanced by the
+ *              finaliser - the launch can then be captured in a CUDA graph and replayed); otherwise the same on every
+ *              rank for the same call and different from the previous call's (count up). Do not mix the two styles.
  *   n_img == 0 is legal here (a rank without images still owes the world its row); pred / target may then be null.
  *   A peer whose row does not arrive within the timeout (default 2000 ms) is given up on: NaN results and error flag 1
  *   in the workspace header instead of a hung GPU.
@@ -130,7 +132,7 @@ int mde_metrics(const void* pred, int pred_dtype, const float* target, int64_t n
 #define MDE_PEER_HANDLE_BYTES 64
 int mde_metrics_sharded(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t hw,
                         unsigned flags, void* ws, double* out_f64, float* out_f32,
-                        double* per_image_values, double* per_image_raw, const void* comm, unsigned seq, void* stream);
+                        double* per_image_values, double* per_image_raw, void* comm, unsigned seq, void* stream);
 int mde_peer_comm_create(void* const* mailboxes /* [world] */, int rank, int world, unsigned timeout_ms /* 0: 2000 */,
                          void** comm_out);
 int mde_peer_comm_destroy(void* comm);

@@ -213,7 +213,8 @@ __constant__ int kValNum[kNM] = {MDE_Q_D1, MDE_Q_D2, MDE_Q_D3, MDE_Q_ABS, MDE_Q_
 struct PeerDesc {                                 // lives in DEVICE memory (mde_peer_comm_create): the kernels take a pointer
   unsigned long long* mailbox[MDE_MAX_PEERS];   // [r] = rank r's mailbox as mapped into THIS process
   int rank, world;
-  unsigned timeout_ms, pad;
+  unsigned timeout_ms;
+  unsigned auto_seq;                            // seq == 0 at launch: the finaliser takes ++auto_seq (CUDA-graph friendly)
 };
 struct PeerXchg {                                 // what the finaliser works with (registers / constant bank)
   const PeerDesc* d;
@@ -265,7 +266,7 @@ __device__ __forceinline__ bool peer_get(const PeerXchg& px, int idx, unsigned l
 
 __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __restrict__ out_f64,
                                               float* __restrict__ out_f32, double* __restrict__ per_image_values,
-                                              double* __restrict__ per_image_raw, double* sm_d, const PeerDesc* pd, unsigned seq) {
+                                              double* __restrict__ per_image_raw, double* sm_d, PeerDesc* pd, unsigned seq) {
   double* iacc = ws.iacc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool own = lane < kNM;  // kNM == kNQ == 12
@@ -309,6 +310,15 @@ __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __re
     for (int w = 0; w < kWarps; ++w) N += sm_d[2 * kWarps * kNM + w];
     if (pd != nullptr) {   // this rank's {P, N, V} -> every peer's mailbox; the world's rows of the own mailbox -> {P, N, V}
       PeerXchg px;
+      if (seq == 0u) {   // the communicator's own counter: every rank's launches advance it in lockstep
+        unsigned sq = 0u;
+        if (lane == 0) {
+          sq = pd->auto_seq + 1u;
+          if (sq == 0u) sq = 1u;
+          pd->auto_seq = sq;
+        }
+        seq = __shfl_sync(0xffffffffu, sq, 0);
+      }
       px.d = pd; px.rank = pd->rank; px.world = pd->world; px.seq = seq;
       if (own) {
         peer_put(px, lane, P);
@@ -355,7 +365,7 @@ template <typename PT, int VEC, unsigned G, bool Ref, bool LONG>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm)
 metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_t n_img, int64_t hw, Chunking chunk,
                void* ws_raw, double* __restrict__ out_f64, float* __restrict__ out_f32,
-               double* __restrict__ per_image_values, double* __restrict__ per_image_raw, const PeerDesc* __restrict__ pd,
+               double* __restrict__ per_image_values, double* __restrict__ per_image_raw, PeerDesc* __restrict__ pd,
                unsigned seq) {
   __shared__ double sm_d[2 * kNM * kWarps + kWarps];
   __shared__ int sm_i[4 * kWarps];
@@ -452,7 +462,7 @@ metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ gt, int64_
 
 // a rank without images (fewer images than ranks) still owes the world its (all-zero) row
 __global__ void __launch_bounds__(kBlock) metrics_empty_shard_kernel(void* ws_raw, double* __restrict__ out_f64, float* __restrict__ out_f32,
-                                                                      const PeerDesc* __restrict__ pd, unsigned seq) {
+                                                                      PeerDesc* __restrict__ pd, unsigned seq) {
   __shared__ double sm_d[2 * kNM * kWarps + kWarps];
   pdl_wait();
   metrics_finalize(ws_view(ws_raw), 0, out_f64, out_f32, nullptr, nullptr, sm_d, pd, seq);
@@ -519,7 +529,7 @@ metrics_resized_kernel(const float* __restrict__ pred, int ph, int pw, const flo
 
 template <typename PT, int VEC, unsigned G, bool Ref, bool LONG>
 int launch_metrics_l(const void* pred, const float* gt, int64_t n_img, int64_t hw, void* ws, double* out_f64,
-                   float* out_f32, double* piv, double* pir, cudaStream_t st, const PeerDesc* pd, unsigned seq) {
+                   float* out_f32, double* piv, double* pir, cudaStream_t st, PeerDesc* pd, unsigned seq) {
   const int64_t units = n_img * (hw / VEC);
   const int64_t per_cta_min = static_cast<int64_t>(kBlock);  // at least one unit per thread
   int64_t grid = (units + per_cta_min - 1) / per_cta_min;
@@ -538,7 +548,7 @@ int launch_metrics_l(const void* pred, const float* gt, int64_t n_img, int64_t h
 
 template <typename PT, int VEC, unsigned G, bool Ref>
 int launch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t hw, void* ws, double* out_f64,
-                   float* out_f32, double* piv, double* pir, cudaStream_t st, const PeerDesc* pd, unsigned seq) {
+                   float* out_f32, double* piv, double* pir, cudaStream_t st, PeerDesc* pd, unsigned seq) {
   // pixels one thread sees of one image: the whole batch is spread over <= 2 CTAs per SM
   const int64_t npx = n_img * hw;
   const int64_t threads = static_cast<int64_t>(sm_count()) * kCtasPerSm * kBlock;
@@ -549,7 +559,7 @@ int launch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t hw,
 
 template <typename PT>
 int dispatch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t hw, unsigned flags, void* ws,
-                     double* out_f64, float* out_f32, double* piv, double* pir, cudaStream_t st, const PeerDesc* pd, unsigned seq) {
+                     double* out_f64, float* out_f32, double* piv, double* pir, cudaStream_t st, PeerDesc* pd, unsigned seq) {
   const bool ref = (flags & MDE_METRICS_REFERENCE_MATH) != 0;
   unsigned g = (flags >> 8) & kGrpMask;
   if ((g & kGrpRsq) && (g & kGrpRel)) g &= kGrpAll;                      // REL already covers the 'rmse' sum
@@ -580,12 +590,11 @@ int dispatch_metrics(const void* pred, const float* gt, int64_t n_img, int64_t h
 
 extern "C" int mde_metrics_sharded(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t hw,
                                    unsigned flags, void* ws, double* out_f64, float* out_f32, double* per_image_values,
-                                   double* per_image_raw, const void* comm, unsigned seq, void* stream) {
+                                   double* per_image_raw, void* comm, unsigned seq, void* stream) {
   using namespace mde;
   MDE_REQUIRE(ws && out_f64, MDE_EINVAL, "null pointer");
   MDE_REQUIRE(aligned_to(out_f64, 8), MDE_EALIGN, "misaligned pointer");
-  const PeerDesc* pd = static_cast<const PeerDesc*>(comm);
-  if (pd != nullptr) MDE_REQUIRE(seq != 0u, MDE_EINVAL, "peer sequence numbers start at 1 (0 is the mailbox's initial tag)");
+  PeerDesc* pd = static_cast<PeerDesc*>(comm);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_img == 0) {   // an empty shard: legal only as a member of an exchange
     MDE_REQUIRE(pd != nullptr, MDE_EINVAL, "empty input");
@@ -666,7 +675,7 @@ extern "C" int mde_peer_comm_create(void* const* mailboxes, int rank, int world,
     MDE_REQUIRE(mailboxes[r] != nullptr && aligned_to(mailboxes[r], 8), MDE_EINVAL, "null / misaligned peer mailbox");
     h.mailbox[r] = static_cast<unsigned long long*>(mailboxes[r]);
   }
-  h.rank = rank; h.world = world; h.timeout_ms = timeout_ms ? timeout_ms : 2000u;
+  h.rank = rank; h.world = world; h.timeout_ms = timeout_ms ? timeout_ms : 2000u; h.auto_seq = 0u;
   void* d = nullptr;
   MDE_CUDA_TRY(cudaMalloc(&d, sizeof(PeerDesc)));
   MDE_CUDA_TRY(cudaMemcpy(d, &h, sizeof(PeerDesc), cudaMemcpyHostToDevice));

@@ -26,9 +26,10 @@ class PeerComm:
     once over the process group (`all_gather_object`), every rank maps the others' blocks into its address space
     (NVLink peer access) and hands the pointer table to the library, which keeps it in a small device-resident
     descriptor. From then on an evaluation is ONE launch per rank and nothing else: the launch's finaliser stores the
-    rank's 25 doubles into every peer's mailbox and sums the world's rows of its own. `next_seq()` numbers the calls; all
-    ranks must make the same calls in the same order (as with any collective). Not for CUDA graphs: the sequence number
-    is a launch argument. Collective constructor; `close()` (collective) releases the mappings."""
+    rank's 25 doubles into every peer's mailbox and sums the world's rows of its own. The calls are numbered by a counter
+    in the descriptor that the finaliser advances (so a launch can be captured in a CUDA graph and replayed); all ranks
+    must make the same calls in the same order (as with any collective). Collective constructor; `close()` (collective)
+    releases the mappings."""
 
     def __init__(self, group=None, timeout_ms=2000):
         import ctypes as C
@@ -68,8 +69,7 @@ class PeerComm:
         dist.barrier(group)          # nobody launches before every mapping exists
 
     def next_seq(self):
-        self.seq = self.seq % 0xFFFFFFFF + 1     # never 0 (the mailboxes' initial tag)
-        return self.seq
+        return 0                                 # 0 = the communicator's own device-resident counter (graph-capturable)
 
     def close(self):
         if self.handle is None:
@@ -132,14 +132,41 @@ def unpack_metric_sums(packed: torch.Tensor, names):
             "n_images": n_img, "n_valid": raw[0], "delta_counts": raw[1:4]}
 
 
+class _EvalViews(dict):
+    """The evaluation dict as VIEWS of a kernel result vector whose sums already cover the whole set. The views are made
+    on first access (a dozen tensor views cost more host time than the launch of an 80-image shard takes on the GPU)."""
+
+    def __init__(self, out_f64, names):
+        super().__init__(packed=packed_view(out_f64), work=None)
+        self._f64, self._names = out_f64, list(names)
+
+    def __missing__(self, key):
+        NM, NQ, f = _lib.METRIC_NM, _lib.METRIC_NQ, self._f64
+        idx = [_lib.METRIC_INDEX[n] for n in self._names]
+        if key == "image_mean":
+            v = {n: f[NM + i] for n, i in zip(self._names, idx)}
+        elif key == "pooled":
+            v = {n: f[i] for n, i in zip(self._names, idx)}
+        elif key == "n_images":
+            v = f[2 * NM + NQ]
+        elif key == "n_valid":
+            v = f[2 * NM]
+        elif key == "delta_counts":
+            v = f[2 * NM + 1:2 * NM + 4]
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+
 def _views_of_result(out_f64: torch.Tensor, names):
-    """The evaluation dict as VIEWS of a kernel result vector whose sums already cover the whole set (no launches)."""
-    NM, NQ = _lib.METRIC_NM, _lib.METRIC_NQ
-    idx = [_lib.METRIC_INDEX[n] for n in names]
-    return {"image_mean": {n: out_f64[NM + i] for n, i in zip(names, idx)},
-            "pooled": {n: out_f64[i] for n, i in zip(names, idx)},
-            "n_images": out_f64[2 * NM + NQ], "n_valid": out_f64[2 * NM], "delta_counts": out_f64[2 * NM + 1:2 * NM + 4],
-            "packed": packed_view(out_f64), "work": None}
+    return _EvalViews(out_f64, names)
 
 
 def sharded_eval(pred_shard, target_shard, names, group=None, all_reduce=True, async_op=False, comm=None):
