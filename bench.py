@@ -367,6 +367,23 @@ def main():
             raw_acc.add_(raw)
         return loss, vals, p.grad, raw
 
+    # N > 1: whatever the ranks exchange goes through NVLink peer mailboxes (distributed.PeerComm): the 25 doubles of a
+    # sharded evaluation INSIDE its launch (mde_metrics_sharded), the 12 pooled metric sums of the training steps through a
+    # one-warp launch (mde_peer_allreduce_f64). If the peer mappings cannot be set up on this box, the process-group path
+    # (NCCL) is timed instead
+    comm = None
+    comm_note = None
+    if world > 1 and os.environ.get("MDE_BENCH_NO_PEER", "0") == "0":
+        try:
+            comm = mdist.PeerComm()
+        except Exception as e:
+            comm_note = "PeerComm unavailable (%s)" % (str(e).splitlines()[0][:120],)
+            comm = None
+        flag = torch.tensor([1 if comm is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # all ranks take the same path
+        if int(flag) == 0:
+            comm = None
+
     pending = []
 
     def exchange():
@@ -375,7 +392,16 @@ def main():
         # (pl.Trainer(gpus=N), train.py:137) - which never synchronises metrics at all (no sync_dist, metrics.py:19-39).
         # Asynchronous: the sums are snapshotted on the step stream and reduced on NCCL's own stream while the
         # steps go on; everything outstanding is waited for before the run ends.
-        if world > 1:
+        if world > 1 and comm is not None:
+            # one one-warp launch on the step stream: read the accumulator, exchange through the mailboxes, write the sum,
+            # clear the accumulator (a collective's kernel would hold an SM for tens of microseconds while the
+            # cooperative step kernel, which needs every SM, waits behind it: 1.2 us per step at N = 8)
+            snap = torch.empty_like(raw_acc)
+            comm.all_reduce_(raw_acc, out=snap, zero_src=True)
+            pending.append((None, snap))
+            if len(pending) > 64:
+                del pending[:32]
+        elif world > 1:
             snap = raw_acc.clone()
             raw_acc.zero_()
             pending.append((dist.all_reduce(snap, async_op=True), snap))
@@ -470,7 +496,8 @@ def main():
                 first = (first + K) % args.ring
             exchange()
             for work, _ in pending:
-                work.wait()
+                if work is not None:
+                    work.wait()
             pending.clear()
             torch.cuda.synchronize()
     t = torch.tensor(rep_ms, dtype=torch.float64, device=dev)
@@ -611,21 +638,6 @@ def main():
         c5_pred, c5_gt = c5_pred[:0], c5_gt[:0]
     c5_px = n_img_total * 480 * 640
 
-    # N > 1: the 25 doubles per rank are exchanged INSIDE the launches (finaliser -> every peer's mailbox over NVLink,
-    # mde_metrics_sharded); if the peer mappings cannot be set up on this box the process-group path (NCCL) is timed instead
-    comm = None
-    comm_note = None
-    if world > 1 and os.environ.get("MDE_BENCH_NO_PEER", "0") == "0":
-        try:
-            comm = mdist.PeerComm()
-        except Exception as e:
-            comm_note = "PeerComm unavailable (%s)" % (str(e).splitlines()[0][:120],)
-            comm = None
-        flag = torch.tensor([1 if comm is not None else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # all ranks take the same path
-        if int(flag) == 0:
-            comm = None
-
     def c5_eval(async_op):
         if comm is not None:
             return mdist.sharded_eval(c5_pred, c5_gt, EVAL_METRICS, comm=comm)
@@ -742,7 +754,8 @@ def main():
                            "timing": "K steps x %d repetitions, each bracketed by barrier+synchronize, CUDA events, max over ranks per "
                                      "repetition, median over repetitions" % R,
                            "metrics_booking": "in the criterion's launch (fuse_metrics(book=True))",
-                           "collective": None if world == 1 else "all-reduce of 12 doubles every %d steps (NCCL, async)" % args.sync_every},
+                           "collective": None if world == 1 else ("sum of 12 doubles every %d steps through NVLink peer mailboxes (one one-warp launch, mde_peer_allreduce_f64)" % args.sync_every
+                                                                   if comm is not None else "all-reduce of 12 doubles every %d steps (NCCL, async)" % args.sync_every)},
                 "timing": timing, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step) * K,
                 "roofline": roofline, "c5_eval": c5, "cpu_baseline": cpu_baseline}
         if cfgs is not None:

@@ -133,6 +133,11 @@ int mde_metrics(const void* pred, int pred_dtype, const float* target, int64_t n
 int mde_metrics_sharded(const void* pred, int pred_dtype, const float* target, int64_t n_img, int64_t hw,
                         unsigned flags, void* ws, double* out_f64, float* out_f32,
                         double* per_image_values, double* per_image_raw, void* comm, unsigned seq, void* stream);
+/* Sum of n <= 31 doubles over the ranks through the same mailboxes (one warp): dst[i] = sum over ranks of src[i], in rank
+ * order (bit-identical on every rank); zero_src != 0 clears src in the same launch (a rank's accumulator between two
+ * exchanges, e.g. the pooled metric sums mde_loss_params.metrics_raw_accum collects - SURVEY 8e). src == dst is allowed
+ * when zero_src == 0. seq as in mde_metrics_sharded; ws: the stream's workspace (receives the error flag on a timeout). */
+int mde_peer_allreduce_f64(double* src, double* dst, int n, int zero_src, void* comm, unsigned seq, void* ws, void* stream);
 int mde_peer_comm_create(void* const* mailboxes /* [world] */, int rank, int world, unsigned timeout_ms /* 0: 2000 */,
                          void** comm_out);
 int mde_peer_comm_destroy(void* comm);

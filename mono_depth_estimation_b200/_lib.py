@@ -45,6 +45,7 @@ _vp, _i64, _i32, _u32, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint, C.c_floa
 SIGNATURES = {
     "mde_metrics": (_i32, [_vp, _i32, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mde_metrics_sharded": (_i32, [_vp, _i32, _vp, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
+    "mde_peer_allreduce_f64": (_i32, [_vp, _vp, _i32, _i32, _vp, _u32, _vp, _vp]),
     "mde_peer_comm_create": (_i32, [C.POINTER(_vp), _i32, _i32, _u32, C.POINTER(_vp)]),
     "mde_peer_comm_destroy": (_i32, [_vp]),
     "mde_peer_alloc": (_i32, [C.c_size_t, C.POINTER(_vp)]),

@@ -468,6 +468,45 @@ __global__ void __launch_bounds__(kBlock) metrics_empty_shard_kernel(void* ws_ra
   metrics_finalize(ws_view(ws_raw), 0, out_f64, out_f32, nullptr, nullptr, sm_d, pd, seq);
 }
 
+// ---- the same exchange as a tiny stand-alone all-reduce (sum) of <= 31 doubles ---------------------------------------------
+// What a training job needs once per logging interval: the ranks' pooled metric sums (12 doubles) added up. One warp:
+// lane i puts value i into every peer's mailbox row and sums the world's rows of its own mailbox in rank order; with
+// `zero_src` the source accumulator is cleared in the same launch (read - exchange - write - clear, nothing else on the
+// stream). A collective kernel would hold an SM for tens of microseconds while the cooperative loss kernels, which need
+// every SM, wait behind it.
+__global__ void __launch_bounds__(32) peer_allreduce_kernel(double* __restrict__ src, double* __restrict__ dst, int n, int zero_src,
+                                                            PeerDesc* __restrict__ pd, unsigned seq, void* ws_raw) {
+  pdl_wait();
+  const int lane = threadIdx.x;
+  if (seq == 0u) {
+    unsigned sq = 0u;
+    if (lane == 0) {
+      sq = pd->auto_seq + 1u;
+      if (sq == 0u) sq = 1u;
+      pd->auto_seq = sq;
+    }
+    seq = __shfl_sync(0xffffffffu, sq, 0);
+  }
+  PeerXchg px;
+  px.d = pd; px.rank = pd->rank; px.world = pd->world; px.seq = seq;
+  double v = 0.0;
+  if (lane < n) {
+    v = src[lane];
+    if (zero_src) src[lane] = 0.0;
+    peer_put(px, lane, v);
+  }
+  unsigned long long t_give_up;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_give_up));
+  t_give_up += static_cast<unsigned long long>(pd->timeout_ms) * 1000000ull;
+  bool ok = true;
+  if (lane < n) ok = peer_get(px, lane, t_give_up, v);
+  if (!__all_sync(0xffffffffu, ok)) {
+    v = __longlong_as_double(0x7ff8000000000000LL);
+    if (lane == 0) ws_view(ws_raw).hdr->error = 1u;
+  }
+  if (lane < n) dst[lane] = v;
+}
+
 // ---- metrics on bilinearly resized inputs -----------------------------------------------
 // The test steps of the eigen / dorn / my modules resize BOTH the prediction and the target to 480 x 640 with
 // F.interpolate(mode='bilinear') (align_corners=False) right before log_test (modules/eigen.py:49-51,
@@ -664,6 +703,18 @@ extern "C" int mde_peer_open(const unsigned char* handle, void** ptr_out) {
   void* p = nullptr;
   MDE_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
   *ptr_out = p;
+  return MDE_OK;
+}
+extern "C" int mde_peer_allreduce_f64(double* src, double* dst, int n, int zero_src, void* comm, unsigned seq, void* ws, void* stream) {
+  using namespace mde;
+  MDE_REQUIRE(src && dst && comm && ws, MDE_EINVAL, "null pointer");
+  MDE_REQUIRE(n >= 1 && n <= 31, MDE_EINVAL, "1 .. 31 doubles (one mailbox row)");
+  MDE_REQUIRE(aligned_to(src, 8) && aligned_to(dst, 8), MDE_EALIGN, "misaligned pointer");
+  PeerDesc* pd = static_cast<PeerDesc*>(comm);
+  void* args[] = {&src, &dst, &n, &zero_src, &pd, &seq, &ws};
+  MDE_CUDA_TRY(launch_pdl(reinterpret_cast<const void*>(&peer_allreduce_kernel), dim3(1), dim3(32), args, 0,
+                          static_cast<cudaStream_t>(stream), false));
+  count_launch();
   return MDE_OK;
 }
 extern "C" int mde_peer_comm_create(void* const* mailboxes, int rank, int world, unsigned timeout_ms, void** comm_out) {

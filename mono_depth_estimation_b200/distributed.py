@@ -71,6 +71,25 @@ class PeerComm:
     def next_seq(self):
         return 0                                 # 0 = the communicator's own device-resident counter (graph-capturable)
 
+    def all_reduce_(self, src: torch.Tensor, out: torch.Tensor = None, zero_src: bool = False) -> torch.Tensor:
+        """Sum of a float64 vector of <= 31 elements over the ranks (C ABI mde_peer_allreduce_f64): one one-warp launch on
+        the current stream, result in `out` (default: in place); `zero_src` clears `src` in the same launch. With one
+        rank: a copy."""
+        assert src.dtype == torch.float64 and src.is_contiguous() and src.numel() <= 31
+        out = src if out is None else out
+        if self.handle is None:
+            if out is not src:
+                out.copy_(src)
+                if zero_src:
+                    src.zero_()
+            return out
+        dev = src.device
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, 1)
+            _lib.check(self.lib.mde_peer_allreduce_f64(_lib.ptr(src), _lib.ptr(out), src.numel(), 1 if zero_src else 0, self.handle,
+                                                       self.next_seq(), _lib.ptr(ws), _lib.stream_ptr(dev)))
+        return out
+
     def close(self):
         if self.handle is None:
             return

@@ -305,6 +305,18 @@ def test_in_kernel_exchange_emulated_on_one_gpu(M):
             assert packed[NQ] == ref[NQ] == 6.0                 # images with a valid pixel
             assert np.array_equal(packed[:4], ref[:4])          # valid count and the three delta counts
             np.testing.assert_allclose(outs[0], single, rtol=2e-6, atol=0)   # fp32 tile sums grouped by other CTA partitions
+        # the stand-alone sum of a few doubles through the same mailboxes (mde_peer_allreduce_f64), clearing the source
+        srcs = [torch.arange(12, dtype=torch.float64, device="cuda") * (r + 1) + 0.25 for r in range(world)]
+        dsts = [torch.empty(12, dtype=torch.float64, device="cuda") for _ in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                ws = _lib.workspace(torch.device("cuda", torch.cuda.current_device()), 1)
+                _lib.check(lib.mde_peer_allreduce_f64(_lib.ptr(srcs[r]), _lib.ptr(dsts[r]), 12, 1, comms[r].handle, comms[r].next_seq(),
+                                                      _lib.ptr(ws), _lib.stream_ptr(srcs[r].device)))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert np.array_equal(dsts[r].cpu().numpy(), np.arange(12) * 6.0 + 0.75) and float(srcs[r].abs().sum()) == 0.0
         keep = [0, 1, 3, 4, 5, 6]                             # the reference's eval loop never sees an image without a valid pixel
         want = ometrics.compute_per_image_mean(pred.cpu()[keep].double(), gt.cpu()[keep].double(), names)
         idx = [ALL.index(n) for n in names]

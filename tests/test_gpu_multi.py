@@ -63,6 +63,12 @@ def _worker(rank, world, port, q):
         one = M.fused_metrics(pred[:1].to(dev), gt[:1].to(dev), names=EVAL)["f64"].cpu()
         out["one_image_single"] = {"n_images": float(one[2 * _lib.METRIC_NM + _lib.METRIC_NQ]), "delta1": float(one[_lib.METRIC_NM + _lib.METRIC_INDEX["delta1"]]),
                                    "n_valid": float(one[2 * _lib.METRIC_NM])}
+    # ---- the stand-alone sum of a few doubles through the same mailboxes (what the training steps exchange per logging interval)
+    acc = torch.arange(12, dtype=torch.float64, device=dev) * (rank + 1) + 0.5
+    tot = torch.empty_like(acc)
+    comm.all_reduce_(acc, out=tot, zero_src=True)
+    torch.cuda.synchronize()
+    out["peer_allreduce"] = {"sum": tot.cpu().numpy(), "src_after": acc.cpu().numpy()}
     comm.close()
     # ---- global-batch losses: C1 batch (8 images) sharded 4 + 4
     pred, gt = synth.config_inputs("C1")
@@ -126,6 +132,8 @@ def test_in_kernel_peer_exchange_equals_collective_and_single_gpu(two_rank_resul
         np.testing.assert_allclose(ev["image_mean"], r["eval"]["image_mean"], rtol=1e-12)
         np.testing.assert_allclose(ev["pooled"], r["eval"]["pooled"], rtol=1e-12)
         assert r["peer_one_image"] == r0["one_image_single"]
+        np.testing.assert_array_equal(r["peer_allreduce"]["sum"], np.arange(12) * 3.0 + 1.0)    # (i + 0.5) + (2 i + 0.5)
+        np.testing.assert_array_equal(r["peer_allreduce"]["src_after"], np.zeros(12))
 
 
 @pytest.mark.parametrize("name", ["silog", "berhu", "laina_berhu", "l1"])
