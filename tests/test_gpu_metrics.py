@@ -327,3 +327,41 @@ def test_in_kernel_exchange_emulated_on_one_gpu(M):
             lib.mde_peer_comm_destroy(c.handle)
         for b in boxes:
             lib.mde_peer_free(b)
+
+
+def test_in_kernel_exchange_gives_up_on_a_missing_peer(M):
+    """A rank whose peer never launches must not hang the GPU: after the communicator's timeout (here 60 ms) the finaliser
+    writes NaN results and raises the workspace's error flag, and the launch completes."""
+    import ctypes as C
+    import time
+    from mono_depth_estimation_b200 import _lib
+    lib = _lib.load()
+    boxes = []
+    for _ in range(2):
+        p = C.c_void_p()
+        _lib.check(lib.mde_peer_alloc(_lib.PEER_MAILBOX_BYTES, C.byref(p)))
+        boxes.append(p)
+    table = (C.c_void_p * 2)(*[b.value for b in boxes])
+    h = C.c_void_p()
+    _lib.check(lib.mde_peer_comm_create(table, 0, 2, 60, C.byref(h)))
+    pred, gt = synth.depth_pair((2, 1, 60, 80), 5)
+    pred, gt = pred.cuda(), gt.cuda()
+    M.fused_metrics(pred, gt, names=["delta1"])
+    torch.cuda.synchronize()
+    try:
+        t0 = time.time()
+        out = M.fused_metrics(pred, gt, names=["delta1"], comm=_EmulatedRank(h, 2))["f64"]
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        assert 0.05 < dt < 2.0, dt
+        assert bool(torch.isnan(out[:12]).all()) and bool(torch.isnan(out[24:37]).all())
+        ws = _lib.workspace(pred.device, 2)
+        assert int(ws[20:24].view(torch.int32)[0]) == 1          # WsHeader.error
+        ws[20:24].zero_()
+        ok = M.fused_metrics(pred, gt, names=["delta1"])["f64"]   # the workspace is clean: the next plain call is right
+        assert abs(float(ok[0]) - float(ometrics.compute(pred.cpu().double(), gt.cpu().double(), ["delta1"])[0])) < 1e-6
+    finally:
+        torch.cuda.synchronize()
+        lib.mde_peer_comm_destroy(h)
+        for b in boxes:
+            lib.mde_peer_free(b)
