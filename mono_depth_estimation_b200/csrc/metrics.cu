@@ -197,10 +197,6 @@ __device__ __forceinline__ void flush_image(MetricThread<G, Ref, LONG>& th, int6
 __constant__ int kValNum[kNM] = {MDE_Q_D1, MDE_Q_D2, MDE_Q_D3, MDE_Q_ABS, MDE_Q_SQ, MDE_Q_LOG10, MDE_Q_SLE,
                                  MDE_Q_ABSREL, MDE_Q_SQREL, MDE_Q_RSQ, MDE_Q_SQ, MDE_Q_LNSQ};
 
-// Run by the LAST CTA only. One WARP per image: lane q < 12 owns raw quantity q and metric value q,
-// so an image costs one coalesced L2 read, two shuffles and one fp64 divide per lane; warps stride
-// over the images, then one shared-memory pass combines the warps. Also re-zeroes the per-image
-// accumulators so the workspace is clean for the next call.
 // ---- in-kernel exchange of the evaluation sums over NVLink peer memory -------------------------------
 // A multi-GPU evaluation shards the images over the ranks and needs ONE sum of 25 doubles per rank (pooled raw sums,
 // number of valid images, sum of per-image values). Instead of a collective launched behind the kernel, the finaliser
@@ -264,44 +260,86 @@ __device__ __forceinline__ bool peer_get(const PeerXchg& px, int idx, unsigned l
   return true;
 }
 
+// Run by the LAST CTA only. One HALF-WARP per image: sub-lane q < 12 owns raw quantity q and metric value q, so an image
+// costs one coalesced L2 read, two shuffles and one division per lane; the 32 half-warps of the CTA stride over the images,
+// four images per step with all their rows requested up front, then the halves of a warp and the warps are combined. Also
+// re-zeroes the per-image accumulators so the workspace is clean for the next call.
+// (Round 1 gave a whole warp one image at a time and divided / took roots with the IEEE fp64 sequences: a chain of L2 round
+// trips and ~1400 cycles of dependent fp64 arithmetic per image, 37 of the 294 us of the C5 launch - measured by presenting
+// the same 200.9 M pixels as 6 images instead of 654, tools/c5_split_probe.py. The per-image quotient is now num x (1 / n)
+// with the reciprocal from the SFU and two Newton steps in fp64 (full double precision up to the last ulp or two), the
+// root likewise from MUFU.RSQ; the POOLED values keep the IEEE operations.)
+__device__ __forceinline__ double fast_quotient(double num, double n) {
+  double inv = static_cast<double>(1.0f / static_cast<float>(n));   // n = a pixel count (exact in fp32); n == 0 -> NaN below, as 0 / 0
+  inv = inv * (2.0 - n * inv);
+  inv = inv * (2.0 - n * inv);
+  return num * inv;
+}
+__device__ __forceinline__ double fast_root(double x) {
+  if (!(x > 1e-30 && x < 1e30)) return sqrt(x);                   // 0, NaN, inf and whatever does not fit fp32: the exact path
+  double y = static_cast<double>(rsqrtf(static_cast<float>(x)));
+  y = y * (1.5 - 0.5 * x * y * y);
+  y = y * (1.5 - 0.5 * x * y * y);
+  return x * y;
+}
 __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __restrict__ out_f64,
                                               float* __restrict__ out_f32, double* __restrict__ per_image_values,
                                               double* __restrict__ per_image_raw, double* sm_d, PeerDesc* pd, unsigned seq) {
   double* iacc = ws.iacc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool own = lane < kNM;  // kNM == kNQ == 12
-  const int num_idx = own ? kValNum[lane] : 0;
+  const int sub = lane & 15, hbase = lane & 16;
+  const bool own = sub < kNM;  // kNM == kNQ == 12
+  const int num_idx = own ? kValNum[sub] : 0;
   double pooled = 0.0, vsum = 0.0, nvalid = 0.0;
-  for (int64_t b = warp; b < n_img; b += kWarps) {
-    double raw = 0.0;
-    if (own) {
-      raw = __ldcg(&iacc[b * kIacc + lane]);
-      iacc[b * kIacc + lane] = 0.0;
+  constexpr int kFinU = 4, kGroups = 2 * kWarps;
+  const int grp = 2 * warp + (lane >> 4);
+  const int64_t steps = (n_img + kGroups * kFinU - 1) / (kGroups * kFinU);   // the same for every half-warp: the shuffles stay warp-wide
+  for (int64_t k = 0; k < steps; ++k) {
+    const int64_t b0 = (k * kGroups + grp) * kFinU;
+    double rawv[kFinU];
+#pragma unroll
+    for (int u = 0; u < kFinU; ++u) {
+      const int64_t b = b0 + u;
+      rawv[u] = (own && b < n_img) ? __ldcg(&iacc[b * kIacc + sub]) : 0.0;
     }
-    const double n = __shfl_sync(0xffffffffu, raw, MDE_Q_NVALID);
-    const double num = __shfl_sync(0xffffffffu, raw, num_idx);
-    double val = num / n;
-    if (lane >= MDE_M_RMSE_TRUE) val = sqrt(val);
-    pooled += raw;
-    if (n > 0.0) {
-      vsum += val;
-      nvalid += 1.0;
-    }
-    if (own) {
-      if (per_image_values) per_image_values[b * kNM + lane] = val;
-      if (per_image_raw) per_image_raw[b * kNQ + lane] = raw;
+#pragma unroll
+    for (int u = 0; u < kFinU; ++u) {
+      const int64_t b = b0 + u;
+      const bool live = b < n_img;
+      const double raw = rawv[u];
+      if (own && live) iacc[b * kIacc + sub] = 0.0;
+      const double n = __shfl_sync(0xffffffffu, raw, hbase + MDE_Q_NVALID);
+      const double num = __shfl_sync(0xffffffffu, raw, hbase + num_idx);
+      double val = fast_quotient(num, n);
+      if (sub >= MDE_M_RMSE_TRUE) val = fast_root(val);
+      if (live) {
+        pooled += raw;
+        if (n > 0.0) {
+          vsum += val;
+          nvalid += 1.0;
+        }
+        if (own) {
+          if (per_image_values) per_image_values[b * kNM + sub] = val;
+          if (per_image_raw) per_image_raw[b * kNQ + sub] = raw;
+        }
+      }
     }
   }
+  // the two half-warps of a warp
+  pooled += __shfl_xor_sync(0xffffffffu, pooled, 16);
+  vsum += __shfl_xor_sync(0xffffffffu, vsum, 16);
+  nvalid += __shfl_xor_sync(0xffffffffu, nvalid, 16);
   // sm_d: [kWarps][12] pooled | [kWarps][12] vsum | [kWarps] nvalid
-  if (own) {
+  if (lane < kNM) {
     sm_d[warp * kNM + lane] = pooled;
     sm_d[kWarps * kNM + warp * kNM + lane] = vsum;
   }
   if (lane == 0) sm_d[2 * kWarps * kNM + warp] = nvalid;
   __syncthreads();
   if (warp == 0) {
+    const bool own0 = lane < kNM;   // (in this block lane q owns quantity q; `own` above is per half-warp)
     double P = 0.0, V = 0.0, N = 0.0;
-    if (own) {
+    if (own0) {
       for (int w = 0; w < kWarps; ++w) {
         P += sm_d[w * kNM + lane];
         V += sm_d[kWarps * kNM + w * kNM + lane];
@@ -320,7 +358,7 @@ __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __re
         seq = __shfl_sync(0xffffffffu, sq, 0);
       }
       px.d = pd; px.rank = pd->rank; px.world = pd->world; px.seq = seq;
-      if (own) {
+      if (own0) {
         peer_put(px, lane, P);
         peer_put(px, kNM + 1 + lane, V);
       }
@@ -329,7 +367,7 @@ __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __re
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_give_up));
       t_give_up += static_cast<unsigned long long>(pd->timeout_ms) * 1000000ull;
       bool ok = true;
-      if (own) ok = peer_get(px, lane, t_give_up, P) && peer_get(px, kNM + 1 + lane, t_give_up, V);
+      if (own0) ok = peer_get(px, lane, t_give_up, P) && peer_get(px, kNM + 1 + lane, t_give_up, V);
       double n_all = N;
       if (lane == 0) ok = peer_get(px, kNM, t_give_up, n_all) && ok;
       N = __shfl_sync(0xffffffffu, n_all, 0);
@@ -340,10 +378,10 @@ __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __re
       }
     }
     const double n = __shfl_sync(0xffffffffu, P, MDE_Q_NVALID);
-    const double num = __shfl_sync(0xffffffffu, P, num_idx);
+    const double num = __shfl_sync(0xffffffffu, P, own0 ? num_idx : 0);
     double val = num / n;
     if (lane >= MDE_M_RMSE_TRUE) val = sqrt(val);
-    if (own) {
+    if (own0) {
       const double mean_v = V / N;
       out_f64[lane] = val;
       out_f64[kNM + lane] = mean_v;
