@@ -262,7 +262,7 @@ __device__ __forceinline__ bool peer_get(const PeerXchg& px, int idx, unsigned l
 
 // Run by the LAST CTA only. One HALF-WARP per image: sub-lane q < 12 owns raw quantity q and metric value q, so an image
 // costs one coalesced L2 read, two shuffles and one division per lane; the 32 half-warps of the CTA stride over the images,
-// four images per step with all their rows requested up front, then the halves of a warp and the warps are combined. Also
+// eight images per step with all their rows requested up front, then the halves of a warp and the warps are combined. Also
 // re-zeroes the per-image accumulators so the workspace is clean for the next call.
 // (Round 1 gave a whole warp one image at a time and divided / took roots with the IEEE fp64 sequences: a chain of L2 round
 // trips and ~1400 cycles of dependent fp64 arithmetic per image, 37 of the 294 us of the C5 launch - measured by presenting
@@ -291,19 +291,24 @@ __device__ __noinline__ void metrics_finalize(Ws ws, int64_t n_img, double* __re
   const bool own = sub < kNM;  // kNM == kNQ == 12
   const int num_idx = own ? kValNum[sub] : 0;
   double pooled = 0.0, vsum = 0.0, nvalid = 0.0;
-  constexpr int kFinU = 4, kGroups = 2 * kWarps;
+  constexpr int kFinU = 8, kGroups = 2 * kWarps;
   const int grp = 2 * warp + (lane >> 4);
-  const int64_t steps = (n_img + kGroups * kFinU - 1) / (kGroups * kFinU);   // the same for every half-warp: the shuffles stay warp-wide
+  // images per half-warp and step: up to kFinU, but never more than it takes to give every half-warp work (a C2 batch of
+  // 16 images is one image for each of 16 half-warps, not eight images for each of two)
+  const int per = static_cast<int>(n_img >= static_cast<int64_t>(kGroups) * kFinU ? kFinU : (n_img + kGroups - 1) / kGroups);
+  const int U = per < 1 ? 1 : per;
+  const int64_t steps = (n_img + static_cast<int64_t>(kGroups) * U - 1) / (static_cast<int64_t>(kGroups) * U);   // the same for every half-warp: the shuffles stay warp-wide
   for (int64_t k = 0; k < steps; ++k) {
-    const int64_t b0 = (k * kGroups + grp) * kFinU;
+    const int64_t b0 = (k * kGroups + grp) * U;
     double rawv[kFinU];
 #pragma unroll
     for (int u = 0; u < kFinU; ++u) {
       const int64_t b = b0 + u;
-      rawv[u] = (own && b < n_img) ? __ldcg(&iacc[b * kIacc + sub]) : 0.0;
+      rawv[u] = (own && u < U && b < n_img) ? __ldcg(&iacc[b * kIacc + sub]) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < kFinU; ++u) {
+      if (u >= U) break;                                        // uniform
       const int64_t b = b0 + u;
       const bool live = b < n_img;
       const double raw = rawv[u];
