@@ -52,6 +52,32 @@ def workload_name(shape):
     return "C2: BTS SILog loss fwd+bwd + metrics, batch %s per GPU" % "x".join(map(str, shape))
 
 
+def pin_to_gpu_cpus(index):
+    """Bind this process to the CPUs NVML reports as local to GPU `index` (the cores of its NUMA node): the pinned staging
+    buffers of the e2e leg are then allocated next to the GPU's PCIe root, and with several ranks per box every rank stays
+    on its own side. Returns what was done (part of the e2e object). MDE_BENCH_NO_AFFINITY=1 leaves the process alone."""
+    info = {"applied": False}
+    if os.environ.get("MDE_BENCH_NO_AFFINITY", "0") != "0" or not hasattr(os, "sched_setaffinity"):
+        return info
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        info.update({"gpu_cpus": len(cpus), "allowed_before": len(allowed)})
+        if want and want != allowed:
+            os.sched_setaffinity(0, want)
+            info["applied"] = True
+        info["allowed_now"] = len(os.sched_getaffinity(0))
+    except Exception as e:   # NVML missing or the container forbids it: measured as is
+        info["error"] = str(e).splitlines()[0][:100]
+    return info
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -339,6 +365,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_to_gpu_cpus(local)        # before any pinned host buffer is allocated (first touch decides its NUMA node)
     if world > 1:
         import datetime
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -624,7 +651,7 @@ def main():
     h2d = 2 * 4 * npx
     e2e = {"value": world * npx / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * (1 + len(TRAIN_METRICS)), "steps": Ke,
-           "h2d_gbs_per_rank": h2d / (e2e_ms * 1e-3) / 1e9, "h2d_gbs_aggregate": world * h2d / (e2e_ms * 1e-3) / 1e9,
+           "h2d_gbs_per_rank": h2d / (e2e_ms * 1e-3) / 1e9, "cpu_affinity": affinity, "h2d_gbs_aggregate": world * h2d / (e2e_ms * 1e-3) / 1e9,
            "note": "pinned host buffers; every rank copies its own 39 MB per step over PCIe - the aggregate figure is the host-side ceiling "
                    "the ranks share (SCALE topology: all GPUs of the box hang off one NUMA node)"}
     del dbuf, hp, hg
