@@ -604,6 +604,8 @@ def main():
     dbuf = [(torch.empty(shape, device=dev), torch.empty(shape, device=dev)) for _ in range(2)]
     res_host = torch.empty(1 + len(TRAIN_METRICS), dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream2 = torch.cuda.Stream(device=dev) if os.environ.get("MDE_BENCH_ONE_COPY_STREAM", "0") == "0" else None
+    ready2 = [torch.cuda.Event(), torch.cuda.Event()]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -612,8 +614,14 @@ def main():
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[b])                     # the step that last used this pair is done with it
             dbuf[b][0].copy_(hp[b], non_blocking=True)
-            dbuf[b][1].copy_(hg[b], non_blocking=True)
+            if copy_stream2 is None:
+                dbuf[b][1].copy_(hg[b], non_blocking=True)
             ready[b].record(copy_stream)
+        if copy_stream2 is not None:                             # prediction and target travel on two copy engines
+            with torch.cuda.stream(copy_stream2):
+                copy_stream2.wait_event(freed[b])
+                dbuf[b][1].copy_(hg[b], non_blocking=True)
+                ready2[b].record(copy_stream2)
 
     def e2e_step(i, last):
         b = i % 2
@@ -621,6 +629,8 @@ def main():
         if not last:
             e2e_prefetch(i + 1)
         cur.wait_event(ready[b])
+        if copy_stream2 is not None:
+            cur.wait_event(ready2[b])
         dp, dg = dbuf[b]
         p = dp.detach().requires_grad_(True)
         loss = crit(p, dg)
