@@ -271,12 +271,13 @@ def config_rows(dev, peak, quick=False):
     mflags = 0
     for n in TRAIN_METRICS:
         mflags |= _lib.METRIC_GROUP.get(n, 0)
-    for kname, kind in (("C1", _lib.LOSS_BERHU), ("C1_silog", _lib.LOSS_SILOG), ("C1_l1", _lib.LOSS_L1)):
+    for kname, kind in (("C1", _lib.LOSS_BERHU), ("C1_silog", _lib.LOSS_SILOG), ("C1_l1", _lib.LOSS_L1), ("C1_laina", _lib.LOSS_LAINA_BERHU)):
         fns = [lambda pr=pr, gt=gt, gr=gr, kind=kind: _lib.check(lib.mde_masked_loss_metrics(
             kind, _lib.ptr(pr), 0, _lib.ptr(gt), None, shape[0], shape[2], shape[3], C.byref(lp), 1.0, mflags, _lib.ptr(ws),
             _lib.ptr(loss_t), None, _lib.ptr(gr), _lib.ptr(o64), _lib.ptr(o32), sp())) for (pr, gt), gr in zip(ring, grads)]
         us, _ = graph_timed(fns, dev, reps)
-        row(kname, {"C1": "berHu", "C1_silog": "SILog", "C1_l1": "L1"}[kname] + " fwd+bwd + 7 metrics, one launch, 8x1x228x304", us, 12.0 * px)
+        row(kname, {"C1": "berHu", "C1_silog": "SILog", "C1_l1": "L1", "C1_laina": "Laina berHu"}[kname] +
+            " fwd+bwd + 7 metrics, one launch (register-resident kernel), 8x1x228x304", us, 12.0 * px)
     del ring, grads
 
     # ---- C3: DORN fused logits -> decode, depth, ordinal loss, grad (K = 68), 8x136x257x353

@@ -87,7 +87,12 @@ constexpr int kIacc = 16;
 constexpr int kSlotCtas = 384;                       // >= resident CTAs of any cooperative launch here (2 x 148)
 constexpr size_t kSlotBytes = static_cast<size_t>(kSlotCtas) * 4 * 2 * 8;
 constexpr size_t kWsHeadBytes = 256 + 2 * kGacc * 8 + 2 * kUkey * 4 + 128;  // 1536
-constexpr size_t kWsFixedBytes = kWsHeadBytes + kSlotBytes;
+// [26112, +49152) mslots[192][32] words {seq:32 | half of a double:32}: per-CTA pooled metric sums of the register-resident
+//              small-input loss kernel (resident_loss.cuh), gathered by its finalising CTA (self-validating like `slots`)
+constexpr int kMetSlotCtas = 192;
+constexpr int kMetSlotWords = 32;
+constexpr size_t kMetSlotBytes = static_cast<size_t>(kMetSlotCtas) * kMetSlotWords * 8;
+constexpr size_t kWsFixedBytes = kWsHeadBytes + kSlotBytes + kMetSlotBytes;
 
 struct Ws {
   WsHeader* hdr;
@@ -95,6 +100,7 @@ struct Ws {
   unsigned* ukey;   // [2][kUkey]
   double* iacc;     // [3][max_images][kIacc]
   unsigned long long* slots;  // [kSlotCtas][4][2]
+  unsigned long long* mslots; // [kMetSlotCtas][kMetSlotWords]
 };
 
 __host__ __device__ inline Ws ws_view(void* base) {
@@ -104,6 +110,7 @@ __host__ __device__ inline Ws ws_view(void* base) {
   w.gacc = reinterpret_cast<double*>(b + 256);
   w.ukey = reinterpret_cast<unsigned*>(b + 256 + 2 * kGacc * 8);
   w.slots = reinterpret_cast<unsigned long long*>(b + kWsHeadBytes);
+  w.mslots = reinterpret_cast<unsigned long long*>(b + kWsHeadBytes + kSlotBytes);
   w.iacc = reinterpret_cast<double*>(b + kWsFixedBytes);
   return w;
 }

@@ -35,6 +35,8 @@ struct LossArgs {
 
 // SS variant of SILog (silog_ss.cu): `taken` = false leaves the call to the generic kernel below
 int launch_silog_ss(LossArgs& a, unsigned mg, cudaStream_t st, bool& taken);
+// register-resident variant of L1 / MSE / berHu / Laina for small inputs (resident_loss.cu); same contract
+int launch_resident(LossArgs& a, int kind, unsigned mg, cudaStream_t st, bool& taken);
 
 namespace {
 
@@ -844,6 +846,13 @@ template <int KIND, typename PT, bool VEC, unsigned MG>
 int launch_loss(LossArgs& a, cudaStream_t st) {
   const int64_t threads = static_cast<int64_t>(sm_count()) * kCtasPerSm * kBlock;
   const bool is_long = (a.n + threads - 1) / threads > 96;
+  if constexpr (std::is_same<PT, float>::value && VEC) {
+    if (!is_long) {   // small inputs (<= 2 quads per thread of one CTA per SM): everything stays in registers
+      bool taken = false;
+      const int rc = launch_resident(a, KIND, MG, st, taken);
+      if (rc != MDE_OK || taken) return rc;
+    }
+  }
   if constexpr (KIND == MDE_LOSS_SILOG && std::is_same<PT, float>::value && VEC) {
     if (!is_long && a.grad != nullptr) {
       bool taken = false;

@@ -219,13 +219,16 @@ def _silog_both(Cr, pred, gt, names=("delta1", "delta2", "delta3", "mse", "mae",
     return (loss, grad), (lf.detach(), p.grad.detach(), torch.stack(vals))
 
 
-def test_silog_shared_memory_variant_rare_quads(Cr):
+@pytest.mark.parametrize("shape", [(2, 1, 40, 64), (4, 1, 480, 640)])
+def test_silog_shared_memory_variant_rare_quads(Cr, shape):
     """The fast path of the SS kernels assumes valid targets > 0.01 and predictions >= 1e-7 per QUAD and sends
     every other quad through the exact arithmetic: targets in (0, 0.01] (valid for the metrics, masked for the
-    loss, criteria.py:730), exactly 0.01, a subnormal target, predictions below the metrics' clamp."""
+    loss, criteria.py:730), exactly 0.01, a subnormal target, predictions below the metrics' clamp.
+    The small shape runs in the register-resident kernel (resident_loss.cuh: up to 2 quads per thread of one CTA per
+    SM), 4x480x640 is just beyond its capacity and takes the shared-memory variant: the same cases for both."""
     from oracle import metrics as ometrics
     names = ["delta1", "delta2", "delta3", "mse", "mae", "log10", "rmse"]
-    pred, gt = synth.depth_pair((2, 1, 40, 64), 81, border=2)
+    pred, gt = synth.depth_pair(shape, 81, border=2)
     gt[0, 0, 10, 8:20] = torch.linspace(1e-4, 0.0099, 12)
     gt[0, 0, 11, 8] = 0.01
     gt[0, 0, 12, 9] = 0.010001
