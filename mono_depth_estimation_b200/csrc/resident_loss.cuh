@@ -76,28 +76,32 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
 
   // ---------------- phase A0: global max (berHu: max(p - t) over ALL pixels; Laina: max n_i) -------------------
   float cthr = 0.f, gmax = 0.f;
+  float4 r4[R];                // Laina: the signed residuals r_i (criteria.py:488-494), one logarithm per pixel and call
+  float tr = 0.f;
+#pragma unroll
+  for (int k = 0; k < R; ++k) r4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   if constexpr (kNeedMax) {
     float mx = -INFINITY;
     bool saw_nan = false;
-    auto px_max = [&](float p, float t) {
-      float x;
+    auto px_max = [&](float p, float t) -> float {
+      float x, r = 0.f;
       if constexpr (KIND == MDE_LOSS_BERHU) {
         x = p - t;                                                // criteria.py:118 - signed, unmasked
       } else {
-        float r;
         x = laina_resid(p, t, t > 0.f, a.use_logs != 0, a.clamp_val, r);
       }
       saw_nan |= (x != x);
       mx = fmaxf(mx, x);
+      return r;
     };
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       if (has[k]) {
-        px_max(p4[k].x, t4[k].x); px_max(p4[k].y, t4[k].y);
-        px_max(p4[k].z, t4[k].z); px_max(p4[k].w, t4[k].w);
+        r4[k].x = px_max(p4[k].x, t4[k].x); r4[k].y = px_max(p4[k].y, t4[k].y);
+        r4[k].z = px_max(p4[k].z, t4[k].z); r4[k].w = px_max(p4[k].w, t4[k].w);
       }
     }
-    if (has_tail) px_max(tp, tt);
+    if (has_tail) tr = px_max(tp, tt);
     const float qnan = __int_as_float(0x7fc00000);
     mx = warp_max(mx);
     const bool wn = __any_sync(0xffffffffu, saw_nan);
@@ -144,7 +148,10 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
   acc.zero();
   int lean_q = 0;
   float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;                   // a thread sees <= 4 R + 1 pixels: float counts are exact
-  auto px_sum = [&](float p, float t) {
+  // Laina's two quotients have the SAME divisor for every pixel: one IEEE reciprocal per thread instead of two divisions
+  // per pixel (a division is a ~30-instruction subroutine: 8 per thread were ~1 us of issue slots at this size)
+  const float laD = 2.f * cthr + 1e-9f, laInvD = 1.f / laD, laInvD2 = laInvD * laInvD;
+  auto px_sum = [&](float p, float t, float r) {
     if constexpr (KIND == MDE_LOSS_L1) {
       const bool v = t > 0.f;
       s0 += v ? fabsf(t - p) : 0.f;
@@ -170,13 +177,11 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
       c1 += hub ? 1.f : 0.f;
     } else {  // LAINA
       const bool m = t > 0.f;
-      float r;
-      const float ni = laina_resid(p, t, m, a.use_logs != 0, a.clamp_val, r);
+      const float ni = fabsf(r) * (m ? 1.f : 0.f);                // n_i = |r_i| m_i
       const bool big = !(ni < cthr);                              // criteria.py:497-498
-      const float D = 2.f * cthr + 1e-9f;
       const float num = fmaf(ni, ni, cthr * cthr);
-      s0 += big ? num / D : ni;
-      s1 += big ? (2.f * cthr * D - 2.f * num) / (D * D) : 0.f;   // d/dc of the quadratic branch
+      s0 += big ? num * laInvD : ni;
+      s1 += big ? (2.f * cthr * laD - 2.f * num) * laInvD2 : 0.f;  // d/dc of the quadratic branch
       c0 += m ? 1.f : 0.f;
       c1 += (ni == gmax) ? 1.f : 0.f;
     }
@@ -184,8 +189,8 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     if (has[k]) {
-      px_sum(p4[k].x, t4[k].x); px_sum(p4[k].y, t4[k].y);
-      px_sum(p4[k].z, t4[k].z); px_sum(p4[k].w, t4[k].w);
+      px_sum(p4[k].x, t4[k].x, r4[k].x); px_sum(p4[k].y, t4[k].y, r4[k].y);
+      px_sum(p4[k].z, t4[k].z, r4[k].z); px_sum(p4[k].w, t4[k].w, r4[k].w);
       if constexpr (MG != 0) {
         if (metric_quad_needs_ref(t4[k])) {                       // a valid subnormal target: exact arithmetic
           metric_add_contrib(metric_px_ref_contrib<kRefG>(p4[k].x, t4[k].x), acc);
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
     }
   }
   if (has_tail) {
-    px_sum(tp, tt);
+    px_sum(tp, tt, tr);
     if constexpr (MG != 0) metric_add_contrib(metric_px_ref_contrib<kRefG>(tp, tt), acc);
   }
   const int lean_px = 4 * lean_q;
@@ -318,7 +323,8 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
 
   // ---------------- gradient from the registers ------------------------------------------------------------------
   if (grad != nullptr) {
-    auto px_grad = [&](float p, float t) -> float {
+    const float inv_k3 = (KIND == MDE_LOSS_LAINA_BERHU) ? 1.f / k3 : 0.f;
+    auto px_grad = [&](float p, float t, float r) -> float {
       if constexpr (KIND == MDE_LOSS_L1) {
         return (t > 0.f) ? -sgn(t - p) * k1 : 0.f;
       } else if constexpr (KIND == MDE_LOSS_MSE) {
@@ -335,13 +341,12 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
         return v ? -sgn(d) * (hub ? fmaf(2.f, ad, 1.f) : 1.f) * k1 : 0.f;
       } else {
         const bool m = t > 0.f;
-        float r;
-        const float ni = laina_resid(p, t, m, a.use_logs != 0, a.clamp_val, r);
+        const float ni = fabsf(r) * (m ? 1.f : 0.f);
         const bool big = !(ni < cthr);
-        float dn = (big ? 2.f * ni / k3 : 1.f) * k1;
+        float dn = (big ? 2.f * ni * inv_k3 : 1.f) * k1;
         if (ni == gmax) dn += k2;
         float dp = m ? sgn(r) : 0.f;                              // dn_i/dp = sign(r) m [p >= cv] / p
-        if (a.use_logs) dp = (p >= a.clamp_val) ? dp / p : 0.f;
+        if (a.use_logs) dp = (p >= a.clamp_val) ? dp * rcp_nr(p) : 0.f;
         return dn * dp;
       }
     };
@@ -349,12 +354,12 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
     for (int k = 0; k < R; ++k) {
       if (has[k]) {
         float4 g;
-        g.x = px_grad(p4[k].x, t4[k].x); g.y = px_grad(p4[k].y, t4[k].y);
-        g.z = px_grad(p4[k].z, t4[k].z); g.w = px_grad(p4[k].w, t4[k].w);
+        g.x = px_grad(p4[k].x, t4[k].x, r4[k].x); g.y = px_grad(p4[k].y, t4[k].y, r4[k].y);
+        g.z = px_grad(p4[k].z, t4[k].z, r4[k].z); g.w = px_grad(p4[k].w, t4[k].w, r4[k].w);
         __stcs(reinterpret_cast<float4*>(grad) + (q0 + k * qs), g);
       }
     }
-    if (has_tail) grad[ti] = px_grad(tp, tt);
+    if (has_tail) grad[ti] = px_grad(tp, tt, tr);
   }
 
   // pooled metric values (one mean over all valid pixels of the call, metrics.py:58-67): the LAST CTA gathers every
