@@ -74,6 +74,35 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
   }
   if (tid == 0) sm_epoch = epoch_reg;
 
+  // The metric suite's per-pixel arithmetic (~45 instructions per pixel: 0.7 us of issue slots per quad and thread at
+  // this size) runs while the FIRST exchange of the kernel travels (one L2 round trip with nothing else to do): behind
+  // the publication of the CTA's maximum (berHu / Laina) or of its loss sums (the other kinds).
+  MetricAcc acc;
+  acc.zero();
+  int lean_q = 0;
+  auto metric_eval = [&] {
+    if constexpr (MG != 0) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if (has[k]) {
+          if (metric_quad_needs_ref(t4[k])) {                     // a valid subnormal target: exact arithmetic
+            metric_add_contrib(metric_px_ref_contrib<kRefG>(p4[k].x, t4[k].x), acc);
+            metric_add_contrib(metric_px_ref_contrib<kRefG>(p4[k].y, t4[k].y), acc);
+            metric_add_contrib(metric_px_ref_contrib<kRefG>(p4[k].z, t4[k].z), acc);
+            metric_add_contrib(metric_px_ref_contrib<kRefG>(p4[k].w, t4[k].w), acc);
+          } else {
+            metric_px_lean<MG, false>(p4[k].x, t4[k].x, acc);
+            metric_px_lean<MG, false>(p4[k].y, t4[k].y, acc);
+            metric_px_lean<MG, false>(p4[k].z, t4[k].z, acc);
+            metric_px_lean<MG, false>(p4[k].w, t4[k].w, acc);
+            ++lean_q;
+          }
+        }
+      }
+      if (has_tail) metric_add_contrib(metric_px_ref_contrib<kRefG>(tp, tt), acc);
+    }
+  };
+
   // ---------------- phase A0: global max (berHu: max(p - t) over ALL pixels; Laina: max n_i) -------------------
   float cthr = 0.f, gmax = 0.f;
   float4 r4[R];                // Laina: the signed residuals r_i (criteria.py:488-494), one logarithm per pixel and call
@@ -117,6 +146,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
         st_relaxed_u64(ws.slots + static_cast<size_t>(kRsMaxBase + cta) * 8,
                        (static_cast<unsigned long long>(seq1) << 32) | __float_as_uint(xn ? qnan : x));
     }
+    metric_eval();                                                // while the maxima travel
     float gm = -INFINITY;
     bool gn = false;
     if (tid < G) {                                                // one slot per thread, every CTA gathers all of them
@@ -143,10 +173,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
     cthr = 0.2f * gmax;                                           // criteria.py:119 / :496 (fp32 product)
   }
 
-  // ---------------- phase A1: masked sums and counts (+ the metric suite) from the registers ------------------
-  MetricAcc acc;
-  acc.zero();
-  int lean_q = 0;
+  // ---------------- phase A1: masked sums and counts from the registers ------------------------------------------
   float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;                   // a thread sees <= 4 R + 1 pixels: float counts are exact
   // Laina's two quotients have the SAME divisor for every pixel: one IEEE reciprocal per thread instead of two divisions
   // per pixel (a division is a ~30-instruction subroutine: 8 per thread were ~1 us of issue slots at this size)
@@ -191,27 +218,13 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
     if (has[k]) {
       px_sum(p4[k].x, t4[k].x, r4[k].x); px_sum(p4[k].y, t4[k].y, r4[k].y);
       px_sum(p4[k].z, t4[k].z, r4[k].z); px_sum(p4[k].w, t4[k].w, r4[k].w);
-      if constexpr (MG != 0) {
-        if (metric_quad_needs_ref(t4[k])) {                       // a valid subnormal target: exact arithmetic
-          metric_add_contrib(metric_px_ref_contrib<kRefG>(p4[k].x, t4[k].x), acc);
-          metric_add_contrib(metric_px_ref_contrib<kRefG>(p4[k].y, t4[k].y), acc);
-          metric_add_contrib(metric_px_ref_contrib<kRefG>(p4[k].z, t4[k].z), acc);
-          metric_add_contrib(metric_px_ref_contrib<kRefG>(p4[k].w, t4[k].w), acc);
-        } else {
-          metric_px_lean<MG, false>(p4[k].x, t4[k].x, acc);
-          metric_px_lean<MG, false>(p4[k].y, t4[k].y, acc);
-          metric_px_lean<MG, false>(p4[k].z, t4[k].z, acc);
-          metric_px_lean<MG, false>(p4[k].w, t4[k].w, acc);
-          ++lean_q;
-        }
-      }
     }
   }
-  if (has_tail) {
-    px_sum(tp, tt, tr);
-    if constexpr (MG != 0) metric_add_contrib(metric_px_ref_contrib<kRefG>(tp, tt), acc);
-  }
-  const int lean_px = 4 * lean_q;
+  if (has_tail) px_sum(tp, tt, tr);
+  // without a max exchange: two quads per thread hide their metric arithmetic behind the sum exchange (8x300x400, L1:
+  // 9.3 -> 8.4 us); with one quad the publication would only be delayed (C1: 6.8 -> 7.1 us), so it comes first
+  constexpr bool kEvalBehindSums = !kNeedMax && R > 1;
+  if constexpr (!kNeedMax && !kEvalBehindSums) metric_eval();
   {
     float run[4] = {s0, s1, c0, c1};
     const float tot = warp_multi_sum<4>(run);                     // quantity (lane >> 3) & 3
@@ -244,6 +257,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
   const unsigned seq3 = epoch * 4u + 3u;
   auto flush_metrics = [&] {
     if constexpr (MG != 0) {
+      const int lean_px = 4 * lean_q;
       const int r0 = __reduce_add_sync(0xffffffffu, acc.n_valid(lean_px)), r1 = __reduce_add_sync(0xffffffffu, acc.count(1, lean_px));
       const int r2 = __reduce_add_sync(0xffffffffu, acc.count(2, lean_px)), r3 = __reduce_add_sync(0xffffffffu, acc.count(3, lean_px));
       if (lane == 0) {
@@ -273,7 +287,10 @@ __global__ void __launch_bounds__(kRsThreads, 1) resident_loss_kernel(LossArgs a
   };
 
   // ---------------- all-reduce of the totals; every CTA derives the coefficients itself --------------------------
-  grid_sum4_counted<kRsWarps>(ws.slots, ukey + 2, epoch * 4u + 2u, sm_own, sm_gather, sm_tot, [&] { flush_metrics(); });
+  grid_sum4_counted<kRsWarps>(ws.slots, ukey + 2, epoch * 4u + 2u, sm_own, sm_gather, sm_tot, [&] {
+    if constexpr (kEvalBehindSums) metric_eval();                 // while the loss sums travel
+    flush_metrics();
+  });
   if (tid < 32) __syncwarp();   // sm_tot was written by threads of warp 0
   if (tid == 0) {
     const double S0 = sm_tot[0], S1 = sm_tot[1], N0 = sm_tot[2], N1 = sm_tot[3];
@@ -452,6 +469,9 @@ int launch_resident_mg(LossArgs& a, cudaStream_t st, bool& taken) {
   const int64_t nt = (nq + kRsThreads - 1) / kRsThreads;
   if (nt > static_cast<int64_t>(cap) * 2) return MDE_OK;
   const int grid = static_cast<int>(nt < cap ? nt : cap);
+  // SILog with the metric suite and two quads per thread: the shared-memory variant shares the logarithm between loss
+  // and metrics and is faster there (8x300x400: 9.4 against 11.6 us)
+  if (KIND == MDE_LOSS_SILOG && MG != 0 && nt > grid && a.grad != nullptr) return MDE_OK;
   a.chunk = make_chunking(nq, 8, grid);
   taken = true;
   return (nt <= grid) ? launch_resident_r<KIND, MG, 1>(a, grid, st) : launch_resident_r<KIND, MG, 2>(a, grid, st);
