@@ -295,10 +295,11 @@ int mde_ordinal_regression_loss(const float* prob, const float* gt_depth, int64_
  * Back-projection, mask logic, the z==0 fix-up quirk (criteria.py:1004), per-triplet loss, the
  * exact 25 % trim (radix select on the fp32 bit pattern) and the scatter-add backward are fused
  * in one cooperative launch.
- *   scratch  device, mde_vnl_scratch_bytes(n_img, n_trip) bytes (per-triplet losses; need not be zeroed)
+ *   scratch  device, mde_vnl_scratch_bytes(n_img, n_trip, h, w) bytes, 16-byte aligned (histograms, per-triplet losses and
+ *            gradient factors, the depths re-laid pixel-major for the gathers; need not be zeroed)
  *   stats_out (nullable) doubles {M valid, q dropped, threshold, n_below, n_tie, kept_sum}
  */
-size_t mde_vnl_scratch_bytes(int64_t n_img, int64_t n_trip);
+size_t mde_vnl_scratch_bytes(int64_t n_img, int64_t n_trip, int64_t h, int64_t w);
 int mde_vnl_loss(const float* gt_depth, const void* pred, int pred_dtype, const int64_t* trip,
                  int64_t n_img, int64_t h, int64_t w, int64_t n_trip, float fx, float fy, int select,
                  float grad_scale, void* ws, void* scratch, float* loss_out, double* stats_out,

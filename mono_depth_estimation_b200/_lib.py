@@ -72,7 +72,7 @@ SIGNATURES = {
                               _vp, _vp, _vp, _vp]),
     "mde_ordinal_regression_loss": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _i32, _f32, _vp, _vp,
                                            _vp, _vp]),
-    "mde_vnl_scratch_bytes": (C.c_size_t, [_i64, _i64]),
+    "mde_vnl_scratch_bytes": (C.c_size_t, [_i64, _i64, _i64, _i64]),
     "mde_vnl_loss": (_i32, [_vp, _vp, _i32, _vp, _i64, _i64, _i64, _i64, _f32, _f32, _i32, _f32, _vp, _vp,
                             _vp, _vp, _vp, _vp]),
     "mde_wcel_loss": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp]),

@@ -444,7 +444,7 @@ class VNL_Loss(nn.Module):
             pc = _compute_copy(p)
             with torch.cuda.device(dev):
                 ws = _lib.workspace(dev, B)
-                scratch = torch.empty(int(lib.mde_vnl_scratch_bytes(B, n_trip)), dtype=torch.uint8, device=dev)
+                scratch = torch.empty(int(lib.mde_vnl_scratch_bytes(B, n_trip, H, W)), dtype=torch.uint8, device=dev)
                 loss = torch.empty((), dtype=torch.float32, device=dev)
                 grad = torch.empty_like(pc) if need_grad else None
                 _lib.check(lib.mde_vnl_loss(_lib.ptr(gt), _lib.ptr(pc), _lib.dtype_code(pc), _lib.ptr(trip), B, H, W,

@@ -180,12 +180,14 @@ namespace mde {
 int set_trace_losses(unsigned long long* buf);
 int set_trace_losses_fused(unsigned long long* buf);
 int set_trace_silog_ss(unsigned long long* buf);
+int set_trace_vnl(unsigned long long* buf);
 }  // namespace mde
 
 extern "C" int mde_debug_set_trace(void* device_buf) {
   unsigned long long* b = static_cast<unsigned long long*>(device_buf);
   const int r1 = mde::set_trace_losses(b), r2 = mde::set_trace_losses_fused(b), r3 = mde::set_trace_silog_ss(b);
-  return (r1 == MDE_OK && r2 == MDE_OK && r3 == MDE_OK) ? MDE_OK : MDE_ECUDA;
+  const int r4 = mde::set_trace_vnl(b);
+  return (r1 == MDE_OK && r2 == MDE_OK && r3 == MDE_OK && r4 == MDE_OK) ? MDE_OK : MDE_ECUDA;
 }
 
 extern "C" const char* mde_last_error(void) { return mde::g_err; }

@@ -49,7 +49,7 @@ def test_version_error_and_sizes(lib):
     assert b"sm_100a" in lib.mde_version()
     assert lib.mde_workspace_bytes(1) >= 1536
     assert lib.mde_workspace_bytes(654) >= 1536 + 3 * 654 * 16 * 8
-    assert lib.mde_vnl_scratch_bytes(8, 100000) >= 8 * 100000 * 4
+    assert lib.mde_vnl_scratch_bytes(8, 100000, 385, 385) >= 8 * 100000 * 4 * 4 + 8 * 385 * 385 * 8
     # argument validation happens before any CUDA call
     rc = lib.mde_metrics(None, 0, None, 1, 1, 0, None, None, None, None, None, None)
     assert rc == -1 and b"null" in lib.mde_last_error()

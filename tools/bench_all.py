@@ -189,7 +189,7 @@ def main():
     px = B * H * W
     n_trip = trip.shape[1]
     ws = _lib.workspace(dev, B)
-    scratch = torch.empty(int(lib.mde_vnl_scratch_bytes(B, n_trip)), dtype=torch.uint8, device=dev)
+    scratch = torch.empty(int(lib.mde_vnl_scratch_bytes(B, n_trip, H, W)), dtype=torch.uint8, device=dev)
     stats = torch.zeros(8, dtype=torch.float64, device=dev)
     grad = torch.empty_like(pred)
     fns = [lambda: _lib.check(lib.mde_vnl_loss(_lib.ptr(gt), _lib.ptr(pred), 0, _lib.ptr(trip), B, H, W, n_trip, 519.0, 519.0, 1, 1.0,

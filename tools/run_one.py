@@ -43,7 +43,7 @@ elif name in ("dorn_fused", "dorn_decode", "ord_loss"):
         f = lambda: _lib.check(lib.mde_ord_loss(_lib.ptr(prob), _lib.ptr(y), N, C2 // 2, H * W, 1.0, _lib.ptr(ws), _lib.ptr(loss_t), _lib.ptr(gp), sp()))
 elif name == "vnl":
     gt, pred, trip = synth.vnl_inputs((8, 1, 385, 385), 104, device=dev)
-    ws = _lib.workspace(dev, 8); scratch = torch.empty(int(lib.mde_vnl_scratch_bytes(8, 100000)), dtype=torch.uint8, device=dev)
+    ws = _lib.workspace(dev, 8); scratch = torch.empty(int(lib.mde_vnl_scratch_bytes(8, 100000, 385, 385)), dtype=torch.uint8, device=dev)
     grad = torch.empty_like(pred)
     f = lambda: _lib.check(lib.mde_vnl_loss(_lib.ptr(gt), _lib.ptr(pred), 0, _lib.ptr(trip), 8, 385, 385, 100000, 519.0, 519.0, 1, 1.0, _lib.ptr(ws), _lib.ptr(scratch),
                                             _lib.ptr(loss_t), None, _lib.ptr(grad), sp()))
