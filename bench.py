@@ -278,6 +278,13 @@ def config_rows(dev, peak, quick=False):
         us, _ = graph_timed(fns, dev, reps)
         row(kname, {"C1": "berHu", "C1_silog": "SILog", "C1_l1": "L1", "C1_laina": "Laina berHu"}[kname] +
             " fwd+bwd + 7 metrics, one launch (register-resident kernel), 8x1x228x304", us, 12.0 * px)
+    # MaskedDepthLoss (the reference's C1 criterion of the eigen module, criteria.py:17-64): fwd+bwd, one launch
+    fns = [lambda pr=pr, gt=gt, gr=gr: _lib.check(lib.mde_masked_loss(
+        _lib.LOSS_EIGEN, _lib.ptr(pr), 0, _lib.ptr(gt), None, shape[0], shape[2], shape[3], C.byref(lp), 1.0, _lib.ptr(ws),
+        _lib.ptr(loss_t), None, _lib.ptr(gr), sp())) for (pr, gt), gr in zip(ring, grads)]
+    us, _ = graph_timed(fns, dev, reps)
+    row("C1_eigen", "MaskedDepthLoss (Eigen scale-invariant + gradient term) fwd+bwd, one launch (register-resident kernel), "
+        "8x1x228x304", us, 12.0 * px)
     del ring, grads
 
     # ---- C3: DORN fused logits -> decode, depth, ordinal loss, grad (K = 68), 8x136x257x353

@@ -134,3 +134,61 @@ def test_resident_is_bit_reproducible(Cr):
             if it % 4 == 0:
                 run(Cr, "silog", other_p, other_g, NAMES7)
                 run(Cr, "berhu", pred[:1], gt[:1])
+
+
+# ---- MaskedDepthLoss (criteria.py:17-64): register-resident variant of csrc/eigen.cu ------------------------------------
+# C1 itself (16.9 CTAs per image: most CTAs hold one image, every 17th two), images of exactly one CTA, images of 4420
+# pixels (every CTA straddles two images), more images than warps (the per-image gather loops), one image, one CTA
+EIGEN_SHAPES = [((8, 1, 228, 304), 0.5), ((8, 1, 228, 304), 3.0), ((5, 1, 120, 160), 3.0), ((3, 1, 64, 64), 0.5),
+                ((2, 1, 65, 68), 3.0), ((37, 1, 64, 64), 0.5), ((1, 1, 64, 64), 3.0), ((1, 1, 300, 400), 0.5)]
+
+
+def run_eigen(Cr, pred, gt, expect_resident=True):
+    from mono_depth_estimation_b200 import _lib
+    p = pred.requires_grad_(True) if pred.is_cuda else pred.cuda().requires_grad_(True)
+    g = gt.cuda()
+    _lib.workspace(p.device, p.shape[0])
+    n0 = _lib.launch_count()
+    loss = Cr.MaskedDepthLoss()(p, g)
+    assert _lib.launch_count() - n0 == 1, "loss and gradient must come from ONE launch"
+    loss.backward()
+    return loss.detach(), p.grad.detach()
+
+
+@pytest.mark.parametrize("shape,noise", EIGEN_SHAPES)
+def test_resident_eigen_vs_oracle_and_generic(Cr, shape, noise):
+    pred, gt = synth.depth_pair(shape, 91 + shape[0], border=2, noise=noise)
+    l64, g64 = olosses.loss_and_grad(olosses.LOSSES["eigen"], pred.double(), gt.double())
+    loss, grad = run_eigen(Cr, pred, gt)
+    close(loss, l64, LOSS_RTOL); grad_close(grad, g64)
+    with torch.no_grad():                              # forward only: same value, no gradient work
+        close(Cr.MaskedDepthLoss()(pred.cuda(), gt.cuda()), l64, LOSS_RTOL)
+    # a prediction 4 bytes off a 16-byte boundary takes the cooperative kernel of the same file: same per-pixel
+    # expressions, different summation order of the fp64 totals
+    buf = torch.zeros(pred.numel() + 1).cuda()
+    buf[1:] = pred.flatten().cuda()
+    lg, gg = run_eigen(Cr, buf[1:].view(pred.shape).detach(), gt)
+    close(loss, lg, 2e-6); close(grad, gg, 2e-6, 1e-7 * float(gg.abs().max()))
+
+
+def test_resident_eigen_sparse_targets_and_reproducibility(Cr):
+    """Images without a valid pixel (n_b = 0 contributes nothing, criteria.py:38-41), an image whose valid pixels have no
+    valid neighbour, and bit-identical results over repeated launches interleaved with other kernels that recycle the
+    same workspace words (slots, mslots rows, parity sets)."""
+    pred, gt = synth.depth_pair((8, 1, 228, 304), 97, border=2, noise=3.0)
+    gt[2] = 0.0
+    gt[5, :, 1::2, :] = 0.0                            # no vertical pairs in image 5
+    l64, g64 = olosses.loss_and_grad(olosses.LOSSES["eigen"], pred.double(), gt.double())
+    ref = None
+    for it in range(10):
+        loss, grad = run_eigen(Cr, pred, gt)
+        if ref is None:
+            ref = (loss, grad)
+            close(loss, l64, LOSS_RTOL); grad_close(grad, g64)
+        else:
+            assert torch.equal(loss, ref[0]) and torch.equal(grad, ref[1]), it
+        if it % 3 == 0:
+            run(Cr, "berhu", pred, gt, NAMES7)
+            run_eigen(Cr, pred[:3, :, :64, :64].contiguous(), gt[:3, :, :64, :64].contiguous())
+    loss, _ = run_eigen(Cr, pred, torch.zeros_like(gt))
+    assert torch.isnan(loss)                           # 0 / 0 like the reference
