@@ -22,6 +22,9 @@
 // e <= 1 - 2^-23 <=> exp(-d) <= 1 - 1.5*2^-24 (ties-to-even at the midpoint) <=> d > 1.5*2^-24
 // (d = 1.5*2^-24 itself gives exp(-d) just above the midpoint). So decode counts pairs with
 // fl(b' - a') > 0x1.8p-24f; equal or non-positive logit pairs (clamped to 1e-8) tie and do not count.
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 #include "metric_math.cuh"
 
@@ -30,6 +33,14 @@ namespace {
 
 constexpr int kDBlock = 256;
 constexpr int kDWarps = kDBlock / 32;
+// pairs per group = half the loads a thread keeps in flight. Measured on one box at C3 (tools/dorn_probe.py, profiles/
+// r02_dorn_ab.jsonl): supervision step 155 us with 4, 151 us with 8; decode only 66.2 us with 4, 67.9 us with 8.
+#ifndef MDE_DORN_U_LOSS
+#define MDE_DORN_U_LOSS 8
+#endif
+#ifndef MDE_DORN_U_PLAIN
+#define MDE_DORN_U_PLAIN 4
+#endif
 constexpr float kTieMargin = 8.940696716308594e-08f;  // 1.5 * 2^-24, exactly representable
 
 __device__ __forceinline__ float clamp_logit(float v) {
@@ -89,10 +100,68 @@ __device__ __forceinline__ bool last_cta(unsigned* ticket) {
   return sm_last;
 }
 
+// U consecutive pairs of ONE pixel: all 2U logits in flight before the first is used. FULL: every pair exists (no
+// predicates, no branches between the pairs - the first version tested k < K per pair and per load, 60 instructions per
+// pair; this form has 40); otherwise only the first `npair` < U do.
+//   pa / ga / pp: channel 2 k0 of the pixel in the logits / their gradient, plane k0 in the probabilities
+//   kf0 = float(k0); y: the pixel's label. LABELLED = false: y is NaN - neither k <= y nor k > y holds (criteria.py:769-770),
+//   the pixel has no loss term and a zero gradient (its own instantiation: the common path carries no select for it)
+template <typename XT, bool HAS_PROB, bool WANT_LOSS, bool HAS_GRAD, int U, bool FULL, bool LABELLED>
+__device__ __forceinline__ void dorn_group(const XT* __restrict__ pa, XT* __restrict__ ga, float* __restrict__ pp, unsigned e,
+                                           unsigned ep, unsigned hwu, int npair, float kf0, float y, float inv_nhw, int& cnt,
+                                           float& l2sum) {
+  float av[U], bv[U];
+  // Element of plane c of the pixel: pa[e + c * hwu] with the index formed in 32 bits. Two callers: tensors of fewer than
+  // 2^32 elements pass the tensor's base pointers (uniform) and the pixel's element index e, so an access is one 32-bit
+  // add (shared by the logit and its gradient) and one IMAD.WIDE; larger tensors pass per-pixel pointers and e = 0
+  // (c * hwu < 2^32: hw < 2^27 is checked on the host, c < 32). The first version multiplied 64-bit plane strides.
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (FULL || u < npair) {
+      av[u] = Elem<XT>::ld1(pa + (e + static_cast<unsigned>(2 * u) * hwu));
+      bv[u] = Elem<XT>::ld1(pa + (e + static_cast<unsigned>(2 * u + 1) * hwu));
+    } else {
+      av[u] = 0.f;
+      bv[u] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!FULL && u >= npair) break;
+    const float ca = clamp_logit(av[u]), cb = clamp_logit(bv[u]);
+    const float d = cb - ca;
+    const float P = pair_prob(d);
+    cnt += (d > kTieMargin) ? 1 : 0;  // == (P > 0.5) of the reference, see header
+    if constexpr (HAS_PROB) __stcs(pp + (ep + static_cast<unsigned>(u) * hwu), P);
+    if constexpr (WANT_LOSS && LABELLED) {
+      const float kf = kf0 + static_cast<float>(u);
+      const bool le = kf <= y;
+      const float q = 1.0f - P;
+      const float xsel = le ? P : q;                     // criteria.py:777-778
+      const bool clamped = xsel < 1e-8f;                 // clamp(., 1e-8, 1e8); the upper bound cannot bind
+      const float xc = clamped ? 1e-8f : xsel;           // NaN stays NaN
+      l2sum += mufu_lg2(xc);
+      // dloss/d(b'-a') = -(1-P)/NHW for k <= y, +P/NHW for k > y, zero where the clamp binds
+      float gz = le ? -q : P;
+      gz = clamped ? 0.f : gz * inv_nhw;
+      if constexpr (HAS_GRAD) {
+        // the clamp of a logit passes the gradient on [1e-8, 1e4]: exactly where the clamp returned the logit itself
+        // (a NaN logit compares unequal and gets 0, as `v >= 1e-8 && v <= 1e4` gave it)
+        Elem<XT>::st1(ga + (e + static_cast<unsigned>(2 * u) * hwu), (ca == av[u]) ? -gz : 0.f);
+        Elem<XT>::st1(ga + (e + static_cast<unsigned>(2 * u + 1) * hwu), (cb == bv[u]) ? gz : 0.f);
+      }
+    } else if constexpr (WANT_LOSS && HAS_GRAD) {
+      Elem<XT>::st1(ga + (e + static_cast<unsigned>(2 * u) * hwu), 0.f);
+      Elem<XT>::st1(ga + (e + static_cast<unsigned>(2 * u + 1) * hwu), 0.f);
+    }
+  }
+}
+
 struct DornArgs {
   const void* x;
   const float* gt;     // metric depth [n,hw] (fused) or SID label [n,hw] (label_mode) or null
   int label_mode;      // gt already holds the float label (ordLoss entry point)
+  int index32;         // n 2K hw < 2^32: element indices fit 32 bits (set by the launcher)
   int64_t n, hw;
   int K;
   float alpha, beta;
@@ -135,47 +204,39 @@ __global__ void __launch_bounds__(kDBlock, 4) dorn_kernel(DornArgs a) {
     }
     int cnt = 0;
     float l2sum = 0.f;   // sum of log2(clamped probability); times ln 2 at the end
-    for (int k0 = 0; k0 < K; k0 += 4) {
-      float av[4], bv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (k0 + u < K) {
-          av[u] = Elem<XT>::ld1(pa + static_cast<int64_t>(2 * u) * hw);
-          bv[u] = Elem<XT>::ld1(pa + static_cast<int64_t>(2 * u + 1) * hw);
+    const unsigned hwu = static_cast<unsigned>(hw);
+    constexpr int kDornU = WANT_LOSS ? MDE_DORN_U_LOSS : MDE_DORN_U_PLAIN;
+    auto walk = [&](auto labelled, auto index32) {
+      constexpr bool L = decltype(labelled)::value;
+      constexpr bool I32 = decltype(index32)::value;
+      // I32: uniform base pointers + 32-bit element indices; otherwise per-pixel pointers that advance, indices from 0
+      const XT* qa = I32 ? x : pa;
+      XT* qg = I32 ? gx : ga;
+      float* qp = I32 ? a.prob : pp;
+      unsigned e = I32 ? static_cast<unsigned>(pa - x) : 0u;
+      unsigned ep = (I32 && HAS_PROB) ? static_cast<unsigned>(pp - a.prob) : 0u;
+      int k0 = 0;
+      for (; k0 + kDornU <= K; k0 += kDornU) {   // full groups: no per-pair predicates, kDornU pairs (2 kDornU loads) in flight
+        dorn_group<XT, HAS_PROB, WANT_LOSS, HAS_GRAD, kDornU, true, L>(qa, qg, qp, e, ep, hwu, kDornU, static_cast<float>(k0), y, inv_nhw, cnt, l2sum);
+        if constexpr (I32) {
+          e += 2u * kDornU * hwu;
+          ep += kDornU * hwu;
         } else {
-          av[u] = 0.f;
-          bv[u] = 0.f;
+          qa += 2 * kDornU * hw;
+          if constexpr (HAS_GRAD) qg += 2 * kDornU * hw;
+          if constexpr (HAS_PROB) qp += kDornU * hw;
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = k0 + u;
-        if (k >= K) break;
-        const float d = clamp_logit(bv[u]) - clamp_logit(av[u]);
-        const float P = pair_prob(d);
-        cnt += (d > kTieMargin) ? 1 : 0;  // == (P > 0.5) of the reference, see header
-        if constexpr (HAS_PROB) __stcs(pp + static_cast<int64_t>(u) * hw, P);
-        if constexpr (want_loss) {
-          const float kf = static_cast<float>(k);
-          const bool le = kf <= y, gt = kf > y;          // both false for a NaN label (criteria.py:769-770)
-          const float q = 1.0f - P;
-          const float xsel = le ? P : q;                   // criteria.py:777-778
-          const bool clamped = xsel < 1e-8f;               // clamp(., 1e-8, 1e8); the upper bound cannot bind
-          const float xc = clamped ? 1e-8f : xsel;         // NaN stays NaN
-          const float l2 = mufu_lg2(xc);
-          l2sum += (le || gt) ? l2 : 0.f;
-          // dloss/d(b'-a') = -(1-P)/NHW for k <= y, +P/NHW for k > y, zero where the clamp binds
-          float gz = le ? -q : P;
-          gz = (clamped || !(le || gt)) ? 0.f : gz * inv_nhw;
-          if constexpr (HAS_GRAD) {
-            Elem<XT>::st1(ga + static_cast<int64_t>(2 * u) * hw, logit_passes(av[u]) ? -gz : 0.f);
-            Elem<XT>::st1(ga + static_cast<int64_t>(2 * u + 1) * hw, logit_passes(bv[u]) ? gz : 0.f);
-          }
-        }
-      }
-      pa += 8 * hw;
-      if constexpr (HAS_GRAD) ga += 8 * hw;
-      if constexpr (HAS_PROB) pp += 4 * hw;
+      if (k0 < K)                                 // the last K % kDornU pairs
+        dorn_group<XT, HAS_PROB, WANT_LOSS, HAS_GRAD, kDornU, false, L>(qa, qg, qp, e, ep, hwu, K - k0, static_cast<float>(k0), y, inv_nhw, cnt, l2sum);
+    };
+    const bool labelled = !want_loss || y == y;   // NaN label (a NaN or negative target under SID): rare, own code path
+    if (a.index32) {
+      if (labelled) walk(std::true_type{}, std::true_type{});
+      else walk(std::false_type{}, std::true_type{});
+    } else {
+      if (labelled) walk(std::true_type{}, std::false_type{});
+      else walk(std::false_type{}, std::false_type{});
     }
     if (a.decode) a.decode[px] = static_cast<int64_t>(cnt);
     if (a.depth) a.depth[px] = label_depth(static_cast<float>(cnt), a.alpha, a.beta, K, a.disc);
@@ -352,6 +413,16 @@ template <typename XT>
 int launch_dorn_t(DornArgs& a, cudaStream_t st) {
   const unsigned grid = px_grid(a.n * a.hw, 4);
   const bool p = a.prob != nullptr, l = a.gt != nullptr, g = a.grad_x != nullptr && l;
+  if (a.hw >= (int64_t(1) << 27)) {
+    set_error("DORN head: more than 2^27 pixels per image");
+    return MDE_ETOOBIG;
+  }
+  a.index32 = (a.n * 2 * static_cast<int64_t>(a.K) * a.hw < (int64_t(1) << 32)) ? 1 : 0;
+  // MDE_DORN_NO_INDEX32=1 sends small tensors down the 64-bit pointer path too (a >= 16 GB tensor is not a test case);
+  // read per call so that a test can switch it
+  if (const char* e = getenv("MDE_DORN_NO_INDEX32")) {
+    if (atoi(e) != 0) a.index32 = 0;
+  }
 #define MDE_DORN(P, L, G) dorn_kernel<XT, P, L, G><<<grid, kDBlock, 0, st>>>(a)
   if (!l) { if (p) MDE_DORN(true, false, false); else MDE_DORN(false, false, false); }
   else if (g) { if (p) MDE_DORN(true, true, true); else MDE_DORN(false, true, true); }

@@ -213,3 +213,38 @@ def test_sid_integer_labels_exact_outside_the_rounding_band(D):
         assert torch.equal(got[~band], ref[~band]), ds
         assert int((got - ref).abs().max()) <= 1, ds
         assert float(band.double().mean()) < 1e-3, ds                    # the band is tiny: this is an exactness test
+
+
+@pytest.mark.parametrize("shape,K", [((2, 136, 40, 52), 68), ((2, 22, 33, 41), 11)])
+def test_nan_labels_and_the_wide_index_path(D, shape, K):
+    """A negative or NaN target has a NaN SID label: neither k <= y nor k > y holds (criteria.py:769-770), the pixel
+    contributes no loss term and its logits get a zero gradient (the kernel runs such pixels through their own code
+    path). Then the same call with 64-bit per-pixel pointers instead of 32-bit element indices (the path of tensors with
+    >= 2^32 elements, MDE_DORN_NO_INDEX32=1): bit-identical outputs."""
+    import os
+    x, gt = synth.dorn_inputs(shape, 43)
+    gt[0, 0, 1, :7] = -1.0
+    gt[1, 0, 2, 3:9] = float("nan")
+    gt[1, 0, -1, -1] = -0.5
+    xd = x.double().clone().requires_grad_(True)
+    dec_ref, P64 = odorn.ordinal_layer(xd)
+    l64 = odorn.ord_loss(P64, odorn.depth_to_label(gt.double(), 0.001, 1.0, K))
+    (g64,) = torch.autograd.grad(l64, xd)
+    assert torch.isfinite(l64) and float(g64[0, :, 1, :7].abs().sum()) == 0.0
+
+    def once():
+        xr = x.cuda().requires_grad_(True)
+        loss, decode, depth, P = D.dorn_fused(xr, gt.cuda(), K, 0.001, 1.0, want_prob=True)
+        loss.backward()
+        return loss.detach(), decode, depth, P.detach(), xr.grad
+    out = once()
+    close(out[0], l64.detach(), LOSS_RTOL)
+    assert torch.equal(out[1].cpu(), dec_ref)
+    grad_close(out[4], g64)
+    assert float(out[4][0, :, 1, :7].abs().sum()) == 0.0 and float(out[4][1, :, 2, 3:9].abs().sum()) == 0.0
+    os.environ["MDE_DORN_NO_INDEX32"] = "1"
+    try:
+        wide = once()
+    finally:
+        del os.environ["MDE_DORN_NO_INDEX32"]
+    assert all(torch.equal(a, b) for a, b in zip(out, wide))
