@@ -256,44 +256,78 @@ __global__ void __launch_bounds__(kDBlock, 4) dorn_kernel(DornArgs a) {
   }
 }
 
-// ordLoss(P, y): elementwise over [n,K,hw] with the label broadcast over K
+// ordLoss(P, y): elementwise over [n,K,hw] with the label broadcast over K. Same walk as dorn_group: full groups of U
+// planes without per-plane predicates, 32-bit element indices (`wide`: per-pixel pointers, indices from 0), pixels with
+// a NaN label on their own code path (no term, zero gradient).
+template <bool HAS_GRAD, int U, bool FULL, bool LABELLED>
+__device__ __forceinline__ void ord_loss_group(const float* __restrict__ pp, float* __restrict__ gp, unsigned e, unsigned hwu,
+                                               int nplane, float kf0, float y, float inv_nhw, float& l2sum) {
+  float pv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) pv[u] = (FULL || u < nplane) ? __ldcs(pp + (e + static_cast<unsigned>(u) * hwu)) : 0.5f;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!FULL && u >= nplane) break;
+    if constexpr (LABELLED) {
+      const float P = pv[u];
+      const bool le = (kf0 + static_cast<float>(u)) <= y;
+      const float xsel = le ? P : 1.0f - P;
+      // clamp(x, 1e-8, 1e8) with NaN kept; the gradient passes inside the closed interval
+      const bool lo = xsel < 1e-8f, hi = xsel > 1e8f;
+      const float xc = lo ? 1e-8f : (hi ? 1e8f : xsel);
+      l2sum += mufu_lg2(xc);
+      if constexpr (HAS_GRAD) {
+        // d/dP: -1/(P NHW) for k <= y, +1/((1-P) NHW) for k > y
+        const float g = (le ? -inv_nhw : inv_nhw) * rcp_nr(xc);
+        __stcs(gp + (e + static_cast<unsigned>(u) * hwu), (lo || hi) ? 0.f : g);
+      }
+    } else if constexpr (HAS_GRAD) {
+      __stcs(gp + (e + static_cast<unsigned>(u) * hwu), 0.f);
+    }
+  }
+}
+
+template <bool HAS_GRAD>
 __global__ void __launch_bounds__(kDBlock, 4)
 ord_loss_kernel(const float* __restrict__ prob, const float* __restrict__ label, int64_t n, int K, int64_t hw,
-                float grad_scale, void* ws_raw, float* loss_out, float* __restrict__ grad) {
+                float grad_scale, void* ws_raw, float* loss_out, float* __restrict__ grad, int index32) {
   __shared__ double sm[kDWarps];
+  constexpr int U = 8;
   const int64_t npx = n * hw;
   const float inv_nhw = grad_scale / static_cast<float>(npx);
+  const unsigned hwu = static_cast<unsigned>(hw);
   double loss_acc = 0.0;
   for (int64_t px = static_cast<int64_t>(blockIdx.x) * kDBlock + threadIdx.x; px < npx;
        px += static_cast<int64_t>(gridDim.x) * kDBlock) {
     const int64_t img = px / hw;
-    const float* pp = prob + img * static_cast<int64_t>(K) * hw + (px - img * hw);
-    float* gp = grad ? grad + img * static_cast<int64_t>(K) * hw + (px - img * hw) : nullptr;
+    const int64_t first = img * static_cast<int64_t>(K) * hw + (px - img * hw);   // plane 0 of this pixel
     const float y = __ldg(label + px);
     float l2sum = 0.f;
-    for (int k0 = 0; k0 < K; k0 += 8) {
-      float pv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) pv[u] = (k0 + u < K) ? __ldcs(pp + static_cast<int64_t>(u) * hw) : 0.5f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int k = k0 + u;
-        if (k >= K) break;
-        const float P = pv[u];
-        const float kf = static_cast<float>(k);
-        const bool le = kf <= y, gt = kf > y;
-        const float xsel = le ? P : 1.0f - P;
-        // clamp(x, 1e-8, 1e8) with NaN kept; the gradient passes inside the closed interval
-        const bool lo = xsel < 1e-8f, hi = xsel > 1e8f;
-        const float xc = lo ? 1e-8f : (hi ? 1e8f : xsel);
-        l2sum += (le || gt) ? mufu_lg2(xc) : 0.f;
-        // d/dP: -1/(P NHW) for k <= y, +1/((1-P) NHW) for k > y
-        float g = (le ? -inv_nhw : inv_nhw) * rcp_nr(xc);
-        g = (lo || hi || !(le || gt)) ? 0.f : g;
-        if (gp) __stcs(gp + static_cast<int64_t>(u) * hw, g);
+    auto walk = [&](auto labelled, auto index32_t) {
+      constexpr bool L = decltype(labelled)::value;
+      constexpr bool I32 = decltype(index32_t)::value;
+      const float* qp = I32 ? prob : prob + first;
+      float* qg = HAS_GRAD ? (I32 ? grad : grad + first) : nullptr;
+      unsigned e = I32 ? static_cast<unsigned>(first) : 0u;
+      int k0 = 0;
+      for (; k0 + U <= K; k0 += U) {
+        ord_loss_group<HAS_GRAD, U, true, L>(qp, qg, e, hwu, U, static_cast<float>(k0), y, inv_nhw, l2sum);
+        if constexpr (I32) {
+          e += U * hwu;
+        } else {
+          qp += U * hw;
+          if constexpr (HAS_GRAD) qg += U * hw;
+        }
       }
-      pp += 8 * hw;
-      if (gp) gp += 8 * hw;
+      if (k0 < K) ord_loss_group<HAS_GRAD, U, false, L>(qp, qg, e, hwu, K - k0, static_cast<float>(k0), y, inv_nhw, l2sum);
+    };
+    const bool labelled = (y == y);
+    if (index32) {
+      if (labelled) walk(std::true_type{}, std::true_type{});
+      else walk(std::false_type{}, std::true_type{});
+    } else {
+      if (labelled) walk(std::true_type{}, std::false_type{});
+      else walk(std::false_type{}, std::false_type{});
     }
     loss_acc += static_cast<double>(l2sum);
   }
@@ -309,27 +343,69 @@ ord_loss_kernel(const float* __restrict__ prob, const float* __restrict__ label,
   }
 }
 
-// backward of OrdinalRegressionLayer: grad_x from grad_P
+// backward of OrdinalRegressionLayer: grad_x from grad_P. Groups of U pairs (3 U loads in flight), 32-bit element
+// indices where the logits have fewer than 2^32 elements.
+template <typename XT, int U, bool FULL>
+__device__ __forceinline__ void layer_bwd_group(const XT* __restrict__ px_x, XT* __restrict__ px_g, const float* __restrict__ px_p,
+                                                unsigned e, unsigned ep, unsigned hwu, int npair) {
+  float av[U], bv[U], gv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (FULL || u < npair) {
+      av[u] = Elem<XT>::ld1(px_x + (e + static_cast<unsigned>(2 * u) * hwu));
+      bv[u] = Elem<XT>::ld1(px_x + (e + static_cast<unsigned>(2 * u + 1) * hwu));
+      gv[u] = __ldcs(px_p + (ep + static_cast<unsigned>(u) * hwu));
+    } else {
+      av[u] = bv[u] = gv[u] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!FULL && u >= npair) break;
+    const float ca = clamp_logit(av[u]), cb = clamp_logit(bv[u]);
+    const float P = pair_prob(cb - ca);
+    const float gz = gv[u] * P * (1.0f - P);  // softmax backward for the 2-way case
+    // the clamp passes the gradient exactly where it returned the logit itself ([1e-8, 1e4]; NaN compares unequal)
+    Elem<XT>::st1(px_g + (e + static_cast<unsigned>(2 * u) * hwu), (ca == av[u]) ? -gz : 0.f);
+    Elem<XT>::st1(px_g + (e + static_cast<unsigned>(2 * u + 1) * hwu), (cb == bv[u]) ? gz : 0.f);
+  }
+}
+
 template <typename XT>
 __global__ void __launch_bounds__(kDBlock, 4)
 ordinal_layer_bwd_kernel(const XT* __restrict__ x, const float* __restrict__ gp, int64_t n, int K, int64_t hw,
-                         XT* __restrict__ gx) {
+                         XT* __restrict__ gx, int index32) {
+  constexpr int U = 4;
   const int64_t npx = n * hw;
+  const unsigned hwu = static_cast<unsigned>(hw);
   for (int64_t px = static_cast<int64_t>(blockIdx.x) * kDBlock + threadIdx.x; px < npx;
        px += static_cast<int64_t>(gridDim.x) * kDBlock) {
     const int64_t img = px / hw;
     const int64_t off = px - img * hw;
     const int64_t base = img * (2 * static_cast<int64_t>(K)) * hw + off;
     const int64_t pbase = img * static_cast<int64_t>(K) * hw + off;
-    for (int k = 0; k < K; ++k) {
-      const float av = Elem<XT>::ld1(x + base + static_cast<int64_t>(2 * k) * hw);
-      const float bv = Elem<XT>::ld1(x + base + static_cast<int64_t>(2 * k + 1) * hw);
-      const float g = __ldcs(gp + pbase + static_cast<int64_t>(k) * hw);
-      const float P = pair_prob(clamp_logit(bv) - clamp_logit(av));
-      const float gz = g * P * (1.0f - P);  // softmax backward for the 2-way case
-      Elem<XT>::st1(gx + base + static_cast<int64_t>(2 * k) * hw, logit_passes(av) ? -gz : 0.f);
-      Elem<XT>::st1(gx + base + static_cast<int64_t>(2 * k + 1) * hw, logit_passes(bv) ? gz : 0.f);
-    }
+    auto walk = [&](auto index32_t) {
+      constexpr bool I32 = decltype(index32_t)::value;
+      const XT* qx = I32 ? x : x + base;
+      XT* qg = I32 ? gx : gx + base;
+      const float* qp = I32 ? gp : gp + pbase;
+      unsigned e = I32 ? static_cast<unsigned>(base) : 0u, ep = I32 ? static_cast<unsigned>(pbase) : 0u;
+      int k0 = 0;
+      for (; k0 + U <= K; k0 += U) {
+        layer_bwd_group<XT, U, true>(qx, qg, qp, e, ep, hwu, U);
+        if constexpr (I32) {
+          e += 2u * U * hwu;
+          ep += U * hwu;
+        } else {
+          qx += 2 * U * hw;
+          qg += 2 * U * hw;
+          qp += U * hw;
+        }
+      }
+      if (k0 < K) layer_bwd_group<XT, U, false>(qx, qg, qp, e, ep, hwu, K - k0);
+    };
+    if (index32) walk(std::true_type{});
+    else walk(std::false_type{});
   }
 }
 
@@ -401,6 +477,15 @@ __global__ void __launch_bounds__(kDBlock) depth_to_label_kernel(const float* __
     label[i] = depth_label(__ldg(depth + i), alpha, beta, K, disc);
 }
 
+// element indices of a tensor fit 32 bits; MDE_DORN_NO_INDEX32=1 sends small tensors down the 64-bit pointer path too
+// (a >= 16 GB tensor is not a test case) - read per call so that a test can switch it
+inline int index32_ok(int64_t n_elem) {
+  if (const char* e = getenv("MDE_DORN_NO_INDEX32")) {
+    if (atoi(e) != 0) return 0;
+  }
+  return n_elem < (int64_t(1) << 32) ? 1 : 0;
+}
+
 inline unsigned px_grid(int64_t npx, int ctas_per_sm) {
   int64_t g = (npx + kDBlock - 1) / kDBlock;
   const int64_t cap = static_cast<int64_t>(sm_count()) * ctas_per_sm;
@@ -417,12 +502,7 @@ int launch_dorn_t(DornArgs& a, cudaStream_t st) {
     set_error("DORN head: more than 2^27 pixels per image");
     return MDE_ETOOBIG;
   }
-  a.index32 = (a.n * 2 * static_cast<int64_t>(a.K) * a.hw < (int64_t(1) << 32)) ? 1 : 0;
-  // MDE_DORN_NO_INDEX32=1 sends small tensors down the 64-bit pointer path too (a >= 16 GB tensor is not a test case);
-  // read per call so that a test can switch it
-  if (const char* e = getenv("MDE_DORN_NO_INDEX32")) {
-    if (atoi(e) != 0) a.index32 = 0;
-  }
+  a.index32 = index32_ok(a.n * 2 * static_cast<int64_t>(a.K) * a.hw);
 #define MDE_DORN(P, L, G) dorn_kernel<XT, P, L, G><<<grid, kDBlock, 0, st>>>(a)
   if (!l) { if (p) MDE_DORN(true, false, false); else MDE_DORN(false, false, false); }
   else if (g) { if (p) MDE_DORN(true, true, true); else MDE_DORN(false, true, true); }
@@ -465,10 +545,12 @@ extern "C" int mde_ordinal_layer_bwd(const void* x, int x_dtype, const float* gr
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = px_grid(n * hw, 4);
   const int k = static_cast<int>(K);
+  MDE_REQUIRE(hw < (int64_t(1) << 27), MDE_ETOOBIG, "more than 2^27 pixels per image");
+  const int i32 = index32_ok(n * 2 * K * hw);
   switch (x_dtype) {
-    case MDE_F32: ordinal_layer_bwd_kernel<float><<<grid, kDBlock, 0, st>>>(static_cast<const float*>(x), grad_prob, n, k, hw, static_cast<float*>(grad_x)); break;
-    case MDE_F16: ordinal_layer_bwd_kernel<__half><<<grid, kDBlock, 0, st>>>(static_cast<const __half*>(x), grad_prob, n, k, hw, static_cast<__half*>(grad_x)); break;
-    case MDE_BF16: ordinal_layer_bwd_kernel<__nv_bfloat16><<<grid, kDBlock, 0, st>>>(static_cast<const __nv_bfloat16*>(x), grad_prob, n, k, hw, static_cast<__nv_bfloat16*>(grad_x)); break;
+    case MDE_F32: ordinal_layer_bwd_kernel<float><<<grid, kDBlock, 0, st>>>(static_cast<const float*>(x), grad_prob, n, k, hw, static_cast<float*>(grad_x), i32); break;
+    case MDE_F16: ordinal_layer_bwd_kernel<__half><<<grid, kDBlock, 0, st>>>(static_cast<const __half*>(x), grad_prob, n, k, hw, static_cast<__half*>(grad_x), i32); break;
+    case MDE_BF16: ordinal_layer_bwd_kernel<__nv_bfloat16><<<grid, kDBlock, 0, st>>>(static_cast<const __nv_bfloat16*>(x), grad_prob, n, k, hw, static_cast<__nv_bfloat16*>(grad_x), i32); break;
     default: set_error("mde_ordinal_layer_bwd: unknown x_dtype %d", x_dtype); return MDE_EINVAL;
   }
   count_launch();
@@ -513,8 +595,14 @@ extern "C" int mde_ord_loss(const float* prob, const float* target_label, int64_
                             float grad_scale, void* ws, float* loss_out, float* grad_prob, void* stream) {
   MDE_REQUIRE(prob && target_label && ws && loss_out, MDE_EINVAL, "null pointer");
   MDE_REQUIRE(n > 0 && K > 0 && hw > 0 && K < 32768, MDE_EINVAL, "bad shape");
-  ord_loss_kernel<<<px_grid(n * hw, 4), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-      prob, target_label, n, static_cast<int>(K), hw, grad_scale, ws, loss_out, grad_prob);
+  MDE_REQUIRE(hw < (int64_t(1) << 27), MDE_ETOOBIG, "more than 2^27 pixels per image");
+  const int i32 = index32_ok(n * K * hw);
+  if (grad_prob)
+    ord_loss_kernel<true><<<px_grid(n * hw, 4), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        prob, target_label, n, static_cast<int>(K), hw, grad_scale, ws, loss_out, grad_prob, i32);
+  else
+    ord_loss_kernel<false><<<px_grid(n * hw, 4), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        prob, target_label, n, static_cast<int>(K), hw, grad_scale, ws, loss_out, nullptr, i32);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;

@@ -216,7 +216,7 @@ def test_sid_integer_labels_exact_outside_the_rounding_band(D):
 
 
 @pytest.mark.parametrize("shape,K", [((2, 136, 40, 52), 68), ((2, 22, 33, 41), 11)])
-def test_nan_labels_and_the_wide_index_path(D, shape, K):
+def test_nan_labels_and_the_wide_index_path(D, Cr, shape, K):
     """A negative or NaN target has a NaN SID label: neither k <= y nor k > y holds (criteria.py:769-770), the pixel
     contributes no loss term and its logits get a zero gradient (the kernel runs such pixels through their own code
     path). Then the same call with 64-bit per-pixel pointers instead of 32-bit element indices (the path of tensors with
@@ -236,8 +236,17 @@ def test_nan_labels_and_the_wide_index_path(D, shape, K):
         xr = x.cuda().requires_grad_(True)
         loss, decode, depth, P = D.dorn_fused(xr, gt.cuda(), K, 0.001, 1.0, want_prob=True)
         loss.backward()
-        return loss.detach(), decode, depth, P.detach(), xr.grad
+        # the reference's own sequence: layer, depth_to_label, ordLoss, backward through both modules
+        x2 = x.cuda().requires_grad_(True)
+        dec2, P2 = D.OrdinalRegressionLayer()(x2)
+        y2 = D.depth_to_label(gt.cuda(), torch.tensor(0.001), torch.tensor(1.0), torch.tensor(K).int())
+        l2 = Cr.ordLoss()(P2, y2)
+        l2.backward()
+        return loss.detach(), decode, depth, P.detach(), xr.grad, l2.detach(), dec2, P2.detach(), x2.grad
     out = once()
+    close(out[5], l64.detach(), LOSS_RTOL)
+    assert torch.equal(out[6].cpu(), dec_ref)
+    grad_close(out[8], g64)
     close(out[0], l64.detach(), LOSS_RTOL)
     assert torch.equal(out[1].cpu(), dec_ref)
     grad_close(out[4], g64)
@@ -248,3 +257,4 @@ def test_nan_labels_and_the_wide_index_path(D, shape, K):
     finally:
         del os.environ["MDE_DORN_NO_INDEX32"]
     assert all(torch.equal(a, b) for a, b in zip(out, wide))
+    assert float(out[8][0, :, 1, :7].abs().sum()) == 0.0

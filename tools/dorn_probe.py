@@ -36,6 +36,25 @@ def main():
     fns = [lambda x=x: _lib.check(lib.mde_ordinal_layer_fwd(_lib.ptr(x), 0, N, C2 // 2, H * W, None, _lib.ptr(dec), sp())) for x, _ in ring]
     us, _ = bench.graph_timed(fns, dev, 20)
     out.update({"decode_us": round(us, 2), "decode_gbs": round((4.0 * C2 + 8.0) * px / us / 1e3, 1)})
+    # the reference's own call sequence (module API): layer forward with P, ordLoss(P, label) fwd+bwd, layer backward
+    x, gt = ring[0]
+    del gxs
+    K = C2 // 2
+    P = torch.empty((N, K, H, W), device=dev)
+    gP = torch.empty((N, K, H, W), device=dev)
+    gx = torch.empty(shape, device=dev)
+    lab = torch.rand((N, 1, H, W), device=dev, generator=torch.Generator(device=dev).manual_seed(7)) * K
+    rows = (("layer_fwd_prob", [lambda: _lib.check(lib.mde_ordinal_layer_fwd(_lib.ptr(x), 0, N, K, H * W, _lib.ptr(P), _lib.ptr(dec), sp()))],
+             (8.0 * K + 4.0 * K + 8.0) * px),
+            ("ord_loss", [lambda: _lib.check(lib.mde_ord_loss(_lib.ptr(P), _lib.ptr(lab), N, K, H * W, 1.0, _lib.ptr(ws1), _lib.ptr(loss_t),
+                                                              _lib.ptr(gP), sp()))], (8.0 * K + 4.0) * px),
+            ("layer_bwd", [lambda: _lib.check(lib.mde_ordinal_layer_bwd(_lib.ptr(x), 0, _lib.ptr(gP), N, K, H * W, _lib.ptr(gx), sp()))],
+             (8.0 * K + 4.0 * K + 8.0 * K) * px))
+    for name, fns, nbytes in rows:
+        us, _ = bench.graph_timed(fns, dev, 20)
+        out[name + "_us"] = round(us, 2)
+        out[name + "_gbs"] = round(nbytes / us / 1e3, 1)
+    out["unfused_check"] = [float(loss_t), float(gP.double().abs().sum()), float(gx.double().abs().sum()), float(P.double().sum())]
     print(json.dumps(out), flush=True)
 
 
