@@ -422,9 +422,10 @@ __global__ void __launch_bounds__(kDBlock, 4) orl_count_kernel(const float* __re
 
 __global__ void __launch_bounds__(kDBlock, 4)
 orl_kernel(const float* __restrict__ prob, const float* __restrict__ gt, int64_t n, int K, int64_t hw, float alpha,
-           float beta, int disc, float grad_scale, void* ws_raw, float* loss_out, float* __restrict__ grad) {
+           float beta, int disc, float grad_scale, void* ws_raw, float* loss_out, float* __restrict__ grad, int index32) {
   __shared__ double sm[kDWarps];
   Ws ws = ws_view(ws_raw);
+  const unsigned hwu = static_cast<unsigned>(hw);
   const double n_valid = __ldcg(&ws.hdr->tacc[8]);
   const float gcoef = -grad_scale / static_cast<float>(n_valid);
   const int64_t npx = n * hw;
@@ -438,14 +439,34 @@ orl_kernel(const float* __restrict__ prob, const float* __restrict__ gt, int64_t
     long long label = 0;
     if (valid) label = __float2ll_rz(depth_label(t, alpha, beta, K, disc));  // .long(): toward zero (:805)
     float lsum = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const bool le = !(static_cast<long long>(k) > label);  // ord_c0 = 1 where not (k > label)  (:809-810)
-      const int64_t i0 = base + static_cast<int64_t>(k) * hw;        // '<=' plane k
-      const int64_t i1 = base + static_cast<int64_t>(K + k) * hw;    // '>'  plane k
-      if (valid) lsum += le ? __ldcs(prob + i0) : __ldcs(prob + i1);
-      if (grad) {
-        __stcs(grad + i0, (valid && le) ? gcoef : 0.f);
-        __stcs(grad + i1, (valid && !le) ? gcoef : 0.f);
+    // planes 0..K-1 hold the '<=' probabilities, K..2K-1 the '>' ones: pixel (k <= label) reads plane k, otherwise
+    // plane K + k. Groups of 8 selected planes in flight, 32-bit element indices (index32) or offsets from the pixel.
+    const bool i32 = index32 != 0;
+    const float* qp = i32 ? prob : prob + base;
+    float* qg = grad ? (i32 ? grad : grad + base) : nullptr;
+    const unsigned e0 = i32 ? static_cast<unsigned>(base) : 0u;
+    const unsigned Khw = static_cast<unsigned>(K) * hwu;
+    // ord_c0 = 1 where not (k > label) (:809-810): k <= label, clamped to the walk's range
+    const int n_le = (label < 0) ? 0 : ((label >= static_cast<long long>(K)) ? K : static_cast<int>(label) + 1);
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float pv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u;
+        const unsigned ek = e0 + static_cast<unsigned>(k) * hwu;
+        pv[u] = (valid && k < K) ? __ldcs(qp + (k < n_le ? ek : ek + Khw)) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u;
+        if (k >= K) break;
+        const bool le = k < n_le;
+        if (valid) lsum += pv[u];
+        if (qg) {
+          const unsigned ek = e0 + static_cast<unsigned>(k) * hwu;
+          __stcs(qg + ek, (valid && le) ? gcoef : 0.f);
+          __stcs(qg + (ek + Khw), (valid && !le) ? gcoef : 0.f);
+        }
       }
     }
     loss_acc -= static_cast<double>(lsum);
@@ -630,8 +651,10 @@ extern "C" int mde_ordinal_regression_loss(const float* prob, const float* gt_de
   orl_count_kernel<<<px_grid(n * hw, 4), kDBlock, 0, st>>>(gt_depth, n * hw, ws);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
+  MDE_REQUIRE(2 * K * hw < (int64_t(1) << 32), MDE_ETOOBIG, "more than 2^32 probabilities per image");
   orl_kernel<<<px_grid(n * hw, 4), kDBlock, 0, st>>>(prob, gt_depth, n, static_cast<int>(K), hw, alpha, beta,
-                                                     discretization, grad_scale, ws, loss_out, grad_prob);
+                                                     discretization, grad_scale, ws, loss_out, grad_prob,
+                                                     index32_ok(n * 2 * K * hw));
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
   return MDE_OK;

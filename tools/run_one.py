@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run ONE hot-path call a few times (for ncu / compute-sanitizer).  python tools/run_one.py <name> [reps]
-names: c5_metrics, c5_metrics10, c2_metrics, c2_fused, dorn_fused, dorn_decode, ord_loss, vnl, c1_berhu, pointcloud, wcel"""
+names: c5_metrics, c5_metrics10, c2_metrics, c2_fused, dorn_fused, dorn_decode, ord_loss, vnl, c1_berhu, c1_eigen, pointcloud, wcel"""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
@@ -27,6 +27,12 @@ elif name in ("c2_fused", "c1_berhu"):
     o64 = torch.empty(_lib.METRICS_OUT_F64, dtype=torch.float64, device=dev); o32 = torch.empty(24, device=dev)
     f = lambda: _lib.check(lib.mde_masked_loss_metrics(kind, _lib.ptr(pr), 0, _lib.ptr(gt), None, shape[0], shape[2], shape[3], C.byref(lp), 1.0, mflags,
                                                        _lib.ptr(ws), _lib.ptr(loss_t), None, _lib.ptr(grad), _lib.ptr(o64), _lib.ptr(o32), sp()))
+elif name == "c1_eigen":
+    shape = (8, 1, 228, 304)
+    pr, gt = synth.depth_pair(shape, 102, device=dev)
+    ws = _lib.workspace(dev, shape[0]); grad = torch.empty(shape, device=dev)
+    f = lambda: _lib.check(lib.mde_masked_loss(_lib.LOSS_EIGEN, _lib.ptr(pr), 0, _lib.ptr(gt), None, shape[0], shape[2], shape[3], C.byref(lp), 1.0,
+                                               _lib.ptr(ws), _lib.ptr(loss_t), None, _lib.ptr(grad), sp()))
 elif name in ("dorn_fused", "dorn_decode", "ord_loss"):
     shape = (8, 136, 257, 353); N, C2, H, W = shape
     x, gt = synth.dorn_inputs(shape, 103, device=dev)
