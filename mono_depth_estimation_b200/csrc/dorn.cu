@@ -38,6 +38,10 @@ constexpr int kDWarps = kDBlock / 32;
 #ifndef MDE_DORN_U_LOSS
 #define MDE_DORN_U_LOSS 8
 #endif
+// resident CTAs of 256 threads per SM the register budget is set for (grid = SMs x this). Measured at C3 on one box
+// (profiles/r02_dorn_ab.jsonl, last block): supervision step 151 us with 4, 150 with 5, 187 with 6; decode only 65.5 / 67.2 / 78.8;
+// layer forward WITH the probabilities (the module path: 12 K B/px, a third of them stores) 116.5 / 104.3 / 106.0.
+constexpr int dorn_ctas(bool has_prob, bool want_loss) { return (has_prob && !want_loss) ? 5 : 4; }
 #ifndef MDE_DORN_U_PLAIN
 #define MDE_DORN_U_PLAIN 4
 #endif
@@ -48,7 +52,6 @@ __device__ __forceinline__ float clamp_logit(float v) {
   v = (v < 1e-8f) ? 1e-8f : v;
   return (v > 1e4f) ? 1e4f : v;
 }
-__device__ __forceinline__ bool logit_passes(float v) { return v >= 1e-8f && v <= 1e4f; }
 
 // P = softmax(a', b')[1] = sigmoid(b' - a'), evaluated as softmax does (exp(x - max) / sum) on the SFU:
 // e = 2^(-|d| log2 e), P = 1/(1+e) or e/(1+e). Relative error ~2e-7.
@@ -178,7 +181,7 @@ struct DornArgs {
 // One kernel for: layer forward only (gt == null), fused supervision step (gt != null).
 // Compile-time switches (which outputs exist) keep the inner loop free of branches.
 template <typename XT, bool HAS_PROB, bool WANT_LOSS, bool HAS_GRAD>
-__global__ void __launch_bounds__(kDBlock, 4) dorn_kernel(DornArgs a) {
+__global__ void __launch_bounds__(kDBlock, dorn_ctas(HAS_PROB, WANT_LOSS)) dorn_kernel(DornArgs a) {
   __shared__ double sm[kDWarps];
   const XT* __restrict__ x = static_cast<const XT*>(a.x);
   XT* __restrict__ gx = static_cast<XT*>(a.grad_x);
@@ -287,12 +290,18 @@ __device__ __forceinline__ void ord_loss_group(const float* __restrict__ pp, flo
   }
 }
 
+#ifndef MDE_ORD_U
+#define MDE_ORD_U 16   // planes per group (C3, one box: 89.9 us with 8, 86.5 with 16; 6 CTAs per SM: 87.4 / 104.6)
+#endif
+#ifndef MDE_ORD_CTAS
+#define MDE_ORD_CTAS 4
+#endif
 template <bool HAS_GRAD>
-__global__ void __launch_bounds__(kDBlock, 4)
+__global__ void __launch_bounds__(kDBlock, MDE_ORD_CTAS)
 ord_loss_kernel(const float* __restrict__ prob, const float* __restrict__ label, int64_t n, int K, int64_t hw,
                 float grad_scale, void* ws_raw, float* loss_out, float* __restrict__ grad, int index32) {
   __shared__ double sm[kDWarps];
-  constexpr int U = 8;
+  constexpr int U = MDE_ORD_U;
   const int64_t npx = n * hw;
   const float inv_nhw = grad_scale / static_cast<float>(npx);
   const unsigned hwu = static_cast<unsigned>(hw);
@@ -517,14 +526,13 @@ inline unsigned px_grid(int64_t npx, int ctas_per_sm) {
 
 template <typename XT>
 int launch_dorn_t(DornArgs& a, cudaStream_t st) {
-  const unsigned grid = px_grid(a.n * a.hw, 4);
   const bool p = a.prob != nullptr, l = a.gt != nullptr, g = a.grad_x != nullptr && l;
   if (a.hw >= (int64_t(1) << 27)) {
     set_error("DORN head: more than 2^27 pixels per image");
     return MDE_ETOOBIG;
   }
   a.index32 = index32_ok(a.n * 2 * static_cast<int64_t>(a.K) * a.hw);
-#define MDE_DORN(P, L, G) dorn_kernel<XT, P, L, G><<<grid, kDBlock, 0, st>>>(a)
+#define MDE_DORN(P, L, G) dorn_kernel<XT, P, L, G><<<px_grid(a.n * a.hw, dorn_ctas(P, L)), kDBlock, 0, st>>>(a)
   if (!l) { if (p) MDE_DORN(true, false, false); else MDE_DORN(false, false, false); }
   else if (g) { if (p) MDE_DORN(true, true, true); else MDE_DORN(false, true, true); }
   else { if (p) MDE_DORN(true, true, false); else MDE_DORN(false, true, false); }
@@ -619,10 +627,10 @@ extern "C" int mde_ord_loss(const float* prob, const float* target_label, int64_
   MDE_REQUIRE(hw < (int64_t(1) << 27), MDE_ETOOBIG, "more than 2^27 pixels per image");
   const int i32 = index32_ok(n * K * hw);
   if (grad_prob)
-    ord_loss_kernel<true><<<px_grid(n * hw, 4), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+    ord_loss_kernel<true><<<px_grid(n * hw, MDE_ORD_CTAS), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(
         prob, target_label, n, static_cast<int>(K), hw, grad_scale, ws, loss_out, grad_prob, i32);
   else
-    ord_loss_kernel<false><<<px_grid(n * hw, 4), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+    ord_loss_kernel<false><<<px_grid(n * hw, MDE_ORD_CTAS), kDBlock, 0, static_cast<cudaStream_t>(stream)>>>(
         prob, target_label, n, static_cast<int>(K), hw, grad_scale, ws, loss_out, nullptr, i32);
   count_launch();
   MDE_CUDA_TRY(cudaGetLastError());
