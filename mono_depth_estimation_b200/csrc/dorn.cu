@@ -6,13 +6,15 @@
 //   OrdinalRegressionLoss.__call__   reference criteria.py:789-836
 //
 // Layout: logits x [n, 2K, hw] with pair k = channels (2k, 2k+1) (Dorn.py:305-306). One thread
-// owns one pixel and walks the K pairs; a warp therefore reads 32 consecutive pixels of one channel
-// plane per load (fully coalesced, also when hw is odd and the planes are only 4-byte aligned),
-// with 4 pairs (8 loads) in flight per thread. Everything the step needs - P, decode, depth, the
-// loss term and both logit gradients - is produced from that single read of the logits:
+// owns one pixel and walks the K pairs in groups (dorn_group: 8 pairs = 16 loads in flight for the
+// supervision step, 4 pairs for the plain layer); a warp therefore reads 32 consecutive pixels of one
+// channel plane per load (fully coalesced, also when hw is odd and the planes are only 4-byte
+// aligned). Everything the step needs - P, decode, depth, the loss term and both logit gradients -
+// is produced from that single read of the logits:
 // 8K (logits) + 4 (gt) + 8K (grad) + 8 (decode) + 4 (depth) = 1104 B/px at K = 68.
 //
-// Per pair the kernel issues ~45 instructions: P through MUFU.EX2 + MUFU.RCP (one Newton step), the
+// Per pair the kernel issues 42 instructions (60 before the groups lost their per-pair predicates and
+// 64-bit stride multiplies): P through MUFU.EX2 + MUFU.RCP (one Newton step), the
 // log of the clamped probability through MUFU.LG2 accumulated in the log2 domain (one multiply by
 // ln 2 per pixel), predicated selects instead of branches. Accuracy of these forms on B200 is in
 // profiles/r01_mathlab_sfu_accuracy.jsonl (relative error ~1e-7, far inside the 1e-5 tolerance).
