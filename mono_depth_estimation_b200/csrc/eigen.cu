@@ -10,6 +10,8 @@
 // (centre, right, down - neighbours come from L1/L2), the grid barrier publishes them, phase B
 // writes the gradient with the 5-point stencil. Pixels are walked flat, one contiguous chunk per
 // CTA; the CTA flushes its per-image sums whenever its chunk crosses an image boundary.
+// Small inputs (fp32, W % 4 == 0, <= 606 k pixels) run in eigen_resident_kernel further down instead: every pixel stays in
+// registers from the first load to the gradient store, no grid barrier and no atomics (C1: 16.3 -> 8.75 us).
 #include "common.cuh"
 
 namespace mde {
